@@ -1,0 +1,277 @@
+// arrow_fill_alpha / arrow_fill_beta: banded, column-scaled forward / backward recursion of
+// every subread against its template slice (Recursor::FillAlpha / FillBeta / FillAlphaBeta,
+// SURVEY.md 8a rows a8-a10; /root/reference/docs/how-does-ccs-work.md:94-96,
+// /root/reference/docs/faq/revio.md:20-25 "filling out matrices at its core").
+//
+// Mapping: one warp octet per (read, template) pair, 16 pairs per 128-thread CTA, pairs sorted
+// by length so the four octets of a warp finish together.  Per column an octet reads one
+// template base + one 16-byte transition row (L1-resident), looks the emissions up in shared
+// memory, and writes one 128-byte line of fp32 cells -- the kernel is HBM-write bound:
+// algorithmic bytes per pair = 4*32*(J-1) cells + 8 (alpha) or 4 (beta) bytes of column info
+// per column + I + J input bytes (DESIGN.md "Roofline").
+#include "arrow_octet.cuh"
+#include "arrow_launch.h"
+
+namespace ccs {
+
+namespace {
+
+__device__ __forceinline__ void load_emissions(const ArrowBatchView& V, float* s_emm, float* s_emi) {
+    for (int k = threadIdx.x; k < 36 * kEmStride; k += blockDim.x) s_emm[k] = V.em_match[k];
+    for (int k = threadIdx.x; k < 17 * kEmStride; k += blockDim.x) s_emi[k] = V.em_ins[k];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
+                                                               const int n_items) {
+    __shared__ float s_emm[36 * kEmStride];
+    __shared__ float s_emi[17 * kEmStride];
+    load_emissions(V, s_emm, s_emi);
+
+    const int item = blockIdx.x * 16 + (threadIdx.x >> 3);
+    const int g = threadIdx.x & 7;
+    int r = -1;
+    if (item < n_items) r = order[item];
+    DevRead rd;
+    rd.J = 0; rd.I = 0; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0; rd.zmw = 0; rd.last_code = 0;
+    if (r >= 0) rd = V.reads[r];
+    const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
+    const int J = valid ? rd.J : 0;
+    const int I = rd.I;
+    int Jmax = J;
+#pragma unroll
+    for (int off = 8; off < 32; off <<= 1) Jmax = max(Jmax, __shfl_xor_sync(kFullMask, Jmax, off));
+
+    const uint8_t* __restrict__ rc = V.rowcode + rd.code_off;
+    const uint8_t* __restrict__ tp = V.tpl + rd.tpl_off;
+    const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
+    float4* __restrict__ acol = reinterpret_cast<float4*>(V.alpha) + (size_t)rd.col_off * 8;
+    ColInfo* __restrict__ cinfo = V.colinfo + rd.col_off;
+    const int code_max = I + kRowCodePad - 1;
+
+    // column 0: alpha(0,0) = 1
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (g == 0) v[0] = 1.f;
+    int s = 0, cum = 0, edge = 0;
+    int code[4], ncode[4];
+    if (valid) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            code[q] = rc[4 * g + q];
+            ncode[q] = rc[min(4 * g + q + 32, code_max)];
+        }
+        acol[g] = make_float4(v[0], v[1], v[2], v[3]);
+        if (g == 0) cinfo[0] = ColInfo{0, 0};
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) code[q] = ncode[q] = 12;
+    }
+    int t0 = 0, t1 = 0, t2 = 0;
+    if (valid) { t0 = tp[0]; t1 = tp[1]; t2 = tp[min(2, J - 1)]; }
+    int cm = kCtxStartRow + t0;          // match/deletion context of column 1: pinned first move
+    int ci = 4 * t0 + t1;                // insertion context of column 1
+    float4 tr_m = valid ? tr[cm] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 tr_i = valid ? tr[ci] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float final_val = 0.f;
+    int final_cum = 0;
+
+    for (int j = 1; j < Jmax; ++j) {
+        const bool alive = j < J;
+        const int s_new = max(s, edge + 2 + kBandMargin - kBandW);
+        const int d = s_new - s;
+        int rel[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int slot = 4 * g + q;
+            const int rel_old = (slot - s) & 31;
+            rel[q] = (slot - s_new) & 31;
+            if (rel_old < d) {   // slot recycled: its row moved down by 32
+                code[q] = ncode[q];
+                ncode[q] = alive ? rc[min(s_new + rel[q] + 32, code_max)] : 12;
+            }
+        }
+        // prefetch next column's transition row and the template base after it
+        const int ci_next = ((ci & 3) << 2) | t2;
+        const float4 tr_next = alive ? tr[ci_next] : tr_i;
+        const int t3 = alive ? tp[min(j + 2, J - 1)] : 0;
+
+        octet_forward_column(v, g, d, rel, code, tr_m.x, tr_m.y, tr_i.z, tr_i.w, s_emm + cm * kEmStride,
+                             s_emi + ci * kEmStride, ci & 3);
+        int edge_rel;
+        bool dead;
+        const int k = octet_scale_column(v, rel, edge_rel, dead);
+        cum += k;
+        edge = s_new + edge_rel - 1;
+        s = s_new;
+        if (alive) {
+            acol[(size_t)j * 8 + g] = make_float4(v[0], v[1], v[2], v[3]);
+            if (g == 0) cinfo[j] = ColInfo{s_new, cum};
+            if (j == J - 1) {   // alpha(I-1, J-1) lives in slot (I-1) mod 32 if it is inside the band
+                const int slot = (I - 1) & 31;
+                const int rrel = (slot - s_new) & 31;
+                const bool inband = (s_new + rrel) == (I - 1);
+                float x = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) x = (4 * g + q == slot && inband) ? v[q] : x;
+                final_val = x;
+                final_cum = cum;
+            }
+        }
+        cm = ci; ci = ci_next; tr_m = tr_i; tr_i = tr_next; t2 = t3;
+    }
+    // gather the final cell from whichever lane owns it, then the pinned last match
+    const float fv = octet_max(final_val);
+    if (valid) {
+        if (g == 0) {
+            const int ctxl = 4 * tp[J - 2] + tp[J - 1];
+            const double a = (double)fv * (double)s_emm[(kCtxEndRow + ctxl) * kEmStride + rd.last_code];
+            const double base = (a > 0.0) ? log(a) + 0.6931471805599453094 * (double)final_cum : -INFINITY;
+            V.base_ll[r] = base;
+            V.ll_alpha[r] = base - (double)I * V.log_cw;
+        }
+    } else if (r >= 0 && g == 0) {
+        V.base_ll[r] = -INFINITY;
+        V.ll_alpha[r] = -INFINITY;
+    }
+}
+
+__global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
+                                                              const int n_items) {
+    __shared__ float s_emm[36 * kEmStride];
+    __shared__ float s_emi[17 * kEmStride];
+    load_emissions(V, s_emm, s_emi);
+
+    const int item = blockIdx.x * 16 + (threadIdx.x >> 3);
+    const int g = threadIdx.x & 7;
+    int r = -1;
+    if (item < n_items) r = order[item];
+    DevRead rd;
+    rd.J = 0; rd.I = 0; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0; rd.zmw = 0; rd.last_code = 0; rd.first_code = 0;
+    if (r >= 0) rd = V.reads[r];
+    const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
+    const int J = valid ? rd.J : 0;
+    const int I = rd.I;
+    int Jmax = J;
+#pragma unroll
+    for (int off = 8; off < 32; off <<= 1) Jmax = max(Jmax, __shfl_xor_sync(kFullMask, Jmax, off));
+
+    const uint8_t* __restrict__ rc = V.rowcode + rd.code_off;
+    const uint8_t* __restrict__ tp = V.tpl + rd.tpl_off;
+    const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
+    float4* __restrict__ bcol = reinterpret_cast<float4*>(V.beta) + (size_t)rd.col_off * 8;
+    const ColInfo* __restrict__ cinfo = V.colinfo + rd.col_off;
+    int32_t* __restrict__ bexp = V.beta_exp + rd.col_off;
+    const int code_max = I + kRowCodePad - 1;
+
+    // The warp walks columns from (Jmax-1) down to 1; an octet is alive once j <= J-1.
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    int code1[4] = {12, 12, 12, 12}, pcode1[4] = {12, 12, 12, 12};
+    int s_next = 0, cum = 0;
+    int s_cur = 0;   // band start of column j (prefetched)
+    int t_hi = 0, t_lo = 0, t_lo2 = 0;   // template bases j, j-1, j-2
+    float4 tr_c = make_float4(0.f, 0.f, 0.f, 0.f), tr_p = tr_c;
+    float first_val = 0.f;
+    int first_cum = 0;
+    bool started = false;
+
+    for (int j = Jmax - 1; j >= 1; --j) {
+        const bool alive = j <= J - 1;
+        if (alive && !started) {
+            // prologue at j == J-1
+            s_cur = cinfo[j].start;
+            s_next = s_cur;
+            t_hi = tp[j]; t_lo = tp[j - 1]; t_lo2 = tp[max(j - 2, 0)];
+            tr_c = tr[4 * t_lo + t_hi];
+            tr_p = tr[4 * t_lo2 + t_lo];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int row = s_cur + ((4 * g + q - s_cur) & 31);
+                code1[q] = rc[min(row + 1, code_max)];
+                pcode1[q] = rc[max(row + 1 - 32, 0)];
+            }
+        }
+        const int ci = 4 * t_lo + t_hi;              // context of column j (= match context of j+1)
+        const int d = s_next - s_cur;
+        int rel[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int slot = 4 * g + q;
+            const int rel_nx = (slot - s_next) & 31;
+            rel[q] = (slot - s_cur) & 31;
+            if (started && rel_nx >= 32 - d) {   // slot recycled: its row moved up by 32
+                code1[q] = pcode1[q];
+                pcode1[q] = alive ? rc[max(s_cur + rel[q] + 1 - 32, 0)] : 12;
+            }
+        }
+        // prefetch for column j-1
+        const int s_prev = (alive && j >= 2) ? cinfo[j - 1].start : s_cur;
+        const int t_lo3 = (alive && j >= 3) ? tp[j - 3] : 0;
+        const float4 tr_pp = alive ? tr[4 * t_lo3 + t_lo2] : tr_p;
+
+        float A[4], G[4];
+        octet_backward_terms(v, g, d, rel, code1, tr_c.x, tr_c.y, tr_c.z, tr_c.w, s_emm + ci * kEmStride,
+                             s_emi + ci * kEmStride, ci & 3, A, G);
+        if (alive && !started) {
+            // last column: beta(I-1, J-1) = pinned last match; rows above it by insertions
+            const float endv = s_emm[(kCtxEndRow + ci) * kEmStride + rd.last_code];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) A[q] = (s_cur + rel[q] == I - 1) ? endv : 0.f;
+        }
+        if (!alive) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { A[q] = 0.f; G[q] = 0.f; }
+        }
+        octet_backward_scan(A, G, g, v);
+        int edge_rel;
+        bool dead;
+        const int k = octet_scale_column(v, rel, edge_rel, dead);
+        if (alive) {
+            cum += k;
+            bcol[(size_t)j * 8 + g] = make_float4(v[0], v[1], v[2], v[3]);
+            if (g == 0) bexp[j] = cum;
+            if (j == 1) {   // beta(1,1) lives in slot 1 if row 1 is inside the band
+                const int rrel = (1 - s_cur) & 31;
+                const bool inband = (s_cur + rrel) == 1;
+                float x = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) x = (4 * g + q == 1 && inband) ? v[q] : x;
+                first_val = x;
+                first_cum = cum;
+            }
+            started = true;
+            s_next = s_cur; s_cur = s_prev;
+            t_hi = t_lo; t_lo = t_lo2; t_lo2 = t_lo3;
+            tr_c = tr_p; tr_p = tr_pp;
+        }
+    }
+    const float fv = octet_max(first_val);
+    if (valid) {
+        if (g == 0) {
+            const double b = (double)fv * (double)s_emm[(kCtxStartRow + tp[0]) * kEmStride + rd.first_code];
+            const double lb = (b > 0.0) ? log(b) + 0.6931471805599453094 * (double)first_cum - (double)I * V.log_cw : -INFINITY;
+            V.ll_beta[r] = lb;
+            const double la = V.ll_alpha[r];
+            int st = 0;  // CCS_READ_VALID
+            if (!(la > -INFINITY) || !(lb > -INFINITY)) st = 3;                 // CCS_READ_DEAD
+            else if (!(fabs(1.0 - la / lb) <= V.ab_tol)) st = 1;               // CCS_READ_ALPHA_BETA_MISMATCH
+            V.status[r] = st;
+        }
+    } else if (r >= 0 && g == 0) {
+        V.ll_beta[r] = -INFINITY;
+        V.status[r] = (rd.active && (rd.J < 2 || rd.I < 2)) ? 2 : (rd.active ? 3 : 4);
+    }
+}
+
+}  // namespace
+
+void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream) {
+    if (n_items <= 0) return;
+    arrow_fill_alpha_kernel<<<(n_items + 15) / 16, 128, 0, stream>>>(V, order, n_items);
+}
+
+void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream) {
+    if (n_items <= 0) return;
+    arrow_fill_beta_kernel<<<(n_items + 15) / 16, 128, 0, stream>>>(V, order, n_items);
+}
+
+}  // namespace ccs

@@ -1,0 +1,20 @@
+// Host-callable launchers of the Arrow kernels (implemented in the .cu files).
+#pragma once
+#include <cuda_runtime.h>
+#include "arrow_device.h"
+
+namespace ccs {
+
+// order[n_items]: read indices, longest template first (keeps a warp's four octets in step)
+void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
+void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
+
+// delta[(zmw.delta_off + p) * 9 + slot], slots {SUB A,C,G,T, DEL, INS A,C,G,T}
+void launch_score(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, double* delta,
+                  cudaStream_t stream);
+void launch_pick(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, const double* delta,
+                 Candidate* out, int cap, int* counter, cudaStream_t stream);
+void launch_qv(const ArrowBatchView& V, const double* delta, uint8_t* qv, long long n_items, const ScoreRange* ranges,
+               int n_ranges, cudaStream_t stream);
+
+}  // namespace ccs

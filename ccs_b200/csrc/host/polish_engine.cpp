@@ -1,0 +1,541 @@
+// Polish Stage host engine -- see polish_engine.h.
+#include "polish_engine.h"
+#include "../cuda/arrow_launch.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace ccs {
+
+namespace {
+
+inline uint64_t tpl_hash(const std::vector<uint8_t>& t) {
+    uint64_t h = 1469598103934665603ull;
+    for (uint8_t b : t) { h ^= b; h *= 1099511628211ull; }
+    return h ^ ((uint64_t)t.size() * 0x9E3779B97F4A7C15ull);
+}
+
+inline int type_rank(int t) { return t == 2 ? 0 : (t == 1 ? 1 : 2); }   // DEL < INS < SUB
+
+// Template::ApplyMutations: muts sorted by position; at most one of SUB/DEL per position
+std::vector<uint8_t> apply_to_template(const std::vector<uint8_t>& tpl, const std::vector<HostMutation>& muts) {
+    std::vector<uint8_t> out;
+    out.reserve(tpl.size() + muts.size());
+    size_t k = 0;
+    const int J = (int)tpl.size();
+    for (int j = 0; j <= J; ++j) {
+        bool skip = false;
+        while (k < muts.size() && muts[k].pos == j) {
+            const HostMutation& m = muts[k++];
+            if (m.type == 1) out.push_back((uint8_t)m.base);
+            else if (m.type == 0) { out.push_back((uint8_t)m.base); skip = true; }
+            else skip = true;
+        }
+        if (j < J && !skip) out.push_back(tpl[j]);
+    }
+    return out;
+}
+
+}  // namespace
+
+ArrowEngine::ArrowEngine(int device, const ArrowModelParams& model, size_t budget_bytes)
+    : device_(device), budget_(budget_bytes), model_(model) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device >= n)
+        throw CudaError(std::string("no usable CUDA device (ccs_b200 has no CPU fallback): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range"));
+    CCS_CUDA(cudaSetDevice(device_));
+    if (budget_ == 0) {
+        size_t fr = 0, tot = 0;
+        CCS_CUDA(cudaMemGetInfo(&fr, &tot));
+        budget_ = fr - fr / 10;
+    }
+    CCS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CCS_CUDA(cudaEventCreate(&ev0_));
+    CCS_CUDA(cudaEventCreate(&ev1_));
+    build_emission_tables(model_, em_);
+    for (auto* b : {&d_emm_, &d_emi_, &d_trans_, &d_alpha_, &d_beta_}) b->budget_used = &used_;
+    d_rowcode_.budget_used = &used_; d_tpl_.budget_used = &used_; d_colinfo_.budget_used = &used_;
+    d_bexp_.budget_used = &used_; d_delta_.budget_used = &used_; d_qv_.budget_used = &used_;
+    d_emm_.ensure(36 * 16);
+    d_emi_.ensure(17 * 16);
+    CCS_CUDA(cudaMemcpyAsync(d_emm_.p, em_.em_match, sizeof(em_.em_match), cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_emi_.p, em_.em_ins, sizeof(em_.em_ins), cudaMemcpyHostToDevice, stream_));
+    d_counter_.ensure(4);
+    h_counter_.ensure(4);
+    CCS_CUDA(cudaStreamSynchronize(stream_));
+}
+
+ArrowEngine::~ArrowEngine() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+ArrowBatchView ArrowEngine::view() const {
+    ArrowBatchView V;
+    V.rowcode = d_rowcode_.p; V.tpl = d_tpl_.p; V.em_match = d_emm_.p; V.em_ins = d_emi_.p; V.trans = d_trans_.p;
+    V.reads = d_reads_.p; V.zmws = d_zmws_.p; V.alpha = d_alpha_.p; V.beta = d_beta_.p; V.colinfo = d_colinfo_.p;
+    V.beta_exp = d_bexp_.p; V.ll_alpha = d_ll_alpha_.p; V.ll_beta = d_ll_beta_.p; V.base_ll = d_base_ll_.p;
+    V.status = d_status_.p; V.n_reads = (int32_t)reads_.size(); V.n_zmws = (int32_t)zmws_.size();
+    V.log_cw = std::log(model_.counter_weight); V.ab_tol = ab_tol_;
+    return V;
+}
+
+// ---------------------------------------------------------------------------------------------
+// load: pack one batch.  Row codes are stored row-indexed with sentinels so the kernels never
+// bounds-check (Recursor::EncodeRead); transition tables per ZMW
+// (ModelConfig::Populate, row a6).
+// ---------------------------------------------------------------------------------------------
+void ArrowEngine::load(const PolishInput& in) {
+    CCS_CUDA(cudaSetDevice(device_));
+    const int nz = in.n_zmws, nr = in.n_reads;
+    zstate_.assign(nz, ZmwState());
+    reads_.assign(nr, DevRead());
+    zmws_.assign(nz, DevZmw());
+    status_.assign(nr, 4);
+    qv_.assign(nz, {});
+    tpl_cap_.assign(nz, 0);
+
+    // row codes
+    int64_t code_total = 0;
+    for (int r = 0; r < nr; ++r) code_total += (in.read_off[r + 1] - in.read_off[r]) + kRowCodePad + 1;
+    code_total = (code_total + 15) & ~15ll;
+    h_rowcode_.ensure((size_t)code_total);
+    std::memset(h_rowcode_.p, kCodeSentinel, (size_t)code_total);
+    int64_t coff = 0;
+    for (int z = 0; z < nz; ++z) {
+        ZmwState& zs = zstate_[z];
+        zs.read_begin = in.zmw_read_off[z];
+        zs.read_end = in.zmw_read_off[z + 1];
+        zs.tpl.assign(in.tpl + in.tpl_off[z], in.tpl + in.tpl_off[z + 1]);
+        zs.seen.assign(1, tpl_hash(zs.tpl));
+        for (int r = zs.read_begin; r < zs.read_end; ++r) {
+            DevRead& rd = reads_[r];
+            std::memset(&rd, 0, sizeof(rd));
+            const int64_t I = in.read_off[r + 1] - in.read_off[r];
+            const uint8_t* src = in.codes + in.read_off[r];
+            rd.code_off = coff;
+            rd.I = (int32_t)I;
+            rd.zmw = z;
+            rd.strand = in.strand[r];
+            rd.ts = in.tstart[r];
+            rd.te = in.tend[r];
+            rd.active = (rd.te > rd.ts) ? 1 : 0;
+            if (rd.active) ++zs.n_mapped;
+            // rowcode[i] = code of DP row i: sentinel at row 0 and at rows >= I (the last read base
+            // is consumed only by the pinned final match)
+            uint8_t* dst = h_rowcode_.p + coff;
+            if (I >= 2) std::memcpy(dst + 1, src, (size_t)(I - 1));
+            rd.first_code = I >= 1 ? src[0] : 0;
+            rd.last_code = I >= 1 ? src[I - 1] : 0;
+            coff += I + kRowCodePad + 1;
+        }
+    }
+    d_rowcode_.ensure((size_t)code_total, budget_);
+    // transitions
+    h_trans_.ensure((size_t)nz * 36 * 4);
+    for (int z = 0; z < nz; ++z) {
+        ZmwTransitions zt;
+        build_zmw_transitions(model_, in.snr + 4 * z, zt);
+        std::memcpy(h_trans_.p + (size_t)z * 36 * 4, zt.tr, sizeof(zt.tr));
+    }
+    d_trans_.ensure((size_t)nz * 36 * 4, budget_);
+    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_rowcode_.p, h_rowcode_.p, (size_t)code_total, cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_trans_.p, h_trans_.p, (size_t)nz * 36 * 4 * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    stats.h2d_bytes += code_total + (int64_t)nz * 36 * 4 * 4;
+    // template capacities: room for the template to grow during polishing
+    for (int z = 0; z < nz; ++z) {
+        const int J = (int)zstate_[z].tpl.size();
+        tpl_cap_[z] = ((J + std::max(256, J / 16)) + 15) & ~15;
+    }
+    upload_templates_and_reads();
+    if (timing_enabled) {
+        CCS_CUDA(cudaEventRecord(ev1_, stream_));
+        CCS_CUDA(cudaEventSynchronize(ev1_));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev0_, ev1_);
+        stats.ms_h2d += ms;
+    }
+}
+
+// (Re)derive DevRead / DevZmw / template buffer / column offsets from the host state and push
+// them.  Called after load() and after every round that edited templates.
+void ArrowEngine::upload_templates_and_reads() {
+    const int nz = (int)zstate_.size(), nr = (int)reads_.size();
+    int64_t toff = 0, cols = 0, drows = 0;
+    for (int z = 0; z < nz; ++z) {
+        ZmwState& zs = zstate_[z];
+        const int J = (int)zs.tpl.size();
+        if (J > tpl_cap_[z]) tpl_cap_[z] = ((J + std::max(256, J / 16)) + 15) & ~15;
+        DevZmw& dz = zmws_[z];
+        dz.read_begin = zs.read_begin; dz.read_end = zs.read_end;
+        dz.fwd_off = (int32_t)toff; dz.rev_off = (int32_t)(toff + tpl_cap_[z]);
+        dz.J = J; dz.delta_off = drows; dz.pad_ = 0;
+        toff += 2 * (int64_t)tpl_cap_[z];
+        drows += J + 1;
+    }
+    if (toff > 0x7fffffffll) throw OomError("template buffer exceeds 2 GiB; use smaller batches");
+    h_tpl_.ensure((size_t)toff + 16);
+    for (int z = 0; z < nz; ++z) {
+        const ZmwState& zs = zstate_[z];
+        const DevZmw& dz = zmws_[z];
+        const int J = dz.J;
+        uint8_t* f = h_tpl_.p + dz.fwd_off;
+        uint8_t* rv = h_tpl_.p + dz.rev_off;
+        std::memcpy(f, zs.tpl.data(), (size_t)J);
+        for (int j = 0; j < J; ++j) rv[j] = (uint8_t)(3 - zs.tpl[J - 1 - j]);
+        for (int r = zs.read_begin; r < zs.read_end; ++r) {
+            DevRead& rd = reads_[r];
+            const int len = rd.te - rd.ts;
+            if (rd.active && (len < 2 || rd.ts < 0 || rd.te > J || rd.I < 2)) { rd.active = 0; status_[r] = 2; }
+            rd.J = rd.active ? len : 0;
+            rd.tpl_off = rd.strand ? dz.rev_off + (J - rd.te) : dz.fwd_off + rd.ts;
+            rd.col_off = cols;
+            if (rd.active) cols += rd.J;
+        }
+    }
+    total_cols_ = cols;
+    total_delta_rows_ = drows;
+    order_.clear();
+    for (int r = 0; r < nr; ++r) if (reads_[r].active) order_.push_back(r);
+    std::stable_sort(order_.begin(), order_.end(), [&](int a, int b) { return reads_[a].J > reads_[b].J; });
+
+    d_tpl_.ensure((size_t)toff + 16, budget_);
+    d_reads_.ensure((size_t)nr + 1);
+    d_zmws_.ensure((size_t)nz + 1);
+    d_order_.ensure((size_t)nr + 1);
+    d_status_.ensure((size_t)nr + 1);
+    d_ll_alpha_.ensure((size_t)nr + 1); d_ll_beta_.ensure((size_t)nr + 1); d_base_ll_.ensure((size_t)nr + 1);
+    d_alpha_.ensure((size_t)(cols + 2) * 32, budget_);
+    d_beta_.ensure((size_t)(cols + 2) * 32, budget_);
+    d_colinfo_.ensure((size_t)cols + 2, budget_);
+    d_bexp_.ensure((size_t)cols + 2, budget_);
+    h_reads_.ensure((size_t)nr + 1); h_zmws_.ensure((size_t)nz + 1); h_order_.ensure((size_t)nr + 1);
+    h_status_.ensure((size_t)nr + 1);
+    std::memcpy(h_reads_.p, reads_.data(), sizeof(DevRead) * nr);
+    std::memcpy(h_zmws_.p, zmws_.data(), sizeof(DevZmw) * nz);
+    std::memcpy(h_order_.p, order_.data(), sizeof(int32_t) * order_.size());
+    std::memcpy(h_status_.p, status_.data(), sizeof(int32_t) * nr);
+    CCS_CUDA(cudaMemcpyAsync(d_tpl_.p, h_tpl_.p, (size_t)toff, cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_reads_.p, h_reads_.p, sizeof(DevRead) * nr, cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_zmws_.p, h_zmws_.p, sizeof(DevZmw) * nz, cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_order_.p, h_order_.p, sizeof(int32_t) * order_.size(), cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_status_.p, h_status_.p, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, stream_));
+    stats.h2d_bytes += toff + (int64_t)sizeof(DevRead) * nr + (int64_t)sizeof(DevZmw) * nz + 8ll * nr;
+}
+
+void ArrowEngine::fill() {
+    CCS_CUDA(cudaSetDevice(device_));
+    const ArrowBatchView V = view();
+    const int n = (int)order_.size();
+    int64_t cells = 0, in_bytes = 0;
+    for (int r : order_) { cells += 32ll * (reads_[r].J - 1); in_bytes += reads_[r].I + reads_[r].J; }
+    float ms = 0;
+    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
+    launch_fill_alpha(V, d_order_.p, n, stream_);
+    if (timing_enabled) {
+        CCS_CUDA(cudaEventRecord(ev1_, stream_));
+        CCS_CUDA(cudaEventSynchronize(ev1_));
+        cudaEventElapsedTime(&ms, ev0_, ev1_);
+        stats.ms_fill_alpha += ms;
+        CCS_CUDA(cudaEventRecord(ev0_, stream_));
+    }
+    launch_fill_beta(V, d_order_.p, n, stream_);
+    if (timing_enabled) {
+        CCS_CUDA(cudaEventRecord(ev1_, stream_));
+        CCS_CUDA(cudaEventSynchronize(ev1_));
+        cudaEventElapsedTime(&ms, ev0_, ev1_);
+        stats.ms_fill_beta += ms;
+    }
+    CCS_CUDA(cudaGetLastError());
+    ++stats.n_fill_alpha; ++stats.n_fill_beta;
+    stats.cells_fill += cells;
+    stats.bytes_fill_alpha += 4 * cells + 8 * (cells / 32) + in_bytes;
+    stats.bytes_fill_beta += 4 * cells + 8 * (cells / 32) + in_bytes;   // 4 B exponent out + 4 B band start in
+    sync_statuses();
+}
+
+void ArrowEngine::sync_statuses() {
+    const int nr = (int)reads_.size();
+    CCS_CUDA(cudaMemcpyAsync(h_status_.p, d_status_.p, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, stream_));
+    CCS_CUDA(cudaStreamSynchronize(stream_));
+    stats.d2h_bytes += 4ll * nr;
+    for (int r = 0; r < nr; ++r) {
+        if (!reads_[r].active) continue;
+        status_[r] = h_status_.p[r];
+        if (status_[r] != 0) reads_[r].active = 0;   // dropped for the rest of the polish (Integrator semantics)
+    }
+}
+
+void ArrowEngine::read_lls(double* ll_alpha, double* ll_beta, int32_t* status) {
+    const int nr = (int)reads_.size();
+    h_ll_.ensure((size_t)2 * nr + 2);
+    CCS_CUDA(cudaMemcpyAsync(h_ll_.p, d_ll_alpha_.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream_));
+    CCS_CUDA(cudaMemcpyAsync(h_ll_.p + nr, d_ll_beta_.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream_));
+    CCS_CUDA(cudaStreamSynchronize(stream_));
+    stats.d2h_bytes += 16ll * nr;
+    for (int r = 0; r < nr; ++r) {
+        const bool filled = status_[r] == 0 || status_[r] == 1 || status_[r] == 3;
+        if (ll_alpha) ll_alpha[r] = (filled && status_[r] != 3) ? h_ll_.p[r] : NAN;
+        if (ll_beta) ll_beta[r] = (filled && status_[r] != 3) ? h_ll_.p[nr + r] : NAN;
+        if (status) status[r] = status_[r];
+    }
+}
+
+void ArrowEngine::dump_pair(int r, float* alpha, float* beta, int32_t* start, int32_t* aexp, int32_t* bexp) {
+    const DevRead& rd = reads_[r];
+    const int J = rd.J;
+    if (J <= 0) return;
+    std::vector<ColInfo> ci(J);
+    CCS_CUDA(cudaStreamSynchronize(stream_));
+    if (alpha) CCS_CUDA(cudaMemcpy(alpha, d_alpha_.p + rd.col_off * 32, sizeof(float) * 32 * J, cudaMemcpyDeviceToHost));
+    if (beta) CCS_CUDA(cudaMemcpy(beta, d_beta_.p + rd.col_off * 32, sizeof(float) * 32 * J, cudaMemcpyDeviceToHost));
+    CCS_CUDA(cudaMemcpy(ci.data(), d_colinfo_.p + rd.col_off, sizeof(ColInfo) * J, cudaMemcpyDeviceToHost));
+    if (bexp) CCS_CUDA(cudaMemcpy(bexp, d_bexp_.p + rd.col_off, sizeof(int32_t) * J, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < J; ++j) { if (start) start[j] = ci[j].start; if (aexp) aexp[j] = ci[j].cumexp; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------------------
+void ArrowEngine::score_ranges(const std::vector<ScoreRange>& ranges, int64_t n_items) {
+    if (ranges.empty() || n_items == 0) return;
+    d_ranges_.ensure(ranges.size());
+    h_ranges_.ensure(ranges.size());
+    std::memcpy(h_ranges_.p, ranges.data(), sizeof(ScoreRange) * ranges.size());
+    d_delta_.ensure((size_t)total_delta_rows_ * 9 + 16, budget_);
+    CCS_CUDA(cudaMemcpyAsync(d_ranges_.p, h_ranges_.p, sizeof(ScoreRange) * ranges.size(), cudaMemcpyHostToDevice, stream_));
+    stats.h2d_bytes += (int64_t)sizeof(ScoreRange) * ranges.size();
+    const ArrowBatchView V = view();
+    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
+    launch_score(V, d_ranges_.p, (int)ranges.size(), n_items, d_delta_.p, stream_);
+    if (timing_enabled) {
+        CCS_CUDA(cudaEventRecord(ev1_, stream_));
+        CCS_CUDA(cudaEventSynchronize(ev1_));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev0_, ev1_);
+        stats.ms_score += ms;
+    }
+    CCS_CUDA(cudaGetLastError());
+    ++stats.n_score;
+    stats.score_items += n_items;
+    n_ranges_ = (int)ranges.size();
+    n_range_items_ = n_items;
+}
+
+void ArrowEngine::score_all_positions() {
+    std::vector<ScoreRange> ranges;
+    int64_t first = 0;
+    for (int z = 0; z < (int)zstate_.size(); ++z) {
+        const ZmwState& zs = zstate_[z];
+        if (zs.failed || zs.tpl.empty()) continue;
+        ranges.push_back(ScoreRange{z, 0, (int32_t)zs.tpl.size(), 0, first});
+        first += (int64_t)zs.tpl.size();
+    }
+    score_ranges(ranges, first);
+}
+
+int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
+    out.clear();
+    if (n_ranges_ == 0 || n_range_items_ == 0) return 0;
+    const ArrowBatchView V = view();
+    size_t cap = std::max<size_t>(d_cand_.cap, (size_t)std::min<int64_t>(n_range_items_, 1 << 20));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        d_cand_.ensure(cap);
+        CCS_CUDA(cudaMemsetAsync(d_counter_.p, 0, sizeof(int32_t), stream_));
+        if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
+        launch_pick(V, d_ranges_.p, n_ranges_, n_range_items_, d_delta_.p, d_cand_.p, (int)d_cand_.cap, d_counter_.p, stream_);
+        if (timing_enabled) CCS_CUDA(cudaEventRecord(ev1_, stream_));
+        CCS_CUDA(cudaMemcpyAsync(h_counter_.p, d_counter_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        CCS_CUDA(cudaStreamSynchronize(stream_));
+        if (timing_enabled) { float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_); stats.ms_pick += ms; }
+        ++stats.n_pick;
+        const int64_t n = h_counter_.p[0];
+        if ((size_t)n <= d_cand_.cap) {
+            h_cand_.ensure((size_t)n + 1);
+            if (n > 0) {
+                CCS_CUDA(cudaMemcpyAsync(h_cand_.p, d_cand_.p, sizeof(Candidate) * n, cudaMemcpyDeviceToHost, stream_));
+                CCS_CUDA(cudaStreamSynchronize(stream_));
+                stats.d2h_bytes += (int64_t)sizeof(Candidate) * n;
+                out.assign(h_cand_.p, h_cand_.p + n);
+            }
+            return n;
+        }
+        cap = (size_t)n + 1024;   // overflow: grow and retry once
+    }
+    throw CudaError("candidate buffer overflow");
+}
+
+void ArrowEngine::download_delta(int z, double* out) {
+    const DevZmw& dz = zmws_[z];
+    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(cudaMemcpy(out, d_delta_.p + dz.delta_off * 9, sizeof(double) * 9 * dz.J, cudaMemcpyDeviceToHost));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Polish(): iterate {score -> keep improving mutations -> greedy best with separation ->
+// apply -> refill} until no mutation improves any ZMW of the batch
+// (docs/how-does-ccs-work.md:96-101).
+// ---------------------------------------------------------------------------------------------
+void ArrowEngine::polish(const PolishParams& pp) {
+    ab_tol_ = pp.ab_mismatch_tol;
+    const int nz = (int)zstate_.size();
+    fill();
+    auto check_usable = [&](int z) {
+        ZmwState& zs = zstate_[z];
+        int act = 0;
+        for (int r = zs.read_begin; r < zs.read_end; ++r) act += reads_[r].active;
+        if (act == 0 || act < pp.min_active_fraction * zs.n_mapped) { zs.failed = true; zs.done = true; }
+    };
+    for (int z = 0; z < nz; ++z) check_usable(z);
+
+    std::vector<Candidate> cands;
+    for (int it = 0; it < pp.max_iterations; ++it) {
+        // ranges to score this round
+        std::vector<ScoreRange> ranges;
+        int64_t first = 0;
+        for (int z = 0; z < nz; ++z) {
+            ZmwState& zs = zstate_[z];
+            if (zs.done) continue;
+            const int J = (int)zs.tpl.size();
+            zs.iterations = it + 1;
+            if (it == 0) {
+                ranges.push_back(ScoreRange{z, 0, J, 0, first});
+                first += J;
+                zs.n_tested += count_canonical(zs.tpl, 0, J);
+            } else {
+                // union of +-neighborhood around the last-applied sites
+                std::vector<std::pair<int, int>> iv;
+                for (int s : zs.sites) iv.push_back({std::max(0, s - pp.neighborhood), std::min(J, s + pp.neighborhood + 1)});
+                std::sort(iv.begin(), iv.end());
+                int cb = -1, ce = -1;
+                auto flush = [&]() {
+                    if (ce > cb) {
+                        const int e = std::min(ce, J);
+                        if (e > cb) {
+                            ranges.push_back(ScoreRange{z, cb, e, 0, first});
+                            first += e - cb;
+                            zs.n_tested += count_canonical(zs.tpl, cb, e);
+                        }
+                    }
+                };
+                for (auto& v : iv) {
+                    if (v.first > ce) { flush(); cb = v.first; ce = v.second; }
+                    else ce = std::max(ce, v.second);
+                }
+                flush();
+            }
+        }
+        if (ranges.empty()) break;
+        ++stats.rounds;
+        score_ranges(ranges, first);
+        pick(cands);
+        // group candidates per ZMW
+        std::vector<std::vector<HostMutation>> per(nz);
+        for (const Candidate& c : cands) per[c.zmw].push_back(HostMutation{c.type, c.pos, c.base, c.score});
+        bool any_applied = false;
+        for (int z = 0; z < nz; ++z) {
+            ZmwState& zs = zstate_[z];
+            if (zs.done) continue;
+            auto& sc = per[z];
+            if (sc.empty()) { zs.converged = true; zs.done = true; continue; }
+            std::sort(sc.begin(), sc.end(), [](const HostMutation& a, const HostMutation& b) {
+                if (a.score != b.score) return a.score > b.score;
+                if (a.pos != b.pos) return a.pos < b.pos;
+                if (a.type != b.type) return type_rank(a.type) < type_rank(b.type);
+                return a.base < b.base;
+            });
+            std::vector<HostMutation> best;
+            for (const auto& m : sc) {
+                bool ok = true;
+                for (const auto& c : best) if (std::abs(c.pos - m.pos) < pp.separation) { ok = false; break; }
+                if (ok) best.push_back(m);
+            }
+            std::sort(best.begin(), best.end(), [](const HostMutation& a, const HostMutation& b) { return a.pos < b.pos; });
+            std::vector<uint8_t> next = apply_to_template(zs.tpl, best);
+            uint64_t h = tpl_hash(next);
+            if (std::find(zs.seen.begin(), zs.seen.end(), h) != zs.seen.end()) {   // cycle guard
+                best.assign(1, sc.front());
+                next = apply_to_template(zs.tpl, best);
+                h = tpl_hash(next);
+            }
+            zs.seen.push_back(h);
+            zs.sites.clear();
+            int off = 0;
+            for (const auto& m : best) {
+                zs.sites.push_back(m.pos + off);
+                off += m.type == 1 ? 1 : (m.type == 2 ? -1 : 0);
+            }
+            zs.n_applied += (int)best.size();
+            // span bookkeeping of the ZMW's reads (Integrator::ApplyMutations)
+            for (int r = zs.read_begin; r < zs.read_end; ++r) {
+                DevRead& rd = reads_[r];
+                int ds = 0, de = 0;
+                for (const auto& m : best) {
+                    if (m.type == 1) { if (m.pos <= rd.ts) ++ds; if (m.pos < rd.te) ++de; }
+                    else if (m.type == 2) { if (m.pos < rd.ts) --ds; if (m.pos < rd.te) --de; }
+                }
+                rd.ts += ds; rd.te += de;
+            }
+            zs.tpl.swap(next);
+            any_applied = true;
+        }
+        if (!any_applied) break;
+        upload_templates_and_reads();
+        fill();
+        for (int z = 0; z < nz; ++z) if (!zstate_[z].done) check_usable(z);
+    }
+    consensus_qvs();
+}
+
+int64_t ArrowEngine::count_canonical(const std::vector<uint8_t>& t, int b, int e) const {
+    const int J = (int)t.size();
+    int64_t n = 0;
+    for (int p = b; p < e; ++p) {
+        n += 3;                                            // substitutions
+        if (!(p > 0 && t[p] == t[p - 1])) ++n;             // deletion
+        if (p >= 1 && p <= J - 1) n += 3;                  // insertions except the one equal to t[p-1]
+    }
+    return n;
+}
+
+void ArrowEngine::consensus_qvs() {
+    const int nz = (int)zstate_.size();
+    std::vector<ScoreRange> ranges;
+    int64_t first = 0;
+    for (int z = 0; z < nz; ++z) {
+        const ZmwState& zs = zstate_[z];
+        if (zs.failed || zs.tpl.empty()) continue;
+        ranges.push_back(ScoreRange{z, 0, (int32_t)zs.tpl.size(), 0, first});
+        first += (int64_t)zs.tpl.size();
+    }
+    for (int z = 0; z < nz; ++z) qv_[z].clear();
+    if (ranges.empty()) return;
+    score_ranges(ranges, first);
+    d_qv_.ensure((size_t)total_delta_rows_ + 16, budget_);
+    h_qv_.ensure((size_t)total_delta_rows_ + 16);
+    const ArrowBatchView V = view();
+    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
+    launch_qv(V, d_delta_.p, d_qv_.p, first, d_ranges_.p, (int)ranges.size(), stream_);
+    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev1_, stream_));
+    CCS_CUDA(cudaMemcpyAsync(h_qv_.p, d_qv_.p, (size_t)total_delta_rows_, cudaMemcpyDeviceToHost, stream_));
+    CCS_CUDA(cudaStreamSynchronize(stream_));
+    if (timing_enabled) { float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_); stats.ms_qv += ms; }
+    CCS_CUDA(cudaGetLastError());
+    ++stats.n_qv;
+    stats.d2h_bytes += total_delta_rows_;
+    for (int z = 0; z < nz; ++z) {
+        const ZmwState& zs = zstate_[z];
+        if (zs.failed || zs.tpl.empty()) continue;
+        const DevZmw& dz = zmws_[z];
+        qv_[z].assign(h_qv_.p + dz.delta_off, h_qv_.p + dz.delta_off + dz.J);
+    }
+}
+
+}  // namespace ccs

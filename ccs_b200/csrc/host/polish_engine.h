@@ -1,0 +1,143 @@
+// Host side of the Polish Stage (the GPU box of /root/reference/docs/img/ccs-impl.png):
+// packs a batch of ZMWs (drafts + mapped subreads) into the device layout of
+// cuda/arrow_device.h, drives the Arrow kernels round by round, and owns the small sequential
+// pieces of Polish() -- greedy mutation selection with separation, template editing, span
+// bookkeeping (docs/how-does-ccs-work.md:96-112).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../common/arrow_tables.h"
+#include "../cuda/arrow_device.h"
+#include "cuda_util.h"
+
+namespace ccs {
+
+struct PolishInput {
+    int32_t n_zmws = 0, n_reads = 0;
+    const int32_t* zmw_read_off = nullptr;   // [n_zmws+1] -> reads
+    const int64_t* read_off = nullptr;       // [n_reads+1] -> codes
+    const uint8_t* codes = nullptr;          // emission codes 4*(pw-1)+base, native read orientation
+    const float* snr = nullptr;              // [n_zmws*4] A,C,G,T
+    const int64_t* tpl_off = nullptr;        // [n_zmws+1] -> tpl
+    const uint8_t* tpl = nullptr;            // draft templates, bases 0..3
+    const uint8_t* strand = nullptr;         // [n_reads] 0 fwd / 1 rev
+    const int32_t* tstart = nullptr;         // [n_reads] span on the draft [tstart,tend); tend<=tstart: unmapped
+    const int32_t* tend = nullptr;
+};
+
+struct PolishParams {
+    int32_t max_iterations = 40;
+    int32_t separation = 10;
+    int32_t neighborhood = 20;
+    double ab_mismatch_tol = 1e-3;
+    double min_rq = 0.99;          // --min-rq
+    int32_t min_length = 10;       // --min-length
+    int32_t max_length = 50000;    // --max-length
+    double min_active_fraction = 0.5;   // TOO_MANY_UNUSABLE below this share of mapped reads
+};
+
+struct HostMutation { int32_t type, pos, base; double score; };
+
+struct ZmwState {
+    std::vector<uint8_t> tpl;          // current forward template
+    int32_t read_begin = 0, read_end = 0;
+    bool converged = false, failed = false, done = false;
+    int32_t iterations = 0, n_applied = 0;
+    int64_t n_tested = 0;
+    std::vector<uint64_t> seen;        // template hashes (cycle guard)
+    std::vector<int32_t> sites;        // positions of the last-applied mutations (new coordinates)
+    int32_t n_mapped = 0;
+};
+
+struct EngineStats {
+    // per-kernel accumulated device time (ms, CUDA events on the engine stream), launches,
+    // algorithmic bytes (DESIGN.md "Roofline") -- reset by reset_stats()
+    double ms_fill_alpha = 0, ms_fill_beta = 0, ms_score = 0, ms_pick = 0, ms_qv = 0, ms_h2d = 0, ms_d2h = 0;
+    int64_t n_fill_alpha = 0, n_fill_beta = 0, n_score = 0, n_pick = 0, n_qv = 0;
+    int64_t bytes_fill_alpha = 0, bytes_fill_beta = 0, bytes_score = 0;
+    int64_t cells_fill = 0, score_items = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int64_t rounds = 0;
+};
+
+class ArrowEngine {
+public:
+    ArrowEngine(int device, const ArrowModelParams& model, size_t budget_bytes);
+    ~ArrowEngine();
+
+    // ---- batch life cycle -------------------------------------------------------------
+    void load(const PolishInput& in);        // pack + H2D; every mapped read starts active
+    void fill();                             // alpha + beta for every active read, statuses updated
+    void score_ranges(const std::vector<ScoreRange>& ranges, int64_t n_items);   // delta-LL of every slot
+    void score_all_positions();
+    int64_t pick(std::vector<Candidate>& out);   // canonical mutations with delta-LL > 0 in the scored ranges
+    void polish(const PolishParams& pp);     // full Polish() loop + QVs
+    void consensus_qvs();                    // ConsensusQualities on the current templates
+
+    // ---- results ----------------------------------------------------------------------
+    int32_t n_reads() const { return (int32_t)reads_.size(); }
+    int32_t n_zmws() const { return (int32_t)zmws_.size(); }
+    const std::vector<ZmwState>& zmw_states() const { return zstate_; }
+    const std::vector<DevRead>& reads() const { return reads_; }
+    void read_lls(double* ll_alpha, double* ll_beta, int32_t* status);
+    void dump_pair(int r, float* alpha, float* beta, int32_t* start, int32_t* aexp, int32_t* bexp);
+    void download_delta(int z, double* out /* [J*9] */);
+    const std::vector<std::vector<uint8_t>>& qvs() const { return qv_; }
+
+    EngineStats stats;
+    void reset_stats() { stats = EngineStats(); }
+    cudaStream_t stream() const { return stream_; }
+    int device() const { return device_; }
+    bool timing_enabled = true;
+
+private:
+    int64_t count_canonical(const std::vector<uint8_t>& t, int b, int e) const;
+    void upload_templates_and_reads();       // (re)build DevRead/DevZmw/template buffer from host state
+    void sync_statuses();
+    ArrowBatchView view() const;
+
+    int device_;
+    size_t budget_;
+    size_t used_ = 0;
+    ArrowModelParams model_;
+    EmissionTables em_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+
+    // host state of the current batch
+    std::vector<ZmwState> zstate_;
+    std::vector<DevRead> reads_;
+    std::vector<DevZmw> zmws_;
+    std::vector<int32_t> order_;             // active reads, longest template first
+    std::vector<int32_t> status_;
+    std::vector<std::vector<uint8_t>> qv_;
+    std::vector<int32_t> tpl_cap_;           // per-ZMW template capacity in the device buffer
+    int64_t total_cols_ = 0, total_delta_rows_ = 0;
+    double ab_tol_ = 1e-3;
+    int n_ranges_ = 0;
+    int64_t n_range_items_ = 0;
+
+    // device buffers
+    DevBuf<uint8_t> d_rowcode_, d_tpl_;
+    DevBuf<float> d_emm_, d_emi_, d_trans_, d_alpha_, d_beta_;
+    DevBuf<DevRead> d_reads_;
+    DevBuf<DevZmw> d_zmws_;
+    DevBuf<ColInfo> d_colinfo_;
+    DevBuf<int32_t> d_bexp_, d_status_, d_order_, d_counter_;
+    DevBuf<double> d_ll_alpha_, d_ll_beta_, d_base_ll_, d_delta_;
+    DevBuf<ScoreRange> d_ranges_;
+    DevBuf<Candidate> d_cand_;
+    DevBuf<uint8_t> d_qv_;
+    // pinned staging
+    PinBuf<uint8_t> h_rowcode_, h_tpl_, h_qv_;
+    PinBuf<float> h_trans_;
+    PinBuf<DevRead> h_reads_;
+    PinBuf<DevZmw> h_zmws_;
+    PinBuf<int32_t> h_order_, h_status_, h_counter_;
+    PinBuf<double> h_ll_;
+    PinBuf<ScoreRange> h_ranges_;
+    PinBuf<Candidate> h_cand_;
+};
+
+}  // namespace ccs

@@ -96,6 +96,102 @@ int  ccs_sim_zmw(const void* model, const ccs_sim_config* cfg, int64_t index, fl
 int  ccs_sim_corrupt(const uint8_t* tpl, int32_t len, double rate, uint64_t seed, uint8_t* out, int32_t out_cap,
                      int32_t* out_len, int32_t* map);
 
+/* ------------------------------------------------------------------------------------
+ * GPU context
+ * ---------------------------------------------------------------------------------- */
+typedef struct ccsgpu_ctx ccsgpu_ctx;
+
+/* One context per GPU.  `model` = blob from ccs_model_synthetic()/ccs_model_load_json();
+ * device_bytes_budget = 0 -> 90 % of free device memory.  Returns NULL on failure and
+ * writes the ccs_error to *err (CCS_ERR_NO_DEVICE when no CUDA device: no CPU fallback). */
+ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_budget, int* err);
+void        ccsgpu_destroy(ccsgpu_ctx* ctx);
+/* Message of the last failure on this ctx (or of the last failed ccsgpu_create if ctx == NULL). */
+const char* ccsgpu_last_error(const ccsgpu_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------
+ * Stage inputs / outputs (struct-of-arrays, caller-owned host memory)
+ * ---------------------------------------------------------------------------------- */
+/* A batch of ZMWs as the reader hands them to the stages (docs/img/ccs-impl.png "queue: ZMWs"). */
+typedef struct ccs_batch {
+    int32_t n_zmws, n_reads;
+    const int32_t* zmw_read_off;  /* [n_zmws+1] ZMW -> reads */
+    const int64_t* read_off;      /* [n_reads+1] read -> codes */
+    const uint8_t* codes;         /* 1 B per base: 4*(min(pw,3)-1) + base(A,C,G,T = 0..3), native orientation
+                                     (Recursor::EncodeRead; pw tag docs/faq/bam-output.md:20) */
+    const float*   snr;           /* [n_zmws*4] `sn` tag order A,C,G,T (docs/faq/bam-output.md:28) */
+    const uint8_t* cx;            /* [n_reads] local-context flags: 1 adapter before, 2 adapter after */
+    const int32_t* hole;          /* [n_zmws] `zm` */
+} ccs_batch;
+
+/* Draft Stage output = Polish Stage input ("queue: ZMWs, Drafts, Windows"). */
+typedef struct ccs_drafts {
+    const int64_t* tpl_off;       /* [n_zmws+1] */
+    const uint8_t* tpl;           /* draft templates, bases 0..3 */
+    const uint8_t* strand;        /* [n_reads] 0 = same strand as the draft, 1 = reverse complement */
+    const int32_t* tstart;        /* [n_reads] span of the read on the draft [tstart,tend); */
+    const int32_t* tend;          /*           tend <= tstart: read not placed (excluded)   */
+} ccs_drafts;
+
+typedef struct ccs_polish_cfg {
+    int32_t max_iterations;       /* 40  */
+    int32_t separation;           /* 10: minimum distance between mutations applied in one round */
+    int32_t neighborhood;         /* 20: re-score +-neighborhood around applied mutations */
+    int32_t min_length;           /* --min-length (docs/how-does-ccs-work.md:51) */
+    int32_t max_length;           /* --max-length */
+    double  min_rq;               /* --min-rq (docs/how-does-ccs-work.md:111-112) */
+    double  ab_mismatch_tol;      /* 1e-3: |1 - LL_alpha/LL_beta| above this drops the read */
+    double  min_active_fraction;  /* 0.5: fewer usable reads -> TOO_MANY_UNUSABLE */
+} ccs_polish_cfg;
+void ccs_polish_cfg_default(ccs_polish_cfg* cfg);
+
+typedef struct ccs_results {
+    int64_t  seq_cap;             /* capacity of seq / qv in bases */
+    int64_t* seq_off;             /* [n_zmws+1] out */
+    uint8_t* seq;                 /* consensus bases 0..3 */
+    uint8_t* qv;                  /* per-base QV 0..93 */
+    float*   rq;                  /* [n_zmws] predicted accuracy = 1 - mean(10^(-QV/10)) */
+    int32_t* status;              /* [n_zmws] ccs_zmw_status */
+    int32_t* n_passes;            /* [n_zmws] `np`: full-length subreads used */
+    int32_t* iterations;          /* [n_zmws] polish rounds run */
+    int32_t* n_applied;           /* [n_zmws] mutations applied */
+    int64_t* n_tested;            /* [n_zmws] mutations scored */
+    double*  read_ll;             /* [n_reads] per-subread Arrow log-likelihood on the final template (NaN: not used) */
+    int32_t* read_status;         /* [n_reads] ccs_read_status */
+} ccs_results;
+
+/* ------------------------------------------------------------------------------------
+ * Stages
+ * ---------------------------------------------------------------------------------- */
+/* Polish Stage: Arrow refinement of every draft with its mapped subreads + per-base QVs
+ * (Integrator + Polish + ConsensusQualities; docs/how-does-ccs-work.md:87-112).
+ * Returns CCS_ERR_CAPACITY (and the needed size in out->seq_cap) if seq/qv are too small. */
+int ccsgpu_polish(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_drafts* drafts, const ccs_polish_cfg* cfg,
+                  ccs_results* out);
+
+/* Test / bench hooks on the two hot kernels --------------------------------------------- */
+/* Recursor::FillAlphaBeta for n independent (read, template) pairs; pair k uses snr[4k..].
+ * Optional dump of pair `dump_pair` (>= 0): alpha/beta cells [J*32] (slot = row mod 32),
+ * band starts [J], cumulative scale exponents of alpha (left to right) / beta (right to left). */
+int ccsgpu_fill_alpha_beta(ccsgpu_ctx* ctx, int32_t n_pairs, const int64_t* tpl_off, const uint8_t* tpl,
+                           const int64_t* read_off, const uint8_t* codes, const float* snr, double* ll_alpha,
+                           double* ll_beta, int32_t* status, int32_t dump_pair, float* alpha_out, float* beta_out,
+                           int32_t* start_out, int32_t* aexp_out, int32_t* bexp_out);
+/* Integrator::LL(Mutation) - LL() for every slot of every draft position, no refinement:
+ * delta[(tpl_off[z] + p) * 9 + slot], slots {SUB A,C,G,T, DEL, INS A,C,G,T}; read_ll[n_reads]. */
+int ccsgpu_score_all(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_drafts* drafts, double* delta, double* read_ll,
+                     int32_t* read_status);
+
+/* Device-time accounting of the ctx since the last reset (CUDA events on the ctx stream). */
+typedef struct ccs_stats {
+    double  ms_fill_alpha, ms_fill_beta, ms_score, ms_pick, ms_qv, ms_h2d, ms_draft;
+    int64_t launches_fill_alpha, launches_fill_beta, launches_score, launches_pick, launches_qv, launches_draft;
+    int64_t bytes_fill_alpha, bytes_fill_beta;   /* algorithmic bytes (DESIGN.md "Roofline") */
+    int64_t cells_fill, score_items, rounds;
+    int64_t h2d_bytes, d2h_bytes;
+} ccs_stats;
+int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset);
+
 #ifdef __cplusplus
 }
 #endif
