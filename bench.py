@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- ZMWs/s of the per-ZMW CCS hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            product arm (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N ...            reference arm (CPU oracle on host cores)
+
+A step = one pass of the hot path over one batch of synthetic ZMWs (config 2 of BASELINE.json:
+1 000 ZMWs, 10 kb insert x 10 passes, Sequel-II-shape reads sampled from the Arrow HMM).
+N > 1 (torchrun): ZMW index ranges are sharded across ranks, no collective on the data path;
+value = all ranks' ZMWs / max-over-ranks time ("weak": per-GPU work fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--zmws", type=int, default=1000, help="ZMWs per step per GPU")
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config id (2 = metric config)")
+    ap.add_argument("--draft-error", type=float, default=0.02)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="ZMWs in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+WORKLOADS = {1: "config1: 1 ZMW 10kb x 10 passes", 2: "config2: 1000 ZMWs, 10 kb insert x 10 passes (+2 partial passes)",
+             3: "config3: 15 kb insert, 5-20 passes", 5: "config5: 25 kb insert x 4 passes"}
+
+
+def make_batch(model, cfg, first, n, draft_error, threads):
+    from ccs_b200 import sim, api
+    a = sim.simulate_batch(model, cfg, first, n, draft_error, threads)
+    b = api.Batch.from_arrays(a["zmw_read_off"], a["read_off"], a["codes"], a["snr"], a["cx"], a["hole"], a["draft_off"],
+                              a["draft"], a["strand"], a["dstart"], a["dend"])
+    return b, a
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_polish_sample(model, arrays, idxs, threads):
+    """CPU oracle (checker) polish of the ZMWs `idxs` of a simulated batch on `threads` host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(z):
+        r0, r1 = arrays["zmw_read_off"][z], arrays["zmw_read_off"][z + 1]
+        reads = [arrays["codes"][arrays["read_off"][r]:arrays["read_off"][r + 1]] for r in range(r0, r1)]
+        d = arrays["draft"][arrays["draft_off"][z]:arrays["draft_off"][z + 1]]
+        return O.polish(model, arrays["snr"][4 * z:4 * z + 4], d, reads, arrays["strand"][r0:r1].astype(np.int32),
+                        arrays["dstart"][r0:r1], arrays["dend"][r0:r1])
+
+    O.olib()
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(one, idxs))
+    return time.perf_counter() - t0, res
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path.  /root/reference holds no source
+    (docs only), so this is the CPU oracle port on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from ccs_b200 import sim
+    model = sim.synthetic_model()
+    cfg = sim.get_config(args.config)
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample or max(cores, 4)
+    times = []
+    for step in range(args.warmup + args.steps):
+        arrays = sim.simulate_batch(model, cfg, 1_000_000 + step * n, n, args.draft_error, cores)
+        dt, _ = oracle_polish_sample(model, arrays, list(range(n)), cores)
+        if step >= args.warmup:
+            times.append(dt)
+    T = sum(times)
+    val = n * len(times) / T
+    line = {"impl": "reference", "metric": "HiFi ZMWs/sec (polish stage: Arrow refinement + QVs of every ZMW)",
+            "value": val, "unit": "ZMW/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS.get(args.config, str(args.config)), "zmws_per_step": n,
+                       "draft": f"truth corrupted at {args.draft_error:.0%} (draft stage not in the timed region)"},
+            "cpu_baseline": {"value": val, "unit": "ZMW/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} ZMWs of the same workload per step, {cores} threads"},
+            "e2e": {"value": val, "unit": "ZMW/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- ccs_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from ccs_b200 import sim, api
+    model = sim.synthetic_model()
+    cfg = sim.get_config(args.config)
+    threads = max(1, (os.cpu_count() or 8) // max(world, 1))
+    ctx = api.Context(model, device=local)
+    pcfg = ctx.default_polish_cfg()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # distinct synthetic ZMW index range per rank and per step (working set >> L2: ~30 GB of DP bands)
+    def step_batch(step):
+        first = (step * world + rank) * args.zmws
+        return make_batch(model, cfg, first, args.zmws, args.draft_error, threads)
+
+    for w in range(args.warmup):
+        b, _ = step_batch(w)
+        ctx.polish(b, pcfg)
+    batches = [step_batch(args.warmup + k) for k in range(args.steps)]
+    ctx.stats(reset=True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    results = []
+    for b, _ in batches:
+        results.append(ctx.polish(b, pcfg))
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    barrier()
+    st = ctx.stats()
+    t_e2e = st["ms_e2e"] / 1e3
+    t_res = st["ms_resident"] / 1e3
+    tt = torch.tensor([t_e2e, t_res, wall], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(args.zmws * args.steps), float(sum(int((r["status"] == 16).sum()) for r in results))],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    t_e2e, t_res, wall = [float(x) for x in tt.tolist()]
+    n_total, n_hifi = [float(x) for x in cnt.tolist()]
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        fa = st["bytes_fill_alpha"] / max(st["launches_fill_alpha"], 1)
+        fa_ms = st["ms_fill_alpha"] / max(st["launches_fill_alpha"], 1)
+        achieved = fa / (fa_ms * 1e-3) / 1e9 if fa_ms > 0 else 0.0
+        kern_ms = {k: st[k] for k in ("ms_fill_alpha", "ms_fill_beta", "ms_score", "ms_pick", "ms_qv", "ms_h2d")}
+        launches = sum(st[k] for k in st if k.startswith("launches"))
+        line = {
+            "metric": "HiFi ZMWs/sec (polish stage: Arrow refinement + QVs of every ZMW)",
+            "value": n_total / t_res, "unit": "ZMW/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS.get(args.config, str(args.config)), "zmws_per_step_per_gpu": args.zmws,
+                       "draft": f"truth corrupted at {args.draft_error:.0%} (draft stage not in the timed region)",
+                       "l2": "inputs larger than L2 (tens of GB of DP bands per step, new ZMWs every step)",
+                       "parallelism": f"zmw-range-shard x{world}, no collective"},
+            "hifi_zmws_per_s": n_hifi / t_res, "hifi_fraction": n_hifi / n_total,
+            "e2e": {"value": n_total / t_e2e, "unit": "ZMW/s", "h2d_bytes_per_step": st["h2d_bytes"] / args.steps,
+                    "d2h_bytes_per_step": st["d2h_bytes"] / args.steps, "wall_s": wall},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "arrow_fill_alpha_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": fa, "ms_per_launch": fa_ms},
+            "kernel_ms": kern_ms, "rounds": st["rounds"], "score_items": st["score_items"],
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            n = args.cpu_sample or max(cores, 4)
+            _, arrays = batches[0]
+            dt, ores = oracle_polish_sample(model, arrays, list(range(n)), cores)
+            # the sample doubles as a parity spot check at full size
+            r = results[0]
+            same = sum(int(np.array_equal(r["seq"][r["seq_off"][z]:r["seq_off"][z + 1]], ores[z]["consensus"]))
+                       for z in range(n))
+            line["cpu_baseline"] = {"value": n / dt, "unit": "ZMW/s", "cores": cores, "kind": "port",
+                                    "sample": f"first {n} ZMWs of step 0, {cores} threads, {dt:.1f} s",
+                                    "consensus_identical": f"{same}/{n}"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

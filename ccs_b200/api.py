@@ -48,7 +48,8 @@ class CStats(C.Structure):
                                           "ms_draft")] + \
                [(n, C.c_int64) for n in ("launches_fill_alpha", "launches_fill_beta", "launches_score", "launches_pick",
                                          "launches_qv", "launches_draft", "bytes_fill_alpha", "bytes_fill_beta",
-                                         "cells_fill", "score_items", "rounds", "h2d_bytes", "d2h_bytes")]
+                                         "cells_fill", "score_items", "rounds", "h2d_bytes", "d2h_bytes")] + \
+               [("ms_resident", C.c_double), ("ms_e2e", C.c_double), ("n_zmws", C.c_int64)]
 
 
 class Batch:
@@ -75,6 +76,36 @@ class Batch:
         self.d = None
         if drafts is not None:
             self.set_drafts(drafts)
+
+    @classmethod
+    def from_arrays(cls, zmw_read_off, read_off, codes, snr, cx, hole, tpl_off=None, tpl=None, strand=None,
+                    tstart=None, tend=None):
+        b = cls.__new__(cls)
+        b.n_zmws = len(zmw_read_off) - 1
+        b.n_reads = int(zmw_read_off[-1])
+        b.zmw_read_off = np.ascontiguousarray(zmw_read_off, np.int32)
+        b.read_off = np.ascontiguousarray(read_off, np.int64)
+        b.codes = np.ascontiguousarray(codes, np.uint8)
+        b.snr = np.ascontiguousarray(snr, np.float32)
+        b.cx = np.ascontiguousarray(cx, np.uint8)
+        b.hole = np.ascontiguousarray(hole, np.int32)
+        b.c = CBatch(b.n_zmws, b.n_reads, _p(b.zmw_read_off, C.c_int32), _p(b.read_off, C.c_int64),
+                     _p(b.codes, C.c_uint8), _p(b.snr, C.c_float), _p(b.cx, C.c_uint8), _p(b.hole, C.c_int32))
+        b.d = None
+        if tpl_off is not None:
+            b.tpl_off = np.ascontiguousarray(tpl_off, np.int64)
+            b.tpl = np.ascontiguousarray(tpl, np.uint8)
+            b.strand = np.ascontiguousarray(strand, np.uint8)
+            b.tstart = np.ascontiguousarray(tstart, np.int32)
+            b.tend = np.ascontiguousarray(tend, np.int32)
+            b.d = CDrafts(_p(b.tpl_off, C.c_int64), _p(b.tpl, C.c_uint8), _p(b.strand, C.c_uint8),
+                          _p(b.tstart, C.c_int32), _p(b.tend, C.c_int32))
+        return b
+
+    def zmw_reads(self, z):
+        """list of code arrays of ZMW z"""
+        r0, r1 = self.zmw_read_off[z], self.zmw_read_off[z + 1]
+        return [self.codes[self.read_off[r]:self.read_off[r + 1]] for r in range(r0, r1)]
 
     def set_drafts(self, drafts):
         self.tpl_off = np.zeros(self.n_zmws + 1, np.int64)

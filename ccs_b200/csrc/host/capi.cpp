@@ -5,6 +5,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <chrono>
 
 using namespace ccs;
 
@@ -112,6 +113,7 @@ int ccsgpu_polish(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_drafts* drafts
                   ccs_results* out) {
     return guarded(ctx, [&]() {
         ArrowEngine& E = *ctx->engine;
+        const auto t_begin = std::chrono::steady_clock::now();
         PolishParams pp;
         if (cfg) {
             pp.max_iterations = cfg->max_iterations; pp.separation = cfg->separation; pp.neighborhood = cfg->neighborhood;
@@ -158,6 +160,7 @@ int ccsgpu_polish(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_drafts* drafts
             }
         }
         out->seq_off[in->n_zmws] = off;
+        E.stats.ms_e2e += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         return (int)CCS_OK;
     });
 }
@@ -173,6 +176,7 @@ int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset) {
         out->bytes_fill_alpha = s.bytes_fill_alpha; out->bytes_fill_beta = s.bytes_fill_beta;
         out->cells_fill = s.cells_fill; out->score_items = s.score_items; out->rounds = s.rounds;
         out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes;
+        out->ms_resident = s.ms_resident; out->ms_e2e = s.ms_e2e; out->n_zmws = s.n_zmws;
         if (reset) ctx->engine->reset_stats();
         return (int)CCS_OK;
     });

@@ -55,6 +55,8 @@ ArrowEngine::ArrowEngine(int device, const ArrowModelParams& model, size_t budge
     CCS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CCS_CUDA(cudaEventCreate(&ev0_));
     CCS_CUDA(cudaEventCreate(&ev1_));
+    CCS_CUDA(cudaEventCreate(&evA_));
+    CCS_CUDA(cudaEventCreate(&evB_));
     build_emission_tables(model_, em_);
     for (auto* b : {&d_emm_, &d_emi_, &d_trans_, &d_alpha_, &d_beta_}) b->budget_used = &used_;
     d_rowcode_.budget_used = &used_; d_tpl_.budget_used = &used_; d_colinfo_.budget_used = &used_;
@@ -73,6 +75,8 @@ ArrowEngine::~ArrowEngine() {
     if (stream_) cudaStreamSynchronize(stream_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
+    if (evA_) cudaEventDestroy(evA_);
+    if (evB_) cudaEventDestroy(evB_);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -386,6 +390,7 @@ void ArrowEngine::download_delta(int z, double* out) {
 void ArrowEngine::polish(const PolishParams& pp) {
     ab_tol_ = pp.ab_mismatch_tol;
     const int nz = (int)zstate_.size();
+    CCS_CUDA(cudaEventRecord(evA_, stream_));   // inputs are resident: load() has been issued on this stream
     fill();
     auto check_usable = [&](int z) {
         ZmwState& zs = zstate_[z];
@@ -492,6 +497,12 @@ void ArrowEngine::polish(const PolishParams& pp) {
         for (int z = 0; z < nz; ++z) if (!zstate_[z].done) check_usable(z);
     }
     consensus_qvs();
+    CCS_CUDA(cudaEventRecord(evB_, stream_));
+    CCS_CUDA(cudaEventSynchronize(evB_));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, evA_, evB_);
+    stats.ms_resident += ms;
+    stats.n_zmws += nz;
 }
 
 int64_t ArrowEngine::count_canonical(const std::vector<uint8_t>& t, int b, int e) const {

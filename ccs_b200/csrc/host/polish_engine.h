@@ -59,6 +59,9 @@ struct EngineStats {
     int64_t cells_fill = 0, score_items = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     int64_t rounds = 0;
+    double ms_resident = 0;   // CUDA-event time of polish() with inputs already in HBM (after load)
+    double ms_e2e = 0;        // host wall time of whole stage calls (pack + H2D + kernels + D2H)
+    int64_t n_zmws = 0;
 };
 
 class ArrowEngine {
@@ -103,7 +106,7 @@ private:
     ArrowModelParams model_;
     EmissionTables em_;
     cudaStream_t stream_ = nullptr;
-    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, evA_ = nullptr, evB_ = nullptr;
 
     // host state of the current batch
     std::vector<ZmwState> zstate_;

@@ -59,3 +59,95 @@ int ccs_sim_corrupt(const uint8_t* tpl, int32_t len, double rate, uint64_t seed,
 }
 
 }  // extern "C"
+
+// ---- batch generation (multi-threaded): opaque handle + copy-out ----------------------------
+#include <thread>
+#include <atomic>
+
+namespace {
+struct SimBatch {
+    std::vector<SimZmw> z;
+    std::vector<std::vector<uint8_t>> draft;
+    std::vector<std::vector<int32_t>> map;
+};
+}  // namespace
+
+extern "C" {
+
+void* ccs_sim_batch_create(const void* model, const ccs_sim_config* cfg, int64_t first_index, int32_t n_zmws,
+                           double draft_error_rate, int32_t n_threads) {
+    SimConfig c;
+    std::memcpy((void*)&c, cfg, sizeof(c));
+    auto* b = new SimBatch();
+    b->z.resize(n_zmws); b->draft.resize(n_zmws); b->map.resize(n_zmws);
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= n_zmws) break;
+            simulate_zmw(*(const ArrowModelParams*)model, c, first_index + k, b->z[k]);
+            if (draft_error_rate >= 0)
+                corrupt_template(b->z[k].tpl, draft_error_rate, (uint64_t)(first_index + k) + 17, b->draft[k], b->map[k]);
+        }
+    };
+    const int nt = std::max(1, std::min<int>(n_threads, n_zmws));
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    return b;
+}
+
+void ccs_sim_batch_free(void* h) { delete (SimBatch*)h; }
+
+// sizes[4] = {n_reads, total_codes, total_truth_bases, total_draft_bases}
+void ccs_sim_batch_sizes(const void* h, int64_t* sizes) {
+    const SimBatch* b = (const SimBatch*)h;
+    int64_t nr = 0, nc = 0, nt = 0, nd = 0;
+    for (size_t k = 0; k < b->z.size(); ++k) {
+        nr += (int64_t)b->z[k].reads.size();
+        for (auto& r : b->z[k].reads) nc += (int64_t)r.codes.size();
+        nt += (int64_t)b->z[k].tpl.size();
+        nd += (int64_t)b->draft[k].size();
+    }
+    sizes[0] = nr; sizes[1] = nc; sizes[2] = nt; sizes[3] = nd;
+}
+
+// Copies the batch into caller arrays (any pointer may be NULL).  Draft spans are the truth
+// spans mapped onto the corrupted draft.
+void ccs_sim_batch_copy(const void* h, int32_t* zmw_read_off, int64_t* read_off, uint8_t* codes, float* snr, uint8_t* cx,
+                        int32_t* hole, int64_t* truth_off, uint8_t* truth, uint8_t* strand, int32_t* tstart,
+                        int32_t* tend, int64_t* draft_off, uint8_t* draft, int32_t* dstart, int32_t* dend) {
+    const SimBatch* b = (const SimBatch*)h;
+    int64_t r = 0, c = 0, t = 0, d = 0;
+    for (size_t k = 0; k < b->z.size(); ++k) {
+        const SimZmw& z = b->z[k];
+        if (zmw_read_off) zmw_read_off[k] = (int32_t)r;
+        if (snr) std::memcpy(snr + 4 * k, z.snr, sizeof(z.snr));
+        if (hole) hole[k] = z.hole;
+        if (truth_off) truth_off[k] = t;
+        if (truth) std::memcpy(truth + t, z.tpl.data(), z.tpl.size());
+        if (draft_off) draft_off[k] = d;
+        if (draft && !b->draft[k].empty()) std::memcpy(draft + d, b->draft[k].data(), b->draft[k].size());
+        for (auto& rd : z.reads) {
+            if (read_off) read_off[r] = c;
+            if (codes) std::memcpy(codes + c, rd.codes.data(), rd.codes.size());
+            if (cx) cx[r] = rd.cx;
+            if (strand) strand[r] = rd.strand;
+            if (tstart) tstart[r] = rd.tstart;
+            if (tend) tend[r] = rd.tend;
+            if (dstart && !b->map[k].empty()) dstart[r] = b->map[k][rd.tstart];
+            if (dend && !b->map[k].empty()) dend[r] = b->map[k][rd.tend];
+            c += (int64_t)rd.codes.size();
+            ++r;
+        }
+        t += (int64_t)z.tpl.size();
+        d += (int64_t)b->draft[k].size();
+    }
+    if (zmw_read_off) zmw_read_off[b->z.size()] = (int32_t)r;
+    if (read_off) read_off[r] = c;
+    if (truth_off) truth_off[b->z.size()] = t;
+    if (draft_off) draft_off[b->z.size()] = d;
+}
+
+}  // extern "C"

@@ -86,3 +86,33 @@ def corrupt(tpl, rate, seed):
     if rc != 0:
         raise RuntimeError(f"ccs_sim_corrupt failed: {rc}")
     return out[:olen.value].copy(), mp
+
+
+def simulate_batch(model, cfg, first_index, n_zmws, draft_error_rate=-1.0, threads=8):
+    """ZMWs [first, first+n) as SoA numpy arrays (multi-threaded C++).  Returns a dict with the
+    batch arrays, the truth templates/spans and (if draft_error_rate >= 0) corrupted drafts with
+    the spans mapped onto them."""
+    L = lib()
+    L.ccs_sim_batch_create.restype = C.c_void_p
+    h = L.ccs_sim_batch_create(model.ctypes.data_as(C.c_void_p), C.byref(cfg), C.c_int64(first_index),
+                               C.c_int32(n_zmws), C.c_double(draft_error_rate), C.c_int32(threads))
+    try:
+        sizes = np.zeros(4, np.int64)
+        L.ccs_sim_batch_sizes(C.c_void_p(h), _p(sizes, C.c_int64))
+        nr, nc, nt, nd = [int(x) for x in sizes]
+        out = dict(zmw_read_off=np.zeros(n_zmws + 1, np.int32), read_off=np.zeros(nr + 1, np.int64),
+                   codes=np.zeros(nc, np.uint8), snr=np.zeros(4 * n_zmws, np.float32), cx=np.zeros(nr, np.uint8),
+                   hole=np.zeros(n_zmws, np.int32), truth_off=np.zeros(n_zmws + 1, np.int64),
+                   truth=np.zeros(nt, np.uint8), strand=np.zeros(nr, np.uint8), tstart=np.zeros(nr, np.int32),
+                   tend=np.zeros(nr, np.int32), draft_off=np.zeros(n_zmws + 1, np.int64),
+                   draft=np.zeros(max(nd, 1), np.uint8), dstart=np.zeros(nr, np.int32), dend=np.zeros(nr, np.int32))
+        L.ccs_sim_batch_copy(C.c_void_p(h), _p(out["zmw_read_off"], C.c_int32), _p(out["read_off"], C.c_int64),
+                             _p(out["codes"], C.c_uint8), _p(out["snr"], C.c_float), _p(out["cx"], C.c_uint8),
+                             _p(out["hole"], C.c_int32), _p(out["truth_off"], C.c_int64), _p(out["truth"], C.c_uint8),
+                             _p(out["strand"], C.c_uint8), _p(out["tstart"], C.c_int32), _p(out["tend"], C.c_int32),
+                             _p(out["draft_off"], C.c_int64), _p(out["draft"], C.c_uint8), _p(out["dstart"], C.c_int32),
+                             _p(out["dend"], C.c_int32))
+        out["draft"] = out["draft"][:nd]
+        return out
+    finally:
+        L.ccs_sim_batch_free(C.c_void_p(h))

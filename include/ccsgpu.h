@@ -96,6 +96,18 @@ int  ccs_sim_zmw(const void* model, const ccs_sim_config* cfg, int64_t index, fl
 int  ccs_sim_corrupt(const uint8_t* tpl, int32_t len, double rate, uint64_t seed, uint8_t* out, int32_t out_cap,
                      int32_t* out_len, int32_t* map);
 
+/* Multi-threaded generation of ZMWs [first_index, first_index+n) into an opaque handle;
+ * draft_error_rate >= 0 also makes a corrupted draft per ZMW (polish-only benches/tests).
+ * sizes[4] = {n_reads, total_codes, total_truth_bases, total_draft_bases}. */
+void* ccs_sim_batch_create(const void* model, const ccs_sim_config* cfg, int64_t first_index, int32_t n_zmws,
+                           double draft_error_rate, int32_t n_threads);
+void  ccs_sim_batch_free(void* handle);
+void  ccs_sim_batch_sizes(const void* handle, int64_t* sizes);
+void  ccs_sim_batch_copy(const void* handle, int32_t* zmw_read_off, int64_t* read_off, uint8_t* codes, float* snr,
+                         uint8_t* cx, int32_t* hole, int64_t* truth_off, uint8_t* truth, uint8_t* strand,
+                         int32_t* tstart, int32_t* tend, int64_t* draft_off, uint8_t* draft, int32_t* dstart,
+                         int32_t* dend);
+
 /* ------------------------------------------------------------------------------------
  * GPU context
  * ---------------------------------------------------------------------------------- */
@@ -189,6 +201,9 @@ typedef struct ccs_stats {
     int64_t bytes_fill_alpha, bytes_fill_beta;   /* algorithmic bytes (DESIGN.md "Roofline") */
     int64_t cells_fill, score_items, rounds;
     int64_t h2d_bytes, d2h_bytes;
+    double  ms_resident;   /* CUDA-event time of the stage with inputs already in HBM */
+    double  ms_e2e;        /* host wall time of the stage calls: pack + H2D + kernels + D2H */
+    int64_t n_zmws;        /* ZMWs processed */
 } ccs_stats;
 int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset);
 
