@@ -14,7 +14,9 @@ namespace ccs {
 constexpr int kBandW = 32;            // band rows per column (spec)
 constexpr int kBandMargin = 2;        // rows kept beyond the leading edge (spec)
 constexpr int kEdgeLog2 = -60;        // leading-edge threshold 2^-60 on unscaled cells (spec)
-constexpr int kRowCodePad = 96;       // sentinel codes after the last real row code
+constexpr int kRowCodePad = 96;
+constexpr int kDeltaStride = 16;       // doubles per template position in the delta store:
+                                      // {SUB A,C,G,T, DEL, INS A,C,G,T, INS' A,C,G,T (reverse-strand share), pad x3}       // sentinel codes after the last real row code
 
 struct ColInfo { int32_t start; int32_t cumexp; };   // per alpha column: band start, cumulative scale exponent
 

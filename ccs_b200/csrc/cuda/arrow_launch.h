@@ -9,9 +9,11 @@ namespace ccs {
 void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
 void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
 
-// delta[(zmw.delta_off + p) * 9 + slot], slots {SUB A,C,G,T, DEL, INS A,C,G,T}
+// delta[(zmw.delta_off + p) * kDeltaStride + slot]; INS total = slot[5+b] + slot[9+b].
+// Ranges of one ZMW must be disjoint and non-touching.  generic = reference kernel (every mutation
+// evaluated independently), used by the tests to cross-check the factored kernel.
 void launch_score(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, double* delta,
-                  cudaStream_t stream);
+                  cudaStream_t stream, bool generic = false);
 void launch_pick(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, const double* delta,
                  Candidate* out, int cap, int* counter, cudaStream_t stream);
 void launch_qv(const ArrowBatchView& V, const double* delta, uint8_t* qv, long long n_items, const ScoreRange* ranges,

@@ -146,7 +146,7 @@ __device__ __forceinline__ float eval_mutation(const ReadCtx& R, const int g, co
     return terminal ? term_v : link_v;
 }
 
-__global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V, const ScoreRange* __restrict__ ranges,
+__global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBatchView V, const ScoreRange* __restrict__ ranges,
                                                           const int n_ranges, const long long n_items,
                                                           double* __restrict__ delta) {
     __shared__ float s_emm[36 * kEmStride];
@@ -254,9 +254,307 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
         }
     }
     if (have && g == 0) {
-        double* out = delta + (size_t)(zm.delta_off + p) * 9;
+        double* out = delta + (size_t)(zm.delta_off + p) * kDeltaStride;
 #pragma unroll
         for (int k = 0; k < 9; ++k) out[k] = acc[k];
+#pragma unroll
+        for (int k = 9; k < 13; ++k) out[k] = 0.0;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Fast path for interior positions: the eight mutations of a position share
+//   * the match/deletion terms of the first extension column (context of t[q-1] unchanged),
+//   * the first extension column X_b per new base b (SUB(q,b), INS(before q,b) and, for
+//     b = t[q+1], DEL(q) all start with context (t[q-1], b)),
+//   * the match/deletion terms of the second extension column per b.
+// => 4 + 7 in-column scans and 8 links per (read, position) instead of 14 + 8 with every
+//    operand reloaded.  Reverse-strand reads compute the insertion BEFORE their local q, which
+//    is forward INS(p+1): those sums go to slots 9..12 of row p+1 (combined by the consumers).
+// -------------------------------------------------------------------------------------------
+struct FastOut { float sub[4]; float del; float ins[4]; int e_sd; int e_in; };
+
+__device__ __forceinline__ float link_dot(const float y[4], const float bx[4], const float bd[4], const int codeL[4],
+                                          const float4 trl, const float* __restrict__ emm_row) {
+    float acc = 0.f;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const float wv = fmaf(trl.x, emm_row[codeL[x]] * bd[x], trl.y * bx[x]);
+        acc = fmaf(y[x], wv, acc);
+    }
+    return octet_sum(acc);
+}
+
+__device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const float* s_emm, const float* s_emi,
+                                          const int q_in, const bool live, FastOut& out) {
+    const int J = R.J, I = R.I;
+    const int q = live ? q_in : 2;
+    const int jm2 = min(max(q - 2, 0), J - 1), jm1 = min(max(q - 1, 0), J - 1), j0 = min(q, J - 1);
+    const int j1 = min(q + 1, J - 1), j2 = min(q + 2, J - 1);
+    const int code_max = I + kRowCodePad - 1;
+    const ColInfo cim1 = R.cinfo[jm1];
+    const int s0 = cim1.start;
+    const int sq0 = R.cinfo[j0].start, sq1 = R.cinfo[j1].start, sq2 = R.cinfo[j2].start;
+    const int s1 = max(s0, sq0), s2 = max(s1, sq1);
+    const float4 a0 = R.acol[(size_t)jm1 * 8 + g];
+    const float4 b1v = R.bcol[(size_t)j1 * 8 + g];
+    const float4 b2v = R.bcol[(size_t)j2 * 8 + g];
+    out.e_sd = cim1.cumexp + R.bexp[j2];
+    out.e_in = cim1.cumexp + R.bexp[j1];
+    const int tm2 = R.tp[jm2], tm1 = R.tp[jm1], t0 = R.tp[j0], tp1 = R.tp[j1];
+
+    int rel1[4], rel2[4], codeU1[4], codeG1[4], codeU2[4], codeG2[4], codeL2[4], codeL1[4], codeLb1[4];
+    float pvm2[4];
+    const float v0[4] = {a0.x, a0.y, a0.z, a0.w};
+    const int d1 = s1 - s0, d2 = s2 - s1;
+    float up1[4];
+    up1[0] = shfl_oct(v0[3], (g + 7) & 7); up1[1] = v0[0]; up1[2] = v0[1]; up1[3] = v0[2];
+    // beta columns, masked onto the rows of the extension bands
+    float bx2[4], bd2[4], bx1[4], bd1[4], bxD[4], bdD[4];
+    const float be2[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, be1[4] = {b1v.x, b1v.y, b1v.z, b1v.w};
+    float dn2[4], dn1[4];
+    dn2[3] = shfl_oct(be2[0], (g + 1) & 7); dn2[0] = be2[1]; dn2[1] = be2[2]; dn2[2] = be2[3];
+    dn1[3] = shfl_oct(be1[0], (g + 1) & 7); dn1[0] = be1[1]; dn1[1] = be1[2]; dn1[2] = be1[3];
+    float A1[4];
+    const int cmq = 4 * tm2 + tm1;
+    const float4 trq = R.tr[cmq];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int slot = 4 * g + x;
+        rel1[x] = (slot - s1) & 31;
+        rel2[x] = (slot - s2) & 31;
+        const int row1 = s1 + rel1[x], row2 = s2 + rel2[x];
+        const int c1 = R.rc[min(row1, code_max)];
+        const int c2 = R.rc[min(row2, code_max)];
+        const int c1n = R.rc[min(row1 + 1, code_max)];
+        const int c2n = R.rc[min(row2 + 1, code_max)];
+        const int rd1 = rel1[x] + d1, rd2 = rel2[x] + d2;
+        const float pv = (rd1 < 32) ? v0[x] : 0.f;
+        codeU1[x] = ((unsigned)(rd1 - 1) < 32u) ? c1 : 12;
+        codeG1[x] = (rel1[x] == 0) ? 12 : c1;
+        codeU2[x] = ((unsigned)(rd2 - 1) < 32u) ? c2 : 12;
+        codeG2[x] = (rel2[x] == 0) ? 12 : c2;
+        pvm2[x] = (rd2 < 32) ? 1.f : 0.f;
+        A1[x] = fmaf(trq.x, s_emm[cmq * kEmStride + codeU1[x]] * up1[x], trq.y * pv);
+        // link operands: beta(i, c) / beta(i+1, c) at the rows of the extension band
+        bx2[x] = (row2 >= sq2 && row2 < sq2 + 32) ? be2[x] : 0.f;
+        bd2[x] = dn2[x];
+        codeL2[x] = (row2 + 1 >= sq2 && row2 + 1 < sq2 + 32) ? c2n : 12;
+        bx1[x] = (row2 >= sq1 && row2 < sq1 + 32) ? be1[x] : 0.f;
+        bd1[x] = dn1[x];
+        codeLb1[x] = (row2 + 1 >= sq1 && row2 + 1 < sq1 + 32) ? c2n : 12;
+        bxD[x] = (row1 >= sq2 && row1 < sq2 + 32) ? be2[x] : 0.f;
+        bdD[x] = dn2[x];
+        codeL1[x] = (row1 + 1 >= sq2 && row1 + 1 < sq2 + 32) ? c1n : 12;
+    }
+    float Xdel[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        const int ci = 4 * tm1 + b;
+        const float4 tri = R.tr[ci];
+        const float* emi_row = s_emi + ci * kEmStride;
+        const float* emm_row = s_emm + ci * kEmStride;
+        float A[4], G[4], X[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            A[x] = A1[x];
+            G[x] = emi_row[codeG1[x]] * (((codeG1[x] & 3) == b) ? tri.z : tri.w);
+        }
+        octet_forward_scan(A, G, g, X);
+        if (b == tp1) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) Xdel[x] = X[x];
+        }
+        // second extension column: match/deletion terms shared by SUB(b) and INS(b)
+        float up2[4], A2[4];
+        up2[0] = shfl_oct(X[3], (g + 7) & 7); up2[1] = X[0]; up2[2] = X[1]; up2[3] = X[2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) A2[x] = fmaf(tri.x, emm_row[codeU2[x]] * up2[x], tri.y * (X[x] * pvm2[x]));
+        {   // SUB(q, b): insertion context (b, t[q+1]); link into beta column q+2
+            const int c2 = 4 * b + tp1;
+            const float4 tr2 = R.tr[c2];
+            const float* e2 = s_emi + c2 * kEmStride;
+            float Aa[4], Ga[4], Y[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                Aa[x] = A2[x];
+                Ga[x] = e2[codeG2[x]] * (((codeG2[x] & 3) == tp1) ? tr2.z : tr2.w);
+            }
+            octet_forward_scan(Aa, Ga, g, Y);
+            const float v = link_dot(Y, bx2, bd2, codeL2, tr2, s_emm + c2 * kEmStride);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k == b) out.sub[k] = v;
+        }
+        {   // INS(before q, b): insertion context (b, t[q]); link into beta column q+1
+            const int c3 = 4 * b + t0;
+            const float4 tr3 = R.tr[c3];
+            const float* e3 = s_emi + c3 * kEmStride;
+            float Aa[4], Ga[4], Z[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                Aa[x] = A2[x];
+                Ga[x] = e3[codeG2[x]] * (((codeG2[x] & 3) == t0) ? tr3.z : tr3.w);
+            }
+            octet_forward_scan(Aa, Ga, g, Z);
+            const float v = link_dot(Z, bx1, bd1, codeLb1, tr3, s_emm + c3 * kEmStride);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k == b) out.ins[k] = v;
+        }
+    }
+    {   // DEL(q): X_{t[q+1]} links straight into beta column q+2 with context (t[q-1], t[q+1])
+        const int cd = 4 * tm1 + tp1;
+        out.del = link_dot(Xdel, bxD, bdD, codeL1, R.tr[cd], s_emm + cd * kEmStride);
+    }
+}
+
+__device__ __forceinline__ double dll_of(const float val, const int e, const double base_ll) {
+    return (val > 0.f) ? (double)logf(val) + 0.6931471805599453094 * (double)e - base_ll : -INFINITY;
+}
+
+__global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V, const ScoreRange* __restrict__ ranges,
+                                                          const int n_ranges, const long long n_items,
+                                                          double* __restrict__ delta) {
+    __shared__ float s_emm[36 * kEmStride];
+    __shared__ float s_emi[17 * kEmStride];
+    for (int k = threadIdx.x; k < 36 * kEmStride; k += blockDim.x) s_emm[k] = V.em_match[k];
+    for (int k = threadIdx.x; k < 17 * kEmStride; k += blockDim.x) s_emi[k] = V.em_ins[k];
+    __syncthreads();
+
+    const long long item = (long long)blockIdx.x * 16 + (threadIdx.x >> 3);
+    const int g = threadIdx.x & 7;
+    const bool have = item < n_items;
+    int z = 0, p = 0, p_begin = 0;
+    if (have) {
+        int lo = 0, hi = n_ranges - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (ranges[mid].first <= item) lo = mid; else hi = mid - 1;
+        }
+        const ScoreRange rg = ranges[lo];
+        z = rg.zmw;
+        p = rg.p_begin + (int)(item - rg.first);
+        p_begin = rg.p_begin;
+    }
+    DevZmw zm;
+    zm.read_begin = zm.read_end = 0; zm.fwd_off = 0; zm.J = 0; zm.delta_off = 0;
+    if (have) zm = V.zmws[z];
+    const int n_reads = zm.read_end - zm.read_begin;
+    int n_max = n_reads;
+    n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 8));
+    n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 16));
+    const int tbase = have ? V.tpl[zm.fwd_off + p] : 0;
+
+    double acc_sd[5], acc_ia[4], acc_ib[4];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc_sd[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { acc_ia[k] = 0.0; acc_ib[k] = 0.0; }
+
+    for (int k = 0; k < n_max; ++k) {
+        const bool has_read = k < n_reads;
+        DevRead rd;
+        rd.active = 0; rd.ts = rd.te = 0; rd.strand = 0; rd.I = 2; rd.J = 2; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0;
+        rd.zmw = 0; rd.last_code = 0;
+        int st = 1;
+        const int r = zm.read_begin + k;
+        if (has_read) { rd = V.reads[r]; st = V.status[r]; }
+        const bool usable = has_read && rd.active && st == 0;
+        const bool cov_sd = usable && p >= rd.ts && p < rd.te;       // SUB / DEL
+        const bool cov_in = usable && p > rd.ts && p < rd.te;        // INS (before p)
+        if (!__any_sync(kFullMask, cov_sd)) continue;
+
+        ReadCtx R;
+        R.rc = V.rowcode + rd.code_off;
+        R.tp = V.tpl + rd.tpl_off;
+        R.tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
+        R.acol = reinterpret_cast<const float4*>(V.alpha) + (size_t)rd.col_off * 8;
+        R.bcol = reinterpret_cast<const float4*>(V.beta) + (size_t)rd.col_off * 8;
+        R.cinfo = V.colinfo + rd.col_off;
+        R.bexp = V.beta_exp + rd.col_off;
+        R.I = rd.I; R.J = rd.J; R.last_code = rd.last_code;
+        const double base_ll = cov_sd ? V.base_ll[r] : 0.0;
+        const int q_sd = cov_sd ? (rd.strand ? rd.te - 1 - p : p - rd.ts) : 0;
+        const bool interior = cov_sd && q_sd >= 2 && q_sd <= rd.J - 4;
+        const bool gen_sd = cov_sd && !interior;
+        const bool prev_interior = rd.strand && p > p_begin && (q_sd + 1 >= 2) && (q_sd + 1 <= rd.J - 4);
+        const bool gen_in = cov_in && (rd.strand ? !prev_interior : !interior);
+
+        if (__any_sync(kFullMask, interior)) {
+            FastOut fo;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { fo.sub[b] = 0.f; fo.ins[b] = 0.f; }
+            fo.del = 0.f; fo.e_sd = 0; fo.e_in = 0;
+            fast_eval(R, g, s_emm, s_emi, q_sd, interior, fo);
+            if (interior) {
+                const int t_loc = rd.strand ? 3 - tbase : tbase;
+                double ds[4], di[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    ds[b] = (b == t_loc) ? 0.0 : dll_of(fo.sub[b], fo.e_sd, base_ll);
+                    di[b] = dll_of(fo.ins[b], fo.e_in, base_ll);
+                }
+                acc_sd[4] += dll_of(fo.del, fo.e_sd, base_ll);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    acc_sd[b] += rd.strand ? ds[3 - b] : ds[b];
+                    if (rd.strand) acc_ib[b] += di[3 - b]; else acc_ia[b] += di[b];
+                }
+            }
+        }
+        if (__any_sync(kFullMask, gen_sd) || __any_sync(kFullMask, gen_in)) {
+            const int q_in = cov_in ? (rd.strand ? rd.te - p : p - rd.ts) : 1;
+            unsigned word_sd = 0, word_in = 0;
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                const int j1 = q_sd - 3 + x, j2 = q_in - 3 + x;
+                const unsigned b1 = (cov_sd && j1 >= 0 && j1 < rd.J) ? R.tp[j1] : 0u;
+                const unsigned b2 = (cov_in && j2 >= 0 && j2 < rd.J) ? R.tp[j2] : 0u;
+                word_sd |= b1 << (2 * x);
+                word_in |= b2 << (2 * x);
+            }
+#pragma unroll 1
+            for (int m = 0; m < 8; ++m) {
+                // m = 0..2 SUB, 3 DEL, 4..7 INS
+                const bool is_ins = m >= 4;
+                const int type = (m < 3) ? 0 : ((m == 3) ? 2 : 1);
+                const int bf = (m < 3) ? ((tbase + 1 + m) & 3) : (is_ins ? m - 4 : 0);
+                const int bl = rd.strand ? 3 - bf : bf;
+                const bool lv = is_ins ? gen_in : (gen_sd && (m != 3 || rd.J >= 3));
+                if (!__any_sync(kFullMask, is_ins ? gen_in : gen_sd)) continue;
+                int e;
+                const float val = eval_mutation(R, g, s_emm, s_emi, is_ins ? word_in : word_sd, type,
+                                                is_ins ? q_in : q_sd, bl, lv, e);
+                double dll = dll_of(val, e, base_ll);
+                if (m == 3 && rd.J < 3) dll = -INFINITY;
+                const bool take = is_ins ? gen_in : gen_sd;
+                if (take) {
+                    if (m < 3) {
+#pragma unroll
+                        for (int s2 = 0; s2 < 4; ++s2) if (s2 == bf) acc_sd[s2] += dll;
+                    } else if (m == 3) {
+                        acc_sd[4] += dll;
+                    } else {
+#pragma unroll
+                        for (int s2 = 0; s2 < 4; ++s2) if (s2 == bf) acc_ia[s2] += dll;
+                    }
+                }
+            }
+        }
+    }
+    if (have && g == 0) {
+        double* out = delta + (size_t)(zm.delta_off + p) * kDeltaStride;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) out[k] = acc_sd[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[5 + k] = acc_ia[k];
+        // reverse-strand insertions before the local position are forward INS(p+1)
+        double* nxt = out + kDeltaStride;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nxt[9 + k] = acc_ib[k];
+        if (p == p_begin) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[9 + k] = 0.0;
+        }
     }
 }
 
@@ -280,10 +578,10 @@ __global__ void __launch_bounds__(256) arrow_pick_kernel(const ArrowBatchView V,
     const uint8_t* t = V.tpl + zm.fwd_off;
     const int tb = t[p];
     const int tprev = (p > 0) ? t[p - 1] : -1;
-    const double* d = delta + (size_t)(zm.delta_off + p) * 9;
+    const double* d = delta + (size_t)(zm.delta_off + p) * kDeltaStride;
 #pragma unroll 1
     for (int s = 0; s < 9; ++s) {
-        const double v = d[s];
+        const double v = (s >= 5) ? d[s] + d[s + 4] : d[s];
         if (!(v > 0.0)) continue;
         int type, base;
         if (s < 4) { type = 0; base = s; if (base == tb) continue; }
@@ -316,13 +614,13 @@ __global__ void __launch_bounds__(256) arrow_qv_kernel(const ArrowBatchView V, c
     const int p = rg.p_begin + (int)(item - rg.first);
     const DevZmw zm = V.zmws[z];
     const int tb = V.tpl[zm.fwd_off + p];
-    const double* d = delta + (size_t)(zm.delta_off + p) * 9;
+    const double* d = delta + (size_t)(zm.delta_off + p) * kDeltaStride;
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         if (k < 4 && k == tb) continue;
         if (k >= 5 && !(p >= 1 && p <= zm.J - 1)) continue;
-        s += exp(d[k]);
+        s += exp((k >= 5) ? d[k] + d[k + 4] : d[k]);
     }
     double q = (s > 0.0) ? -10.0 * log10(s / (1.0 + s)) : 93.0;
     if (!(q < 93.0)) q = 93.0;
@@ -333,10 +631,11 @@ __global__ void __launch_bounds__(256) arrow_qv_kernel(const ArrowBatchView V, c
 }  // namespace
 
 void launch_score(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, double* delta,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, bool generic) {
     if (n_items <= 0) return;
     const long long blocks = (n_items + 15) / 16;
-    arrow_score_kernel<<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    if (generic) arrow_score_generic_kernel<<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    else arrow_score_kernel<<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
 }
 
 void launch_pick(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, const double* delta,

@@ -3,6 +3,7 @@
 #include "polish_engine.h"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <memory>
 #include <string>
 #include <chrono>
@@ -55,6 +56,7 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
     std::memcpy(&ctx->model, model, sizeof(ArrowModelParams));
     try {
         ctx->engine.reset(new ArrowEngine(device, ctx->model, device_bytes_budget));
+        if (const char* e = std::getenv("CCS_B200_GENERIC_SCORE")) ctx->engine->generic_score = (e[0] == '1');
     } catch (const std::exception& e) {
         g_create_error = e.what();
         if (err) *err = CCS_ERR_NO_DEVICE;

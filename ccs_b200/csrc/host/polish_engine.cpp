@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <thread>
+#include <atomic>
 
 namespace ccs {
 
@@ -77,8 +79,62 @@ ArrowEngine::~ArrowEngine() {
     if (ev1_) cudaEventDestroy(ev1_);
     if (evA_) cudaEventDestroy(evA_);
     if (evB_) cudaEventDestroy(evB_);
+    for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
 }
+
+cudaEvent_t ArrowEngine::next_event() {
+    if (ev_used_ == ev_pool_.size()) {
+        cudaEvent_t e;
+        CCS_CUDA(cudaEventCreate(&e));
+        ev_pool_.push_back(e);
+    }
+    return ev_pool_[ev_used_++];
+}
+
+void ArrowEngine::span_begin(double* acc) {
+    if (!timing_enabled) return;
+    Span sp{next_event(), next_event(), acc};
+    CCS_CUDA(cudaEventRecord(sp.a, stream_));
+    spans_.push_back(sp);
+}
+
+void ArrowEngine::span_end() {
+    if (!timing_enabled) return;
+    CCS_CUDA(cudaEventRecord(spans_.back().b, stream_));
+}
+
+// call only when the stream is known to be idle (after a synchronize)
+void ArrowEngine::resolve_spans() {
+    for (const Span& sp : spans_) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) *sp.acc += ms;
+    }
+    spans_.clear();
+    ev_used_ = 0;
+}
+
+namespace {
+// chunked parallel-for over ZMWs for the host-side pieces of a round
+template <class F>
+void parallel_for(int n, int n_threads, F&& f) {
+    if (n <= 0) return;
+    n_threads = std::max(1, std::min(n_threads, n / 8));
+    if (n_threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::vector<std::thread> th;
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int b = next.fetch_add(16);
+            if (b >= n) break;
+            for (int i = b; i < std::min(n, b + 16); ++i) f(i);
+        }
+    };
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
+}  // namespace
 
 ArrowBatchView ArrowEngine::view() const {
     ArrowBatchView V;
@@ -149,7 +205,7 @@ void ArrowEngine::load(const PolishInput& in) {
         std::memcpy(h_trans_.p + (size_t)z * 36 * 4, zt.tr, sizeof(zt.tr));
     }
     d_trans_.ensure((size_t)nz * 36 * 4, budget_);
-    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
+    span_begin(&stats.ms_h2d);
     CCS_CUDA(cudaMemcpyAsync(d_rowcode_.p, h_rowcode_.p, (size_t)code_total, cudaMemcpyHostToDevice, stream_));
     CCS_CUDA(cudaMemcpyAsync(d_trans_.p, h_trans_.p, (size_t)nz * 36 * 4 * sizeof(float), cudaMemcpyHostToDevice, stream_));
     stats.h2d_bytes += code_total + (int64_t)nz * 36 * 4 * 4;
@@ -159,13 +215,7 @@ void ArrowEngine::load(const PolishInput& in) {
         tpl_cap_[z] = ((J + std::max(256, J / 16)) + 15) & ~15;
     }
     upload_templates_and_reads();
-    if (timing_enabled) {
-        CCS_CUDA(cudaEventRecord(ev1_, stream_));
-        CCS_CUDA(cudaEventSynchronize(ev1_));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev0_, ev1_);
-        stats.ms_h2d += ms;
-    }
+    span_end();
 }
 
 // (Re)derive DevRead / DevZmw / template buffer / column offsets from the host state and push
@@ -186,7 +236,20 @@ void ArrowEngine::upload_templates_and_reads() {
     }
     if (toff > 0x7fffffffll) throw OomError("template buffer exceeds 2 GiB; use smaller batches");
     h_tpl_.ensure((size_t)toff + 16);
+    // column offsets (serial prefix), then the per-ZMW copies in parallel
     for (int z = 0; z < nz; ++z) {
+        const ZmwState& zs = zstate_[z];
+        const int J = zmws_[z].J;
+        for (int r = zs.read_begin; r < zs.read_end; ++r) {
+            DevRead& rd = reads_[r];
+            const int len = rd.te - rd.ts;
+            if (rd.active && (len < 2 || rd.ts < 0 || rd.te > J || rd.I < 2)) { rd.active = 0; status_[r] = 2; }
+            rd.J = rd.active ? len : 0;
+            rd.col_off = cols;
+            if (rd.active) cols += rd.J;
+        }
+    }
+    parallel_for(nz, host_threads, [&](int z) {
         const ZmwState& zs = zstate_[z];
         const DevZmw& dz = zmws_[z];
         const int J = dz.J;
@@ -196,14 +259,9 @@ void ArrowEngine::upload_templates_and_reads() {
         for (int j = 0; j < J; ++j) rv[j] = (uint8_t)(3 - zs.tpl[J - 1 - j]);
         for (int r = zs.read_begin; r < zs.read_end; ++r) {
             DevRead& rd = reads_[r];
-            const int len = rd.te - rd.ts;
-            if (rd.active && (len < 2 || rd.ts < 0 || rd.te > J || rd.I < 2)) { rd.active = 0; status_[r] = 2; }
-            rd.J = rd.active ? len : 0;
             rd.tpl_off = rd.strand ? dz.rev_off + (J - rd.te) : dz.fwd_off + rd.ts;
-            rd.col_off = cols;
-            if (rd.active) cols += rd.J;
         }
-    }
+    });
     total_cols_ = cols;
     total_delta_rows_ = drows;
     order_.clear();
@@ -240,23 +298,12 @@ void ArrowEngine::fill() {
     const int n = (int)order_.size();
     int64_t cells = 0, in_bytes = 0;
     for (int r : order_) { cells += 32ll * (reads_[r].J - 1); in_bytes += reads_[r].I + reads_[r].J; }
-    float ms = 0;
-    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
+    span_begin(&stats.ms_fill_alpha);
     launch_fill_alpha(V, d_order_.p, n, stream_);
-    if (timing_enabled) {
-        CCS_CUDA(cudaEventRecord(ev1_, stream_));
-        CCS_CUDA(cudaEventSynchronize(ev1_));
-        cudaEventElapsedTime(&ms, ev0_, ev1_);
-        stats.ms_fill_alpha += ms;
-        CCS_CUDA(cudaEventRecord(ev0_, stream_));
-    }
+    span_end();
+    span_begin(&stats.ms_fill_beta);
     launch_fill_beta(V, d_order_.p, n, stream_);
-    if (timing_enabled) {
-        CCS_CUDA(cudaEventRecord(ev1_, stream_));
-        CCS_CUDA(cudaEventSynchronize(ev1_));
-        cudaEventElapsedTime(&ms, ev0_, ev1_);
-        stats.ms_fill_beta += ms;
-    }
+    span_end();
     CCS_CUDA(cudaGetLastError());
     ++stats.n_fill_alpha; ++stats.n_fill_beta;
     stats.cells_fill += cells;
@@ -269,6 +316,7 @@ void ArrowEngine::sync_statuses() {
     const int nr = (int)reads_.size();
     CCS_CUDA(cudaMemcpyAsync(h_status_.p, d_status_.p, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, stream_));
     CCS_CUDA(cudaStreamSynchronize(stream_));
+    resolve_spans();
     stats.d2h_bytes += 4ll * nr;
     for (int r = 0; r < nr; ++r) {
         if (!reads_[r].active) continue;
@@ -313,19 +361,13 @@ void ArrowEngine::score_ranges(const std::vector<ScoreRange>& ranges, int64_t n_
     d_ranges_.ensure(ranges.size());
     h_ranges_.ensure(ranges.size());
     std::memcpy(h_ranges_.p, ranges.data(), sizeof(ScoreRange) * ranges.size());
-    d_delta_.ensure((size_t)total_delta_rows_ * 9 + 16, budget_);
+    d_delta_.ensure((size_t)(total_delta_rows_ + 2) * kDeltaStride, budget_);
     CCS_CUDA(cudaMemcpyAsync(d_ranges_.p, h_ranges_.p, sizeof(ScoreRange) * ranges.size(), cudaMemcpyHostToDevice, stream_));
     stats.h2d_bytes += (int64_t)sizeof(ScoreRange) * ranges.size();
     const ArrowBatchView V = view();
-    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
-    launch_score(V, d_ranges_.p, (int)ranges.size(), n_items, d_delta_.p, stream_);
-    if (timing_enabled) {
-        CCS_CUDA(cudaEventRecord(ev1_, stream_));
-        CCS_CUDA(cudaEventSynchronize(ev1_));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev0_, ev1_);
-        stats.ms_score += ms;
-    }
+    span_begin(&stats.ms_score);
+    launch_score(V, d_ranges_.p, (int)ranges.size(), n_items, d_delta_.p, stream_, generic_score);
+    span_end();
     CCS_CUDA(cudaGetLastError());
     ++stats.n_score;
     stats.score_items += n_items;
@@ -353,12 +395,12 @@ int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
     for (int attempt = 0; attempt < 2; ++attempt) {
         d_cand_.ensure(cap);
         CCS_CUDA(cudaMemsetAsync(d_counter_.p, 0, sizeof(int32_t), stream_));
-        if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
+        span_begin(&stats.ms_pick);
         launch_pick(V, d_ranges_.p, n_ranges_, n_range_items_, d_delta_.p, d_cand_.p, (int)d_cand_.cap, d_counter_.p, stream_);
-        if (timing_enabled) CCS_CUDA(cudaEventRecord(ev1_, stream_));
+        span_end();
         CCS_CUDA(cudaMemcpyAsync(h_counter_.p, d_counter_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
         CCS_CUDA(cudaStreamSynchronize(stream_));
-        if (timing_enabled) { float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_); stats.ms_pick += ms; }
+        resolve_spans();
         ++stats.n_pick;
         const int64_t n = h_counter_.p[0];
         if ((size_t)n <= d_cand_.cap) {
@@ -379,7 +421,11 @@ int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
 void ArrowEngine::download_delta(int z, double* out) {
     const DevZmw& dz = zmws_[z];
     CCS_CUDA(cudaStreamSynchronize(stream_));
-    CCS_CUDA(cudaMemcpy(out, d_delta_.p + dz.delta_off * 9, sizeof(double) * 9 * dz.J, cudaMemcpyDeviceToHost));
+    std::vector<double> tmp((size_t)dz.J * kDeltaStride);
+    CCS_CUDA(cudaMemcpy(tmp.data(), d_delta_.p + dz.delta_off * kDeltaStride, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+    for (int p = 0; p < dz.J; ++p)
+        for (int s = 0; s < 9; ++s)
+            out[(size_t)p * 9 + s] = tmp[(size_t)p * kDeltaStride + s] + (s >= 5 ? tmp[(size_t)p * kDeltaStride + s + 4] : 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -444,23 +490,27 @@ void ArrowEngine::polish(const PolishParams& pp) {
         // group candidates per ZMW
         std::vector<std::vector<HostMutation>> per(nz);
         for (const Candidate& c : cands) per[c.zmw].push_back(HostMutation{c.type, c.pos, c.base, c.score});
-        bool any_applied = false;
-        for (int z = 0; z < nz; ++z) {
+        std::atomic<int> applied_flag(0);
+        parallel_for(nz, host_threads, [&](int z) {
             ZmwState& zs = zstate_[z];
-            if (zs.done) continue;
+            if (zs.done) return;
             auto& sc = per[z];
-            if (sc.empty()) { zs.converged = true; zs.done = true; continue; }
+            if (sc.empty()) { zs.converged = true; zs.done = true; return; }
             std::sort(sc.begin(), sc.end(), [](const HostMutation& a, const HostMutation& b) {
                 if (a.score != b.score) return a.score > b.score;
                 if (a.pos != b.pos) return a.pos < b.pos;
                 if (a.type != b.type) return type_rank(a.type) < type_rank(b.type);
                 return a.base < b.base;
             });
+            // BestMutations: greedy by score, chosen sites >= separation apart
+            const int J = (int)zs.tpl.size();
+            std::vector<uint8_t> blocked((size_t)J + 2, 0);
             std::vector<HostMutation> best;
             for (const auto& m : sc) {
-                bool ok = true;
-                for (const auto& c : best) if (std::abs(c.pos - m.pos) < pp.separation) { ok = false; break; }
-                if (ok) best.push_back(m);
+                if (blocked[m.pos]) continue;
+                best.push_back(m);
+                const int lo = std::max(0, m.pos - pp.separation + 1), hi = std::min(J + 1, m.pos + pp.separation - 1);
+                for (int x = lo; x <= hi; ++x) blocked[x] = 1;
             }
             std::sort(best.begin(), best.end(), [](const HostMutation& a, const HostMutation& b) { return a.pos < b.pos; });
             std::vector<uint8_t> next = apply_to_template(zs.tpl, best);
@@ -489,8 +539,9 @@ void ArrowEngine::polish(const PolishParams& pp) {
                 rd.ts += ds; rd.te += de;
             }
             zs.tpl.swap(next);
-            any_applied = true;
-        }
+            applied_flag.store(1, std::memory_order_relaxed);
+        });
+        const bool any_applied = applied_flag.load() != 0;
         if (!any_applied) break;
         upload_templates_and_reads();
         fill();
@@ -532,12 +583,12 @@ void ArrowEngine::consensus_qvs() {
     d_qv_.ensure((size_t)total_delta_rows_ + 16, budget_);
     h_qv_.ensure((size_t)total_delta_rows_ + 16);
     const ArrowBatchView V = view();
-    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev0_, stream_));
+    span_begin(&stats.ms_qv);
     launch_qv(V, d_delta_.p, d_qv_.p, first, d_ranges_.p, (int)ranges.size(), stream_);
-    if (timing_enabled) CCS_CUDA(cudaEventRecord(ev1_, stream_));
+    span_end();
     CCS_CUDA(cudaMemcpyAsync(h_qv_.p, d_qv_.p, (size_t)total_delta_rows_, cudaMemcpyDeviceToHost, stream_));
     CCS_CUDA(cudaStreamSynchronize(stream_));
-    if (timing_enabled) { float ms = 0; cudaEventElapsedTime(&ms, ev0_, ev1_); stats.ms_qv += ms; }
+    resolve_spans();
     CCS_CUDA(cudaGetLastError());
     ++stats.n_qv;
     stats.d2h_bytes += total_delta_rows_;

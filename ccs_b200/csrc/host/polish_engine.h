@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <string>
 #include <vector>
+#include <functional>
 #include "../common/arrow_tables.h"
 #include "../cuda/arrow_device.h"
 #include "cuda_util.h"
@@ -93,8 +94,19 @@ public:
     cudaStream_t stream() const { return stream_; }
     int device() const { return device_; }
     bool timing_enabled = true;
+    int host_threads = 8;         // threads for the per-ZMW host pieces of a round
+    bool generic_score = false;   // use the unfactored reference scoring kernel (tests)
 
 private:
+    // in-stream timing: spans are recorded without host syncs and resolved at the next natural sync
+    struct Span { cudaEvent_t a, b; double* acc; };
+    void span_begin(double* acc);
+    void span_end();
+    void resolve_spans();
+    std::vector<Span> spans_;
+    std::vector<cudaEvent_t> ev_pool_;
+    size_t ev_used_ = 0;
+    cudaEvent_t next_event();
     int64_t count_canonical(const std::vector<uint8_t>& t, int b, int e) const;
     void upload_templates_and_reads();       // (re)build DevRead/DevZmw/template buffer from host state
     void sync_statuses();
