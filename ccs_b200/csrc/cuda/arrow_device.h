@@ -21,7 +21,8 @@ constexpr int kDeltaStride = 16;       // doubles per template position in the d
 struct ColInfo { int32_t start; int32_t cumexp; };   // per alpha column: band start, cumulative scale exponent
 
 struct DevRead {
-    int64_t code_off;    // rowcode[code_off + i] = emission code of DP row i (sentinel at i = 0 and i >= I)
+    int64_t code_off;    // rowcode[code_off + i] = 4 * emission code of DP row i (sentinel 48 at i = 0 and i >= I);
+                         // a second copy shifted by one row (code of row i+1) follows at code_off + code_stride
     int64_t col_off;     // first column of this pair in the alpha / beta / colinfo stores
     int32_t I;           // read length
     int32_t J;           // template slice length (columns 0..J-1)
@@ -32,7 +33,7 @@ struct DevRead {
     uint8_t active;      // 0: skip (filtered / dropped)
     uint8_t first_code;  // e_0
     uint8_t last_code;   // e_{I-1}
-    int32_t pad_;
+    int32_t code_stride; // bytes of one row-code copy (multiple of 16)
 };
 static_assert(sizeof(DevRead) == 48, "DevRead layout");
 

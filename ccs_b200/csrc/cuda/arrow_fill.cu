@@ -9,6 +9,11 @@
 // memory, and writes one 128-byte line of fp32 cells -- the kernel is HBM-write bound:
 // algorithmic bytes per pair = 4*32*(J-1) cells + 8 (alpha) or 4 (beta) bytes of column info
 // per column + I + J input bytes (DESIGN.md "Roofline").
+//
+// Row codes: a lane's four slots hold rows 32*lap + 4g + {0..3}; one aligned 32-bit word of the
+// row-code array carries exactly those four codes, so a lane keeps the words of the current
+// and next lap (plus one prefetched) and assembles its codes with a single byte-permute; a
+// new word is loaded once every 32 columns (coalesced 32 B per octet).
 #include "arrow_octet.cuh"
 #include "arrow_launch.h"
 
@@ -22,6 +27,17 @@ __device__ __forceinline__ void load_emissions(const ArrowBatchView& V, float* s
     __syncthreads();
 }
 
+// codes of this lane's four slots for band start s: slots below the start slot are one lap ahead
+__device__ __forceinline__ void lane_codes(const unsigned w_lo, const unsigned w_hi, const int s, const int g, int code[4]) {
+    const int t = min(max((s & 31) - 4 * g, 0), 4);          // how many of the lane's slots are in the next lap
+    const unsigned sel = 0x3210u | (0x4444u & ((1u << (4 * t)) - 1u));
+    const unsigned cw = __byte_perm(w_lo, w_hi, sel);
+    code[0] = (int)(cw & 0xffu);
+    code[1] = (int)__byte_perm(cw, 0u, 0x4441u);
+    code[2] = (int)__byte_perm(cw, 0u, 0x4442u);
+    code[3] = (int)(cw >> 24);
+}
+
 __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
                                                                const int n_items) {
     __shared__ float s_emm[36 * kEmStride];
@@ -33,45 +49,39 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
     int r = -1;
     if (item < n_items) r = order[item];
     DevRead rd;
-    rd.J = 0; rd.I = 0; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0; rd.zmw = 0; rd.last_code = 0;
+    rd.J = 0; rd.I = 0; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0; rd.zmw = 0; rd.last_code = 0; rd.code_stride = 64;
+    rd.active = 0;
     if (r >= 0) rd = V.reads[r];
     const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
     const int J = valid ? rd.J : 0;
+    const int Jc = valid ? rd.J : 2;      // clamp bound for harmless loads of idle octets
     const int I = rd.I;
     int Jmax = J;
 #pragma unroll
     for (int off = 8; off < 32; off <<= 1) Jmax = max(Jmax, __shfl_xor_sync(kFullMask, Jmax, off));
 
-    const uint8_t* __restrict__ rc = V.rowcode + rd.code_off;
+    const unsigned* __restrict__ rc32 = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off);
+    const int wmax = (rd.code_stride >> 2) - 1;
     const uint8_t* __restrict__ tp = V.tpl + rd.tpl_off;
     const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
-    float4* __restrict__ acol = reinterpret_cast<float4*>(V.alpha) + (size_t)rd.col_off * 8;
+    float4* __restrict__ acol = reinterpret_cast<float4*>(V.alpha) + (size_t)rd.col_off * 8 + g;
     ColInfo* __restrict__ cinfo = V.colinfo + rd.col_off;
-    const int code_max = I + kRowCodePad - 1;
 
     // column 0: alpha(0,0) = 1
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (g == 0) v[0] = 1.f;
-    int s = 0, cum = 0, edge = 0;
-    int code[4], ncode[4];
+    int s = 0, cum = 0, edge = 0, lap = 0;
+    unsigned w0 = rc32[min(g, wmax)], w1 = rc32[min(8 + g, wmax)], w2 = rc32[min(16 + g, wmax)];
     if (valid) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            code[q] = rc[4 * g + q];
-            ncode[q] = rc[min(4 * g + q + 32, code_max)];
-        }
-        acol[g] = make_float4(v[0], v[1], v[2], v[3]);
+        acol[0] = make_float4(v[0], v[1], v[2], v[3]);
         if (g == 0) cinfo[0] = ColInfo{0, 0};
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) code[q] = ncode[q] = 12;
     }
-    int t0 = 0, t1 = 0, t2 = 0;
-    if (valid) { t0 = tp[0]; t1 = tp[1]; t2 = tp[min(2, J - 1)]; }
+    const int t0 = tp[0], t1 = tp[min(1, Jc - 1)];
+    int t2 = tp[min(2, Jc - 1)];
     int cm = kCtxStartRow + t0;          // match/deletion context of column 1: pinned first move
     int ci = 4 * t0 + t1;                // insertion context of column 1
-    float4 tr_m = valid ? tr[cm] : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 tr_i = valid ? tr[ci] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 tr_m = tr[cm];
+    float4 tr_i = tr[ci];
     float final_val = 0.f;
     int final_cum = 0;
 
@@ -79,24 +89,22 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
         const bool alive = j < J;
         const int s_new = max(s, edge + 2 + kBandMargin - kBandW);
         const int d = s_new - s;
-        int rel[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int slot = 4 * g + q;
-            const int rel_old = (slot - s) & 31;
-            rel[q] = (slot - s_new) & 31;
-            if (rel_old < d) {   // slot recycled: its row moved down by 32
-                code[q] = ncode[q];
-                ncode[q] = alive ? rc[min(s_new + rel[q] + 32, code_max)] : 12;
-            }
+        if ((s_new >> 5) != lap) {       // octet-uniform, once every 32 columns
+            lap = s_new >> 5;
+            w0 = w1; w1 = w2;
+            w2 = rc32[min(8 * (lap + 2) + g, wmax)];
         }
+        int rel[4], code[4];
+        lane_codes(w0, w1, s_new, g, code);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rel[q] = (4 * g + q - s_new) & 31;
         // prefetch next column's transition row and the template base after it
         const int ci_next = ((ci & 3) << 2) | t2;
-        const float4 tr_next = alive ? tr[ci_next] : tr_i;
-        const int t3 = alive ? tp[min(j + 2, J - 1)] : 0;
+        const float4 tr_next = tr[ci_next];
+        const int t3 = tp[min(j + 2, Jc - 1)];
 
         octet_forward_column(v, g, d, rel, code, tr_m.x, tr_m.y, tr_i.z, tr_i.w, s_emm + cm * kEmStride,
-                             s_emi + ci * kEmStride, ci & 3);
+                             s_emi + ci * kEmStride, (ci & 3) << 2);
         int edge_rel;
         bool dead;
         const int k = octet_scale_column(v, rel, edge_rel, dead);
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
         edge = s_new + edge_rel - 1;
         s = s_new;
         if (alive) {
-            acol[(size_t)j * 8 + g] = make_float4(v[0], v[1], v[2], v[3]);
+            acol[(size_t)j * 8] = make_float4(v[0], v[1], v[2], v[3]);
             if (g == 0) cinfo[j] = ColInfo{s_new, cum};
             if (j == J - 1) {   // alpha(I-1, J-1) lives in slot (I-1) mod 32 if it is inside the band
                 const int slot = (I - 1) & 31;
@@ -147,6 +155,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     if (item < n_items) r = order[item];
     DevRead rd;
     rd.J = 0; rd.I = 0; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0; rd.zmw = 0; rd.last_code = 0; rd.first_code = 0;
+    rd.code_stride = 64; rd.active = 0;
     if (r >= 0) rd = V.reads[r];
     const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
     const int J = valid ? rd.J : 0;
@@ -155,20 +164,21 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
 #pragma unroll
     for (int off = 8; off < 32; off <<= 1) Jmax = max(Jmax, __shfl_xor_sync(kFullMask, Jmax, off));
 
-    const uint8_t* __restrict__ rc = V.rowcode + rd.code_off;
+    // second copy of the row codes, shifted by one row: word k holds the codes of rows 4k+1 .. 4k+4
+    const unsigned* __restrict__ rc32 = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off + rd.code_stride);
+    const int wmax = (rd.code_stride >> 2) - 1;
     const uint8_t* __restrict__ tp = V.tpl + rd.tpl_off;
     const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
-    float4* __restrict__ bcol = reinterpret_cast<float4*>(V.beta) + (size_t)rd.col_off * 8;
+    float4* __restrict__ bcol = reinterpret_cast<float4*>(V.beta) + (size_t)rd.col_off * 8 + g;
     const ColInfo* __restrict__ cinfo = V.colinfo + rd.col_off;
     int32_t* __restrict__ bexp = V.beta_exp + rd.col_off;
-    const int code_max = I + kRowCodePad - 1;
 
     // The warp walks columns from (Jmax-1) down to 1; an octet is alive once j <= J-1.
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    int code1[4] = {12, 12, 12, 12}, pcode1[4] = {12, 12, 12, 12};
-    int s_next = 0, cum = 0;
+    int s_next = 0, cum = 0, lap = 0;
     int s_cur = 0;   // band start of column j (prefetched)
     int t_hi = 0, t_lo = 0, t_lo2 = 0;   // template bases j, j-1, j-2
+    unsigned w0 = 0x30303030u, w1 = 0x30303030u, wm = 0x30303030u;   // laps L, L+1, L-1 (sentinels)
     float4 tr_c = make_float4(0.f, 0.f, 0.f, 0.f), tr_p = tr_c;
     float first_val = 0.f;
     int first_cum = 0;
@@ -183,26 +193,22 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
             t_hi = tp[j]; t_lo = tp[j - 1]; t_lo2 = tp[max(j - 2, 0)];
             tr_c = tr[4 * t_lo + t_hi];
             tr_p = tr[4 * t_lo2 + t_lo];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int row = s_cur + ((4 * g + q - s_cur) & 31);
-                code1[q] = rc[min(row + 1, code_max)];
-                pcode1[q] = rc[max(row + 1 - 32, 0)];
-            }
+            lap = s_cur >> 5;
+            w0 = rc32[min(8 * lap + g, wmax)];
+            w1 = rc32[min(8 * (lap + 1) + g, wmax)];
+            wm = rc32[min(8 * max(lap - 1, 0) + g, wmax)];
+        }
+        if (alive && (s_cur >> 5) != lap) {   // moved up into the previous lap
+            lap = s_cur >> 5;
+            w1 = w0; w0 = wm;
+            wm = rc32[min(8 * max(lap - 1, 0) + g, wmax)];
         }
         const int ci = 4 * t_lo + t_hi;              // context of column j (= match context of j+1)
         const int d = s_next - s_cur;
-        int rel[4];
+        int rel[4], code1[4];
+        lane_codes(w0, w1, s_cur, g, code1);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int slot = 4 * g + q;
-            const int rel_nx = (slot - s_next) & 31;
-            rel[q] = (slot - s_cur) & 31;
-            if (started && rel_nx >= 32 - d) {   // slot recycled: its row moved up by 32
-                code1[q] = pcode1[q];
-                pcode1[q] = alive ? rc[max(s_cur + rel[q] + 1 - 32, 0)] : 12;
-            }
-        }
+        for (int q = 0; q < 4; ++q) rel[q] = (4 * g + q - s_cur) & 31;
         // prefetch for column j-1
         const int s_prev = (alive && j >= 2) ? cinfo[j - 1].start : s_cur;
         const int t_lo3 = (alive && j >= 3) ? tp[j - 3] : 0;
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
 
         float A[4], G[4];
         octet_backward_terms(v, g, d, rel, code1, tr_c.x, tr_c.y, tr_c.z, tr_c.w, s_emm + ci * kEmStride,
-                             s_emi + ci * kEmStride, ci & 3, A, G);
+                             s_emi + ci * kEmStride, (ci & 3) << 2, A, G);
         if (alive && !started) {
             // last column: beta(I-1, J-1) = pinned last match; rows above it by insertions
             const float endv = s_emm[(kCtxEndRow + ci) * kEmStride + rd.last_code];
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
         const int k = octet_scale_column(v, rel, edge_rel, dead);
         if (alive) {
             cum += k;
-            bcol[(size_t)j * 8 + g] = make_float4(v[0], v[1], v[2], v[3]);
+            bcol[(size_t)j * 8] = make_float4(v[0], v[1], v[2], v[3]);
             if (g == 0) bexp[j] = cum;
             if (j == 1) {   // beta(1,1) lives in slot 1 if row 1 is inside the band
                 const int rrel = (1 - s_cur) & 31;

@@ -26,6 +26,12 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kEmStride = 16;
 constexpr int kCtxStartRow = 16;
 constexpr int kCtxEndRow = 20;
+constexpr int kC4Sentinel = 48;   // row codes are stored pre-multiplied by 4 (byte offset into a table row)
+
+// table row lookup by pre-scaled code
+__device__ __forceinline__ float ldtab(const float* __restrict__ row, const int c4) {
+    return *reinterpret_cast<const float*>(reinterpret_cast<const char*>(row) + c4);
+}
 
 __device__ __forceinline__ float shfl_oct(float x, int src_lane_in_octet) {
     return __shfl_sync(kFullMask, x, src_lane_in_octet, 8);
@@ -42,7 +48,7 @@ __device__ __forceinline__ int shfl_oct_i(int x, int src_lane_in_octet) {
 __device__ __forceinline__ void octet_forward_terms(const float v[4], const int g, const int d, const int rel[4],
                                                     const int code[4], const float M, const float D, const float B,
                                                     const float S, const float* __restrict__ emm_row,
-                                                    const float* __restrict__ emi_row, const int cur_base,
+                                                    const float* __restrict__ emi_row, const int cur_base4 /* (base of the context's current template base) << 2 */,
                                                     float A[4], float G[4]) {
     float up[4];   // previous column one row up: slot - 1
     up[0] = shfl_oct(v[3], (g + 7) & 7);
@@ -52,9 +58,9 @@ __device__ __forceinline__ void octet_forward_terms(const float v[4], const int 
         const int rd = rel[q] + d;                 // position of this row in the previous band
         const float pv = (rd < 32) ? v[q] : 0.f;   // row inside previous band
         const float uv = (rd >= 1 && rd <= 32) ? up[q] : 0.f;
-        const float em = emm_row[code[q]];
+        const float em = ldtab(emm_row, code[q]);
         A[q] = fmaf(M, em * uv, D * pv);
-        const float gi = emi_row[code[q]] * (((code[q] & 3) == cur_base) ? B : S);
+        const float gi = ldtab(emi_row, code[q]) * (((code[q] & 12) == cur_base4) ? B : S);
         G[q] = (rel[q] == 0) ? 0.f : gi;           // band start: no in-band predecessor
     }
 }
@@ -80,9 +86,9 @@ __device__ __forceinline__ void octet_forward_scan(float A[4], float G[4], const
 __device__ __forceinline__ void octet_forward_column(float v[4], const int g, const int d, const int rel[4],
                                                      const int code[4], const float M, const float D, const float B,
                                                      const float S, const float* __restrict__ emm_row,
-                                                     const float* __restrict__ emi_row, const int cur_base) {
+                                                     const float* __restrict__ emi_row, const int cur_base4) {
     float A[4], G[4];
-    octet_forward_terms(v, g, d, rel, code, M, D, B, S, emm_row, emi_row, cur_base, A, G);
+    octet_forward_terms(v, g, d, rel, code, M, D, B, S, emm_row, emi_row, cur_base4, A, G);
     octet_forward_scan(A, G, g, v);
 }
 
@@ -91,7 +97,7 @@ __device__ __forceinline__ void octet_forward_column(float v[4], const int g, co
 __device__ __forceinline__ void octet_backward_terms(const float v[4], const int g, const int d, const int rel[4],
                                                      const int code1[4], const float M, const float D, const float B,
                                                      const float S, const float* __restrict__ emm_row,
-                                                     const float* __restrict__ emi_row, const int cur_base,
+                                                     const float* __restrict__ emi_row, const int cur_base4 /* (base of the context's current template base) << 2 */,
                                                      float A[4], float G[4]) {
     float dn[4];
     dn[3] = shfl_oct(v[0], (g + 1) & 7);
@@ -100,9 +106,9 @@ __device__ __forceinline__ void octet_backward_terms(const float v[4], const int
     for (int q = 0; q < 4; ++q) {
         const float nx = (rel[q] >= d) ? v[q] : 0.f;                            // beta(i, j+1)
         const float nd = (rel[q] >= d - 1 && rel[q] <= d + 30) ? dn[q] : 0.f;   // beta(i+1, j+1)
-        const float em = emm_row[code1[q]];
+        const float em = ldtab(emm_row, code1[q]);
         A[q] = fmaf(M, em * nd, D * nx);
-        const float gi = emi_row[code1[q]] * (((code1[q] & 3) == cur_base) ? B : S);
+        const float gi = ldtab(emi_row, code1[q]) * (((code1[q] & 12) == cur_base4) ? B : S);
         G[q] = (rel[q] == 31) ? 0.f : gi;          // band end: no in-band successor
     }
 }

@@ -86,11 +86,11 @@ __device__ __forceinline__ float eval_mutation(const ReadCtx& R, const int g, co
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
             rel[x] = (4 * g + x - S_new) & 31;
-            code[x] = real ? R.rc[min(S_new + rel[x], code_max)] : 12;
+            code[x] = real ? R.rc[min(S_new + rel[x], code_max)] : kC4Sentinel;
         }
         float A[4], G[4];
         octet_forward_terms(v, g, d, rel, code, trm.x, trm.y, tri.z, tri.w, s_emm + (real ? cm : 0) * kEmStride,
-                            s_emi + (real ? ci : 0) * kEmStride, ci & 3, A, G);
+                            s_emi + (real ? ci : 0) * kEmStride, (ci & 3) << 2, A, G);
         float w[4];
         octet_forward_scan(A, G, g, w);
         if (real) {
@@ -136,8 +136,8 @@ __device__ __forceinline__ float eval_mutation(const ReadCtx& R, const int g, co
             const int row = S + ((4 * g + x - S) & 31);
             const float bx = (row >= sb && row < sb + 32) ? bv[x] : 0.f;
             const float bd = (row + 1 >= sb && row + 1 < sb + 32) ? dn[x] : 0.f;
-            const int c1 = lk ? R.rc[min(row + 1, code_max)] : 12;
-            const float wv = fmaf(trl.x, emm_row[c1] * bd, trl.y * bx);
+            const int c1 = lk ? R.rc[min(row + 1, code_max)] : kC4Sentinel;
+            const float wv = fmaf(trl.x, ldtab(emm_row, c1) * bd, trl.y * bx);
             acc = fmaf(v[x], wv, acc);
         }
         link_v = octet_sum(acc);
@@ -279,7 +279,7 @@ __device__ __forceinline__ float link_dot(const float y[4], const float bx[4], c
     float acc = 0.f;
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
-        const float wv = fmaf(trl.x, emm_row[codeL[x]] * bd[x], trl.y * bx[x]);
+        const float wv = fmaf(trl.x, ldtab(emm_row, codeL[x]) * bd[x], trl.y * bx[x]);
         acc = fmaf(y[x], wv, acc);
     }
     return octet_sum(acc);
@@ -330,22 +330,22 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const f
         const int c2n = R.rc[min(row2 + 1, code_max)];
         const int rd1 = rel1[x] + d1, rd2 = rel2[x] + d2;
         const float pv = (rd1 < 32) ? v0[x] : 0.f;
-        codeU1[x] = ((unsigned)(rd1 - 1) < 32u) ? c1 : 12;
-        codeG1[x] = (rel1[x] == 0) ? 12 : c1;
-        codeU2[x] = ((unsigned)(rd2 - 1) < 32u) ? c2 : 12;
-        codeG2[x] = (rel2[x] == 0) ? 12 : c2;
+        codeU1[x] = ((unsigned)(rd1 - 1) < 32u) ? c1 : kC4Sentinel;
+        codeG1[x] = (rel1[x] == 0) ? kC4Sentinel : c1;
+        codeU2[x] = ((unsigned)(rd2 - 1) < 32u) ? c2 : kC4Sentinel;
+        codeG2[x] = (rel2[x] == 0) ? kC4Sentinel : c2;
         pvm2[x] = (rd2 < 32) ? 1.f : 0.f;
-        A1[x] = fmaf(trq.x, s_emm[cmq * kEmStride + codeU1[x]] * up1[x], trq.y * pv);
+        A1[x] = fmaf(trq.x, ldtab(s_emm + cmq * kEmStride, codeU1[x]) * up1[x], trq.y * pv);
         // link operands: beta(i, c) / beta(i+1, c) at the rows of the extension band
         bx2[x] = (row2 >= sq2 && row2 < sq2 + 32) ? be2[x] : 0.f;
         bd2[x] = dn2[x];
-        codeL2[x] = (row2 + 1 >= sq2 && row2 + 1 < sq2 + 32) ? c2n : 12;
+        codeL2[x] = (row2 + 1 >= sq2 && row2 + 1 < sq2 + 32) ? c2n : kC4Sentinel;
         bx1[x] = (row2 >= sq1 && row2 < sq1 + 32) ? be1[x] : 0.f;
         bd1[x] = dn1[x];
-        codeLb1[x] = (row2 + 1 >= sq1 && row2 + 1 < sq1 + 32) ? c2n : 12;
+        codeLb1[x] = (row2 + 1 >= sq1 && row2 + 1 < sq1 + 32) ? c2n : kC4Sentinel;
         bxD[x] = (row1 >= sq2 && row1 < sq2 + 32) ? be2[x] : 0.f;
         bdD[x] = dn2[x];
-        codeL1[x] = (row1 + 1 >= sq2 && row1 + 1 < sq2 + 32) ? c1n : 12;
+        codeL1[x] = (row1 + 1 >= sq2 && row1 + 1 < sq2 + 32) ? c1n : kC4Sentinel;
     }
     float Xdel[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -358,7 +358,7 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const f
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
             A[x] = A1[x];
-            G[x] = emi_row[codeG1[x]] * (((codeG1[x] & 3) == b) ? tri.z : tri.w);
+            G[x] = ldtab(emi_row, codeG1[x]) * (((codeG1[x] & 12) == (b << 2)) ? tri.z : tri.w);
         }
         octet_forward_scan(A, G, g, X);
         if (b == tp1) {
@@ -369,7 +369,7 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const f
         float up2[4], A2[4];
         up2[0] = shfl_oct(X[3], (g + 7) & 7); up2[1] = X[0]; up2[2] = X[1]; up2[3] = X[2];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) A2[x] = fmaf(tri.x, emm_row[codeU2[x]] * up2[x], tri.y * (X[x] * pvm2[x]));
+        for (int x = 0; x < 4; ++x) A2[x] = fmaf(tri.x, ldtab(emm_row, codeU2[x]) * up2[x], tri.y * (X[x] * pvm2[x]));
         {   // SUB(q, b): insertion context (b, t[q+1]); link into beta column q+2
             const int c2 = 4 * b + tp1;
             const float4 tr2 = R.tr[c2];
@@ -378,7 +378,7 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const f
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 Aa[x] = A2[x];
-                Ga[x] = e2[codeG2[x]] * (((codeG2[x] & 3) == tp1) ? tr2.z : tr2.w);
+                Ga[x] = ldtab(e2, codeG2[x]) * (((codeG2[x] & 12) == (tp1 << 2)) ? tr2.z : tr2.w);
             }
             octet_forward_scan(Aa, Ga, g, Y);
             const float v = link_dot(Y, bx2, bd2, codeL2, tr2, s_emm + c2 * kEmStride);
@@ -393,7 +393,7 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const f
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 Aa[x] = A2[x];
-                Ga[x] = e3[codeG2[x]] * (((codeG2[x] & 3) == t0) ? tr3.z : tr3.w);
+                Ga[x] = ldtab(e3, codeG2[x]) * (((codeG2[x] & 12) == (t0 << 2)) ? tr3.z : tr3.w);
             }
             octet_forward_scan(Aa, Ga, g, Z);
             const float v = link_dot(Z, bx1, bd1, codeLb1, tr3, s_emm + c3 * kEmStride);

@@ -161,39 +161,48 @@ void ArrowEngine::load(const PolishInput& in) {
     qv_.assign(nz, {});
     tpl_cap_.assign(nz, 0);
 
-    // row codes
+    // row codes: two 16-byte aligned copies per read (row i, and row i+1 for the backward pass),
+    // pre-multiplied by 4 = byte offset into an emission-table row
     int64_t code_total = 0;
-    for (int r = 0; r < nr; ++r) code_total += (in.read_off[r + 1] - in.read_off[r]) + kRowCodePad + 1;
-    code_total = (code_total + 15) & ~15ll;
-    h_rowcode_.ensure((size_t)code_total);
-    std::memset(h_rowcode_.p, kCodeSentinel, (size_t)code_total);
-    int64_t coff = 0;
+    for (int r = 0; r < nr; ++r) code_total += 2 * (((in.read_off[r + 1] - in.read_off[r]) + kRowCodePad + 1 + 15) & ~15ll);
+    h_rowcode_.ensure((size_t)code_total + 64);
+    std::vector<int64_t> coffs(nr + 1, 0);
+    for (int r = 0; r < nr; ++r)
+        coffs[r + 1] = coffs[r] + 2 * (((in.read_off[r + 1] - in.read_off[r]) + kRowCodePad + 1 + 15) & ~15ll);
     for (int z = 0; z < nz; ++z) {
         ZmwState& zs = zstate_[z];
         zs.read_begin = in.zmw_read_off[z];
         zs.read_end = in.zmw_read_off[z + 1];
         zs.tpl.assign(in.tpl + in.tpl_off[z], in.tpl + in.tpl_off[z + 1]);
         zs.seen.assign(1, tpl_hash(zs.tpl));
+    }
+    parallel_for(nr, host_threads, [&](int r) {
+        DevRead& rd = reads_[r];
+        std::memset(&rd, 0, sizeof(rd));
+        const int64_t I = in.read_off[r + 1] - in.read_off[r];
+        const uint8_t* src = in.codes + in.read_off[r];
+        const int64_t stride = (coffs[r + 1] - coffs[r]) / 2;
+        rd.code_off = coffs[r];
+        rd.code_stride = (int32_t)stride;
+        rd.I = (int32_t)I;
+        rd.strand = in.strand[r];
+        rd.ts = in.tstart[r];
+        rd.te = in.tend[r];
+        rd.active = (rd.te > rd.ts) ? 1 : 0;
+        // copy A: A[i] = 4*code of DP row i: sentinel at row 0 and at rows >= I (the last read base
+        // is consumed only by the pinned final match); copy B[i] = A[i+1]
+        uint8_t* a = h_rowcode_.p + coffs[r];
+        uint8_t* b = a + stride;
+        std::memset(a, 4 * kCodeSentinel, (size_t)(2 * stride));
+        for (int64_t i = 1; i <= I - 1; ++i) { const uint8_t c = (uint8_t)(4 * src[i - 1]); a[i] = c; b[i - 1] = c; }
+        rd.first_code = I >= 1 ? src[0] : 0;
+        rd.last_code = I >= 1 ? src[I - 1] : 0;
+    });
+    for (int z = 0; z < nz; ++z) {
+        ZmwState& zs = zstate_[z];
         for (int r = zs.read_begin; r < zs.read_end; ++r) {
-            DevRead& rd = reads_[r];
-            std::memset(&rd, 0, sizeof(rd));
-            const int64_t I = in.read_off[r + 1] - in.read_off[r];
-            const uint8_t* src = in.codes + in.read_off[r];
-            rd.code_off = coff;
-            rd.I = (int32_t)I;
-            rd.zmw = z;
-            rd.strand = in.strand[r];
-            rd.ts = in.tstart[r];
-            rd.te = in.tend[r];
-            rd.active = (rd.te > rd.ts) ? 1 : 0;
-            if (rd.active) ++zs.n_mapped;
-            // rowcode[i] = code of DP row i: sentinel at row 0 and at rows >= I (the last read base
-            // is consumed only by the pinned final match)
-            uint8_t* dst = h_rowcode_.p + coff;
-            if (I >= 2) std::memcpy(dst + 1, src, (size_t)(I - 1));
-            rd.first_code = I >= 1 ? src[0] : 0;
-            rd.last_code = I >= 1 ? src[I - 1] : 0;
-            coff += I + kRowCodePad + 1;
+            reads_[r].zmw = z;
+            if (reads_[r].active) ++zs.n_mapped;
         }
     }
     d_rowcode_.ensure((size_t)code_total, budget_);
