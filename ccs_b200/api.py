@@ -26,7 +26,19 @@ class CBatch(C.Structure):
 
 class CDrafts(C.Structure):
     _fields_ = [("tpl_off", C.POINTER(C.c_int64)), ("tpl", C.POINTER(C.c_uint8)), ("strand", C.POINTER(C.c_uint8)),
-                ("tstart", C.POINTER(C.c_int32)), ("tend", C.POINTER(C.c_int32))]
+                ("tstart", C.POINTER(C.c_int32)), ("tend", C.POINTER(C.c_int32)), ("rstart", C.POINTER(C.c_int32)),
+                ("rend", C.POINTER(C.c_int32))]
+
+
+class CDraftCfg(C.Structure):
+    _fields_ = [("min_snr", C.c_double), ("min_passes", C.c_int32), ("top_passes", C.c_int32),
+                ("max_poa_reads", C.c_int32), ("min_length", C.c_int32), ("max_length", C.c_int32)]
+
+
+class CDraftsOut(C.Structure):
+    _fields_ = [("tpl_cap", C.c_int64), ("tpl_off", C.POINTER(C.c_int64)), ("tpl", C.POINTER(C.c_uint8)),
+                ("strand", C.POINTER(C.c_uint8)), ("tstart", C.POINTER(C.c_int32)), ("tend", C.POINTER(C.c_int32)),
+                ("rstart", C.POINTER(C.c_int32)), ("rend", C.POINTER(C.c_int32)), ("status", C.POINTER(C.c_int32))]
 
 
 class CPolishCfg(C.Structure):
@@ -49,6 +61,8 @@ class CStats(C.Structure):
                [(n, C.c_int64) for n in ("launches_fill_alpha", "launches_fill_beta", "launches_score", "launches_pick",
                                          "launches_qv", "launches_draft", "bytes_fill_alpha", "bytes_fill_beta",
                                          "cells_fill", "score_items", "rounds", "h2d_bytes", "d2h_bytes")] + \
+               [("ms_poa_align", C.c_double)] + \
+               [(n, C.c_int64) for n in ("launches_poa", "poa_tasks", "poa_rows", "bytes_poa_align")] + \
                [("ms_resident", C.c_double), ("ms_e2e", C.c_double), ("n_zmws", C.c_int64)]
 
 
@@ -99,7 +113,7 @@ class Batch:
             b.tstart = np.ascontiguousarray(tstart, np.int32)
             b.tend = np.ascontiguousarray(tend, np.int32)
             b.d = CDrafts(_p(b.tpl_off, C.c_int64), _p(b.tpl, C.c_uint8), _p(b.strand, C.c_uint8),
-                          _p(b.tstart, C.c_int32), _p(b.tend, C.c_int32))
+                          _p(b.tstart, C.c_int32), _p(b.tend, C.c_int32), None, None)
         return b
 
     def zmw_reads(self, z):
@@ -115,7 +129,7 @@ class Batch:
         self.tstart = np.ascontiguousarray(np.concatenate([np.asarray(d[2], np.int32) for d in drafts]))
         self.tend = np.ascontiguousarray(np.concatenate([np.asarray(d[3], np.int32) for d in drafts]))
         self.d = CDrafts(_p(self.tpl_off, C.c_int64), _p(self.tpl, C.c_uint8), _p(self.strand, C.c_uint8),
-                         _p(self.tstart, C.c_int32), _p(self.tend, C.c_int32))
+                         _p(self.tstart, C.c_int32), _p(self.tend, C.c_int32), None, None)
 
 
 class CcsGpuError(RuntimeError):
@@ -209,6 +223,57 @@ class Context:
                 cap = int(res.seq_cap) + 1024
                 continue
             self._check(rc, "ccsgpu_polish")
+            break
+        return dict(seq_off=seq_off, seq=seq, qv=qv, rq=rq, status=status, n_passes=npass, iterations=its,
+                    n_applied=napp, n_tested=ntest, read_ll=rll, read_status=rst)
+
+    def default_draft_cfg(self):
+        cfg = CDraftCfg()
+        self._L.ccs_draft_cfg_default(C.byref(cfg))
+        return cfg
+
+    def draft(self, batch, cfg=None):
+        """Draft Stage: returns dict(tpl_off, tpl, strand, tstart, tend, rstart, rend, status)."""
+        if cfg is None:
+            cfg = self.default_draft_cfg()
+        nz, nr = batch.n_zmws, batch.n_reads
+        cap = int(np.diff(batch.read_off).max(initial=1)) * nz * 2 + 1024
+        while True:
+            tpl_off = np.zeros(nz + 1, np.int64); tpl = np.zeros(cap, np.uint8); strand = np.zeros(nr, np.uint8)
+            ts = np.zeros(nr, np.int32); te = np.zeros(nr, np.int32); rs = np.zeros(nr, np.int32)
+            re = np.zeros(nr, np.int32); status = np.zeros(nz, np.int32)
+            out = CDraftsOut(cap, _p(tpl_off, C.c_int64), _p(tpl, C.c_uint8), _p(strand, C.c_uint8), _p(ts, C.c_int32),
+                             _p(te, C.c_int32), _p(rs, C.c_int32), _p(re, C.c_int32), _p(status, C.c_int32))
+            rc = self._L.ccsgpu_draft(C.c_void_p(self._h), C.byref(batch.c), C.byref(cfg), C.byref(out))
+            if rc == -1:
+                cap = int(out.tpl_cap) + 1024
+                continue
+            self._check(rc, "ccsgpu_draft")
+            break
+        return dict(tpl_off=tpl_off, tpl=tpl[:tpl_off[-1]], strand=strand, tstart=ts, tend=te, rstart=rs, rend=re,
+                    status=status)
+
+    def ccs(self, batch, dcfg=None, pcfg=None):
+        """Whole per-ZMW hot path (draft + polish + gates) for a batch."""
+        if dcfg is None:
+            dcfg = self.default_draft_cfg()
+        if pcfg is None:
+            pcfg = self.default_polish_cfg()
+        nz, nr = batch.n_zmws, batch.n_reads
+        cap = int(np.diff(batch.read_off).max(initial=1)) * nz * 2 + 1024
+        while True:
+            seq_off = np.zeros(nz + 1, np.int64); seq = np.zeros(cap, np.uint8); qv = np.zeros(cap, np.uint8)
+            rq = np.zeros(nz, np.float32); status = np.zeros(nz, np.int32); npass = np.zeros(nz, np.int32)
+            its = np.zeros(nz, np.int32); napp = np.zeros(nz, np.int32); ntest = np.zeros(nz, np.int64)
+            rll = np.zeros(nr); rst = np.zeros(nr, np.int32)
+            res = CResults(cap, _p(seq_off, C.c_int64), _p(seq, C.c_uint8), _p(qv, C.c_uint8), _p(rq, C.c_float),
+                           _p(status, C.c_int32), _p(npass, C.c_int32), _p(its, C.c_int32), _p(napp, C.c_int32),
+                           _p(ntest, C.c_int64), _p(rll, C.c_double), _p(rst, C.c_int32))
+            rc = self._L.ccsgpu_ccs(C.c_void_p(self._h), C.byref(batch.c), C.byref(dcfg), C.byref(pcfg), C.byref(res))
+            if rc == -1:
+                cap = int(res.seq_cap) + 1024
+                continue
+            self._check(rc, "ccsgpu_ccs")
             break
         return dict(seq_off=seq_off, seq=seq, qv=qv, rq=rq, status=status, n_passes=npass, iterations=its,
                     n_applied=napp, n_tested=ntest, read_ll=rll, read_status=rst)

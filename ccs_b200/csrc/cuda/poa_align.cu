@@ -1,0 +1,199 @@
+// poa_align: banded local alignment of a read against a partial-order graph, one warp per
+// (graph, read) task, one 64-cell DP row per vertex in topological order
+// (SparsePoa::OrientAndAddRead -> PoaGraph::TryAddRead, SURVEY.md 8a row a2 and Appendix B;
+// "approximate draft consensus from a few subreads", /root/reference/docs/how-does-ccs-work.md:14,34-47).
+//
+//   C[v][i] = max(0, max_u H[u][i-1] + s(v, r_i), max_u H[u][i] + DEL)        u in pred(v)
+//   H[v][i] = max(C[v][i], H[v][i-1] + INS)            -- in-row chain = warp prefix-max scan
+//
+// int32 max-plus arithmetic, bit-exact against the oracle.  Each lane owns two adjacent cells;
+// the previous row lives in shared memory (the common predecessor), older rows are re-read from
+// global memory only when a vertex has a non-adjacent predecessor.  Per vertex the kernel writes
+// 64 B of traceback moves (+ 256 B of scores for DAGs): algorithmic bytes per task
+// = V * (64 [+256] + 8) + n.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "poa_device.h"
+#include "poa_launch.h"
+
+namespace ccs {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWarpsPerCta = 4;
+
+__device__ __forceinline__ int row_get(const int* __restrict__ row, const int idx) {
+    return ((unsigned)idx < (unsigned)kPoaBand) ? row[idx] : 0;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
+    const PoaTask* __restrict__ tasks, const int n_tasks, const uint8_t* __restrict__ vbase,
+    const int32_t* __restrict__ pred_off, const int32_t* __restrict__ preds, const uint8_t* __restrict__ reads,
+    int32_t* __restrict__ lo_arr, int32_t* __restrict__ besti_arr, uint8_t* __restrict__ moves,
+    int32_t* __restrict__ hrows, PoaResult* __restrict__ results) {
+    __shared__ int s_row[kWarpsPerCta][kPoaBand];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int task_id = blockIdx.x * kWarpsPerCta + warp;
+    if (task_id >= n_tasks) return;
+    const PoaTask T = tasks[task_id];
+    const uint8_t* __restrict__ base = vbase + T.vert_off;
+    const int32_t* __restrict__ poff = pred_off + T.poff_off;   // V+1 entries per graph
+    const int32_t* __restrict__ pl = preds + T.pred_base;
+    const uint8_t* __restrict__ rd = reads + T.read_off;
+    int32_t* __restrict__ lo_r = lo_arr + T.row_off;
+    int32_t* __restrict__ bi_r = besti_arr + T.row_off;
+    uint8_t* __restrict__ mv_r = moves + T.row_off * kPoaBand;
+    int32_t* __restrict__ h_r = hrows ? hrows + T.row_off * kPoaBand : nullptr;
+    const int n = T.n, V = T.V;
+    const bool store_h = !T.linear && h_r != nullptr;
+    const int lo_max = max(0, n + 1 - kPoaBand);
+    int* srow = s_row[warp];
+
+    int gbest = 0, gt = -1, gi = -1;
+    int prev_lo = 0, prev_besti = 0;
+    srow[2 * lane] = 0; srow[2 * lane + 1] = 0;
+    __syncwarp();
+
+    for (int t = 0; t < V; ++t) {
+        const int vb = base[t];
+        int p0, p1;
+        if (T.linear) { p0 = 0; p1 = (t > 0) ? 1 : 0; }
+        else { p0 = poff[t]; p1 = poff[t + 1]; }
+        const int npred = p1 - p0;
+        // band start from the predecessors' best cells
+        int lo = 0;
+        if (npred > 0) {
+            int m = 0;
+            for (int k = 0; k < npred; ++k) {
+                const int pr = T.linear ? t - 1 : pl[p0 + k];
+                m = max(m, (pr == t - 1) ? prev_besti : bi_r[pr]);
+            }
+            lo = min(max(m + 1 - kPoaBand / 2, 0), lo_max);
+        }
+        const int i0 = lo + 2 * lane, i1 = i0 + 1;
+        const int rb0 = (i0 >= 1 && i0 <= n) ? rd[i0 - 1] : 255;
+        const int rb1 = (i1 >= 1 && i1 <= n) ? rd[i1 - 1] : 255;
+        const int sc0 = (rb0 == vb) ? kPoaMatch : kPoaMismatch;
+        const int sc1 = (rb1 == vb) ? kPoaMatch : kPoaMismatch;
+        int bm0 = 0, bm1 = 0, bd0 = 0, bd1 = 0;        // best match / deletion candidates (must be > 0 to count)
+        int km0 = 0, km1 = 0, kd0 = 0, kd1 = 0;
+        if (npred == 0) {
+            if (rb0 != 255 && sc0 > 0) { bm0 = sc0; km0 = 63; }
+            if (rb1 != 255 && sc1 > 0) { bm1 = sc1; km1 = 63; }
+        }
+        for (int k = 0; k < npred; ++k) {
+            const int pr = T.linear ? t - 1 : pl[p0 + k];
+            const bool adj = (pr == t - 1);
+            const int* __restrict__ row = adj ? srow : (h_r + (size_t)pr * kPoaBand);
+            const int dl = lo - (adj ? prev_lo : lo_r[pr]);
+            const int a = 2 * lane + dl;
+            const int hm1 = row_get(row, a - 1), h0 = row_get(row, a), h1 = row_get(row, a + 1);
+            if (rb0 != 255) { const int c = hm1 + sc0; if (c > bm0) { bm0 = c; km0 = k; } }
+            if (rb1 != 255) { const int c = h0 + sc1; if (c > bm1) { bm1 = c; km1 = k; } }
+            if (i0 <= n) { const int c = h0 + kPoaDel; if (c > bd0) { bd0 = c; kd0 = k; } }
+            if (i1 <= n) { const int c = h1 + kPoaDel; if (c > bd1) { bd1 = c; kd1 = k; } }
+        }
+        // match wins ties against deletion (oracle evaluation order)
+        int c0, c1;
+        unsigned m0, m1;
+        if (bm0 >= bd0) { c0 = bm0; m0 = bm0 > 0 ? (1u | (km0 << 2)) : 0u; } else { c0 = bd0; m0 = 2u | (kd0 << 2); }
+        if (bm1 >= bd1) { c1 = bm1; m1 = bm1 > 0 ? (1u | (km1 << 2)) : 0u; } else { c1 = bd1; m1 = 2u | (kd1 << 2); }
+        __syncwarp();   // everyone has read the previous row
+        // insertion chain: H[c] = max(C[c], H[c-1] + INS) over the row's cells with i <= n
+        const int NEG = -(1 << 29);
+        int x0 = (i0 <= n) ? c0 - kPoaIns * (2 * lane) : NEG;
+        int x1 = (i1 <= n) ? c1 - kPoaIns * (2 * lane + 1) : NEG;
+        x1 = max(x1, x0);
+        int sc = x1;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(kFull, sc, off);
+            if (lane >= off) sc = max(sc, y);
+        }
+        int carry = __shfl_up_sync(kFull, sc, 1);
+        if (lane == 0) carry = NEG;
+        x0 = max(x0, carry);
+        x1 = max(x1, x0);
+        int H0 = (i0 <= n) ? x0 + kPoaIns * (2 * lane) : 0;
+        int H1 = (i1 <= n) ? x1 + kPoaIns * (2 * lane + 1) : 0;
+        if (H0 > c0) m0 = 3u;
+        if (H1 > c1) m1 = 3u;
+        // row outputs
+        *reinterpret_cast<uchar2*>(mv_r + (size_t)t * kPoaBand + 2 * lane) = make_uchar2((unsigned char)m0, (unsigned char)m1);
+        srow[2 * lane] = H0; srow[2 * lane + 1] = H1;
+        if (store_h) *reinterpret_cast<int2*>(h_r + (size_t)t * kPoaBand + 2 * lane) = make_int2(H0, H1);
+        // best cell of the row: largest value, smallest read prefix on ties
+        const int hv = max(H0, H1);
+        const int rmax = __reduce_max_sync(kFull, hv);
+        const unsigned who = __ballot_sync(kFull, hv == rmax);
+        const int wl = __ffs(who) - 1;
+        const int wc = __shfl_sync(kFull, (H0 == rmax) ? 2 * lane : 2 * lane + 1, wl);
+        const int besti = (rmax > 0) ? lo + wc : lo;
+        if (lane == 0) { lo_r[t] = lo; bi_r[t] = besti; }
+        if (rmax > gbest) { gbest = rmax; gt = t; gi = besti; }
+        prev_lo = lo; prev_besti = besti;
+        __syncwarp();   // row visible in shared memory before the next vertex reads it
+    }
+    if (lane == 0) {
+        PoaResult r;
+        r.score = gbest; r.end_t = gt; r.end_i = gi; r.path_len = 0;
+        r.first_t = r.first_i = r.last_t = r.last_i = -1;
+        results[task_id] = r;
+    }
+}
+
+// Traceback: one thread per task follows the stored moves from the best cell back to the local
+// start; writes the moves (end -> start) and the aligned extents.
+__global__ void __launch_bounds__(128) poa_traceback_kernel(const PoaTask* __restrict__ tasks, const int n_tasks,
+                                                            const int32_t* __restrict__ pred_off,
+                                                            const int32_t* __restrict__ preds,
+                                                            const int32_t* __restrict__ lo_arr,
+                                                            const uint8_t* __restrict__ moves,
+                                                            uint8_t* __restrict__ paths, PoaResult* __restrict__ results) {
+    const int task_id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (task_id >= n_tasks) return;
+    const PoaTask T = tasks[task_id];
+    PoaResult r = results[task_id];
+    const int32_t* __restrict__ poff = pred_off + T.poff_off;
+    const int32_t* __restrict__ pl = preds + T.pred_base;
+    const int32_t* __restrict__ lo_r = lo_arr + T.row_off;
+    const uint8_t* __restrict__ mv_r = moves + T.row_off * kPoaBand;
+    uint8_t* __restrict__ out = paths ? paths + T.path_off : nullptr;
+    int t = r.end_t, i = r.end_i, len = 0;
+    while (t >= 0) {
+        const int c = i - lo_r[t];
+        if ((unsigned)c >= (unsigned)kPoaBand) break;
+        const unsigned m = mv_r[(size_t)t * kPoaBand + c];
+        const unsigned kind = m & 3u, k = m >> 2;
+        if (kind == 0u) break;
+        if (out) out[len] = (uint8_t)m;
+        ++len;
+        if (kind == 1u) {           // match / mismatch: read base i-1 on vertex t
+            if (r.last_t < 0) { r.last_t = t; r.last_i = i - 1; }
+            r.first_t = t; r.first_i = i - 1;
+            if (k == 63u) break;
+            t = T.linear ? t - 1 : pl[poff[t] + k];
+            i -= 1;
+        } else if (kind == 2u) {    // deletion: vertex skipped
+            t = T.linear ? t - 1 : pl[poff[t] + k];
+        } else {                    // insertion: read base i-1 without a vertex
+            i -= 1;
+        }
+    }
+    r.path_len = len;
+    results[task_id] = r;
+}
+
+}  // namespace
+
+void launch_poa_align(const PoaTask* tasks, int n_tasks, const uint8_t* vbase, const int32_t* pred_off,
+                      const int32_t* preds, const uint8_t* reads, int32_t* lo, int32_t* besti, uint8_t* moves,
+                      int32_t* hrows, uint8_t* paths, PoaResult* results, cudaStream_t stream) {
+    if (n_tasks <= 0) return;
+    poa_align_kernel<<<(n_tasks + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, stream>>>(
+        tasks, n_tasks, vbase, pred_off, preds, reads, lo, besti, moves, hrows, results);
+    poa_traceback_kernel<<<(n_tasks + 127) / 128, 128, 0, stream>>>(tasks, n_tasks, pred_off, preds, lo, moves, paths, results);
+}
+
+}  // namespace ccs

@@ -1,0 +1,327 @@
+// Draft Stage host engine -- see draft_engine.h.
+#include "draft_engine.h"
+#include "poa_graph.h"
+#include "parallel.h"
+#include "../cuda/poa_launch.h"
+#include "../../../include/ccsgpu.h"
+#include <algorithm>
+#include <cstring>
+
+namespace ccs {
+
+namespace {
+
+// FilterReads (docs/how-does-ccs-work.md:19-32): drop reads <50 % or >200 % of the median length,
+// cap the full-length passes at top_passes; returns the number of full-length reads kept.
+int filter_reads(const int32_t* lens, const uint8_t* cx, int n, int top_passes, uint8_t* keep) {
+    std::vector<int32_t> s(lens, lens + n);
+    std::sort(s.begin(), s.end());
+    const int median = (n & 1) ? s[n / 2] : (s[n / 2 - 1] + s[n / 2]) / 2;
+    int nfull = 0;
+    for (int r = 0; r < n; ++r) {
+        keep[r] = 0;
+        if (2 * lens[r] < median || lens[r] > 2 * median) continue;
+        if ((cx[r] & 3) == 3) {
+            if (nfull >= top_passes) continue;
+            ++nfull;
+        }
+        keep[r] = 1;
+    }
+    return nfull;
+}
+
+// K-mer presence set of a reference + hit counting: the seeding half of SdpRangeFinder, used to
+// orient a read before it is aligned.
+struct KmerSet {
+    std::vector<uint32_t> tab;
+    uint32_t mask = 0;
+    void build(const uint8_t* s, int n) {
+        size_t cap = 1024;
+        while (cap < (size_t)n * 4) cap <<= 1;
+        tab.assign(cap, 0u);
+        mask = (uint32_t)cap - 1;
+        if (n < kPoaKmer) return;
+        const uint32_t kmask = (1u << (2 * kPoaKmer)) - 1;
+        uint32_t k = 0;
+        for (int i = 0; i < n; ++i) {
+            k = ((k << 2) | s[i]) & kmask;
+            if (i >= kPoaKmer - 1) insert(k);
+        }
+    }
+    static uint32_t hash(uint32_t k) { k *= 0x9E3779B1u; return k ^ (k >> 15); }
+    void insert(uint32_t k) {
+        uint32_t h = hash(k) & mask;
+        while (tab[h] != 0u && tab[h] != k + 1) h = (h + 1) & mask;
+        tab[h] = k + 1;
+    }
+    bool has(uint32_t k) const {
+        uint32_t h = hash(k) & mask;
+        while (tab[h] != 0u) { if (tab[h] == k + 1) return true; h = (h + 1) & mask; }
+        return false;
+    }
+    // shared k-mers of seq (forward) and of its reverse complement
+    void count(const uint8_t* codes, int n, int64_t& fwd, int64_t& rev) const {
+        fwd = rev = 0;
+        if (n < kPoaKmer) return;
+        const uint32_t kmask = (1u << (2 * kPoaKmer)) - 1;
+        uint32_t kf = 0, kr = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint32_t b = codes[i] & 3u;
+            kf = ((kf << 2) | b) & kmask;
+            kr = (kr >> 2) | ((3u - b) << (2 * (kPoaKmer - 1)));
+            if (i >= kPoaKmer - 1) { fwd += has(kf); rev += has(kr); }
+        }
+    }
+};
+
+void orient(const uint8_t* codes, int n, bool rev, uint8_t* out) {
+    if (!rev) for (int i = 0; i < n; ++i) out[i] = codes[i] & 3;
+    else for (int i = 0; i < n; ++i) out[i] = (uint8_t)(3 - (codes[n - 1 - i] & 3));
+}
+
+}  // namespace
+
+DraftEngine::DraftEngine(int device, size_t scratch_budget_bytes) : device_(device), budget_(scratch_budget_bytes) {
+    CCS_CUDA(cudaSetDevice(device_));
+    CCS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CCS_CUDA(cudaEventCreate(&ev0_));
+    CCS_CUDA(cudaEventCreate(&ev1_));
+    if (budget_ == 0) budget_ = 12ull << 30;
+}
+
+DraftEngine::~DraftEngine() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+// One GPU pass over a task list (already chunked to the scratch budget by the caller).
+void DraftEngine::align_tasks(const std::vector<PoaTask>& tasks, bool any_dag, bool want_paths, int64_t rows,
+                              int64_t path_bytes, const std::vector<uint8_t>& vbase, const std::vector<int32_t>& poff,
+                              const std::vector<int32_t>& preds, const std::vector<uint8_t>& reads,
+                              std::vector<PoaResult>& results, std::vector<uint8_t>& paths) {
+    const int nt = (int)tasks.size();
+    results.resize(nt);
+    if (nt == 0) return;
+    CCS_CUDA(cudaSetDevice(device_));
+    d_tasks_.ensure(nt); d_vbase_.ensure(vbase.size() + 16); d_reads_.ensure(reads.size() + 16);
+    d_poff_.ensure(poff.size() + 16); d_preds_.ensure(preds.size() + 16);
+    d_lo_.ensure((size_t)rows + 16); d_besti_.ensure((size_t)rows + 16); d_moves_.ensure((size_t)rows * kPoaBand + 16);
+    if (any_dag) d_hrows_.ensure((size_t)rows * kPoaBand + 16);
+    if (want_paths) d_paths_.ensure((size_t)path_bytes + 16);
+    d_results_.ensure(nt);
+    CCS_CUDA(cudaMemcpyAsync(d_tasks_.p, tasks.data(), sizeof(PoaTask) * nt, cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_vbase_.p, vbase.data(), vbase.size(), cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_reads_.p, reads.data(), reads.size(), cudaMemcpyHostToDevice, stream_));
+    if (!poff.empty()) CCS_CUDA(cudaMemcpyAsync(d_poff_.p, poff.data(), poff.size() * 4, cudaMemcpyHostToDevice, stream_));
+    if (!preds.empty()) CCS_CUDA(cudaMemcpyAsync(d_preds_.p, preds.data(), preds.size() * 4, cudaMemcpyHostToDevice, stream_));
+    stats.h2d_bytes += (int64_t)(sizeof(PoaTask) * nt + vbase.size() + reads.size() + 4 * (poff.size() + preds.size()));
+    CCS_CUDA(cudaEventRecord(ev0_, stream_));
+    launch_poa_align(d_tasks_.p, nt, d_vbase_.p, d_poff_.p, d_preds_.p, d_reads_.p, d_lo_.p, d_besti_.p, d_moves_.p,
+                     any_dag ? d_hrows_.p : nullptr, want_paths ? d_paths_.p : nullptr, d_results_.p, stream_);
+    CCS_CUDA(cudaEventRecord(ev1_, stream_));
+    CCS_CUDA(cudaMemcpyAsync(results.data(), d_results_.p, sizeof(PoaResult) * nt, cudaMemcpyDeviceToHost, stream_));
+    if (want_paths) {
+        paths.resize((size_t)path_bytes);
+        CCS_CUDA(cudaMemcpyAsync(paths.data(), d_paths_.p, (size_t)path_bytes, cudaMemcpyDeviceToHost, stream_));
+        stats.d2h_bytes += path_bytes;
+    }
+    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0_, ev1_);
+    stats.ms_align += ms;
+    stats.n_align_launches += 2;
+    stats.n_tasks += nt;
+    stats.rows += rows;
+    stats.d2h_bytes += (int64_t)sizeof(PoaResult) * nt;
+    int64_t rb = 0;
+    for (const PoaTask& t : tasks) rb += t.n;
+    stats.bytes_align += rows * (kPoaBand + 8 + (any_dag ? 4 * kPoaBand : 0)) + rb + (int64_t)vbase.size();
+}
+
+void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& out) {
+    const int nz = in.n_zmws, nr = in.n_reads;
+    out.status.assign(nz, CCS_ZMW_EXCEPTION_THROWN);
+    out.draft.assign(nz, {});
+    out.maps.assign(nr, ReadMap());
+    out.keep.assign(nr, 0);
+    std::vector<int32_t> lens(nr);
+    for (int r = 0; r < nr; ++r) lens[r] = (int32_t)(in.read_off[r + 1] - in.read_off[r]);
+
+    // ---- a1: filtering, POA read selection, seed graph, orientation votes ------------------
+    struct ZmwWork {
+        std::vector<int32_t> poa_reads;   // global read indices, seed first
+        std::vector<uint8_t> poa_rev;     // orientation of each (vs the seed)
+        std::vector<uint8_t> seed;
+        HostPoaGraph graph;
+        std::vector<int32_t> order;       // export of the current round
+        int64_t vert_off = 0, poff_off = 0, pred_base = 0;
+        bool alive = false;
+    };
+    std::vector<ZmwWork> work(nz);
+    parallel_for(nz, host_threads, [&](int z) {
+        const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
+        const int n = r1 - r0;
+        if (n == 0) { out.status[z] = CCS_ZMW_NO_SUBREADS; return; }
+        const float* s = in.snr + 4 * z;
+        if (std::min(std::min(s[0], s[1]), std::min(s[2], s[3])) < dp.min_snr) { out.status[z] = CCS_ZMW_POOR_SNR; return; }
+        const int nfull = filter_reads(lens.data() + r0, in.cx + r0, n, dp.top_passes, out.keep.data() + r0);
+        if (nfull < dp.min_passes) { out.status[z] = CCS_ZMW_TOO_FEW_PASSES; return; }
+        ZmwWork& w = work[z];
+        for (int r = r0; r < r1 && (int)w.poa_reads.size() < dp.max_poa_reads; ++r)
+            if (out.keep[r] && (in.cx[r] & 3) == 3) w.poa_reads.push_back(r);
+        const int sr = w.poa_reads[0];
+        w.seed.resize(lens[sr]);
+        orient(in.codes + in.read_off[sr], lens[sr], false, w.seed.data());
+        w.graph.init(w.seed.data(), lens[sr]);
+        KmerSet ks;
+        ks.build(w.seed.data(), lens[sr]);
+        w.poa_rev.assign(w.poa_reads.size(), 0);
+        for (size_t k = 1; k < w.poa_reads.size(); ++k) {
+            int64_t f, c;
+            ks.count(in.codes + in.read_off[w.poa_reads[k]], lens[w.poa_reads[k]], f, c);
+            w.poa_rev[k] = c > f;
+        }
+        w.alive = true;
+    });
+
+    // ---- a2: SparsePoa rounds: round k aligns the k-th POA read of every ZMW on the GPU ----
+    std::vector<PoaTask> tasks;
+    std::vector<int> task_zmw;
+    std::vector<uint8_t> vbase, reads, paths;
+    std::vector<int32_t> poff, preds;
+    std::vector<PoaResult> results;
+    for (int round = 1; round < dp.max_poa_reads; ++round) {
+        // chunk ZMWs so that the DP scratch stays inside the budget
+        int z = 0;
+        while (z < nz) {
+            tasks.clear(); task_zmw.clear(); vbase.clear(); reads.clear(); poff.clear(); preds.clear();
+            int64_t rows = 0, path_bytes = 0;
+            for (; z < nz; ++z) {
+                ZmwWork& w = work[z];
+                if (!w.alive || (int)w.poa_reads.size() <= round) continue;
+                const int V = w.graph.size();
+                const int rd = w.poa_reads[round];
+                const int64_t need = (int64_t)V * (kPoaBand * 5 + 8) + V + lens[rd];
+                if (!tasks.empty() && (rows * (kPoaBand * 5 + 8) + need) > (int64_t)budget_) break;
+                PoaTask t;
+                t.vert_off = (int64_t)vbase.size(); t.poff_off = (int64_t)poff.size(); t.pred_base = (int64_t)preds.size();
+                w.graph.export_topo(w.order, vbase, poff, preds);
+                w.poff_off = t.poff_off; w.pred_base = t.pred_base;
+                t.read_off = (int64_t)reads.size();
+                reads.resize(reads.size() + lens[rd]);
+                orient(in.codes + in.read_off[rd], lens[rd], w.poa_rev[round], reads.data() + t.read_off);
+                t.row_off = rows; t.path_off = path_bytes; t.V = V; t.n = lens[rd]; t.linear = 0; t.pad_ = 0;
+                rows += V; path_bytes += V + lens[rd];
+                tasks.push_back(t);
+                task_zmw.push_back(z);
+            }
+            if (tasks.empty()) break;
+            align_tasks(tasks, true, true, rows, path_bytes, vbase, poff, preds, reads, results, paths);
+            parallel_for((int)tasks.size(), host_threads, [&](int k) {
+                ZmwWork& w = work[task_zmw[k]];
+                const PoaTask& t = tasks[k];
+                const PoaResult& r = results[k];
+                if (r.score >= t.n && r.path_len > 0)   // placed: CommitAdd
+                    w.graph.commit(paths.data() + t.path_off, r.path_len, r.end_t, r.end_i, w.order,
+                                   poff.data() + t.poff_off, preds.data() + t.pred_base, reads.data() + t.read_off);
+            });
+        }
+    }
+
+    // ---- a4: consensus + length gates ---------------------------------------------------------
+    parallel_for(nz, host_threads, [&](int z) {
+        ZmwWork& w = work[z];
+        if (!w.alive) return;
+        const int n = w.graph.n_reads();
+        const int min_cov = n < 5 ? 1 : (n + 1) / 2 - 1;
+        w.graph.consensus(min_cov, out.draft[z]);
+        const int J = (int)out.draft[z].size();
+        if (J == 0) { out.status[z] = CCS_ZMW_DRAFT_FAILURE; w.alive = false; }
+        else if (J < dp.min_length) { out.status[z] = CCS_ZMW_TOO_SHORT; w.alive = false; }
+        else if (J > dp.max_length) { out.status[z] = CCS_ZMW_TOO_LONG; w.alive = false; }
+    });
+
+    // ---- a5: subread -> draft mapping of every kept read (linear graphs on the same kernel) ---
+    std::vector<std::vector<uint8_t>> rev_flag(nz);
+    parallel_for(nz, host_threads, [&](int z) {
+        ZmwWork& w = work[z];
+        if (!w.alive) return;
+        const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
+        KmerSet ks;
+        ks.build(out.draft[z].data(), (int)out.draft[z].size());
+        rev_flag[z].assign(r1 - r0, 0);
+        for (int r = r0; r < r1; ++r) {
+            if (!out.keep[r]) continue;
+            int64_t f, c;
+            ks.count(in.codes + in.read_off[r], lens[r], f, c);
+            rev_flag[z][r - r0] = c > f;
+        }
+    });
+    {
+        int z = 0;
+        std::vector<int> task_read;
+        while (z < nz) {
+            tasks.clear(); task_read.clear(); vbase.clear(); reads.clear();
+            int64_t rows = 0;
+            for (; z < nz; ++z) {
+                ZmwWork& w = work[z];
+                if (!w.alive) continue;
+                const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
+                const int J = (int)out.draft[z].size();
+                int nk = 0;
+                for (int r = r0; r < r1; ++r) nk += out.keep[r];
+                if (!tasks.empty() && (rows + (int64_t)nk * J) * (kPoaBand + 8) > (int64_t)budget_) break;
+                const int64_t voff = (int64_t)vbase.size();
+                vbase.insert(vbase.end(), out.draft[z].begin(), out.draft[z].end());
+                for (int r = r0; r < r1; ++r) {
+                    if (!out.keep[r]) continue;
+                    PoaTask t;
+                    t.vert_off = voff; t.poff_off = 0; t.pred_base = 0;
+                    t.read_off = (int64_t)reads.size();
+                    reads.resize(reads.size() + lens[r]);
+                    orient(in.codes + in.read_off[r], lens[r], rev_flag[z][r - r0], reads.data() + t.read_off);
+                    t.row_off = rows; t.path_off = 0; t.V = J; t.n = lens[r]; t.linear = 1; t.pad_ = 0;
+                    rows += J;
+                    tasks.push_back(t);
+                    task_read.push_back(r);
+                }
+            }
+            if (tasks.empty()) break;
+            poff.clear(); preds.clear();
+            align_tasks(tasks, false, false, rows, 0, vbase, poff, preds, reads, results, paths);
+            for (size_t k = 0; k < tasks.size(); ++k) {
+                const int r = task_read[k];
+                const PoaResult& pr = results[k];
+                ReadMap& m = out.maps[r];
+                m.score = pr.score;
+                if (pr.first_t < 0) continue;
+                m.tstart = pr.first_t; m.tend = pr.last_t + 1;
+                int rs = pr.first_i, re = pr.last_i + 1;
+                // strand: recover from the zmw's vote
+                m.mapped = pr.score >= tasks[k].n;
+                m.rstart = rs; m.rend = re;
+            }
+        }
+    }
+    parallel_for(nz, host_threads, [&](int z) {
+        ZmwWork& w = work[z];
+        if (!w.alive) return;
+        const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
+        int mapped_full = 0;
+        for (int r = r0; r < r1; ++r) {
+            if (!out.keep[r]) continue;
+            ReadMap& m = out.maps[r];
+            m.strand = rev_flag[z][r - r0];
+            if (m.strand) { const int rs = lens[r] - m.rend, re = lens[r] - m.rstart; m.rstart = rs; m.rend = re; }
+            if (m.mapped && (m.tend - m.tstart < 2 || m.rend - m.rstart < 2)) m.mapped = 0;
+            if (m.mapped && (in.cx[r] & 3) == 3) ++mapped_full;
+        }
+        out.status[z] = mapped_full < dp.min_passes ? CCS_ZMW_TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT : CCS_ZMW_SUCCESS;
+    });
+}
+
+}  // namespace ccs

@@ -1,6 +1,7 @@
 // Polish Stage host engine -- see polish_engine.h.
 #include "polish_engine.h"
 #include "../cuda/arrow_launch.h"
+#include "parallel.h"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -114,28 +115,6 @@ void ArrowEngine::resolve_spans() {
     ev_used_ = 0;
 }
 
-namespace {
-// chunked parallel-for over ZMWs for the host-side pieces of a round
-template <class F>
-void parallel_for(int n, int n_threads, F&& f) {
-    if (n <= 0) return;
-    n_threads = std::max(1, std::min(n_threads, n / 8));
-    if (n_threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
-    std::vector<std::thread> th;
-    std::atomic<int> next(0);
-    auto work = [&]() {
-        for (;;) {
-            const int b = next.fetch_add(16);
-            if (b >= n) break;
-            for (int i = b; i < std::min(n, b + 16); ++i) f(i);
-        }
-    };
-    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
-}
-}  // namespace
-
 ArrowBatchView ArrowEngine::view() const {
     ArrowBatchView V;
     V.rowcode = d_rowcode_.p; V.tpl = d_tpl_.p; V.em_match = d_emm_.p; V.em_ins = d_emi_.p; V.trans = d_trans_.p;
@@ -164,11 +143,12 @@ void ArrowEngine::load(const PolishInput& in) {
     // row codes: two 16-byte aligned copies per read (row i, and row i+1 for the backward pass),
     // pre-multiplied by 4 = byte offset into an emission-table row
     int64_t code_total = 0;
-    for (int r = 0; r < nr; ++r) code_total += 2 * (((in.read_off[r + 1] - in.read_off[r]) + kRowCodePad + 1 + 15) & ~15ll);
+    auto rlen = [&](int r) -> int64_t { return in.rstart ? std::max(0, in.rend[r] - in.rstart[r]) : (in.read_off[r + 1] - in.read_off[r]); };
+    for (int r = 0; r < nr; ++r) code_total += 2 * ((rlen(r) + kRowCodePad + 1 + 15) & ~15ll);
     h_rowcode_.ensure((size_t)code_total + 64);
     std::vector<int64_t> coffs(nr + 1, 0);
     for (int r = 0; r < nr; ++r)
-        coffs[r + 1] = coffs[r] + 2 * (((in.read_off[r + 1] - in.read_off[r]) + kRowCodePad + 1 + 15) & ~15ll);
+        coffs[r + 1] = coffs[r] + 2 * ((rlen(r) + kRowCodePad + 1 + 15) & ~15ll);
     for (int z = 0; z < nz; ++z) {
         ZmwState& zs = zstate_[z];
         zs.read_begin = in.zmw_read_off[z];
@@ -179,8 +159,8 @@ void ArrowEngine::load(const PolishInput& in) {
     parallel_for(nr, host_threads, [&](int r) {
         DevRead& rd = reads_[r];
         std::memset(&rd, 0, sizeof(rd));
-        const int64_t I = in.read_off[r + 1] - in.read_off[r];
-        const uint8_t* src = in.codes + in.read_off[r];
+        const int64_t I = rlen(r);
+        const uint8_t* src = in.codes + in.read_off[r] + (in.rstart ? in.rstart[r] : 0);
         const int64_t stride = (coffs[r + 1] - coffs[r]) / 2;
         rd.code_off = coffs[r];
         rd.code_stride = (int32_t)stride;

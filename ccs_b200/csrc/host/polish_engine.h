@@ -25,6 +25,8 @@ struct PolishInput {
     const uint8_t* strand = nullptr;         // [n_reads] 0 fwd / 1 rev
     const int32_t* tstart = nullptr;         // [n_reads] span on the draft [tstart,tend); tend<=tstart: unmapped
     const int32_t* tend = nullptr;
+    const int32_t* rstart = nullptr;         // optional clip of each read [rstart,rend), native orientation
+    const int32_t* rend = nullptr;
 };
 
 struct PolishParams {

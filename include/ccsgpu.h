@@ -143,6 +143,8 @@ typedef struct ccs_drafts {
     const uint8_t* strand;        /* [n_reads] 0 = same strand as the draft, 1 = reverse complement */
     const int32_t* tstart;        /* [n_reads] span of the read on the draft [tstart,tend); */
     const int32_t* tend;          /*           tend <= tstart: read not placed (excluded)   */
+    const int32_t* rstart;        /* [n_reads] aligned part of the read [rstart,rend) in its native   */
+    const int32_t* rend;          /*           orientation; both NULL: whole reads (ExtractMappedRead) */
 } ccs_drafts;
 
 typedef struct ccs_polish_cfg {
@@ -172,9 +174,41 @@ typedef struct ccs_results {
     int32_t* read_status;         /* [n_reads] ccs_read_status */
 } ccs_results;
 
+typedef struct ccs_draft_cfg {
+    double  min_snr;              /* --min-snr    (docs/how-does-ccs-work.md:21) */
+    int32_t min_passes;           /* --min-passes (docs/how-does-ccs-work.md:25) */
+    int32_t top_passes;           /* --top-passes (docs/faq/accuracy-vs-passes.md:48-52) */
+    int32_t max_poa_reads;        /* full-length subreads threaded into the POA ("a few subreads") */
+    int32_t min_length;           /* --min-length / --max-length gate on the draft (docs/how-does-ccs-work.md:51) */
+    int32_t max_length;
+} ccs_draft_cfg;
+void ccs_draft_cfg_default(ccs_draft_cfg* cfg);
+
+/* Draft Stage output, caller-owned (mutable twin of ccs_drafts). */
+typedef struct ccs_drafts_out {
+    int64_t  tpl_cap;             /* capacity of tpl in bases; on CCS_ERR_CAPACITY the needed size is written back */
+    int64_t* tpl_off;             /* [n_zmws+1] */
+    uint8_t* tpl;
+    uint8_t* strand;              /* [n_reads] */
+    int32_t* tstart;              /* [n_reads] */
+    int32_t* tend;                /* [n_reads] (0,0 when the read was filtered or not placed) */
+    int32_t* rstart;              /* [n_reads] */
+    int32_t* rend;                /* [n_reads] */
+    int32_t* status;              /* [n_zmws] ccs_zmw_status; CCS_ZMW_SUCCESS = draft stage passed */
+} ccs_drafts_out;
+
 /* ------------------------------------------------------------------------------------
  * Stages
  * ---------------------------------------------------------------------------------- */
+/* Draft Stage: FilterReads -> SparsePoa (GPU sequence-to-DAG alignment, host graph threading) ->
+ * FindConsensus -> subread-to-draft mapping (docs/how-does-ccs-work.md:19-55). */
+int ccsgpu_draft(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_draft_cfg* cfg, ccs_drafts_out* out);
+
+/* The whole per-ZMW hot path: Draft Stage + Polish Stage + final gates; per-ZMW status in the
+ * reference's order (docs/faq/reports-aux-files.md:143-159). */
+int ccsgpu_ccs(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_draft_cfg* dcfg, const ccs_polish_cfg* pcfg,
+               ccs_results* out);
+
 /* Polish Stage: Arrow refinement of every draft with its mapped subreads + per-base QVs
  * (Integrator + Polish + ConsensusQualities; docs/how-does-ccs-work.md:87-112).
  * Returns CCS_ERR_CAPACITY (and the needed size in out->seq_cap) if seq/qv are too small. */
@@ -201,6 +235,8 @@ typedef struct ccs_stats {
     int64_t bytes_fill_alpha, bytes_fill_beta;   /* algorithmic bytes (DESIGN.md "Roofline") */
     int64_t cells_fill, score_items, rounds;
     int64_t h2d_bytes, d2h_bytes;
+    double  ms_poa_align;  /* poa_align + traceback kernels */
+    int64_t launches_poa, poa_tasks, poa_rows, bytes_poa_align;
     double  ms_resident;   /* CUDA-event time of the stage with inputs already in HBM */
     double  ms_e2e;        /* host wall time of the stage calls: pack + H2D + kernels + D2H */
     int64_t n_zmws;        /* ZMWs processed */

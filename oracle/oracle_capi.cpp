@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE -- C ABI over the CPU oracle for ctypes (tests/, smoke(), bench.py
 // cpu_baseline / --impl reference only).  See arrow_oracle.h for provenance.
 #include "arrow_oracle.h"
+#include "pipeline_oracle.h"
 #include <atomic>
 #include <cmath>
 #include <cstring>
@@ -166,6 +167,57 @@ int oracle_score_all(const void* model, const float* snr, const uint8_t* draft, 
             if (ok) v = ai.delta_ll(m);
             out[(size_t)p * 9 + s] = v;
         }
+    return 0;
+}
+
+
+// ---- draft stage / whole pipeline ------------------------------------------------------
+// cfg_i[8] = {min_passes, top_passes, max_poa_reads, min_length, max_length, max_iterations(-1 default), 0, 0}
+// cfg_d[4] = {min_snr, min_rq, min_active_fraction, 0}
+static CcsConfig make_cfg(const int32_t* ci, const double* cd) {
+    CcsConfig c;
+    if (ci) {
+        c.min_passes = ci[0]; c.top_passes = ci[1]; c.max_poa_reads = ci[2]; c.min_length = ci[3]; c.max_length = ci[4];
+        if (ci[5] >= 0) c.polish.max_iterations = ci[5];
+    }
+    if (cd) { c.min_snr = cd[0]; c.min_rq = cd[1]; c.min_active_fraction = cd[2]; }
+    return c;
+}
+
+// Draft stage only: draft + per-read mapping.  maps[r*6..] = {mapped, strand, tstart, tend, rstart, rend}
+int oracle_draft_zmw(const int32_t* cfg_i, const double* cfg_d, const float* snr, int nreads, const uint8_t* codes,
+                     const int64_t* read_off, const uint8_t* cx, uint8_t* draft, int draft_cap, int32_t* draft_len,
+                     int32_t* maps, int32_t* status) {
+    CcsConfig cfg = make_cfg(cfg_i, cfg_d);
+    CcsZmwResult res;
+    std::vector<char> keep;
+    draft_zmw(cfg, nreads, codes, read_off, cx, snr, res, keep);
+    *status = res.status;
+    *draft_len = (int32_t)res.draft.size();
+    if ((int)res.draft.size() > draft_cap) return -1;
+    if (!res.draft.empty()) std::memcpy(draft, res.draft.data(), res.draft.size());
+    for (int r = 0; r < nreads; ++r) {
+        const ReadMapping& m = res.maps[r];
+        int32_t* o = maps + 6 * r;
+        o[0] = m.mapped; o[1] = m.strand; o[2] = m.tstart; o[3] = m.tend; o[4] = m.rstart; o[5] = m.rend;
+    }
+    return 0;
+}
+
+// Whole per-ZMW path.  stats[8] = {status, np, converged, iterations, n_tested, n_applied, draft_len, 0}
+int oracle_ccs_zmw(const void* model, const int32_t* cfg_i, const double* cfg_d, const float* snr, int nreads,
+                   const uint8_t* codes, const int64_t* read_off, const uint8_t* cx, uint8_t* seq, int seq_cap,
+                   int32_t* seq_len, uint8_t* qv, double* rq, int64_t* stats, double* read_ll, int32_t* read_status) {
+    CcsConfig cfg = make_cfg(cfg_i, cfg_d);
+    CcsZmwResult res;
+    ccs_zmw(*(const ccs::ArrowModelParams*)model, cfg, nreads, codes, read_off, cx, snr, res);
+    *seq_len = (int32_t)res.seq.size();
+    if ((int)res.seq.size() > seq_cap) return -1;
+    if (!res.seq.empty()) { std::memcpy(seq, res.seq.data(), res.seq.size()); std::memcpy(qv, res.qv.data(), res.qv.size()); }
+    *rq = res.rq;
+    stats[0] = res.status; stats[1] = res.np; stats[2] = res.pr.converged; stats[3] = res.pr.iterations;
+    stats[4] = res.pr.n_tested; stats[5] = res.pr.n_applied; stats[6] = (int64_t)res.draft.size(); stats[7] = 0;
+    for (int r = 0; r < nreads; ++r) { read_ll[r] = res.read_ll[r]; read_status[r] = res.read_status[r]; }
     return 0;
 }
 

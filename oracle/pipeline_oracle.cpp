@@ -1,0 +1,138 @@
+// TEST INFRASTRUCTURE -- see pipeline_oracle.h.
+#include "pipeline_oracle.h"
+#include <algorithm>
+#include <cmath>
+
+namespace oracle {
+
+int filter_reads(const std::vector<int>& lens, const uint8_t* cx, int top_passes, std::vector<char>& keep) {
+    const int n = (int)lens.size();
+    keep.assign(n, 0);
+    if (n == 0) return 0;
+    std::vector<int> s(lens);
+    std::sort(s.begin(), s.end());
+    const int median = (n & 1) ? s[n / 2] : (s[n / 2 - 1] + s[n / 2]) / 2;
+    int nfull = 0;
+    for (int r = 0; r < n; ++r) {
+        if (2 * lens[r] < median || lens[r] > 2 * median) continue;   // <50 % or >200 % of the median
+        const bool full = (cx[r] & 3) == 3;
+        if (full) {
+            if (nfull >= top_passes) continue;
+            ++nfull;
+        }
+        keep[r] = 1;
+    }
+    return nfull;
+}
+
+static std::vector<uint8_t> bases_of(const uint8_t* codes, int n, bool rc) {
+    std::vector<uint8_t> b(n);
+    if (!rc) for (int i = 0; i < n; ++i) b[i] = codes[i] & 3;
+    else for (int i = 0; i < n; ++i) b[i] = (uint8_t)(3 - (codes[n - 1 - i] & 3));
+    return b;
+}
+
+void draft_zmw(const CcsConfig& cfg, int nreads, const uint8_t* codes, const int64_t* read_off, const uint8_t* cx,
+               const float snr[4], CcsZmwResult& out, std::vector<char>& keep) {
+    out = CcsZmwResult();
+    out.maps.assign(nreads, ReadMapping());
+    keep.assign(nreads, 0);
+    if (nreads == 0) { out.status = Z_NO_SUBREADS; return; }
+    if (std::min(std::min(snr[0], snr[1]), std::min(snr[2], snr[3])) < cfg.min_snr) { out.status = Z_POOR_SNR; return; }
+    std::vector<int> lens(nreads);
+    for (int r = 0; r < nreads; ++r) lens[r] = (int)(read_off[r + 1] - read_off[r]);
+    const int nfull = filter_reads(lens, cx, cfg.top_passes, keep);
+    if (nfull < cfg.min_passes) { out.status = Z_TOO_FEW_PASSES; return; }
+    // SparsePoa over the first max_poa_reads full-length reads
+    PoaGraph g;
+    std::vector<uint8_t> seed;
+    int used = 0;
+    for (int r = 0; r < nreads && used < cfg.max_poa_reads; ++r) {
+        if (!keep[r] || (cx[r] & 3) != 3) continue;
+        const uint8_t* c = codes + read_off[r];
+        if (used == 0) {
+            seed = bases_of(c, lens[r], false);
+            g.add_first(seed.data(), lens[r]);
+        } else {
+            std::vector<uint8_t> fwd = bases_of(c, lens[r], false);
+            const bool rev = kmer_vote_reverse(seed.data(), (int)seed.size(), fwd.data(), lens[r]);
+            std::vector<uint8_t> b = rev ? bases_of(c, lens[r], true) : fwd;
+            PoaAlignment a = g.align(b.data(), lens[r]);
+            if (a.score >= lens[r]) g.commit(a, b.data());
+        }
+        ++used;
+    }
+    const int n = g.n_reads;
+    const int min_cov = n < 5 ? 1 : (n + 1) / 2 - 1;
+    std::vector<int> path = g.consensus(min_cov);
+    out.draft.resize(path.size());
+    for (size_t k = 0; k < path.size(); ++k) out.draft[k] = g.v[path[k]].base;
+    const int J = (int)out.draft.size();
+    if (J == 0) { out.status = Z_DRAFT_FAILURE; return; }
+    if (J < cfg.min_length) { out.status = Z_TOO_SHORT; return; }
+    if (J > cfg.max_length) { out.status = Z_TOO_LONG; return; }
+    // subread -> draft mapping of every kept read
+    int mapped_full = 0;
+    for (int r = 0; r < nreads; ++r) {
+        if (!keep[r]) continue;
+        const uint8_t* c = codes + read_off[r];
+        std::vector<uint8_t> fwd = bases_of(c, lens[r], false);
+        const bool rev = kmer_vote_reverse(out.draft.data(), J, fwd.data(), lens[r]);
+        std::vector<uint8_t> b = rev ? bases_of(c, lens[r], true) : fwd;
+        ReadMapping m = map_to_template(out.draft.data(), J, b.data(), lens[r]);
+        m.strand = rev ? 1 : 0;
+        if (rev) { const int rs = lens[r] - m.rend, re = lens[r] - m.rstart; m.rstart = rs; m.rend = re; }
+        if (m.mapped && (m.tend - m.tstart < 2 || m.rend - m.rstart < 2)) m.mapped = false;
+        out.maps[r] = m;
+        if (m.mapped && (cx[r] & 3) == 3) ++mapped_full;
+    }
+    if (mapped_full < cfg.min_passes) { out.status = Z_TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT; return; }
+    out.status = Z_SUCCESS;   // draft stage passed
+}
+
+void ccs_zmw(const ccs::ArrowModelParams& model, const CcsConfig& cfg, int nreads, const uint8_t* codes,
+             const int64_t* read_off, const uint8_t* cx, const float snr[4], CcsZmwResult& out) {
+    std::vector<char> keep;
+    draft_zmw(cfg, nreads, codes, read_off, cx, snr, out, keep);
+    out.read_ll.assign(nreads, NAN);
+    out.read_status.assign(nreads, 4);
+    if (out.status != Z_SUCCESS) return;
+    Integrator<double> ai;
+    ai.init(model, snr, out.draft.data(), (int)out.draft.size(), cfg.polish);
+    std::vector<int> idx;
+    int n_mapped = 0;
+    for (int r = 0; r < nreads; ++r) {
+        const ReadMapping& m = out.maps[r];
+        if (!m.mapped) continue;
+        MappedRead mr;
+        mr.codes.assign(codes + read_off[r] + m.rstart, codes + read_off[r] + m.rend);
+        mr.strand = m.strand; mr.tstart = m.tstart; mr.tend = m.tend;
+        ai.add_read(mr);
+        idx.push_back(r);
+        ++n_mapped;
+    }
+    auto usable = [&]() { const int a = ai.n_active(); return a > 0 && a >= cfg.min_active_fraction * n_mapped; };
+    bool failed = !usable();
+    if (!failed) {
+        out.pr = polish(ai);
+        failed = !usable();
+    }
+    for (size_t k = 0; k < idx.size(); ++k) {
+        out.read_status[idx[k]] = ai.recs[k].status;
+        out.read_ll[idx[k]] = ai.active[k] ? ai.recs[k].ll() : NAN;
+    }
+    if (failed) { out.status = Z_TOO_MANY_UNUSABLE; return; }
+    consensus_qvs(ai, out.qv);
+    out.seq = ai.fwd;
+    out.rq = predicted_accuracy(out.qv);
+    out.np = 0;
+    for (size_t k = 0; k < idx.size(); ++k) if (ai.active[k] && (cx[idx[k]] & 3) == 3) ++out.np;
+    const int J = (int)out.seq.size();
+    if (!out.pr.converged) out.status = Z_NON_CONVERGENT;
+    else if (J < cfg.min_length) out.status = Z_TOO_SHORT;
+    else if (J > cfg.max_length) out.status = Z_TOO_LONG;
+    else if (out.rq < cfg.min_rq) out.status = Z_POOR_QUALITY;
+    else out.status = Z_SUCCESS;
+}
+
+}  // namespace oracle

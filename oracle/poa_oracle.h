@@ -1,0 +1,49 @@
+// TEST INFRASTRUCTURE -- CPU restatement of the Draft Stage:
+// FilterReads, k-mer orientation vote (the seeding half of SdpRangeFinder), SparsePoa
+// (banded local sequence-to-DAG alignment, CommitAdd, FindConsensus) and the subread -> draft
+// mapping.  PARITY UNPINNED: see arrow_oracle.h; behaviour anchored on
+// /root/reference/docs/how-does-ccs-work.md:19-55 and SURVEY.md Appendix B; every rule below
+// that the docs leave open (band rule, tie breaks, vertex placement) is fixed in DESIGN.md
+// "Draft stage" and restated here independently of the product code in ccs_b200/.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace oracle {
+
+constexpr int POA_MATCH = 3, POA_MISMATCH = -5, POA_INS = -4, POA_DEL = -4;
+constexpr int POA_BAND = 64;
+constexpr int POA_KMER = 11;
+
+enum PoaMove : uint8_t { PM_STOP = 0, PM_MATCH = 1, PM_DEL = 2, PM_INS = 3 };
+
+struct PathStep { int vertex; int readpos; uint8_t move; };   // MATCH: both; DEL: vertex only; INS: readpos only
+
+struct PoaAlignment {
+    int score = 0;
+    std::vector<PathStep> path;   // start -> end
+};
+
+struct PoaGraph {
+    struct Vertex { uint8_t base; int nreads; int next, prev; std::vector<int> in, out; };
+    std::vector<Vertex> v;
+    int head = -1, tail = -1;
+    std::vector<std::pair<int, int>> spans;   // (first, last) vertex of every threaded read
+    int n_reads = 0;
+
+    void add_first(const uint8_t* seq, int n);
+    void order(std::vector<int>& ord, std::vector<int>& rank) const;
+    PoaAlignment align(const uint8_t* seq, int n) const;
+    void commit(const PoaAlignment& a, const uint8_t* seq);
+    // consensus vertices in order; min_cov per SURVEY.md Appendix B
+    std::vector<int> consensus(int min_cov) const;
+};
+
+// true if the reverse complement of `read` shares more K-mers with `ref` than `read` does
+bool kmer_vote_reverse(const uint8_t* ref, int nref, const uint8_t* read, int n);
+
+struct ReadMapping { int strand = 0, tstart = 0, tend = 0, rstart = 0, rend = 0, score = 0; bool mapped = false; };
+// align read (already oriented by the vote) to a linear template; extents of the aligned part
+ReadMapping map_to_template(const uint8_t* tpl, int J, const uint8_t* read_bases, int n);
+
+}  // namespace oracle

@@ -118,3 +118,47 @@ def score_all(model, snr, draft, reads, strand, tstart, tend, W=32):
                             _p(off, C.c_int64), _p(strand, C.c_int32), _p(tstart, C.c_int32), _p(tend, C.c_int32), W,
                             _p(out, C.c_double), _p(rll, C.c_double))
     return out, rll
+
+
+def _cfg_arrays(min_passes=3, top_passes=60, max_poa_reads=5, min_length=10, max_length=50000, max_iterations=-1,
+                min_snr=2.5, min_rq=0.99, min_active_fraction=0.5):
+    ci = np.array([min_passes, top_passes, max_poa_reads, min_length, max_length, max_iterations, 0, 0], np.int32)
+    cd = np.array([min_snr, min_rq, min_active_fraction, 0.0])
+    return ci, cd
+
+
+def draft_zmw(snr, reads, cx, **cfg):
+    ci, cd = _cfg_arrays(**cfg)
+    snr = np.ascontiguousarray(snr, np.float32)
+    codes, off = _pack_reads(reads)
+    cx = np.ascontiguousarray(cx, np.uint8)
+    n = len(reads)
+    cap = int(max([len(r) for r in reads] + [1]) * 2 + 64)
+    draft = np.zeros(cap, np.uint8); dlen = C.c_int32(); maps = np.zeros((n, 6), np.int32); st = C.c_int32()
+    rc = olib().oracle_draft_zmw(_p(ci, C.c_int32), _p(cd, C.c_double), _p(snr, C.c_float), n, _p(codes, C.c_uint8),
+                                 _p(off, C.c_int64), _p(cx, C.c_uint8), _p(draft, C.c_uint8), cap, C.byref(dlen),
+                                 _p(maps, C.c_int32), C.byref(st))
+    if rc != 0:
+        raise RuntimeError("oracle_draft_zmw capacity")
+    return dict(status=st.value, draft=draft[:dlen.value].copy(), maps=maps)
+
+
+def ccs_zmw(model, snr, reads, cx, **cfg):
+    ci, cd = _cfg_arrays(**cfg)
+    snr = np.ascontiguousarray(snr, np.float32)
+    codes, off = _pack_reads(reads)
+    cx = np.ascontiguousarray(cx, np.uint8)
+    n = len(reads)
+    cap = int(max([len(r) for r in reads] + [1]) * 2 + 64)
+    seq = np.zeros(cap, np.uint8); qv = np.zeros(cap, np.uint8); slen = C.c_int32(); rq = C.c_double()
+    stats = np.zeros(8, np.int64); rll = np.zeros(n); rst = np.zeros(n, np.int32)
+    rc = olib().oracle_ccs_zmw(_vp(model), _p(ci, C.c_int32), _p(cd, C.c_double), _p(snr, C.c_float), n,
+                               _p(codes, C.c_uint8), _p(off, C.c_int64), _p(cx, C.c_uint8), _p(seq, C.c_uint8), cap,
+                               C.byref(slen), _p(qv, C.c_uint8), C.byref(rq), _p(stats, C.c_int64), _p(rll, C.c_double),
+                               _p(rst, C.c_int32))
+    if rc != 0:
+        raise RuntimeError("oracle_ccs_zmw capacity")
+    L = slen.value
+    return dict(status=int(stats[0]), np=int(stats[1]), converged=bool(stats[2]), iterations=int(stats[3]),
+                n_tested=int(stats[4]), n_applied=int(stats[5]), draft_len=int(stats[6]), seq=seq[:L].copy(),
+                qv=qv[:L].copy(), rq=rq.value, read_ll=rll, read_status=rst)
