@@ -8,6 +8,8 @@
 #include <memory>
 #include <string>
 #include <chrono>
+#include <thread>
+#include <algorithm>
 
 using namespace ccs;
 
@@ -15,6 +17,7 @@ struct ccsgpu_ctx {
     std::unique_ptr<ArrowEngine> engine;
     std::unique_ptr<DraftEngine> draft;
     int device = 0;
+    double ms_draft = 0;   // wall time of the Draft Stage calls (host graph work + GPU alignment)
     ArrowModelParams model;
     std::string last_error;
 };
@@ -62,6 +65,9 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
         ctx->engine.reset(new ArrowEngine(device, ctx->model, device_bytes_budget));
         ctx->draft.reset(new DraftEngine(device, 0));
         ctx->device = device;
+        { int hc = (int)std::thread::hardware_concurrency(); if (hc < 1) hc = 8;
+          if (const char* e = std::getenv("CCS_B200_THREADS")) hc = std::max(1, std::atoi(e));
+          ctx->engine->host_threads = hc; ctx->draft->host_threads = hc; }
         if (const char* e = std::getenv("CCS_B200_GENERIC_SCORE")) ctx->engine->generic_score = (e[0] == '1');
     } catch (const std::exception& e) {
         g_create_error = e.what();
@@ -239,6 +245,7 @@ int ccsgpu_ccs(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_draft_cfg* dcfg, 
         const auto t_begin = std::chrono::steady_clock::now();
         DraftOutput d;
         ctx->draft->run(to_draft_input(in), to_draft_params(dcfg), d);
+        ctx->ms_draft += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         // Polish Stage input from the Draft Stage output; ZMWs that failed the draft get an empty template
         const int nz = in->n_zmws, nr = in->n_reads;
         std::vector<int64_t> tpl_off(nz + 1, 0);
@@ -284,9 +291,9 @@ int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset) {
         out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes;
         { const DraftStats& ds = ctx->draft->stats;
           out->ms_poa_align = ds.ms_align; out->launches_poa = ds.n_align_launches; out->poa_tasks = ds.n_tasks;
-          out->poa_rows = ds.rows; out->bytes_poa_align = ds.bytes_align; out->launches_draft = ds.n_align_launches; }
+          out->ms_draft = ctx->ms_draft; out->poa_rows = ds.rows; out->bytes_poa_align = ds.bytes_align; out->launches_draft = ds.n_align_launches; }
         out->ms_resident = s.ms_resident; out->ms_e2e = s.ms_e2e; out->n_zmws = s.n_zmws;
-        if (reset) { ctx->engine->reset_stats(); ctx->draft->stats = DraftStats(); }
+        if (reset) { ctx->engine->reset_stats(); ctx->draft->stats = DraftStats(); ctx->ms_draft = 0; }
         return (int)CCS_OK;
     });
 }

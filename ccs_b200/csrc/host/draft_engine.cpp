@@ -97,35 +97,31 @@ DraftEngine::~DraftEngine() {
     if (stream_) cudaStreamDestroy(stream_);
 }
 
-// One GPU pass over a task list (already chunked to the scratch budget by the caller).
-void DraftEngine::align_tasks(const std::vector<PoaTask>& tasks, bool any_dag, bool want_paths, int64_t rows,
-                              int64_t path_bytes, const std::vector<uint8_t>& vbase, const std::vector<int32_t>& poff,
-                              const std::vector<int32_t>& preds, const std::vector<uint8_t>& reads,
-                              std::vector<PoaResult>& results, std::vector<uint8_t>& paths) {
-    const int nt = (int)tasks.size();
-    results.resize(nt);
+// One GPU pass over the task list staged in the pinned buffers (already chunked to the scratch budget).
+void DraftEngine::align_tasks(int nt, bool any_dag, bool want_paths, int64_t rows, int64_t path_bytes, size_t n_vbase,
+                              size_t n_poff, size_t n_preds, size_t n_reads) {
     if (nt == 0) return;
     CCS_CUDA(cudaSetDevice(device_));
-    d_tasks_.ensure(nt); d_vbase_.ensure(vbase.size() + 16); d_reads_.ensure(reads.size() + 16);
-    d_poff_.ensure(poff.size() + 16); d_preds_.ensure(preds.size() + 16);
+    d_tasks_.ensure(nt); d_vbase_.ensure(n_vbase + 16); d_reads_.ensure(n_reads + 16);
+    d_poff_.ensure(n_poff + 16); d_preds_.ensure(n_preds + 16);
     d_lo_.ensure((size_t)rows + 16); d_besti_.ensure((size_t)rows + 16); d_moves_.ensure((size_t)rows * kPoaBand + 16);
     if (any_dag) d_hrows_.ensure((size_t)rows * kPoaBand + 16);
-    if (want_paths) d_paths_.ensure((size_t)path_bytes + 16);
+    if (want_paths) { d_paths_.ensure((size_t)path_bytes + 16); h_paths_.ensure((size_t)path_bytes + 16); }
     d_results_.ensure(nt);
-    CCS_CUDA(cudaMemcpyAsync(d_tasks_.p, tasks.data(), sizeof(PoaTask) * nt, cudaMemcpyHostToDevice, stream_));
-    CCS_CUDA(cudaMemcpyAsync(d_vbase_.p, vbase.data(), vbase.size(), cudaMemcpyHostToDevice, stream_));
-    CCS_CUDA(cudaMemcpyAsync(d_reads_.p, reads.data(), reads.size(), cudaMemcpyHostToDevice, stream_));
-    if (!poff.empty()) CCS_CUDA(cudaMemcpyAsync(d_poff_.p, poff.data(), poff.size() * 4, cudaMemcpyHostToDevice, stream_));
-    if (!preds.empty()) CCS_CUDA(cudaMemcpyAsync(d_preds_.p, preds.data(), preds.size() * 4, cudaMemcpyHostToDevice, stream_));
-    stats.h2d_bytes += (int64_t)(sizeof(PoaTask) * nt + vbase.size() + reads.size() + 4 * (poff.size() + preds.size()));
+    h_results_.ensure(nt);
+    CCS_CUDA(cudaMemcpyAsync(d_tasks_.p, h_tasks_.p, sizeof(PoaTask) * nt, cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_vbase_.p, h_vbase_.p, n_vbase, cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_reads_.p, h_reads_.p, n_reads, cudaMemcpyHostToDevice, stream_));
+    if (n_poff) CCS_CUDA(cudaMemcpyAsync(d_poff_.p, h_poff_.p, n_poff * 4, cudaMemcpyHostToDevice, stream_));
+    if (n_preds) CCS_CUDA(cudaMemcpyAsync(d_preds_.p, h_preds_.p, n_preds * 4, cudaMemcpyHostToDevice, stream_));
+    stats.h2d_bytes += (int64_t)(sizeof(PoaTask) * nt + n_vbase + n_reads + 4 * (n_poff + n_preds));
     CCS_CUDA(cudaEventRecord(ev0_, stream_));
     launch_poa_align(d_tasks_.p, nt, d_vbase_.p, d_poff_.p, d_preds_.p, d_reads_.p, d_lo_.p, d_besti_.p, d_moves_.p,
                      any_dag ? d_hrows_.p : nullptr, want_paths ? d_paths_.p : nullptr, d_results_.p, stream_);
     CCS_CUDA(cudaEventRecord(ev1_, stream_));
-    CCS_CUDA(cudaMemcpyAsync(results.data(), d_results_.p, sizeof(PoaResult) * nt, cudaMemcpyDeviceToHost, stream_));
+    CCS_CUDA(cudaMemcpyAsync(h_results_.p, d_results_.p, sizeof(PoaResult) * nt, cudaMemcpyDeviceToHost, stream_));
     if (want_paths) {
-        paths.resize((size_t)path_bytes);
-        CCS_CUDA(cudaMemcpyAsync(paths.data(), d_paths_.p, (size_t)path_bytes, cudaMemcpyDeviceToHost, stream_));
+        CCS_CUDA(cudaMemcpyAsync(h_paths_.p, d_paths_.p, (size_t)path_bytes, cudaMemcpyDeviceToHost, stream_));
         stats.d2h_bytes += path_bytes;
     }
     CCS_CUDA(cudaStreamSynchronize(stream_));
@@ -137,9 +133,7 @@ void DraftEngine::align_tasks(const std::vector<PoaTask>& tasks, bool any_dag, b
     stats.n_tasks += nt;
     stats.rows += rows;
     stats.d2h_bytes += (int64_t)sizeof(PoaResult) * nt;
-    int64_t rb = 0;
-    for (const PoaTask& t : tasks) rb += t.n;
-    stats.bytes_align += rows * (kPoaBand + 8 + (any_dag ? 4 * kPoaBand : 0)) + rb + (int64_t)vbase.size();
+    stats.bytes_align += rows * (kPoaBand + 8 + (any_dag ? 4 * kPoaBand : 0)) + (int64_t)n_reads + (int64_t)n_vbase;
 }
 
 void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& out) {
@@ -158,7 +152,6 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
         std::vector<uint8_t> seed;
         HostPoaGraph graph;
         std::vector<int32_t> order;       // export of the current round
-        int64_t vert_off = 0, poff_off = 0, pred_base = 0;
         bool alive = false;
     };
     std::vector<ZmwWork> work(nz);
@@ -189,50 +182,55 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
     });
 
     // ---- a2: SparsePoa rounds: round k aligns the k-th POA read of every ZMW on the GPU ----
-    std::vector<PoaTask> tasks;
     std::vector<int> task_zmw;
-    std::vector<uint8_t> vbase, reads, paths;
-    std::vector<int32_t> poff, preds;
-    std::vector<PoaResult> results;
+    const int64_t row_bytes = kPoaBand * 5 + 8;   // moves + score row + lo/best per vertex
     for (int round = 1; round < dp.max_poa_reads; ++round) {
-        // chunk ZMWs so that the DP scratch stays inside the budget
         int z = 0;
         while (z < nz) {
-            tasks.clear(); task_zmw.clear(); vbase.clear(); reads.clear(); poff.clear(); preds.clear();
-            int64_t rows = 0, path_bytes = 0;
+            // pass 1 (serial, cheap): lay out the chunk
+            task_zmw.clear();
+            int64_t rows = 0, path_bytes = 0, n_preds = 0, n_reads = 0, n_poff = 0;
+            std::vector<PoaTask> tl;
             for (; z < nz; ++z) {
                 ZmwWork& w = work[z];
                 if (!w.alive || (int)w.poa_reads.size() <= round) continue;
                 const int V = w.graph.size();
                 const int rd = w.poa_reads[round];
-                const int64_t need = (int64_t)V * (kPoaBand * 5 + 8) + V + lens[rd];
-                if (!tasks.empty() && (rows * (kPoaBand * 5 + 8) + need) > (int64_t)budget_) break;
+                if (!tl.empty() && (rows + V) * row_bytes > (int64_t)budget_) break;
                 PoaTask t;
-                t.vert_off = (int64_t)vbase.size(); t.poff_off = (int64_t)poff.size(); t.pred_base = (int64_t)preds.size();
-                w.graph.export_topo(w.order, vbase, poff, preds);
-                w.poff_off = t.poff_off; w.pred_base = t.pred_base;
-                t.read_off = (int64_t)reads.size();
-                reads.resize(reads.size() + lens[rd]);
-                orient(in.codes + in.read_off[rd], lens[rd], w.poa_rev[round], reads.data() + t.read_off);
+                t.vert_off = rows; t.poff_off = n_poff; t.pred_base = n_preds; t.read_off = n_reads;
                 t.row_off = rows; t.path_off = path_bytes; t.V = V; t.n = lens[rd]; t.linear = 0; t.pad_ = 0;
-                rows += V; path_bytes += V + lens[rd];
-                tasks.push_back(t);
+                rows += V; n_poff += V + 1; n_preds += w.graph.n_edges(); n_reads += lens[rd]; path_bytes += V + lens[rd];
+                tl.push_back(t);
                 task_zmw.push_back(z);
             }
-            if (tasks.empty()) break;
-            align_tasks(tasks, true, true, rows, path_bytes, vbase, poff, preds, reads, results, paths);
-            parallel_for((int)tasks.size(), host_threads, [&](int k) {
+            const int nt = (int)tl.size();
+            if (nt == 0) break;
+            h_tasks_.ensure(nt); h_vbase_.ensure((size_t)rows + 16); h_poff_.ensure((size_t)n_poff + 16);
+            h_preds_.ensure((size_t)n_preds + 16); h_reads_.ensure((size_t)n_reads + 16);
+            std::memcpy(h_tasks_.p, tl.data(), sizeof(PoaTask) * nt);
+            // pass 2 (parallel): export graphs and orient reads straight into pinned memory
+            parallel_for(nt, host_threads, [&](int k) {
                 ZmwWork& w = work[task_zmw[k]];
-                const PoaTask& t = tasks[k];
-                const PoaResult& r = results[k];
+                const PoaTask& t = tl[k];
+                w.graph.export_topo(w.order, h_vbase_.p + t.vert_off, h_poff_.p + t.poff_off, h_preds_.p + t.pred_base);
+                const int rd = w.poa_reads[round];
+                orient(in.codes + in.read_off[rd], lens[rd], w.poa_rev[round], h_reads_.p + t.read_off);
+            });
+            align_tasks(nt, true, true, rows, path_bytes, (size_t)rows, (size_t)n_poff, (size_t)n_preds, (size_t)n_reads);
+            parallel_for(nt, host_threads, [&](int k) {
+                ZmwWork& w = work[task_zmw[k]];
+                const PoaTask& t = tl[k];
+                const PoaResult& r = h_results_.p[k];
                 if (r.score >= t.n && r.path_len > 0)   // placed: CommitAdd
-                    w.graph.commit(paths.data() + t.path_off, r.path_len, r.end_t, r.end_i, w.order,
-                                   poff.data() + t.poff_off, preds.data() + t.pred_base, reads.data() + t.read_off);
+                    w.graph.commit(h_paths_.p + t.path_off, r.path_len, r.end_t, r.end_i, w.order,
+                                   h_poff_.p + t.poff_off, h_preds_.p + t.pred_base, h_reads_.p + t.read_off);
             });
         }
     }
 
-    // ---- a4: consensus + length gates ---------------------------------------------------------
+    // ---- a4: consensus + length gates; a3: orientation of every kept read against the draft ----
+    std::vector<std::vector<uint8_t>> rev_flag(nz);
     parallel_for(nz, host_threads, [&](int z) {
         ZmwWork& w = work[z];
         if (!w.alive) return;
@@ -243,16 +241,10 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
         if (J == 0) { out.status[z] = CCS_ZMW_DRAFT_FAILURE; w.alive = false; }
         else if (J < dp.min_length) { out.status[z] = CCS_ZMW_TOO_SHORT; w.alive = false; }
         else if (J > dp.max_length) { out.status[z] = CCS_ZMW_TOO_LONG; w.alive = false; }
-    });
-
-    // ---- a5: subread -> draft mapping of every kept read (linear graphs on the same kernel) ---
-    std::vector<std::vector<uint8_t>> rev_flag(nz);
-    parallel_for(nz, host_threads, [&](int z) {
-        ZmwWork& w = work[z];
         if (!w.alive) return;
         const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
         KmerSet ks;
-        ks.build(out.draft[z].data(), (int)out.draft[z].size());
+        ks.build(out.draft[z].data(), J);
         rev_flag[z].assign(r1 - r0, 0);
         for (int r = r0; r < r1; ++r) {
             if (!out.keep[r]) continue;
@@ -261,12 +253,15 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
             rev_flag[z][r - r0] = c > f;
         }
     });
+
+    // ---- a5: subread -> draft mapping of every kept read (linear graphs on the same kernel) ---
     {
         int z = 0;
         std::vector<int> task_read;
+        std::vector<PoaTask> tl;
         while (z < nz) {
-            tasks.clear(); task_read.clear(); vbase.clear(); reads.clear();
-            int64_t rows = 0;
+            tl.clear(); task_read.clear();
+            int64_t rows = 0, n_vbase = 0, n_reads = 0;
             for (; z < nz; ++z) {
                 ZmwWork& w = work[z];
                 if (!w.alive) continue;
@@ -274,36 +269,38 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
                 const int J = (int)out.draft[z].size();
                 int nk = 0;
                 for (int r = r0; r < r1; ++r) nk += out.keep[r];
-                if (!tasks.empty() && (rows + (int64_t)nk * J) * (kPoaBand + 8) > (int64_t)budget_) break;
-                const int64_t voff = (int64_t)vbase.size();
-                vbase.insert(vbase.end(), out.draft[z].begin(), out.draft[z].end());
+                if (!tl.empty() && (rows + (int64_t)nk * J) * (kPoaBand + 8) > (int64_t)budget_) break;
                 for (int r = r0; r < r1; ++r) {
                     if (!out.keep[r]) continue;
                     PoaTask t;
-                    t.vert_off = voff; t.poff_off = 0; t.pred_base = 0;
-                    t.read_off = (int64_t)reads.size();
-                    reads.resize(reads.size() + lens[r]);
-                    orient(in.codes + in.read_off[r], lens[r], rev_flag[z][r - r0], reads.data() + t.read_off);
-                    t.row_off = rows; t.path_off = 0; t.V = J; t.n = lens[r]; t.linear = 1; t.pad_ = 0;
-                    rows += J;
-                    tasks.push_back(t);
+                    t.vert_off = n_vbase; t.poff_off = 0; t.pred_base = 0; t.read_off = n_reads;
+                    t.row_off = rows; t.path_off = 0; t.V = J; t.n = lens[r]; t.linear = 1; t.pad_ = z;
+                    rows += J; n_reads += lens[r];
+                    tl.push_back(t);
                     task_read.push_back(r);
                 }
+                n_vbase += J;
             }
-            if (tasks.empty()) break;
-            poff.clear(); preds.clear();
-            align_tasks(tasks, false, false, rows, 0, vbase, poff, preds, reads, results, paths);
-            for (size_t k = 0; k < tasks.size(); ++k) {
-                const int r = task_read[k];
-                const PoaResult& pr = results[k];
-                ReadMap& m = out.maps[r];
+            const int nt = (int)tl.size();
+            if (nt == 0) break;
+            h_tasks_.ensure(nt); h_vbase_.ensure((size_t)n_vbase + 16); h_reads_.ensure((size_t)n_reads + 16);
+            std::memcpy(h_tasks_.p, tl.data(), sizeof(PoaTask) * nt);
+            parallel_for(nt, host_threads, [&](int k) {
+                const PoaTask& t = tl[k];
+                const int r = task_read[k], zz = t.pad_;
+                if (k == 0 || tl[k - 1].pad_ != zz)   // first task of the ZMW copies the draft
+                    std::memcpy(h_vbase_.p + t.vert_off, out.draft[zz].data(), out.draft[zz].size());
+                orient(in.codes + in.read_off[r], lens[r], rev_flag[zz][r - in.zmw_read_off[zz]], h_reads_.p + t.read_off);
+            });
+            align_tasks(nt, false, false, rows, 0, (size_t)n_vbase, 0, 0, (size_t)n_reads);
+            for (int k = 0; k < nt; ++k) {
+                const PoaResult& pr = h_results_.p[k];
+                ReadMap& m = out.maps[task_read[k]];
                 m.score = pr.score;
                 if (pr.first_t < 0) continue;
                 m.tstart = pr.first_t; m.tend = pr.last_t + 1;
-                int rs = pr.first_i, re = pr.last_i + 1;
-                // strand: recover from the zmw's vote
-                m.mapped = pr.score >= tasks[k].n;
-                m.rstart = rs; m.rend = re;
+                m.rstart = pr.first_i; m.rend = pr.last_i + 1;
+                m.mapped = pr.score >= tl[k].n;
             }
         }
     }

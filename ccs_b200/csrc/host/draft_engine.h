@@ -53,9 +53,9 @@ public:
 
 private:
     struct TaskHost { int zmw; int read; int rev; int V; int n; const uint8_t* bases; };   // bases: oriented read
-    void align_tasks(const std::vector<PoaTask>& tasks, bool any_dag, bool want_paths, int64_t rows, int64_t path_bytes,
-                     const std::vector<uint8_t>& vbase, const std::vector<int32_t>& poff, const std::vector<int32_t>& preds,
-                     const std::vector<uint8_t>& reads, std::vector<PoaResult>& results, std::vector<uint8_t>& paths);
+    // staged in pinned memory by the caller: h_tasks_[0..nt), h_vbase_, h_poff_, h_preds_, h_reads_
+    void align_tasks(int nt, bool any_dag, bool want_paths, int64_t rows, int64_t path_bytes, size_t n_vbase,
+                     size_t n_poff, size_t n_preds, size_t n_reads);
     int device_;
     size_t budget_;
     cudaStream_t stream_ = nullptr;
@@ -64,6 +64,10 @@ private:
     DevBuf<uint8_t> d_vbase_, d_reads_, d_moves_, d_paths_;
     DevBuf<int32_t> d_poff_, d_preds_, d_lo_, d_besti_, d_hrows_;
     DevBuf<PoaResult> d_results_;
+    PinBuf<PoaTask> h_tasks_;
+    PinBuf<uint8_t> h_vbase_, h_reads_, h_paths_;
+    PinBuf<int32_t> h_poff_, h_preds_;
+    PinBuf<PoaResult> h_results_;
 };
 
 }  // namespace ccs

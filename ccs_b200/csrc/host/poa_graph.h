@@ -28,6 +28,7 @@ public:
             if (i > 0) { in_[(size_t)i * kPoaMaxPred] = i - 1; nin_[i] = 1; }
         }
         head_ = n ? 0 : -1;
+        n_edges_ = n ? n - 1 : 0;
         spans_.clear();
         if (n) spans_.push_back({0, n - 1});
         n_reads_ = 1;
@@ -35,24 +36,25 @@ public:
     int size() const { return (int)base_.size(); }
     int n_reads() const { return n_reads_; }
 
-    // Topological export: order[t] = vertex id, and the device arrays of this graph appended to
-    // base/pred_off/preds (predecessor ranks ascending).
-    void export_topo(std::vector<int32_t>& order, std::vector<uint8_t>& base, std::vector<int32_t>& pred_off,
-                     std::vector<int32_t>& preds) const {
+    int n_edges() const { return n_edges_; }
+
+    // Topological export into caller buffers: order[t] = vertex id; base[V]; pred_off[V+1] (relative
+    // to this graph's list); preds[n_edges] = predecessor ranks, ascending per vertex.
+    void export_topo(std::vector<int32_t>& order, uint8_t* base, int32_t* pred_off, int32_t* preds) const {
         const int V = size();
         order.clear(); order.reserve(V);
         rank_.assign(V, -1);
         for (int x = head_; x >= 0; x = next_[x]) { rank_[x] = (int)order.size(); order.push_back(x); }
-        const size_t p_base = preds.size();
+        int32_t np = 0;
         for (int t = 0; t < V; ++t) {
             const int x = order[t];
-            base.push_back(base_[x]);
-            pred_off.push_back((int32_t)(preds.size() - p_base));
-            const size_t b = preds.size();
-            for (int k = 0; k < nin_[x]; ++k) preds.push_back(rank_[in_[(size_t)x * kPoaMaxPred + k]]);
-            std::sort(preds.begin() + b, preds.end());
+            base[t] = base_[x];
+            pred_off[t] = np;
+            const int b = np;
+            for (int k = 0; k < nin_[x]; ++k) preds[np++] = rank_[in_[(size_t)x * kPoaMaxPred + k]];
+            std::sort(preds + b, preds + np);
         }
-        pred_off.push_back((int32_t)(preds.size() - p_base));
+        pred_off[V] = np;
     }
 
     // CommitAdd: replay the traceback (moves end -> start from the GPU) against the exported
@@ -139,12 +141,12 @@ private:
         if (u < 0) return;
         int32_t* e = &in_[(size_t)w * kPoaMaxPred];
         for (int k = 0; k < nin_[w]; ++k) if (e[k] == u) return;
-        if (nin_[w] < kPoaMaxPred) e[nin_[w]++] = u;
+        if (nin_[w] < kPoaMaxPred) { e[nin_[w]++] = u; ++n_edges_; }
     }
     std::vector<uint8_t> base_;
     std::vector<int32_t> nreads_, next_, prev_, in_;
     std::vector<uint8_t> nin_;
-    int head_ = -1, n_reads_ = 0;
+    int head_ = -1, n_reads_ = 0, n_edges_ = 0;
     std::vector<std::pair<int32_t, int32_t>> spans_;
     mutable std::vector<int32_t> rank_;
     std::vector<std::pair<int32_t, int32_t>> steps_;
