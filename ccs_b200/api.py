@@ -278,6 +278,9 @@ class Context:
         return dict(seq_off=seq_off, seq=seq, qv=qv, rq=rq, status=status, n_passes=npass, iterations=its,
                     n_applied=napp, n_tested=ntest, read_ll=rll, read_status=rst)
 
+    def set_lanes(self, n):
+        self._check(self._L.ccsgpu_set_lanes(C.c_void_p(self._h), int(n)), "ccsgpu_set_lanes")
+
     def stats(self, reset=False):
         s = CStats()
         self._check(self._L.ccsgpu_get_stats(C.c_void_p(self._h), C.byref(s), int(reset)), "ccsgpu_get_stats")

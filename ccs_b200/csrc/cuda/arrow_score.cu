@@ -191,6 +191,10 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
         const int r = zm.read_begin + k;
         if (has_read) { rd = V.reads[r]; st = V.status[r]; }
         const bool usable = has_read && rd.active && st == 0;
+        if (!usable) {   // idle octets still execute the shared instruction stream: give them harmless operands
+            rd.ts = rd.te = 0; rd.strand = 0; rd.I = 2; rd.J = 2; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0;
+            rd.zmw = 0; rd.last_code = 0;
+        }
         const bool cov_sd = usable && p >= rd.ts && p < rd.te;       // SUB / DEL
         const bool cov_in = usable && p > rd.ts && p < rd.te;        // INS (before p)
         if (!__any_sync(kFullMask, cov_sd)) continue;
@@ -459,6 +463,10 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
         const int r = zm.read_begin + k;
         if (has_read) { rd = V.reads[r]; st = V.status[r]; }
         const bool usable = has_read && rd.active && st == 0;
+        if (!usable) {   // idle octets still execute the shared instruction stream: give them harmless operands
+            rd.ts = rd.te = 0; rd.strand = 0; rd.I = 2; rd.J = 2; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0;
+            rd.zmw = 0; rd.last_code = 0;
+        }
         const bool cov_sd = usable && p >= rd.ts && p < rd.te;       // SUB / DEL
         const bool cov_in = usable && p > rd.ts && p < rd.te;        // INS (before p)
         if (!__any_sync(kFullMask, cov_sd)) continue;

@@ -89,10 +89,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
             const int dl = lo - (adj ? prev_lo : lo_r[pr]);
             const int a = 2 * lane + dl;
             const int hm1 = row_get(row, a - 1), h0 = row_get(row, a), h1 = row_get(row, a + 1);
-            if (rb0 != 255) { const int c = hm1 + sc0; if (c > bm0) { bm0 = c; km0 = k; } }
-            if (rb1 != 255) { const int c = h0 + sc1; if (c > bm1) { bm1 = c; km1 = k; } }
-            if (i0 <= n) { const int c = h0 + kPoaDel; if (c > bd0) { bd0 = c; kd0 = k; } }
-            if (i1 <= n) { const int c = h1 + kPoaDel; if (c > bd1) { bd1 = c; kd1 = k; } }
+            const int kk = adj ? 62 : k;   // 62 = "predecessor is rank t-1": the traceback needs no list lookup
+            if (rb0 != 255) { const int c = hm1 + sc0; if (c > bm0) { bm0 = c; km0 = kk; } }
+            if (rb1 != 255) { const int c = h0 + sc1; if (c > bm1) { bm1 = c; km1 = kk; } }
+            if (i0 <= n) { const int c = h0 + kPoaDel; if (c > bd0) { bd0 = c; kd0 = kk; } }
+            if (i1 <= n) { const int c = h1 + kPoaDel; if (c > bd1) { bd1 = c; kd1 = kk; } }
         }
         // match wins ties against deletion (oracle evaluation order)
         int c0, c1;
@@ -143,15 +144,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     }
 }
 
-// Traceback: one thread per task follows the stored moves from the best cell back to the local
-// start; writes the moves (end -> start) and the aligned extents.
-__global__ void __launch_bounds__(128) poa_traceback_kernel(const PoaTask* __restrict__ tasks, const int n_tasks,
-                                                            const int32_t* __restrict__ pred_off,
-                                                            const int32_t* __restrict__ preds,
-                                                            const int32_t* __restrict__ lo_arr,
-                                                            const uint8_t* __restrict__ moves,
-                                                            uint8_t* __restrict__ paths, PoaResult* __restrict__ results) {
-    const int task_id = blockIdx.x * blockDim.x + threadIdx.x;
+// Traceback: one warp per task follows the stored moves from the best cell back to the local
+// start.  The walk is sequential, so the warp stages a window of the next 32 rows (their band
+// starts and 64-byte move rows, one coalesced 2 KB read) in shared memory and every lane walks
+// it redundantly from there; only a jump to a non-adjacent predecessor touches global memory.
+__global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
+    const PoaTask* __restrict__ tasks, const int n_tasks, const int32_t* __restrict__ pred_off,
+    const int32_t* __restrict__ preds, const int32_t* __restrict__ lo_arr, const uint8_t* __restrict__ moves,
+    uint8_t* __restrict__ paths, PoaResult* __restrict__ results) {
+    __shared__ __align__(16) uint8_t s_mv[kWarpsPerCta][32 * kPoaBand];
+    __shared__ int s_lo[kWarpsPerCta][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int task_id = blockIdx.x * kWarpsPerCta + warp;
     if (task_id >= n_tasks) return;
     const PoaTask T = tasks[task_id];
     PoaResult r = results[task_id];
@@ -161,28 +165,43 @@ __global__ void __launch_bounds__(128) poa_traceback_kernel(const PoaTask* __res
     const uint8_t* __restrict__ mv_r = moves + T.row_off * kPoaBand;
     uint8_t* __restrict__ out = paths ? paths + T.path_off : nullptr;
     int t = r.end_t, i = r.end_i, len = 0;
-    while (t >= 0) {
-        const int c = i - lo_r[t];
-        if ((unsigned)c >= (unsigned)kPoaBand) break;
-        const unsigned m = mv_r[(size_t)t * kPoaBand + c];
-        const unsigned kind = m & 3u, k = m >> 2;
-        if (kind == 0u) break;
-        if (out) out[len] = (uint8_t)m;
-        ++len;
-        if (kind == 1u) {           // match / mismatch: read base i-1 on vertex t
-            if (r.last_t < 0) { r.last_t = t; r.last_i = i - 1; }
-            r.first_t = t; r.first_i = i - 1;
-            if (k == 63u) break;
-            t = T.linear ? t - 1 : pl[poff[t] + k];
-            i -= 1;
-        } else if (kind == 2u) {    // deletion: vertex skipped
-            t = T.linear ? t - 1 : pl[poff[t] + k];
-        } else {                    // insertion: read base i-1 without a vertex
-            i -= 1;
+    bool done = t < 0;
+    while (!done) {
+        const int wbase = max(t - 31, 0);
+        {   // stage rows wbase .. t
+            const int row = wbase + lane;
+            if (row <= t) {
+                s_lo[warp][lane] = lo_r[row];
+                const uint4* src = reinterpret_cast<const uint4*>(mv_r + (size_t)row * kPoaBand);
+                uint4* dst = reinterpret_cast<uint4*>(&s_mv[warp][lane * kPoaBand]);
+                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+            }
         }
+        __syncwarp();
+        while (t >= wbase) {
+            const int c = i - s_lo[warp][t - wbase];
+            if ((unsigned)c >= (unsigned)kPoaBand) { done = true; break; }
+            const unsigned m = s_mv[warp][(t - wbase) * kPoaBand + c];
+            const unsigned kind = m & 3u, k = m >> 2;
+            if (kind == 0u) { done = true; break; }
+            if (out && lane == 0) out[len] = (uint8_t)m;
+            ++len;
+            if (kind == 1u) {           // match / mismatch: read base i-1 on vertex t
+                if (r.last_t < 0) { r.last_t = t; r.last_i = i - 1; }
+                r.first_t = t; r.first_i = i - 1;
+                if (k == 63u) { done = true; break; }
+                t = (k == 62u) ? t - 1 : pl[poff[t] + k];
+                i -= 1;
+            } else if (kind == 2u) {    // deletion: vertex skipped
+                t = (k == 62u) ? t - 1 : pl[poff[t] + k];
+            } else {                    // insertion: read base i-1 without a vertex
+                i -= 1;
+            }
+        }
+        if (t < 0) done = true;
+        __syncwarp();
     }
-    r.path_len = len;
-    results[task_id] = r;
+    if (lane == 0) { r.path_len = len; results[task_id] = r; }
 }
 
 }  // namespace
@@ -193,7 +212,8 @@ void launch_poa_align(const PoaTask* tasks, int n_tasks, const uint8_t* vbase, c
     if (n_tasks <= 0) return;
     poa_align_kernel<<<(n_tasks + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, stream>>>(
         tasks, n_tasks, vbase, pred_off, preds, reads, lo, besti, moves, hrows, results);
-    poa_traceback_kernel<<<(n_tasks + 127) / 128, 128, 0, stream>>>(tasks, n_tasks, pred_off, preds, lo, moves, paths, results);
+    poa_traceback_kernel<<<(n_tasks + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, stream>>>(
+        tasks, n_tasks, pred_off, preds, lo, moves, paths, results);
 }
 
 }  // namespace ccs

@@ -10,12 +10,30 @@
 #include <chrono>
 #include <thread>
 #include <algorithm>
+#include <vector>
+#include <exception>
 
 using namespace ccs;
 
-struct ccsgpu_ctx {
+// A lane = one Draft + one Polish engine with their own streams and buffers.  A stage call splits its
+// batch into one contiguous ZMW chunk per lane and runs the lanes on concurrent host threads, so one
+// lane's host round logic and latency-bound kernels overlap another lane's issue-bound kernels.
+struct Lane {
     std::unique_ptr<ArrowEngine> engine;
     std::unique_ptr<DraftEngine> draft;
+    double ms_draft = 0;
+};
+
+struct ccsgpu_ctx {
+    std::unique_ptr<ArrowEngine> engine;     // lane 0 (also serves the single-lane hooks)
+    std::unique_ptr<DraftEngine> draft;
+    std::vector<Lane> extra;                 // lanes 1..n-1
+    int n_lanes = 1;
+    int host_threads = 8;
+    size_t budget = 0;
+    bool generic_score = false;
+    double ms_e2e = 0;
+    int64_t n_zmws = 0;
     int device = 0;
     double ms_draft = 0;   // wall time of the Draft Stage calls (host graph work + GPU alignment)
     ArrowModelParams model;
@@ -67,8 +85,13 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
         ctx->device = device;
         { int hc = (int)std::thread::hardware_concurrency(); if (hc < 1) hc = 8;
           if (const char* e = std::getenv("CCS_B200_THREADS")) hc = std::max(1, std::atoi(e));
-          ctx->engine->host_threads = hc; ctx->draft->host_threads = hc; }
-        if (const char* e = std::getenv("CCS_B200_GENERIC_SCORE")) ctx->engine->generic_score = (e[0] == '1');
+          ctx->host_threads = hc; ctx->engine->host_threads = hc; ctx->draft->host_threads = hc; }
+        if (const char* e = std::getenv("CCS_B200_GENERIC_SCORE")) ctx->generic_score = (e[0] == '1');
+        ctx->engine->generic_score = ctx->generic_score;
+        ctx->budget = device_bytes_budget;
+        int lanes = 3;
+        if (const char* e = std::getenv("CCS_B200_LANES")) lanes = std::max(1, std::min(8, std::atoi(e)));
+        ccsgpu_set_lanes(ctx, lanes);
     } catch (const std::exception& e) {
         g_create_error = e.what();
         if (err) *err = CCS_ERR_NO_DEVICE;
@@ -79,6 +102,27 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
 }
 
 void ccsgpu_destroy(ccsgpu_ctx* ctx) { delete ctx; }
+
+int ccsgpu_set_lanes(ccsgpu_ctx* ctx, int n_lanes) {
+    if (!ctx || !ctx->engine || n_lanes < 1 || n_lanes > 8) return CCS_ERR_ARG;
+    try {
+        while ((int)ctx->extra.size() < n_lanes - 1) {
+            Lane l;
+            l.engine.reset(new ArrowEngine(ctx->device, ctx->model, ctx->budget));
+            l.draft.reset(new DraftEngine(ctx->device, 0));
+            l.engine->generic_score = ctx->generic_score;
+            ctx->extra.push_back(std::move(l));
+        }
+    } catch (const std::exception& e) {
+        ctx->last_error = e.what();
+        return CCS_ERR_CUDA;
+    }
+    ctx->n_lanes = n_lanes;
+    const int th = std::max(1, ctx->host_threads / n_lanes);
+    ctx->engine->host_threads = th; ctx->draft->host_threads = th;
+    for (auto& l : ctx->extra) { l.engine->host_threads = th; l.draft->host_threads = th; }
+    return CCS_OK;
+}
 
 const char* ccsgpu_last_error(const ccsgpu_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
 
@@ -133,61 +177,166 @@ static PolishParams to_params(const ccs_polish_cfg* cfg) {
     return pp;
 }
 
-// Writes the engine's polish results; draft_status (optional) carries the Draft Stage verdicts.
-static int write_results(ArrowEngine& E, const ccs_batch* in, const PolishParams& pp, const int32_t* draft_status,
-                         ccs_results* out) {
+// Results of one lane's chunk, merged into the caller's ccs_results afterwards.
+struct ChunkOut {
+    std::vector<uint8_t> seq, qv;
+    std::vector<int64_t> seq_len, n_tested;
+    std::vector<float> rq;
+    std::vector<int32_t> status, n_passes, iterations, n_applied, read_status;
+    std::vector<double> read_ll;
+};
+
+// Collects the engine's polish results; draft_status (optional) carries the Draft Stage verdicts.
+static void collect_results(ArrowEngine& E, int nz, int nr, const uint8_t* cx, const PolishParams& pp,
+                            const int32_t* draft_status, ChunkOut& co) {
     const auto& zs = E.zmw_states();
     const auto& qv = E.qvs();
-    int64_t need = 0;
-    for (const auto& z : zs) need += (int64_t)z.tpl.size();
-    if (need > out->seq_cap) { out->seq_cap = need; return (int)CCS_ERR_CAPACITY; }
-    if (out->read_ll || out->read_status) E.read_lls(out->read_ll, nullptr, out->read_status);
-    int64_t off = 0;
-    for (int z = 0; z < in->n_zmws; ++z) {
+    co.seq.clear(); co.qv.clear();
+    co.seq_len.assign(nz, 0); co.n_tested.assign(nz, 0); co.rq.assign(nz, 0.f);
+    co.status.assign(nz, 0); co.n_passes.assign(nz, 0); co.iterations.assign(nz, 0); co.n_applied.assign(nz, 0);
+    co.read_ll.assign(nr, NAN); co.read_status.assign(nr, 4);
+    E.read_lls(co.read_ll.data(), nullptr, co.read_status.data());
+    for (int z = 0; z < nz; ++z) {
         const ZmwState& s = zs[z];
-        out->seq_off[z] = off;
         const int J = (int)s.tpl.size();
         int status = CCS_ZMW_SUCCESS;
         double rq = 0.0;
         if (draft_status && draft_status[z] != CCS_ZMW_SUCCESS) status = draft_status[z];
         else if (s.failed || (int)qv[z].size() != J) status = CCS_ZMW_TOO_MANY_UNUSABLE;
         else {
-            std::memcpy(out->seq + off, s.tpl.data(), (size_t)J);
+            co.seq.insert(co.seq.end(), s.tpl.begin(), s.tpl.end());
+            co.qv.insert(co.qv.end(), qv[z].begin(), qv[z].end());
+            static const std::vector<double> err_of_qv = [] { std::vector<double> t(256); for (int q = 0; q < 256; ++q) t[q] = std::pow(10.0, -0.1 * q); return t; }();
             double e = 0;
-            for (int j = 0; j < J; ++j) { out->qv[off + j] = qv[z][j]; e += std::pow(10.0, -0.1 * qv[z][j]); }
+            for (int j = 0; j < J; ++j) e += err_of_qv[qv[z][j]];
             rq = J ? 1.0 - e / J : 0.0;
             if (!s.converged) status = CCS_ZMW_NON_CONVERGENT;
             else if (J < pp.min_length) status = CCS_ZMW_TOO_SHORT;
             else if (J > pp.max_length) status = CCS_ZMW_TOO_LONG;
             else if (rq < pp.min_rq) status = CCS_ZMW_POOR_QUALITY;
-            off += J;
+            co.seq_len[z] = J;
         }
-        if (out->rq) out->rq[z] = (float)rq;
-        if (out->status) out->status[z] = status;
-        if (out->iterations) out->iterations[z] = s.iterations;
-        if (out->n_applied) out->n_applied[z] = s.n_applied;
-        if (out->n_tested) out->n_tested[z] = s.n_tested;
-        if (out->n_passes) {
-            int np = 0;
-            for (int r = s.read_begin; r < s.read_end; ++r)
-                if (E.reads()[r].active && in->cx && (in->cx[r] & 3) == 3) ++np;
-            out->n_passes[z] = np;
+        co.rq[z] = (float)rq; co.status[z] = status; co.iterations[z] = s.iterations; co.n_applied[z] = s.n_applied;
+        co.n_tested[z] = s.n_tested;
+        int np = 0;
+        for (int r = s.read_begin; r < s.read_end; ++r)
+            if (E.reads()[r].active && cx && (cx[r] & 3) == 3) ++np;
+        co.n_passes[z] = np;
+    }
+}
+
+// A contiguous ZMW range of a batch with offsets rebased to the chunk.
+struct SubBatch {
+    int z0 = 0, z1 = 0, r0 = 0, r1 = 0;
+    std::vector<int32_t> zmw_read_off;
+    std::vector<int64_t> read_off, tpl_off;
+    ccs_batch b;
+    ccs_drafts d;
+};
+
+static void make_sub(const ccs_batch* in, const ccs_drafts* dr, int z0, int z1, SubBatch& sb) {
+    sb.z0 = z0; sb.z1 = z1; sb.r0 = in->zmw_read_off[z0]; sb.r1 = in->zmw_read_off[z1];
+    const int nz = z1 - z0, nr = sb.r1 - sb.r0;
+    sb.zmw_read_off.resize(nz + 1);
+    for (int z = 0; z <= nz; ++z) sb.zmw_read_off[z] = in->zmw_read_off[z0 + z] - sb.r0;
+    sb.read_off.resize(nr + 1);
+    const int64_t c0 = in->read_off[sb.r0];
+    for (int r = 0; r <= nr; ++r) sb.read_off[r] = in->read_off[sb.r0 + r] - c0;
+    sb.b.n_zmws = nz; sb.b.n_reads = nr; sb.b.zmw_read_off = sb.zmw_read_off.data(); sb.b.read_off = sb.read_off.data();
+    sb.b.codes = in->codes + c0; sb.b.snr = in->snr + 4 * (size_t)z0;
+    sb.b.cx = in->cx ? in->cx + sb.r0 : nullptr; sb.b.hole = in->hole ? in->hole + z0 : nullptr;
+    if (dr) {
+        sb.tpl_off.resize(nz + 1);
+        const int64_t t0 = dr->tpl_off[z0];
+        for (int z = 0; z <= nz; ++z) sb.tpl_off[z] = dr->tpl_off[z0 + z] - t0;
+        sb.d.tpl_off = sb.tpl_off.data(); sb.d.tpl = dr->tpl + t0; sb.d.strand = dr->strand + sb.r0;
+        sb.d.tstart = dr->tstart + sb.r0; sb.d.tend = dr->tend + sb.r0;
+        sb.d.rstart = dr->rstart ? dr->rstart + sb.r0 : nullptr; sb.d.rend = dr->rend ? dr->rend + sb.r0 : nullptr;
+    }
+}
+
+// contiguous chunks with ~equal numbers of read bases
+static std::vector<int> split_zmws(const ccs_batch* in, int n_chunks) {
+    std::vector<int> cut(1, 0);
+    const int nz = in->n_zmws;
+    n_chunks = std::max(1, std::min(n_chunks, std::max(1, nz / 8)));
+    const int64_t total = in->read_off[in->n_reads];
+    for (int c = 1; c < n_chunks; ++c) {
+        const int64_t want = total * c / n_chunks;
+        int z = cut.back();
+        while (z < nz && in->read_off[in->zmw_read_off[z]] < want) ++z;
+        cut.push_back(std::max(z, cut.back()));
+    }
+    cut.push_back(nz);
+    return cut;
+}
+
+static int merge_chunks(const ccs_batch* in, const std::vector<int>& cut, const std::vector<ChunkOut>& cos, ccs_results* out) {
+    int64_t need = 0;
+    for (const auto& c : cos) need += (int64_t)c.seq.size();
+    if (need > out->seq_cap) { out->seq_cap = need; return (int)CCS_ERR_CAPACITY; }
+    int64_t off = 0;
+    for (size_t k = 0; k < cos.size(); ++k) {
+        const ChunkOut& c = cos[k];
+        const int z0 = cut[k], nz = cut[k + 1] - cut[k], r0 = in->zmw_read_off[z0], nr = in->zmw_read_off[cut[k + 1]] - r0;
+        if (!c.seq.empty()) { std::memcpy(out->seq + off, c.seq.data(), c.seq.size()); std::memcpy(out->qv + off, c.qv.data(), c.qv.size()); }
+        for (int z = 0; z < nz; ++z) {
+            out->seq_off[z0 + z] = off;
+            off += c.seq_len[z];
+            if (out->rq) out->rq[z0 + z] = c.rq[z];
+            if (out->status) out->status[z0 + z] = c.status[z];
+            if (out->n_passes) out->n_passes[z0 + z] = c.n_passes[z];
+            if (out->iterations) out->iterations[z0 + z] = c.iterations[z];
+            if (out->n_applied) out->n_applied[z0 + z] = c.n_applied[z];
+            if (out->n_tested) out->n_tested[z0 + z] = c.n_tested[z];
+        }
+        for (int r = 0; r < nr; ++r) {
+            if (out->read_ll) out->read_ll[r0 + r] = c.read_ll[r];
+            if (out->read_status) out->read_status[r0 + r] = c.read_status[r];
         }
     }
     out->seq_off[in->n_zmws] = off;
     return (int)CCS_OK;
 }
 
+static ArrowEngine& lane_engine(ccsgpu_ctx* ctx, int k) { return k == 0 ? *ctx->engine : *ctx->extra[k - 1].engine; }
+static DraftEngine& lane_draft(ccsgpu_ctx* ctx, int k) { return k == 0 ? *ctx->draft : *ctx->extra[k - 1].draft; }
+
+}  // extern "C"
+
+// Runs f(chunk) for every chunk on its own host thread; rethrows the first failure.
+template <class F>
+static void run_lanes(int n_chunks, F&& f) {
+    std::vector<std::exception_ptr> errs(n_chunks);
+    std::vector<std::thread> th;
+    auto body = [&](int k) { try { f(k); } catch (...) { errs[k] = std::current_exception(); } };
+    for (int k = 1; k < n_chunks; ++k) th.emplace_back(body, k);
+    body(0);
+    for (auto& t : th) t.join();
+    for (auto& e : errs) if (e) std::rethrow_exception(e);
+}
+
+extern "C" {
+
 int ccsgpu_polish(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_drafts* drafts, const ccs_polish_cfg* cfg,
                   ccs_results* out) {
     return guarded(ctx, [&]() {
-        ArrowEngine& E = *ctx->engine;
         const auto t_begin = std::chrono::steady_clock::now();
         const PolishParams pp = to_params(cfg);
-        E.load(make_input(in, drafts));
-        E.polish(pp);
-        const int rc = write_results(E, in, pp, nullptr, out);
-        E.stats.ms_e2e += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        const std::vector<int> cut = split_zmws(in, ctx->n_lanes);
+        const int nc = (int)cut.size() - 1;
+        std::vector<ChunkOut> cos(nc);
+        std::vector<SubBatch> subs(nc);
+        run_lanes(nc, [&](int k) {
+            make_sub(in, drafts, cut[k], cut[k + 1], subs[k]);
+            ArrowEngine& E = lane_engine(ctx, k);
+            E.load(make_input(&subs[k].b, &subs[k].d));
+            E.polish(pp);
+            collect_results(E, subs[k].b.n_zmws, subs[k].b.n_reads, subs[k].b.cx, pp, nullptr, cos[k]);
+        });
+        const int rc = merge_chunks(in, cut, cos, out);
+        ctx->ms_e2e += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        ctx->n_zmws += in->n_zmws;
         return rc;
     });
 }
@@ -239,61 +388,88 @@ int ccsgpu_draft(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_draft_cfg* cfg,
     });
 }
 
+// Draft Stage output -> Polish Stage input for one chunk, then polish + collect.
+static void ccs_chunk(ccsgpu_ctx* ctx, int lane, const ccs_batch* in, const DraftParams& dpar, const PolishParams& pp,
+                      ChunkOut& co) {
+    const auto t0 = std::chrono::steady_clock::now();
+    DraftOutput d;
+    lane_draft(ctx, lane).run(to_draft_input(in), dpar, d);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (lane == 0) ctx->ms_draft += ms; else ctx->extra[lane - 1].ms_draft += ms;
+    // ZMWs that failed the draft get an empty template and no reads
+    const int nz = in->n_zmws, nr = in->n_reads;
+    std::vector<int64_t> tpl_off(nz + 1, 0);
+    for (int z = 0; z < nz; ++z)
+        tpl_off[z + 1] = tpl_off[z] + (d.status[z] == CCS_ZMW_SUCCESS ? (int64_t)d.draft[z].size() : 0);
+    std::vector<uint8_t> tpl((size_t)tpl_off[nz] + 1), strand(nr);
+    std::vector<int32_t> ts(nr), te(nr), rs(nr), re(nr);
+    for (int z = 0; z < nz; ++z) {
+        const bool ok = d.status[z] == CCS_ZMW_SUCCESS;
+        if (ok) std::memcpy(tpl.data() + tpl_off[z], d.draft[z].data(), d.draft[z].size());
+        for (int r = in->zmw_read_off[z]; r < in->zmw_read_off[z + 1]; ++r) {
+            const ReadMap& m = d.maps[r];
+            const bool use = ok && m.mapped;
+            strand[r] = (uint8_t)m.strand;
+            ts[r] = use ? m.tstart : 0; te[r] = use ? m.tend : 0;
+            rs[r] = use ? m.rstart : 0; re[r] = use ? m.rend : 0;
+        }
+    }
+    PolishInput p;
+    p.n_zmws = nz; p.n_reads = nr; p.zmw_read_off = in->zmw_read_off; p.read_off = in->read_off; p.codes = in->codes;
+    p.snr = in->snr; p.tpl_off = tpl_off.data(); p.tpl = tpl.data(); p.strand = strand.data();
+    p.tstart = ts.data(); p.tend = te.data(); p.rstart = rs.data(); p.rend = re.data();
+    ArrowEngine& E = lane_engine(ctx, lane);
+    E.load(p);
+    E.polish(pp);
+    collect_results(E, nz, nr, in->cx, pp, d.status.data(), co);
+}
+
 int ccsgpu_ccs(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_draft_cfg* dcfg, const ccs_polish_cfg* pcfg,
                ccs_results* out) {
     return guarded(ctx, [&]() {
         const auto t_begin = std::chrono::steady_clock::now();
-        DraftOutput d;
-        ctx->draft->run(to_draft_input(in), to_draft_params(dcfg), d);
-        ctx->ms_draft += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-        // Polish Stage input from the Draft Stage output; ZMWs that failed the draft get an empty template
-        const int nz = in->n_zmws, nr = in->n_reads;
-        std::vector<int64_t> tpl_off(nz + 1, 0);
-        for (int z = 0; z < nz; ++z)
-            tpl_off[z + 1] = tpl_off[z] + (d.status[z] == CCS_ZMW_SUCCESS ? (int64_t)d.draft[z].size() : 0);
-        std::vector<uint8_t> tpl((size_t)tpl_off[nz] + 1), strand(nr);
-        std::vector<int32_t> ts(nr), te(nr), rs(nr), re(nr);
-        for (int z = 0; z < nz; ++z) {
-            const bool ok = d.status[z] == CCS_ZMW_SUCCESS;
-            if (ok) std::memcpy(tpl.data() + tpl_off[z], d.draft[z].data(), d.draft[z].size());
-            for (int r = in->zmw_read_off[z]; r < in->zmw_read_off[z + 1]; ++r) {
-                const ReadMap& m = d.maps[r];
-                const bool use = ok && m.mapped;
-                strand[r] = (uint8_t)m.strand;
-                ts[r] = use ? m.tstart : 0; te[r] = use ? m.tend : 0;
-                rs[r] = use ? m.rstart : 0; re[r] = use ? m.rend : 0;
-            }
-        }
-        PolishInput p;
-        p.n_zmws = nz; p.n_reads = nr; p.zmw_read_off = in->zmw_read_off; p.read_off = in->read_off; p.codes = in->codes;
-        p.snr = in->snr; p.tpl_off = tpl_off.data(); p.tpl = tpl.data(); p.strand = strand.data();
-        p.tstart = ts.data(); p.tend = te.data(); p.rstart = rs.data(); p.rend = re.data();
-        ArrowEngine& E = *ctx->engine;
+        const DraftParams dpar = to_draft_params(dcfg);
         const PolishParams pp = to_params(pcfg);
-        E.load(p);
-        E.polish(pp);
-        const int rc = write_results(E, in, pp, d.status.data(), out);
-        E.stats.ms_e2e += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        const std::vector<int> cut = split_zmws(in, ctx->n_lanes);
+        const int nc = (int)cut.size() - 1;
+        std::vector<ChunkOut> cos(nc);
+        std::vector<SubBatch> subs(nc);
+        run_lanes(nc, [&](int k) {
+            make_sub(in, nullptr, cut[k], cut[k + 1], subs[k]);
+            ccs_chunk(ctx, k, &subs[k].b, dpar, pp, cos[k]);
+        });
+        const int rc = merge_chunks(in, cut, cos, out);
+        ctx->ms_e2e += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        ctx->n_zmws += in->n_zmws;
         return rc;
     });
 }
 
 int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset) {
     return guarded(ctx, [&]() {
-        const EngineStats& s = ctx->engine->stats;
         std::memset(out, 0, sizeof(*out));
-        out->ms_fill_alpha = s.ms_fill_alpha; out->ms_fill_beta = s.ms_fill_beta; out->ms_score = s.ms_score;
-        out->ms_pick = s.ms_pick; out->ms_qv = s.ms_qv; out->ms_h2d = s.ms_h2d;
-        out->launches_fill_alpha = s.n_fill_alpha; out->launches_fill_beta = s.n_fill_beta;
-        out->launches_score = s.n_score; out->launches_pick = s.n_pick; out->launches_qv = s.n_qv;
-        out->bytes_fill_alpha = s.bytes_fill_alpha; out->bytes_fill_beta = s.bytes_fill_beta;
-        out->cells_fill = s.cells_fill; out->score_items = s.score_items; out->rounds = s.rounds;
-        out->h2d_bytes = s.h2d_bytes; out->d2h_bytes = s.d2h_bytes;
-        { const DraftStats& ds = ctx->draft->stats;
-          out->ms_poa_align = ds.ms_align; out->launches_poa = ds.n_align_launches; out->poa_tasks = ds.n_tasks;
-          out->ms_draft = ctx->ms_draft; out->poa_rows = ds.rows; out->bytes_poa_align = ds.bytes_align; out->launches_draft = ds.n_align_launches; }
-        out->ms_resident = s.ms_resident; out->ms_e2e = s.ms_e2e; out->n_zmws = s.n_zmws;
-        if (reset) { ctx->engine->reset_stats(); ctx->draft->stats = DraftStats(); ctx->ms_draft = 0; }
+        const int n = 1 + (int)ctx->extra.size();
+        for (int k = 0; k < n; ++k) {
+            const EngineStats& s = lane_engine(ctx, k).stats;
+            const DraftStats& ds = lane_draft(ctx, k).stats;
+            out->ms_fill_alpha += s.ms_fill_alpha; out->ms_fill_beta += s.ms_fill_beta; out->ms_score += s.ms_score;
+            out->ms_pick += s.ms_pick; out->ms_qv += s.ms_qv; out->ms_h2d += s.ms_h2d;
+            out->launches_fill_alpha += s.n_fill_alpha; out->launches_fill_beta += s.n_fill_beta;
+            out->launches_score += s.n_score; out->launches_pick += s.n_pick; out->launches_qv += s.n_qv;
+            out->bytes_fill_alpha += s.bytes_fill_alpha; out->bytes_fill_beta += s.bytes_fill_beta;
+            out->cells_fill += s.cells_fill; out->score_items += s.score_items; out->rounds += s.rounds;
+            out->h2d_bytes += s.h2d_bytes + ds.h2d_bytes; out->d2h_bytes += s.d2h_bytes + ds.d2h_bytes;
+            out->ms_resident += s.ms_resident;
+            out->ms_poa_align += ds.ms_align; out->launches_poa += ds.n_align_launches; out->poa_tasks += ds.n_tasks;
+            out->poa_rows += ds.rows; out->bytes_poa_align += ds.bytes_align; out->launches_draft += ds.n_align_launches;
+            out->ms_draft += (k == 0 ? ctx->ms_draft : ctx->extra[k - 1].ms_draft);
+        }
+        out->ms_e2e = ctx->ms_e2e; out->n_zmws = ctx->n_zmws;
+        if (reset) {
+            for (int k = 0; k < n; ++k) { lane_engine(ctx, k).reset_stats(); lane_draft(ctx, k).stats = DraftStats(); }
+            ctx->ms_draft = 0; for (auto& l : ctx->extra) l.ms_draft = 0;
+            ctx->ms_e2e = 0; ctx->n_zmws = 0;
+        }
         return (int)CCS_OK;
     });
 }

@@ -69,9 +69,9 @@ public:
             if (kind == 1u) {
                 steps_.push_back({order[t], i - 1});
                 if (ord == 63u) break;
-                t = preds[pred_off[t] + ord]; i -= 1;
+                t = (ord == 62u) ? t - 1 : preds[pred_off[t] + ord]; i -= 1;
             } else if (kind == 2u) {
-                t = preds[pred_off[t] + ord];          // vertex skipped: nothing to thread
+                t = (ord == 62u) ? t - 1 : preds[pred_off[t] + ord];   // vertex skipped: nothing to thread
             } else {
                 steps_.push_back({-1, i - 1});
                 i -= 1;

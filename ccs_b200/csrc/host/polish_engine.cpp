@@ -203,6 +203,20 @@ void ArrowEngine::load(const PolishInput& in) {
         const int J = (int)zstate_[z].tpl.size();
         tpl_cap_[z] = ((J + std::max(256, J / 16)) + 15) & ~15;
     }
+    // fixed column slots per read (span + the template's growth room), so unchanged ZMWs keep their bands
+    col_base_.assign(nr, 0); col_cap_.assign(nr, 0);
+    {
+        int64_t cb = 0;
+        for (int z = 0; z < nz; ++z) {
+            const int J = (int)zstate_[z].tpl.size();
+            const int grow = tpl_cap_[z] - J;
+            zstate_[z].dirty = true;
+            for (int r = zstate_[z].read_begin; r < zstate_[z].read_end; ++r) {
+                col_base_[r] = cb;
+                if (reads_[r].active) { col_cap_[r] = (reads_[r].te - reads_[r].ts) + grow; cb += col_cap_[r]; }
+            }
+        }
+    }
     upload_templates_and_reads();
     span_end();
 }
@@ -215,7 +229,7 @@ void ArrowEngine::upload_templates_and_reads() {
     for (int z = 0; z < nz; ++z) {
         ZmwState& zs = zstate_[z];
         const int J = (int)zs.tpl.size();
-        if (J > tpl_cap_[z]) tpl_cap_[z] = ((J + std::max(256, J / 16)) + 15) & ~15;
+        if (J > tpl_cap_[z]) throw OomError("template outgrew its capacity");
         DevZmw& dz = zmws_[z];
         dz.read_begin = zs.read_begin; dz.read_end = zs.read_end;
         dz.fwd_off = (int32_t)toff; dz.rev_off = (int32_t)(toff + tpl_cap_[z]);
@@ -234,8 +248,9 @@ void ArrowEngine::upload_templates_and_reads() {
             const int len = rd.te - rd.ts;
             if (rd.active && (len < 2 || rd.ts < 0 || rd.te > J || rd.I < 2)) { rd.active = 0; status_[r] = 2; }
             rd.J = rd.active ? len : 0;
-            rd.col_off = cols;
-            if (rd.active) cols += rd.J;
+            if (col_cap_[r] < rd.J) throw OomError("column capacity of a read exceeded");   // cannot happen: growth is bounded by the template capacity
+            rd.col_off = col_base_[r];
+            cols = std::max<int64_t>(cols, col_base_[r] + col_cap_[r]);
         }
     }
     parallel_for(nz, host_threads, [&](int z) {
@@ -253,8 +268,12 @@ void ArrowEngine::upload_templates_and_reads() {
     });
     total_cols_ = cols;
     total_delta_rows_ = drows;
+    // reads to (re)fill: every active read of a ZMW whose template changed since its last fill
     order_.clear();
-    for (int r = 0; r < nr; ++r) if (reads_[r].active) order_.push_back(r);
+    for (int z = 0; z < nz; ++z) {
+        if (!zstate_[z].dirty) continue;
+        for (int r = zstate_[z].read_begin; r < zstate_[z].read_end; ++r) if (reads_[r].active) order_.push_back(r);
+    }
     std::stable_sort(order_.begin(), order_.end(), [&](int a, int b) { return reads_[a].J > reads_[b].J; });
 
     d_tpl_.ensure((size_t)toff + 16, budget_);
@@ -294,6 +313,7 @@ void ArrowEngine::fill() {
     launch_fill_beta(V, d_order_.p, n, stream_);
     span_end();
     CCS_CUDA(cudaGetLastError());
+    for (auto& zs : zstate_) zs.dirty = false;
     ++stats.n_fill_alpha; ++stats.n_fill_beta;
     stats.cells_fill += cells;
     stats.bytes_fill_alpha += 4 * cells + 8 * (cells / 32) + in_bytes;
@@ -528,6 +548,7 @@ void ArrowEngine::polish(const PolishParams& pp) {
                 rd.ts += ds; rd.te += de;
             }
             zs.tpl.swap(next);
+            zs.dirty = true;
             applied_flag.store(1, std::memory_order_relaxed);
         });
         const bool any_applied = applied_flag.load() != 0;

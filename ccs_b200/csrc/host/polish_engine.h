@@ -46,6 +46,7 @@ struct ZmwState {
     std::vector<uint8_t> tpl;          // current forward template
     int32_t read_begin = 0, read_end = 0;
     bool converged = false, failed = false, done = false;
+    bool dirty = true;                 // template changed since the last alpha/beta fill of its reads
     int32_t iterations = 0, n_applied = 0;
     int64_t n_tested = 0;
     std::vector<uint64_t> seen;        // template hashes (cycle guard)
@@ -129,6 +130,8 @@ private:
     std::vector<int32_t> order_;             // active reads, longest template first
     std::vector<int32_t> status_;
     std::vector<std::vector<uint8_t>> qv_;
+    std::vector<int64_t> col_base_;          // fixed first column of each read's band slot
+    std::vector<int32_t> col_cap_;           // columns reserved for it
     std::vector<int32_t> tpl_cap_;           // per-ZMW template capacity in the device buffer
     int64_t total_cols_ = 0, total_delta_rows_ = 0;
     double ab_tol_ = 1e-3;

@@ -118,6 +118,9 @@ typedef struct ccsgpu_ctx ccsgpu_ctx;
  * writes the ccs_error to *err (CCS_ERR_NO_DEVICE when no CUDA device: no CPU fallback). */
 ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_budget, int* err);
 void        ccsgpu_destroy(ccsgpu_ctx* ctx);
+/* Number of concurrent lanes (engine sets with their own CUDA streams) a stage call spreads its batch
+ * over; default 3 (env CCS_B200_LANES).  1 = strictly serial kernels (used for per-kernel timing). */
+int         ccsgpu_set_lanes(ccsgpu_ctx* ctx, int n_lanes);
 /* Message of the last failure on this ctx (or of the last failed ccsgpu_create if ctx == NULL). */
 const char* ccsgpu_last_error(const ccsgpu_ctx* ctx);
 
@@ -239,6 +242,7 @@ typedef struct ccs_stats {
     int64_t launches_poa, poa_tasks, poa_rows, bytes_poa_align;
     double  ms_resident;   /* CUDA-event time of the stage with inputs already in HBM */
     double  ms_e2e;        /* host wall time of the stage calls: pack + H2D + kernels + D2H */
+    /* with more than one lane the per-kernel ms above are sums over concurrently running lanes */
     int64_t n_zmws;        /* ZMWs processed */
 } ccs_stats;
 int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset);

@@ -227,9 +227,14 @@ bool kmer_vote_reverse(const uint8_t* ref, int nref, const uint8_t* read, int n)
     for (int i = 0; i < n; ++i) rc[i] = (uint8_t)(3 - read[n - 1 - i]);
     kmers(read, n, fk);
     kmers(rc.data(), n, ck);
+    // every 8th window of the read votes (window start = 0 mod 8 in forward coordinates); the reverse
+    // complement of forward window w is window (nk-1-w) of the reverse-complemented read
     long long f = 0, c = 0;
-    for (uint32_t k : fk) f += std::binary_search(rk.begin(), rk.end(), k);
-    for (uint32_t k : ck) c += std::binary_search(rk.begin(), rk.end(), k);
+    const size_t nk = fk.size();
+    for (size_t w = 0; w < nk; w += 8) {
+        f += std::binary_search(rk.begin(), rk.end(), fk[w]);
+        c += std::binary_search(rk.begin(), rk.end(), ck[nk - 1 - w]);
+    }
     return c > f;
 }
 

@@ -1,0 +1,10 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_draft.py tests/test_gpu_arrow.py -x -q -m gpu 2>&1 | tail -5
+for L in 1 3; do
+python bench.py --steps 2 --warmup 1 --lanes $L --no-cpu-baseline > gpurun_out/bench_r1_g_l$L.json 2> gpurun_out/bench_r1_g_l$L.err
+python - <<PY
+import json; d=json.load(open('gpurun_out/bench_r1_g_l$L.json')); print('lanes',$L,'value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'roof',round(d['roofline']['frac'],3), {k:(round(v,1) if isinstance(v,float) else v) for k,v in d['kernel_ms'].items()})
+PY
+tail -3 gpurun_out/bench_r1_g_l$L.err
+done
