@@ -6,8 +6,9 @@
 namespace ccs {
 
 // order[n_items]: read indices, longest template first (keeps a warp's four octets in step)
-void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
-void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
+// cells_per_lane selects the lane mapping: 4 = octet (8 lanes per pair) ... 32 = one lane per pair
+void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream, int cells_per_lane = 4);
+void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream, int cells_per_lane = 4);
 
 // delta[(zmw.delta_off + p) * kDeltaStride + slot]; INS total = slot[5+b] + slot[9+b].
 // Ranges of one ZMW must be disjoint and non-touching.  generic = reference kernel (every mutation

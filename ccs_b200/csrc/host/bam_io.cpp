@@ -1,0 +1,371 @@
+// See bam_io.h.  BGZF: RFC1952 gzip members with a 'BC' extra field carrying the block size;
+// BAM: little-endian records (SAM spec section 4).  PacBio conventions per SURVEY.md Appendix C.
+#include "bam_io.h"
+#include <zlib.h>
+#include <algorithm>
+#include <cstring>
+
+namespace ccs {
+
+namespace {
+
+inline uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline void wr16(std::vector<uint8_t>& v, uint16_t x) { v.push_back(x & 255); v.push_back(x >> 8); }
+inline void wr32(std::vector<uint8_t>& v, uint32_t x) { for (int k = 0; k < 4; ++k) v.push_back((x >> (8 * k)) & 255); }
+inline void wrf(std::vector<uint8_t>& v, float f) { uint32_t u; std::memcpy(&u, &f, 4); wr32(v, u); }
+inline void wrs(std::vector<uint8_t>& v, const std::string& s) { v.insert(v.end(), s.begin(), s.end()); }
+
+const uint8_t kBgzfEof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0,
+                              0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+constexpr size_t kBlockData = 0xff00;   // uncompressed payload per BGZF block
+
+void tag_i(std::vector<uint8_t>& v, const char* t, int32_t x) { v.push_back(t[0]); v.push_back(t[1]); v.push_back('i'); wr32(v, (uint32_t)x); }
+void tag_f(std::vector<uint8_t>& v, const char* t, float x) { v.push_back(t[0]); v.push_back(t[1]); v.push_back('f'); wrf(v, x); }
+void tag_Z(std::vector<uint8_t>& v, const char* t, const std::string& s) { v.push_back(t[0]); v.push_back(t[1]); v.push_back('Z'); wrs(v, s); v.push_back(0); }
+void tag_Bf(std::vector<uint8_t>& v, const char* t, const float* x, int n) {
+    v.push_back(t[0]); v.push_back(t[1]); v.push_back('B'); v.push_back('f'); wr32(v, (uint32_t)n);
+    for (int k = 0; k < n; ++k) wrf(v, x[k]);
+}
+
+// core of an unmapped BAM record; returns the offset of the block_size field to patch afterwards
+size_t begin_record(std::vector<uint8_t>& v, const std::string& name, int32_t l_seq) {
+    const size_t at = v.size();
+    wr32(v, 0);                                  // block_size (patched)
+    wr32(v, (uint32_t)-1); wr32(v, (uint32_t)-1);   // refID, pos
+    v.push_back((uint8_t)(name.size() + 1));     // l_read_name
+    v.push_back(255);                            // mapq
+    wr16(v, 4680);                               // bin of an unmapped read (reg2bin(-1,0))
+    wr16(v, 0);                                  // n_cigar_op
+    wr16(v, 4);                                  // flag: unmapped
+    wr32(v, (uint32_t)l_seq);
+    wr32(v, (uint32_t)-1); wr32(v, (uint32_t)-1); wr32(v, 0);   // next refID, next pos, tlen
+    wrs(v, name); v.push_back(0);
+    return at;
+}
+
+void put_seq(std::vector<uint8_t>& v, const uint8_t* bases, int32_t n) {
+    static const uint8_t nib[4] = {1, 2, 4, 8};   // =ACMGRSVTWYHKDBN
+    for (int32_t i = 0; i < n; i += 2) {
+        const uint8_t hi = nib[bases[i] & 3], lo = (i + 1 < n) ? nib[bases[i + 1] & 3] : 0;
+        v.push_back((uint8_t)((hi << 4) | lo));
+    }
+}
+
+void end_record(std::vector<uint8_t>& v, size_t at) {
+    const uint32_t bs = (uint32_t)(v.size() - at - 4);
+    for (int k = 0; k < 4; ++k) v[at + k] = (bs >> (8 * k)) & 255;
+}
+
+std::string header_field(const std::string& line, const std::string& key) {   // "\tKEY:value"
+    const size_t p = line.find("\t" + key + ":");
+    if (p == std::string::npos) return "";
+    const size_t b = p + key.size() + 2, e = line.find('\t', b);
+    return line.substr(b, e == std::string::npos ? std::string::npos : e - b);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+BgzfReader::~BgzfReader() { if (f_) std::fclose(f_); }
+
+bool BgzfReader::open(const std::string& path) {
+    f_ = std::fopen(path.c_str(), "rb");
+    block_.clear(); pos_ = 0;
+    return f_ != nullptr;
+}
+
+bool BgzfReader::fill() {
+    uint8_t h[18];
+    for (;;) {
+        if (std::fread(h, 1, 18, f_) != 18) return false;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || rd16(h + 10) != 6 || h[12] != 'B' || h[13] != 'C') return false;
+        const size_t bsize = (size_t)rd16(h + 16) + 1;
+        const size_t clen = bsize - 18 - 8;
+        comp_.resize(clen + 8);
+        if (std::fread(comp_.data(), 1, clen + 8, f_) != clen + 8) return false;
+        const uint32_t isize = rd32(comp_.data() + clen + 4);
+        block_.resize(isize);
+        pos_ = 0;
+        if (isize == 0) continue;                 // empty block (EOF marker or flush point)
+        z_stream zs;
+        std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) return false;
+        zs.next_in = comp_.data(); zs.avail_in = (uInt)clen;
+        zs.next_out = block_.data(); zs.avail_out = (uInt)isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (rc != Z_STREAM_END) return false;
+        return true;
+    }
+}
+
+bool BgzfReader::read(void* dst, size_t n) {
+    uint8_t* d = (uint8_t*)dst;
+    while (n > 0) {
+        if (pos_ == block_.size() && !fill()) return false;
+        const size_t k = std::min(n, block_.size() - pos_);
+        std::memcpy(d, block_.data() + pos_, k);
+        pos_ += k; d += k; n -= k;
+    }
+    return true;
+}
+
+bool BgzfReader::eof() {
+    if (pos_ < block_.size()) return false;
+    return !fill();
+}
+
+BgzfWriter::~BgzfWriter() { close(); }
+
+bool BgzfWriter::open(const std::string& path, int level) {
+    f_ = std::fopen(path.c_str(), "wb");
+    level_ = level;
+    buf_.clear();
+    return f_ != nullptr;
+}
+
+void BgzfWriter::flush_block() {
+    if (buf_.empty() || !f_) return;
+    size_t done = 0;
+    while (done < buf_.size()) {
+        const size_t n = std::min(kBlockData, buf_.size() - done);
+        comp_.resize(compressBound((uLong)n) + 64);
+        z_stream zs;
+        std::memset(&zs, 0, sizeof(zs));
+        deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+        zs.next_in = buf_.data() + done; zs.avail_in = (uInt)n;
+        zs.next_out = comp_.data(); zs.avail_out = (uInt)comp_.size();
+        deflate(&zs, Z_FINISH);
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf_.data() + done, (uInt)n);
+        uint8_t h[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
+        const uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1);
+        h[16] = bsize & 255; h[17] = bsize >> 8;
+        std::fwrite(h, 1, 18, f_);
+        std::fwrite(comp_.data(), 1, clen, f_);
+        uint8_t t[8];
+        for (int k = 0; k < 4; ++k) { t[k] = (crc >> (8 * k)) & 255; t[4 + k] = ((uint32_t)n >> (8 * k)) & 255; }
+        std::fwrite(t, 1, 8, f_);
+        done += n;
+    }
+    buf_.clear();
+}
+
+void BgzfWriter::write(const void* src, size_t n) {
+    const uint8_t* s = (const uint8_t*)src;
+    buf_.insert(buf_.end(), s, s + n);
+    if (buf_.size() >= 16 * kBlockData) flush_block();
+}
+
+void BgzfWriter::close() {
+    if (!f_) return;
+    flush_block();
+    std::fwrite(kBgzfEof, 1, sizeof(kBgzfEof), f_);
+    std::fclose(f_);
+    f_ = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+bool SubreadBamReader::open(const std::string& path, std::string& err) {
+    if (!in_.open(path)) { err = "cannot open " + path; return false; }
+    uint8_t magic[4];
+    if (!in_.read(magic, 4) || std::memcmp(magic, "BAM\1", 4) != 0) { err = path + " is not a BAM file"; return false; }
+    uint8_t b4[4];
+    if (!in_.read(b4, 4)) { err = "truncated header"; return false; }
+    header_.resize(rd32(b4));
+    if (!header_.empty() && !in_.read(&header_[0], header_.size())) { err = "truncated header"; return false; }
+    while (!header_.empty() && header_.back() == 0) header_.pop_back();
+    if (!in_.read(b4, 4)) { err = "truncated header"; return false; }
+    for (uint32_t r = rd32(b4); r > 0; --r) {     // reference sequences (none in PacBio unaligned BAMs)
+        if (!in_.read(b4, 4)) return false;
+        std::vector<uint8_t> skip(rd32(b4) + 4);
+        if (!in_.read(skip.data(), skip.size())) return false;
+    }
+    // read group: movie (PU), id, chemistry triple in DS
+    size_t p = 0;
+    while (p < header_.size()) {
+        size_t e = header_.find('\n', p);
+        if (e == std::string::npos) e = header_.size();
+        const std::string line = header_.substr(p, e - p);
+        if (line.compare(0, 3, "@RG") == 0 && rg_id_.empty()) {
+            rg_id_ = header_field(line, "ID");
+            movie_ = header_field(line, "PU");
+            const std::string ds = header_field(line, "DS");
+            chem_ok_ = ds.find("BINDINGKIT=") != std::string::npos && ds.find("SEQUENCINGKIT=") != std::string::npos &&
+                       ds.find("BASECALLERVERSION=") != std::string::npos;
+        }
+        p = e + 1;
+    }
+    if (rg_id_.empty()) { err = "no @RG line in the BAM header"; return false; }
+    return true;
+}
+
+bool SubreadBamReader::next_record(Subread& s) {
+    uint8_t b4[4];
+    if (!in_.read(b4, 4)) return false;
+    std::vector<uint8_t> rec(rd32(b4));
+    if (rec.size() < 32 || !in_.read(rec.data(), rec.size())) return false;
+    const uint8_t* r = rec.data();
+    const int l_name = r[8];
+    const int n_cigar = rd16(r + 12);
+    const int32_t l_seq = (int32_t)rd32(r + 16);
+    const uint8_t* p = r + 32;
+    const std::string name((const char*)p, l_name > 0 ? l_name - 1 : 0);
+    p += l_name + 4 * n_cigar;
+    const uint8_t* seq = p;
+    p += (l_seq + 1) / 2 + l_seq;               // packed bases + qualities
+    s = Subread();
+    std::vector<uint8_t> pw;
+    const uint8_t* end = r + rec.size();
+    while (p + 3 <= end) {
+        const char t0 = (char)p[0], t1 = (char)p[1], ty = (char)p[2];
+        p += 3;
+        auto is = [&](const char* t) { return t0 == t[0] && t1 == t[1]; };
+        size_t sz = 0;
+        switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'Z': case 'H': sz = std::strlen((const char*)p) + 1; break;
+            case 'B': {
+                const char sub = (char)p[0];
+                const uint32_t n = rd32(p + 1);
+                const size_t es = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
+                if (is("sn") && sub == 'f' && n == 4) for (int k = 0; k < 4; ++k) { uint32_t u = rd32(p + 5 + 4 * k); std::memcpy(&s.snr[k], &u, 4); }
+                if (is("pw")) {
+                    pw.resize(n);
+                    for (uint32_t k = 0; k < n; ++k) pw[k] = (es == 1) ? p[5 + k] : (uint8_t)std::min<uint32_t>(255, rd16(p + 5 + 2 * k));
+                }
+                sz = 5 + es * n;
+                break;
+            }
+            default: return false;
+        }
+        if (ty != 'B') {
+            int32_t iv = 0;
+            if (ty == 'i' || ty == 'I') iv = (int32_t)rd32(p);
+            else if (ty == 's') iv = (int16_t)rd16(p); else if (ty == 'S') iv = rd16(p);
+            else if (ty == 'c') iv = (int8_t)p[0]; else if (ty == 'C') iv = p[0];
+            if (is("zm")) s.hole = iv;
+            else if (is("qs")) s.qs = iv;
+            else if (is("qe")) s.qe = iv;
+            else if (is("cx")) s.cx = (uint8_t)iv;
+        }
+        p += sz;
+    }
+    if (s.hole == 0 && !name.empty()) {          // fall back to the read name movie/zmw/qs_qe
+        const size_t a = name.find('/'), b = name.find('/', a + 1);
+        if (a != std::string::npos && b != std::string::npos) s.hole = std::atoi(name.substr(a + 1, b - a - 1).c_str());
+    }
+    static const int8_t dec[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1};
+    s.codes.resize(l_seq);
+    for (int32_t i = 0; i < l_seq; ++i) {
+        const int nibble = (i & 1) ? (seq[i >> 1] & 15) : (seq[i >> 1] >> 4);
+        const int b = dec[nibble] < 0 ? 0 : dec[nibble];
+        const int w = (i < (int32_t)pw.size()) ? std::min<int>(std::max<int>(pw[i], 1), 3) : 1;
+        s.codes[i] = (uint8_t)(4 * (w - 1) + b);     // Recursor::EncodeRead
+    }
+    return true;
+}
+
+bool SubreadBamReader::next_zmw(ZmwSubreads& z) {
+    z.reads.clear();
+    if (!have_pending_) {
+        if (!next_record(pending_)) return false;
+        have_pending_ = true;
+    }
+    z.hole = pending_.hole;
+    std::memcpy(z.snr, pending_.snr, sizeof(z.snr));
+    while (have_pending_ && pending_.hole == z.hole) {
+        z.reads.push_back(std::move(pending_));
+        have_pending_ = next_record(pending_);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+bool CcsBamWriter::open(const std::string& path, const std::string& in_header, const std::string& movie,
+                        const std::string& rg_id, const std::string& program_cl) {
+    if (!out_.open(path)) return false;
+    movie_ = movie; rg_ = rg_id;
+    std::string text;
+    size_t p = 0;
+    while (p < in_header.size()) {
+        size_t e = in_header.find('\n', p);
+        if (e == std::string::npos) e = in_header.size();
+        std::string line = in_header.substr(p, e - p);
+        const size_t q = line.find("READTYPE=SUBREAD");
+        if (q != std::string::npos) line.replace(q, 16, "READTYPE=CCS");
+        if (!line.empty()) text += line + "\n";
+        p = e + 1;
+    }
+    text += "@PG\tID:ccs\tPN:ccs\tVN:ccs-b200-0.1\tDS:Generate circular consensus sequences (ccs) from subreads.\tCL:" + program_cl + "\n";
+    std::vector<uint8_t> h;
+    wrs(h, std::string("BAM\1", 4));
+    wr32(h, (uint32_t)text.size());
+    wrs(h, text);
+    wr32(h, 0);
+    out_.write(h.data(), h.size());
+    return true;
+}
+
+void CcsBamWriter::write(const CcsRecord& r) {
+    rec_.clear();
+    const std::string name = movie_ + "/" + std::to_string(r.hole) + "/ccs";
+    const size_t at = begin_record(rec_, name, r.len);
+    put_seq(rec_, r.seq, r.len);
+    rec_.insert(rec_.end(), r.qv, r.qv + r.len);
+    tag_Z(rec_, "RG", rg_);                 // fixed per-read tags: RG zm np rq sn ec (docs/faq/bam-output.md:45-49)
+    tag_i(rec_, "zm", r.hole);
+    tag_i(rec_, "np", r.np);
+    tag_f(rec_, "rq", r.rq);
+    tag_Bf(rec_, "sn", r.snr, 4);
+    tag_f(rec_, "ec", r.ec);
+    end_record(rec_, at);
+    out_.write(rec_.data(), rec_.size());
+}
+
+void CcsBamWriter::close() { out_.close(); }
+
+bool SubreadBamWriter::open(const std::string& path, const std::string& movie, bool with_chemistry) {
+    if (!out_.open(path)) return false;
+    movie_ = movie; rg_ = "b200sim0";
+    std::string ds = "READTYPE=SUBREAD;Ipd:CodecV1=ip;PulseWidth:CodecV1=pw";
+    if (with_chemistry) ds += ";BINDINGKIT=000-000-000;SEQUENCINGKIT=000-000-001;BASECALLERVERSION=0.0.0;FRAMERATEHZ=100.000000";
+    const std::string text = "@HD\tVN:1.5\tSO:unknown\tpb:3.0.1\n@RG\tID:" + rg_ + "\tPL:PACBIO\tDS:" + ds + "\tPU:" + movie_ +
+                             "\tPM:SEQUELII\n";
+    std::vector<uint8_t> h;
+    wrs(h, std::string("BAM\1", 4));
+    wr32(h, (uint32_t)text.size());
+    wrs(h, text);
+    wr32(h, 0);
+    out_.write(h.data(), h.size());
+    return true;
+}
+
+void SubreadBamWriter::write(const SubreadOut& s) {
+    rec_.clear();
+    const std::string name = movie_ + "/" + std::to_string(s.hole) + "/" + std::to_string(s.qs) + "_" + std::to_string(s.qe);
+    const size_t at = begin_record(rec_, name, s.len);
+    std::vector<uint8_t> bases(s.len);
+    for (int32_t i = 0; i < s.len; ++i) bases[i] = s.codes[i] & 3;
+    put_seq(rec_, bases.data(), s.len);
+    rec_.insert(rec_.end(), (size_t)s.len, (uint8_t)0xff);   // subreads carry no qualities
+    tag_Z(rec_, "RG", rg_);
+    tag_i(rec_, "zm", s.hole);
+    tag_i(rec_, "qs", s.qs);
+    tag_i(rec_, "qe", s.qe);
+    tag_i(rec_, "cx", s.cx);
+    tag_Bf(rec_, "sn", s.snr, 4);
+    tag_f(rec_, "rq", 0.8f);
+    rec_.push_back('p'); rec_.push_back('w'); rec_.push_back('B'); rec_.push_back('C'); wr32(rec_, (uint32_t)s.len);
+    for (int32_t i = 0; i < s.len; ++i) rec_.push_back((uint8_t)((s.codes[i] >> 2) + 1));
+    end_record(rec_, at);
+    out_.write(rec_.data(), rec_.size());
+}
+
+void SubreadBamWriter::close() { out_.close(); }
+
+}  // namespace ccs

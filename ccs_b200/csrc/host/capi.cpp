@@ -32,6 +32,7 @@ struct ccsgpu_ctx {
     int host_threads = 8;
     size_t budget = 0;
     bool generic_score = false;
+    int fill_cpl = 4;
     double ms_e2e = 0;
     int64_t n_zmws = 0;
     int device = 0;
@@ -88,6 +89,8 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
           ctx->host_threads = hc; ctx->engine->host_threads = hc; ctx->draft->host_threads = hc; }
         if (const char* e = std::getenv("CCS_B200_GENERIC_SCORE")) ctx->generic_score = (e[0] == '1');
         ctx->engine->generic_score = ctx->generic_score;
+        if (const char* e = std::getenv("CCS_B200_FILL_CPL")) ctx->fill_cpl = std::atoi(e);
+        ctx->engine->fill_cells_per_lane = ctx->fill_cpl;
         ctx->budget = device_bytes_budget;
         int lanes = 3;
         if (const char* e = std::getenv("CCS_B200_LANES")) lanes = std::max(1, std::min(8, std::atoi(e)));
@@ -111,6 +114,7 @@ int ccsgpu_set_lanes(ccsgpu_ctx* ctx, int n_lanes) {
             l.engine.reset(new ArrowEngine(ctx->device, ctx->model, ctx->budget));
             l.draft.reset(new DraftEngine(ctx->device, 0));
             l.engine->generic_score = ctx->generic_score;
+            l.engine->fill_cells_per_lane = ctx->fill_cpl;
             ctx->extra.push_back(std::move(l));
         }
     } catch (const std::exception& e) {

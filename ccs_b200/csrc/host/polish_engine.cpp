@@ -201,7 +201,7 @@ void ArrowEngine::load(const PolishInput& in) {
     // template capacities: room for the template to grow during polishing
     for (int z = 0; z < nz; ++z) {
         const int J = (int)zstate_[z].tpl.size();
-        tpl_cap_[z] = ((J + std::max(256, J / 16)) + 15) & ~15;
+        tpl_cap_[z] = ((J + std::max(512, J / 8)) + 15) & ~15;
     }
     // fixed column slots per read (span + the template's growth room), so unchanged ZMWs keep their bands
     col_base_.assign(nr, 0); col_cap_.assign(nr, 0);
@@ -307,10 +307,10 @@ void ArrowEngine::fill() {
     int64_t cells = 0, in_bytes = 0;
     for (int r : order_) { cells += 32ll * (reads_[r].J - 1); in_bytes += reads_[r].I + reads_[r].J; }
     span_begin(&stats.ms_fill_alpha);
-    launch_fill_alpha(V, d_order_.p, n, stream_);
+    launch_fill_alpha(V, d_order_.p, n, stream_, fill_cells_per_lane);
     span_end();
     span_begin(&stats.ms_fill_beta);
-    launch_fill_beta(V, d_order_.p, n, stream_);
+    launch_fill_beta(V, d_order_.p, n, stream_, fill_cells_per_lane);
     span_end();
     CCS_CUDA(cudaGetLastError());
     for (auto& zs : zstate_) zs.dirty = false;
@@ -535,6 +535,12 @@ void ArrowEngine::polish(const PolishParams& pp) {
             for (const auto& m : best) {
                 zs.sites.push_back(m.pos + off);
                 off += m.type == 1 ? 1 : (m.type == 2 ? -1 : 0);
+            }
+            if ((int)next.size() > tpl_cap_[z]) {
+                // the template keeps growing past its reserved room (only seen on junk ZMWs whose reads do not
+                // agree): stop refining it; reported as NON_CONVERGENT
+                zs.done = true;
+                return;
             }
             zs.n_applied += (int)best.size();
             // span bookkeeping of the ZMW's reads (Integrator::ApplyMutations)

@@ -98,6 +98,7 @@ public:
     int device() const { return device_; }
     bool timing_enabled = true;
     int host_threads = 8;         // threads for the per-ZMW host pieces of a round
+    int fill_cells_per_lane = 4;  // lane mapping of the fill kernels (4, 8, 16, 32)
     bool generic_score = false;   // use the unfactored reference scoring kernel (tests)
 
 private:

@@ -151,3 +151,30 @@ void ccs_sim_batch_copy(const void* h, int32_t* zmw_read_off, int64_t* read_off,
 }
 
 }  // extern "C"
+
+// ---- synthetic subreads.bam (tests / demos of the `ccs` command line) --------------------------
+#include "bam_io.h"
+
+extern "C" {
+
+int ccs_sim_write_subreads_bam(const char* path, const char* movie, const void* model, const ccs_sim_config* cfg,
+                               int64_t first_index, int32_t n_zmws, int32_t with_chemistry) {
+    SimConfig c;
+    std::memcpy((void*)&c, cfg, sizeof(c));
+    SubreadBamWriter w;
+    if (!w.open(path, movie, with_chemistry != 0)) return CCS_ERR_IO;
+    for (int32_t k = 0; k < n_zmws; ++k) {
+        SimZmw z;
+        simulate_zmw(*(const ArrowModelParams*)model, c, first_index + k, z);
+        int32_t q = 0;
+        for (const SimRead& r : z.reads) {
+            SubreadOut s{z.hole + 1, q, q + (int32_t)r.codes.size(), z.snr, r.cx, r.codes.data(), (int32_t)r.codes.size()};
+            w.write(s);
+            q += (int32_t)r.codes.size() + 45;   // adapter gap
+        }
+    }
+    w.close();
+    return CCS_OK;
+}
+
+}  // extern "C"

@@ -108,6 +108,11 @@ void  ccs_sim_batch_copy(const void* handle, int32_t* zmw_read_off, int64_t* rea
                          int32_t* tstart, int32_t* tend, int64_t* draft_off, uint8_t* draft, int32_t* dstart,
                          int32_t* dend);
 
+/* Writes ZMWs [first_index, first_index+n) of a config as a PacBio-style subreads.bam (hole = index+1;
+ * tags zm qs qe cx sn pw RG) -- input for the `ccs` command line (ccs_b200/bin/ccs). */
+int   ccs_sim_write_subreads_bam(const char* path, const char* movie, const void* model, const ccs_sim_config* cfg,
+                                 int64_t first_index, int32_t n_zmws, int32_t with_chemistry);
+
 /* ------------------------------------------------------------------------------------
  * GPU context
  * ---------------------------------------------------------------------------------- */
