@@ -63,7 +63,8 @@ class CStats(C.Structure):
                                          "cells_fill", "score_items", "rounds", "h2d_bytes", "d2h_bytes")] + \
                [("ms_poa_align", C.c_double)] + \
                [(n, C.c_int64) for n in ("launches_poa", "poa_tasks", "poa_rows", "bytes_poa_align")] + \
-               [("ms_resident", C.c_double), ("ms_e2e", C.c_double), ("n_zmws", C.c_int64)]
+               [("ms_resident", C.c_double), ("ms_e2e", C.c_double), ("n_zmws", C.c_int64),
+                ("top_fill_alpha_bytes", C.c_int64), ("top_fill_alpha_ms", C.c_double)]
 
 
 class Batch:

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     int32_t* __restrict__ lo_arr, int32_t* __restrict__ besti_arr, uint8_t* __restrict__ moves,
     int32_t* __restrict__ hrows, PoaResult* __restrict__ results) {
     __shared__ int s_row[kWarpsPerCta][kPoaBand];
+    __shared__ int s_meta[kWarpsPerCta][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task_id = blockIdx.x * kWarpsPerCta + warp;
     if (task_id >= n_tasks) return;
@@ -53,25 +54,58 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     int gbest = 0, gt = -1, gi = -1;
     int prev_lo = 0, prev_besti = 0;
     srow[2 * lane] = 0; srow[2 * lane + 1] = 0;
+    int* smeta = s_meta[warp];          // per block of 32 vertices: base, first predecessor offset, count, first predecessor
     __syncwarp();
 
     for (int t = 0; t < V; ++t) {
-        const int vb = base[t];
-        int p0, p1;
-        if (T.linear) { p0 = 0; p1 = (t > 0) ? 1 : 0; }
-        else { p0 = poff[t]; p1 = poff[t + 1]; }
-        const int npred = p1 - p0;
+        // Vertex metadata does not depend on the DP state: every 32 vertices the lanes fetch one
+        // vertex each (base, predecessor range, first predecessor) so that the per-vertex dependent
+        // chain below never waits on global memory for them.
+        if ((t & 31) == 0) {
+            const int tt = min(t + lane, V - 1);
+            int mb = base[tt], mp0 = 0, mn = 0, mf = tt - 1;
+            if (T.linear) { mn = (tt > 0) ? 1 : 0; }
+            else { mp0 = poff[tt]; mn = poff[tt + 1] - mp0; if (mn > 0) mf = pl[mp0]; }
+            __syncwarp();
+            smeta[lane] = mb; smeta[32 + lane] = mp0; smeta[64 + lane] = mn; smeta[96 + lane] = mf;
+            __syncwarp();
+        }
+        const int vb = smeta[t & 31];
+        const int p0 = smeta[32 + (t & 31)];
+        const int npred = smeta[64 + (t & 31)];
+        const int first_pred = smeta[96 + (t & 31)];
+        int lo, c0, c1;
+        unsigned m0, m1;
+        int i0, i1;
+        if (npred == 1 && first_pred == t - 1) {
+            // fast path (every vertex of a linear template, almost every vertex of a POA graph): the only
+            // predecessor is the previous row, which sits in shared memory
+            lo = min(max(prev_besti + 1 - kPoaBand / 2, 0), lo_max);
+            i0 = lo + 2 * lane; i1 = i0 + 1;
+            const int a = 2 * lane + (lo - prev_lo);
+            const int hm1 = row_get(srow, a - 1), h0 = row_get(srow, a), h1 = row_get(srow, a + 1);
+            const bool v0 = (i0 >= 1 && i0 <= n), v1 = (i1 >= 1 && i1 <= n);
+            const int rb0 = v0 ? rd[i0 - 1] : 255, rb1 = v1 ? rd[i1 - 1] : 255;
+            const int bm0 = v0 ? hm1 + ((rb0 == vb) ? kPoaMatch : kPoaMismatch) : 0;
+            const int bm1 = v1 ? h0 + ((rb1 == vb) ? kPoaMatch : kPoaMismatch) : 0;
+            const int bd0 = (i0 <= n) ? h0 + kPoaDel : 0;
+            const int bd1 = (i1 <= n) ? h1 + kPoaDel : 0;
+            // match wins ties against deletion; candidates must be > 0
+            c0 = max(max(bm0, bd0), 0); c1 = max(max(bm1, bd1), 0);
+            m0 = (c0 == 0) ? 0u : ((bm0 >= bd0) ? (1u | (62u << 2)) : (2u | (62u << 2)));
+            m1 = (c1 == 0) ? 0u : ((bm1 >= bd1) ? (1u | (62u << 2)) : (2u | (62u << 2)));
+        } else {
         // band start from the predecessors' best cells
-        int lo = 0;
+        lo = 0;
         if (npred > 0) {
             int m = 0;
             for (int k = 0; k < npred; ++k) {
-                const int pr = T.linear ? t - 1 : pl[p0 + k];
+                const int pr = (k == 0) ? first_pred : pl[p0 + k];
                 m = max(m, (pr == t - 1) ? prev_besti : bi_r[pr]);
             }
             lo = min(max(m + 1 - kPoaBand / 2, 0), lo_max);
         }
-        const int i0 = lo + 2 * lane, i1 = i0 + 1;
+        i0 = lo + 2 * lane; i1 = i0 + 1;
         const int rb0 = (i0 >= 1 && i0 <= n) ? rd[i0 - 1] : 255;
         const int rb1 = (i1 >= 1 && i1 <= n) ? rd[i1 - 1] : 255;
         const int sc0 = (rb0 == vb) ? kPoaMatch : kPoaMismatch;
@@ -83,7 +117,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
             if (rb1 != 255 && sc1 > 0) { bm1 = sc1; km1 = 63; }
         }
         for (int k = 0; k < npred; ++k) {
-            const int pr = T.linear ? t - 1 : pl[p0 + k];
+            const int pr = (k == 0) ? first_pred : pl[p0 + k];
             const bool adj = (pr == t - 1);
             const int* __restrict__ row = adj ? srow : (h_r + (size_t)pr * kPoaBand);
             const int dl = lo - (adj ? prev_lo : lo_r[pr]);
@@ -96,10 +130,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
             if (i1 <= n) { const int c = h1 + kPoaDel; if (c > bd1) { bd1 = c; kd1 = kk; } }
         }
         // match wins ties against deletion (oracle evaluation order)
-        int c0, c1;
-        unsigned m0, m1;
         if (bm0 >= bd0) { c0 = bm0; m0 = bm0 > 0 ? (1u | (km0 << 2)) : 0u; } else { c0 = bd0; m0 = 2u | (kd0 << 2); }
         if (bm1 >= bd1) { c1 = bm1; m1 = bm1 > 0 ? (1u | (km1 << 2)) : 0u; } else { c1 = bd1; m1 = 2u | (kd1 << 2); }
+        }
         __syncwarp();   // everyone has read the previous row
         // insertion chain: H[c] = max(C[c], H[c-1] + INS) over the row's cells with i <= n
         const int NEG = -(1 << 29);

@@ -464,6 +464,7 @@ int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset) {
             out->cells_fill += s.cells_fill; out->score_items += s.score_items; out->rounds += s.rounds;
             out->h2d_bytes += s.h2d_bytes + ds.h2d_bytes; out->d2h_bytes += s.d2h_bytes + ds.d2h_bytes;
             out->ms_resident += s.ms_resident;
+            if (s.top_fill_alpha_bytes > out->top_fill_alpha_bytes) { out->top_fill_alpha_bytes = s.top_fill_alpha_bytes; out->top_fill_alpha_ms = s.top_fill_alpha_ms; }
             out->ms_poa_align += ds.ms_align; out->launches_poa += ds.n_align_launches; out->poa_tasks += ds.n_tasks;
             out->poa_rows += ds.rows; out->bytes_poa_align += ds.bytes_align; out->launches_draft += ds.n_align_launches;
             out->ms_draft += (k == 0 ? ctx->ms_draft : ctx->extra[k - 1].ms_draft);

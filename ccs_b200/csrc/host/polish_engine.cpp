@@ -93,9 +93,9 @@ cudaEvent_t ArrowEngine::next_event() {
     return ev_pool_[ev_used_++];
 }
 
-void ArrowEngine::span_begin(double* acc) {
+void ArrowEngine::span_begin(double* acc, int64_t bytes, int64_t* top_bytes, double* top_ms) {
     if (!timing_enabled) return;
-    Span sp{next_event(), next_event(), acc};
+    Span sp{next_event(), next_event(), acc, bytes, top_bytes, top_ms};
     CCS_CUDA(cudaEventRecord(sp.a, stream_));
     spans_.push_back(sp);
 }
@@ -109,7 +109,10 @@ void ArrowEngine::span_end() {
 void ArrowEngine::resolve_spans() {
     for (const Span& sp : spans_) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) *sp.acc += ms;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            *sp.acc += ms;
+            if (sp.top_bytes && sp.bytes > *sp.top_bytes) { *sp.top_bytes = sp.bytes; *sp.top_ms = ms; }
+        }
     }
     spans_.clear();
     ev_used_ = 0;
@@ -306,7 +309,7 @@ void ArrowEngine::fill() {
     const int n = (int)order_.size();
     int64_t cells = 0, in_bytes = 0;
     for (int r : order_) { cells += 32ll * (reads_[r].J - 1); in_bytes += reads_[r].I + reads_[r].J; }
-    span_begin(&stats.ms_fill_alpha);
+    span_begin(&stats.ms_fill_alpha, 4 * cells + 8 * (cells / 32) + in_bytes, &stats.top_fill_alpha_bytes, &stats.top_fill_alpha_ms);
     launch_fill_alpha(V, d_order_.p, n, stream_, fill_cells_per_lane);
     span_end();
     span_begin(&stats.ms_fill_beta);

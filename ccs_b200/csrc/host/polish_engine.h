@@ -63,6 +63,8 @@ struct EngineStats {
     int64_t cells_fill = 0, score_items = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     int64_t rounds = 0;
+    int64_t top_fill_alpha_bytes = 0;   // largest single arrow_fill_alpha launch: algorithmic bytes ...
+    double top_fill_alpha_ms = 0;       // ... and its CUDA-event duration
     double ms_resident = 0;   // CUDA-event time of polish() with inputs already in HBM (after load)
     double ms_e2e = 0;        // host wall time of whole stage calls (pack + H2D + kernels + D2H)
     int64_t n_zmws = 0;
@@ -103,8 +105,8 @@ public:
 
 private:
     // in-stream timing: spans are recorded without host syncs and resolved at the next natural sync
-    struct Span { cudaEvent_t a, b; double* acc; };
-    void span_begin(double* acc);
+    struct Span { cudaEvent_t a, b; double* acc; int64_t bytes; int64_t* top_bytes; double* top_ms; };
+    void span_begin(double* acc, int64_t bytes = 0, int64_t* top_bytes = nullptr, double* top_ms = nullptr);
     void span_end();
     void resolve_spans();
     std::vector<Span> spans_;

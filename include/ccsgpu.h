@@ -249,6 +249,8 @@ typedef struct ccs_stats {
     double  ms_e2e;        /* host wall time of the stage calls: pack + H2D + kernels + D2H */
     /* with more than one lane the per-kernel ms above are sums over concurrently running lanes */
     int64_t n_zmws;        /* ZMWs processed */
+    int64_t top_fill_alpha_bytes;   /* the largest single arrow_fill_alpha launch: algorithmic bytes */
+    double  top_fill_alpha_ms;      /* and its duration (roofline numerator/denominator) */
 } ccs_stats;
 int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset);
 
