@@ -245,7 +245,7 @@ def main():
     clocks = sampler.stop()
     barrier()
     st = ctx.stats()
-    lanes = args.lanes if args.lanes > 0 else int(os.environ.get("CCS_B200_LANES", "3"))
+    lanes = args.lanes if args.lanes > 0 else int(os.environ.get("CCS_B200_LANES", "4"))
     t_e2e = st["ms_e2e"] / 1e3
     # `value`: same run with the batch upload taken out (inputs resident): the initial H2D of the packed
     # read codes / templates is the only input traffic; its CUDA-event span (per lane, lanes overlap) is
@@ -275,6 +275,12 @@ def main():
         fa = st1["top_fill_alpha_bytes"]
         fa_ms = st1["top_fill_alpha_ms"]
         achieved = fa / (fa_ms * 1e-3) / 1e9 if fa_ms > 0 else 0.0
+        traffic = None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same launch, `ncu --set full` (profiles/r1_summary.json)
+            if args.config == 2 and args.zmws == 1000:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_summary.json")))["arrow_fill_alpha"]["dram_bytes"]
+        except Exception:
+            traffic = None
         kern_ms = {k: st1[k] for k in ("ms_fill_alpha", "ms_fill_beta", "ms_score", "ms_pick", "ms_qv", "ms_h2d",
                                        "ms_poa_align", "ms_draft", "ms_resident", "ms_e2e")}
         kern_ms["note"] = "one step, single lane (serial kernels); the timed region runs %d overlapping lanes" % lanes
@@ -294,7 +300,7 @@ def main():
                     "d2h_bytes_per_step": st["d2h_bytes"] / args.steps, "wall_s": wall},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "arrow_fill_alpha_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": fa, "ms_per_launch": fa_ms,
                          "launch": "largest arrow_fill_alpha launch of one step (all reads of the batch), single lane",
                          "all_launches_GBps": st1["bytes_fill_alpha"] / max(st1["ms_fill_alpha"], 1e-9) / 1e6},

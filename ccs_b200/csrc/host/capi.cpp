@@ -92,7 +92,7 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
         if (const char* e = std::getenv("CCS_B200_FILL_CPL")) ctx->fill_cpl = std::atoi(e);
         ctx->engine->fill_cells_per_lane = ctx->fill_cpl;
         ctx->budget = device_bytes_budget;
-        int lanes = 3;
+        int lanes = 4;
         if (const char* e = std::getenv("CCS_B200_LANES")) lanes = std::max(1, std::min(8, std::atoi(e)));
         ccsgpu_set_lanes(ctx, lanes);
     } catch (const std::exception& e) {

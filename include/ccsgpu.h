@@ -124,7 +124,7 @@ typedef struct ccsgpu_ctx ccsgpu_ctx;
 ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_budget, int* err);
 void        ccsgpu_destroy(ccsgpu_ctx* ctx);
 /* Number of concurrent lanes (engine sets with their own CUDA streams) a stage call spreads its batch
- * over; default 3 (env CCS_B200_LANES).  1 = strictly serial kernels (used for per-kernel timing). */
+ * over; default 4 (env CCS_B200_LANES).  1 = strictly serial kernels (used for per-kernel timing). */
 int         ccsgpu_set_lanes(ccsgpu_ctx* ctx, int n_lanes);
 /* Message of the last failure on this ctx (or of the last failed ccsgpu_create if ctx == NULL). */
 const char* ccsgpu_last_error(const ccsgpu_ctx* ctx);

@@ -1,0 +1,99 @@
+"""Turns gpurun_out/r1_full_*.ncu-rep + the launch list into profiles/r1_summary.md / .json (run here, no GPU)."""
+import collections
+import csv
+import io
+import json
+import subprocess
+import sys
+
+KERNELS = ["arrow_fill_alpha", "arrow_fill_beta", "arrow_score", "poa_align"]
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__warps_eligible.avg.per_cycle_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__inst_executed_pipe_tensor.sum"]
+UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "s": 1.0, "ns": 1e-9}
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2]
+    d = {}
+    for h, u, v in zip(hdr, units, data):
+        if h in WANT:
+            try:
+                x = float(v.replace(",", ""))
+            except ValueError:
+                continue
+            d[h] = x * UNIT.get(u, 1.0) if u in UNIT else x
+    return d
+
+
+def stalls(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, data = rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    names = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    tot = collections.Counter()
+    samples = 0
+    for r in data:
+        if len(r) < len(hdr):
+            continue
+        samples += int(r[ix["# Samples"]])
+        for s in names:
+            tot[s] += int(r[ix[s]])
+    return {k[6:]: round(100.0 * v / max(samples, 1), 1) for k, v in tot.most_common(6)}
+
+
+def main():
+    res = {}
+    for k in KERNELS:
+        rep = "gpurun_out/r1_full_%s.ncu-rep" % k
+        d = raw(rep)
+        d["stall_pct"] = stalls(rep)
+        d["dram_bytes"] = d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
+        res[k] = d
+    # launch list
+    rows = list(csv.reader(open("gpurun_out/r1_launches_bench.csv")))
+    hdr = None
+    agg = collections.OrderedDict()
+    for r in rows:
+        if "Kernel Name" in r:
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            name = d["Kernel Name"].split("(")[0].split("::")[-1]
+            agg.setdefault(name, []).append(float(d["Metric Value"].replace(",", "")) / 1e6)
+    tot = sum(sum(v) for v in agg.values())
+    res["launch_list"] = {n: {"launches": len(v), "total_ms": round(sum(v), 2), "share": round(sum(v) / tot, 3),
+                              "max_ms": round(max(v), 2)} for n, v in agg.items()}
+    json.dump(res, open("profiles/r1_summary.json", "w"), indent=1)
+    with open("profiles/r1_summary.md", "w") as f:
+        f.write("# Round-1 ncu summary (B200, config 2: 1000 ZMWs, 10 kb x 10 passes, `bench.py --lanes 1`)\n\n")
+        f.write("Source: `gpurun_out/r1_full_*.ncu-rep` (`ncu --set full --clock-control none --import-source on`, first launch of "
+                "each kernel = the full-population launch) and `profiles/r1_launches_bench.csv` (`ncu --metrics "
+                "gpu__time_duration.sum --clock-control none` over `python bench.py --steps 1 --warmup 1`; per-launch times "
+                "are cold-cache and serialised, compare shares). Regenerate with `python scripts/summarize_profiles.py`.\n\n")
+        f.write("| kernel | duration ms | DRAM read GB | DRAM write GB | DRAM %peak | issue-active % | warp-instr | regs | warps active % | top stalls (% of samples) |\n|---|---|---|---|---|---|---|---|---|---|\n")
+        for k in KERNELS:
+            d = res[k]
+            f.write("| %s | %.2f | %.3f | %.3f | %.1f | %.1f | %.3g | %d | %.1f | %s |\n" % (
+                k, d["gpu__time_duration.sum"] * 1e3, d.get("dram__bytes_read.sum", 0) / 1e9,
+                d.get("dram__bytes_write.sum", 0) / 1e9, d.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 0),
+                d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0), d.get("smsp__inst_executed.sum", 0),
+                int(d.get("launch__registers_per_thread", 0)), d.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0),
+                ", ".join("%s %.0f" % kv for kv in d["stall_pct"].items())))
+        f.write("\nTensor pipe instructions: %s (none by design: no dense contraction on this path).\n\n" %
+                {k: res[k].get("sm__inst_executed_pipe_tensor.sum", 0) for k in KERNELS})
+        f.write("## Launch list of the bench command (share of summed kernel time)\n\n| kernel | launches | total ms | share | max ms |\n|---|---|---|---|---|\n")
+        for n, v in res["launch_list"].items():
+            f.write("| %s | %d | %.2f | %.3f | %.2f |\n" % (n, v["launches"], v["total_ms"], v["share"], v["max_ms"]))
+    print(open("profiles/r1_summary.md").read())
+
+
+if __name__ == "__main__":
+    main()
