@@ -50,6 +50,9 @@ static_assert(sizeof(DevZmw) == 32, "DevZmw layout");
 // range's first position in the flattened work list.
 struct ScoreRange { int32_t zmw; int32_t p_begin; int32_t p_end; int32_t pad_; int64_t first; };
 
+// Delta rows of one edited ZMW to re-index (arrow_remap_delta_kernel).
+struct RemapJob { int64_t delta_off; int64_t scratch_off; int32_t J_old, J_new; int32_t site_off, n_sites; };
+
 // One positive-scoring canonical mutation found by the pick kernel.
 struct Candidate { float score_hi; int32_t zmw; int32_t pos; int16_t type; int16_t base; double score; };
 

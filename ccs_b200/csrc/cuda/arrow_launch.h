@@ -15,6 +15,10 @@ void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items
 // evaluated independently), used by the tests to cross-check the factored kernel.
 void launch_score(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, double* delta,
                   cudaStream_t stream, bool generic = false);
+// re-index delta rows after template edits: sites[] = edit positions in NEW coordinates (ascending per job),
+// shifts[] = cumulative length change up to and including that edit
+void launch_remap_delta(const RemapJob* jobs, int n_jobs, const int32_t* sites, const int32_t* shifts, double* delta,
+                        double* scratch, cudaStream_t stream);
 void launch_pick(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, const double* delta,
                  Candidate* out, int cap, int* counter, cudaStream_t stream);
 void launch_qv(const ArrowBatchView& V, const double* delta, uint8_t* qv, long long n_items, const ScoreRange* ranges,

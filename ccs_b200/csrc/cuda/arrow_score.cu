@@ -636,6 +636,36 @@ __global__ void __launch_bounds__(256) arrow_qv_kernel(const ArrowBatchView V, c
     qv[zm.delta_off + p] = (uint8_t)llrint(q);
 }
 
+
+// Re-index the delta rows of ZMWs whose template was just edited: row p' of the new template takes
+// the row of the old position p = p' - shift(p'), shift = net length change of the edits before p'.
+// Rows near an edit are re-scored in the next round anyway; rows far from every edit keep their
+// delta-LLs (an edit more than `neighborhood` positions away does not change them beyond rounding),
+// which is what lets ConsensusQualities reuse them instead of re-scoring the whole template.
+__global__ void __launch_bounds__(256) arrow_remap_delta_kernel(const RemapJob* __restrict__ jobs, const int n_jobs,
+                                                                const int32_t* __restrict__ sites,
+                                                                const int32_t* __restrict__ shifts,
+                                                                const double* __restrict__ src, double* __restrict__ dst,
+                                                                const int to_scratch) {
+    const int job = blockIdx.y;
+    if (job >= n_jobs) return;
+    const RemapJob jb = jobs[job];
+    const int lane = threadIdx.x & 15;                       // 16 doubles per row
+    for (int p = blockIdx.x * 16 + (threadIdx.x >> 4); p <= jb.J_new; p += gridDim.x * 16) {
+        if (to_scratch) {
+            // number of edits whose new-coordinate site is <= p
+            int lo = 0, hi = jb.n_sites;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sites[jb.site_off + mid] <= p) lo = mid + 1; else hi = mid; }
+            const int sh = lo ? shifts[jb.site_off + lo - 1] : 0;
+            const int q = p - sh;
+            const double v = (q >= 0 && q <= jb.J_old) ? src[(size_t)(jb.delta_off + q) * kDeltaStride + lane] : 0.0;
+            dst[(size_t)(jb.scratch_off + p) * kDeltaStride + lane] = v;
+        } else {
+            dst[(size_t)(jb.delta_off + p) * kDeltaStride + lane] = src[(size_t)(jb.scratch_off + p) * kDeltaStride + lane];
+        }
+    }
+}
+
 }  // namespace
 
 void launch_score(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, double* delta,
@@ -660,4 +690,14 @@ void launch_qv(const ArrowBatchView& V, const double* delta, uint8_t* qv, long l
     arrow_qv_kernel<<<(unsigned)blocks, 256, 0, stream>>>(V, delta, qv, n_items, ranges, n_ranges);
 }
 
+}  // namespace ccs
+
+namespace ccs {
+void launch_remap_delta(const RemapJob* jobs, int n_jobs, const int32_t* sites, const int32_t* shifts, double* delta,
+                        double* scratch, cudaStream_t stream) {
+    if (n_jobs <= 0) return;
+    dim3 grid(64, n_jobs);
+    arrow_remap_delta_kernel<<<grid, 256, 0, stream>>>(jobs, n_jobs, sites, shifts, delta, scratch, 1);
+    arrow_remap_delta_kernel<<<grid, 256, 0, stream>>>(jobs, n_jobs, sites, shifts, scratch, delta, 0);
+}
 }  // namespace ccs

@@ -33,6 +33,7 @@ struct ccsgpu_ctx {
     size_t budget = 0;
     bool generic_score = false;
     int fill_cpl = 4;
+    bool reuse_scores = false;
     double ms_e2e = 0;
     int64_t n_zmws = 0;
     int device = 0;
@@ -91,6 +92,8 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
         ctx->engine->generic_score = ctx->generic_score;
         if (const char* e = std::getenv("CCS_B200_FILL_CPL")) ctx->fill_cpl = std::atoi(e);
         ctx->engine->fill_cells_per_lane = ctx->fill_cpl;
+        if (const char* e = std::getenv("CCS_B200_REUSE_SCORES")) ctx->reuse_scores = (e[0] != '0');
+        ctx->engine->reuse_scores = ctx->reuse_scores;
         ctx->budget = device_bytes_budget;
         int lanes = 4;
         if (const char* e = std::getenv("CCS_B200_LANES")) lanes = std::max(1, std::min(8, std::atoi(e)));
@@ -115,6 +118,7 @@ int ccsgpu_set_lanes(ccsgpu_ctx* ctx, int n_lanes) {
             l.draft.reset(new DraftEngine(ctx->device, 0));
             l.engine->generic_score = ctx->generic_score;
             l.engine->fill_cells_per_lane = ctx->fill_cpl;
+            l.engine->reuse_scores = ctx->reuse_scores;
             ctx->extra.push_back(std::move(l));
         }
     } catch (const std::exception& e) {

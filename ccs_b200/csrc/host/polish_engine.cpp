@@ -238,7 +238,7 @@ void ArrowEngine::upload_templates_and_reads() {
         dz.fwd_off = (int32_t)toff; dz.rev_off = (int32_t)(toff + tpl_cap_[z]);
         dz.J = J; dz.delta_off = drows; dz.pad_ = 0;
         toff += 2 * (int64_t)tpl_cap_[z];
-        drows += J + 1;
+        drows += tpl_cap_[z] + 2;   // fixed slot: delta rows survive template edits (re-indexed, not moved)
     }
     if (toff > 0x7fffffffll) throw OomError("template buffer exceeds 2 GiB; use smaller batches");
     h_tpl_.ensure((size_t)toff + 16);
@@ -333,7 +333,10 @@ void ArrowEngine::sync_statuses() {
     for (int r = 0; r < nr; ++r) {
         if (!reads_[r].active) continue;
         status_[r] = h_status_.p[r];
-        if (status_[r] != 0) reads_[r].active = 0;   // dropped for the rest of the polish (Integrator semantics)
+        if (status_[r] != 0) {
+            reads_[r].active = 0;   // dropped for the rest of the polish (Integrator semantics)
+            if (stats.n_score > score_mark_) zstate_[reads_[r].zmw].stale_scores = true;
+        }
     }
 }
 
@@ -448,6 +451,7 @@ void ArrowEngine::download_delta(int z, double* out) {
 void ArrowEngine::polish(const PolishParams& pp) {
     ab_tol_ = pp.ab_mismatch_tol;
     const int nz = (int)zstate_.size();
+    score_mark_ = stats.n_score;
     CCS_CUDA(cudaEventRecord(evA_, stream_));   // inputs are resident: load() has been issued on this stream
     fill();
     auto check_usable = [&](int z) {
@@ -546,6 +550,10 @@ void ArrowEngine::polish(const PolishParams& pp) {
                 return;
             }
             zs.n_applied += (int)best.size();
+            zs.J_before = (int32_t)zs.tpl.size();
+            zs.remap_sites = zs.sites;
+            zs.remap_shifts.clear();
+            { int acc = 0; for (const auto& m : best) { acc += m.type == 1 ? 1 : (m.type == 2 ? -1 : 0); zs.remap_shifts.push_back(acc); } }
             // span bookkeeping of the ZMW's reads (Integrator::ApplyMutations)
             for (int r = zs.read_begin; r < zs.read_end; ++r) {
                 DevRead& rd = reads_[r];
@@ -563,6 +571,7 @@ void ArrowEngine::polish(const PolishParams& pp) {
         const bool any_applied = applied_flag.load() != 0;
         if (!any_applied) break;
         upload_templates_and_reads();
+        if (reuse_scores) remap_deltas();
         fill();
         for (int z = 0; z < nz; ++z) if (!zstate_[z].done) check_usable(z);
     }
@@ -573,6 +582,35 @@ void ArrowEngine::polish(const PolishParams& pp) {
     cudaEventElapsedTime(&ms, evA_, evB_);
     stats.ms_resident += ms;
     stats.n_zmws += nz;
+}
+
+// Re-index the stored delta rows of the ZMWs edited in this round (see arrow_remap_delta_kernel).
+void ArrowEngine::remap_deltas() {
+    std::vector<RemapJob> jobs;
+    std::vector<int32_t> sites, shifts;
+    int64_t scratch = 0;
+    for (size_t z = 0; z < zstate_.size(); ++z) {
+        ZmwState& zs = zstate_[z];
+        if (!zs.dirty || zs.remap_sites.empty()) continue;
+        RemapJob j;
+        j.delta_off = zmws_[z].delta_off; j.scratch_off = scratch; j.J_old = zs.J_before; j.J_new = (int32_t)zs.tpl.size();
+        j.site_off = (int32_t)sites.size(); j.n_sites = (int32_t)zs.remap_sites.size();
+        sites.insert(sites.end(), zs.remap_sites.begin(), zs.remap_sites.end());
+        shifts.insert(shifts.end(), zs.remap_shifts.begin(), zs.remap_shifts.end());
+        scratch += j.J_new + 2;
+        jobs.push_back(j);
+        zs.remap_sites.clear(); zs.remap_shifts.clear();
+    }
+    if (jobs.empty() || !d_delta_.p) return;
+    d_delta_scratch_.ensure((size_t)(scratch + 2) * kDeltaStride);
+    d_remap_jobs_.ensure(jobs.size()); d_remap_sites_.ensure(sites.size() + 1); d_remap_shifts_.ensure(shifts.size() + 1);
+    // small pageable copies: synchronous with respect to the host buffers, ordered on the engine stream
+    CCS_CUDA(cudaMemcpyAsync(d_remap_jobs_.p, jobs.data(), sizeof(RemapJob) * jobs.size(), cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_remap_sites_.p, sites.data(), 4 * sites.size(), cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_remap_shifts_.p, shifts.data(), 4 * shifts.size(), cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaStreamSynchronize(stream_));
+    launch_remap_delta(d_remap_jobs_.p, (int)jobs.size(), d_remap_sites_.p, d_remap_shifts_.p, d_delta_.p,
+                       d_delta_scratch_.p, stream_);
 }
 
 int64_t ArrowEngine::count_canonical(const std::vector<uint8_t>& t, int b, int e) const {
@@ -588,17 +626,29 @@ int64_t ArrowEngine::count_canonical(const std::vector<uint8_t>& t, int b, int e
 
 void ArrowEngine::consensus_qvs() {
     const int nz = (int)zstate_.size();
-    std::vector<ScoreRange> ranges;
-    int64_t first = 0;
+    std::vector<ScoreRange> ranges, rescoring;
+    int64_t first = 0, first_rs = 0;
     for (int z = 0; z < nz; ++z) {
         const ZmwState& zs = zstate_[z];
         if (zs.failed || zs.tpl.empty()) continue;
         ranges.push_back(ScoreRange{z, 0, (int32_t)zs.tpl.size(), 0, first});
         first += (int64_t)zs.tpl.size();
+        // every position was last scored after all edits within `neighborhood` of it had been applied, unless the
+        // ZMW stopped without converging or lost a read after scoring began: only those are scored again
+        if (!reuse_scores || !zs.converged || zs.stale_scores) {
+            rescoring.push_back(ScoreRange{z, 0, (int32_t)zs.tpl.size(), 0, first_rs});
+            first_rs += (int64_t)zs.tpl.size();
+        }
     }
     for (int z = 0; z < nz; ++z) qv_[z].clear();
     if (ranges.empty()) return;
-    score_ranges(ranges, first);
+    if (!rescoring.empty()) score_ranges(rescoring, first_rs);
+    // the QV kernel walks every position of every live ZMW
+    d_ranges_.ensure(ranges.size());
+    h_ranges_.ensure(ranges.size());
+    std::memcpy(h_ranges_.p, ranges.data(), sizeof(ScoreRange) * ranges.size());
+    CCS_CUDA(cudaMemcpyAsync(d_ranges_.p, h_ranges_.p, sizeof(ScoreRange) * ranges.size(), cudaMemcpyHostToDevice, stream_));
+    d_delta_.ensure((size_t)(total_delta_rows_ + 2) * kDeltaStride, budget_);
     d_qv_.ensure((size_t)total_delta_rows_ + 16, budget_);
     h_qv_.ensure((size_t)total_delta_rows_ + 16);
     const ArrowBatchView V = view();

@@ -46,6 +46,9 @@ struct ZmwState {
     std::vector<uint8_t> tpl;          // current forward template
     int32_t read_begin = 0, read_end = 0;
     bool converged = false, failed = false, done = false;
+    bool stale_scores = false;         // a read was dropped after scoring began: stored delta-LLs no longer add up
+    std::vector<int32_t> remap_sites, remap_shifts;   // this round's edits (new coordinates, cumulative shift)
+    int32_t J_before = 0;
     bool dirty = true;                 // template changed since the last alpha/beta fill of its reads
     int32_t iterations = 0, n_applied = 0;
     int64_t n_tested = 0;
@@ -100,6 +103,10 @@ public:
     int device() const { return device_; }
     bool timing_enabled = true;
     int host_threads = 8;         // threads for the per-ZMW host pieces of a round
+    // ConsensusQualities reuses the delta-LLs of positions farther than `neighborhood` from every edit instead of
+    // re-scoring the whole template (-35 % scoring work).  NOT exact: in repeats an edit reaches further, measured
+    // 28 of 1.66 M positions off by more than 1 QV, so it is off by default (CCS_B200_REUSE_SCORES=1 enables it).
+    bool reuse_scores = false;
     int fill_cells_per_lane = 4;  // lane mapping of the fill kernels (4, 8, 16, 32)
     bool generic_score = false;   // use the unfactored reference scoring kernel (tests)
 
@@ -116,6 +123,7 @@ private:
     int64_t count_canonical(const std::vector<uint8_t>& t, int b, int e) const;
     void upload_templates_and_reads();       // (re)build DevRead/DevZmw/template buffer from host state
     void sync_statuses();
+    void remap_deltas();
     ArrowBatchView view() const;
 
     int device_;
@@ -138,6 +146,7 @@ private:
     std::vector<int32_t> tpl_cap_;           // per-ZMW template capacity in the device buffer
     int64_t total_cols_ = 0, total_delta_rows_ = 0;
     double ab_tol_ = 1e-3;
+    int64_t score_mark_ = 0;                 // stats.n_score when the current polish() began
     int n_ranges_ = 0;
     int64_t n_range_items_ = 0;
 
@@ -148,7 +157,9 @@ private:
     DevBuf<DevZmw> d_zmws_;
     DevBuf<ColInfo> d_colinfo_;
     DevBuf<int32_t> d_bexp_, d_status_, d_order_, d_counter_;
-    DevBuf<double> d_ll_alpha_, d_ll_beta_, d_base_ll_, d_delta_;
+    DevBuf<double> d_ll_alpha_, d_ll_beta_, d_base_ll_, d_delta_, d_delta_scratch_;
+    DevBuf<RemapJob> d_remap_jobs_;
+    DevBuf<int32_t> d_remap_sites_, d_remap_shifts_;
     DevBuf<ScoreRange> d_ranges_;
     DevBuf<Candidate> d_cand_;
     DevBuf<uint8_t> d_qv_;
