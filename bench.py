@@ -238,8 +238,11 @@ def main():
     sampler.start()
     t0 = time.perf_counter()
     results = []
+    step_s = []
     for b, _ in batches:
+        ts = time.perf_counter()
         results.append(run_step(b))
+        step_s.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -297,7 +300,8 @@ def main():
                        "value_def": "e2e wall time of the calls minus the batch-upload span (inputs resident)"},
             "hifi_zmws_per_s": n_hifi / t_res, "hifi_fraction": n_hifi / n_total,
             "e2e": {"value": n_total / t_e2e, "unit": "ZMW/s", "h2d_bytes_per_step": st["h2d_bytes"] / args.steps,
-                    "d2h_bytes_per_step": st["d2h_bytes"] / args.steps, "wall_s": wall},
+                    "d2h_bytes_per_step": st["d2h_bytes"] / args.steps, "wall_s": wall,
+                    "step_s": [round(x, 4) for x in step_s]},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "arrow_fill_alpha_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -352,7 +352,7 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const f
         codeL1[x] = (row1 + 1 >= sq2 && row1 + 1 < sq2 + 32) ? c1n : kC4Sentinel;
     }
     float Xdel[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll
     for (int b = 0; b < 4; ++b) {
         const int ci = 4 * tm1 + b;
         const float4 tri = R.tr[ci];
@@ -411,6 +411,25 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const f
     }
 }
 
+// Running product of the per-read link values of one mutation slot, kept as a mantissa in [1,2) times
+// 2^pexp (pexp also absorbs the scale exponents of the stored columns): sum_r log(val_r) costs one FMUL and
+// a few integer ops per read instead of a logf and fp64 adds; a non-positive value zeroes the product (-inf).
+__device__ __forceinline__ void prod_mul(float& prod, int& pexp, float val, const int e) {
+    int adj = e;
+    if (val < 1.17549435e-38f) { val *= 1.8446744073709552e19f; adj -= 64; }   // subnormal -> normal
+    const unsigned u = __float_as_uint(val);
+    const bool nz = val > 0.f;
+    float p = prod * __uint_as_float((u & 0x007fffffu) | 0x3f800000u);
+    int ev = (int)(u >> 23) - 127 + adj;
+    if (p >= 2.f) { p *= 0.5f; ev += 1; }
+    prod = nz ? p : 0.f;
+    pexp += nz ? ev : 0;
+}
+
+__device__ __forceinline__ double prod_dll(const float prod, const int pexp, const double base_sum) {
+    return (prod > 0.f) ? (double)logf(prod) + 0.6931471805599453094 * (double)pexp - base_sum : -INFINITY;
+}
+
 __device__ __forceinline__ double dll_of(const float val, const int e, const double base_ll) {
     return (val > 0.f) ? (double)logf(val) + 0.6931471805599453094 * (double)e - base_ll : -INFINITY;
 }
@@ -448,11 +467,15 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
     n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 16));
     const int tbase = have ? V.tpl[zm.fwd_off + p] : 0;
 
-    double acc_sd[5], acc_ia[4], acc_ib[4];
+    // per-slot running products {SUB A,C,G,T, DEL}, {INS A,C,G,T}, {INS' A,C,G,T} and, per group, the sum of the
+    // contributing reads' base log-likelihoods
+    float pr_sd[5], pr_ia[4], pr_ib[4];
+    int px_sd[5], px_ia[4], px_ib[4];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) acc_sd[k] = 0.0;
+    for (int k = 0; k < 5; ++k) { pr_sd[k] = 1.f; px_sd[k] = 0; }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { acc_ia[k] = 0.0; acc_ib[k] = 0.0; }
+    for (int k = 0; k < 4; ++k) { pr_ia[k] = 1.f; px_ia[k] = 0; pr_ib[k] = 1.f; px_ib[k] = 0; }
+    double bs_sd = 0.0, bs_ia = 0.0, bs_ib = 0.0;
 
     for (int k = 0; k < n_max; ++k) {
         const bool has_read = k < n_reads;
@@ -494,19 +517,16 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
             fo.del = 0.f; fo.e_sd = 0; fo.e_in = 0;
             fast_eval(R, g, s_emm, s_emi, q_sd, interior, fo);
             if (interior) {
-                const int t_loc = rd.strand ? 3 - tbase : tbase;
-                double ds[4], di[4];
+                bs_sd += base_ll;
+                if (rd.strand) bs_ib += base_ll; else bs_ia += base_ll;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    ds[b] = (b == t_loc) ? 0.0 : dll_of(fo.sub[b], fo.e_sd, base_ll);
-                    di[b] = dll_of(fo.ins[b], fo.e_in, base_ll);
+                for (int b = 0; b < 4; ++b) {                        // b = forward-strand base of the slot
+                    const float vs = rd.strand ? fo.sub[3 - b] : fo.sub[b];
+                    const float vi = rd.strand ? fo.ins[3 - b] : fo.ins[b];
+                    if (b != tbase) prod_mul(pr_sd[b], px_sd[b], vs, fo.e_sd);
+                    if (rd.strand) prod_mul(pr_ib[b], px_ib[b], vi, fo.e_in); else prod_mul(pr_ia[b], px_ia[b], vi, fo.e_in);
                 }
-                acc_sd[4] += dll_of(fo.del, fo.e_sd, base_ll);
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    acc_sd[b] += rd.strand ? ds[3 - b] : ds[b];
-                    if (rd.strand) acc_ib[b] += di[3 - b]; else acc_ia[b] += di[b];
-                }
+                prod_mul(pr_sd[4], px_sd[4], fo.del, fo.e_sd);
             }
         }
         if (__any_sync(kFullMask, gen_sd) || __any_sync(kFullMask, gen_in)) {
@@ -520,6 +540,8 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
                 word_sd |= b1 << (2 * x);
                 word_in |= b2 << (2 * x);
             }
+            if (gen_sd) bs_sd += base_ll;
+            if (gen_in) bs_ia += base_ll;
 #pragma unroll 1
             for (int m = 0; m < 8; ++m) {
                 // m = 0..2 SUB, 3 DEL, 4..7 INS
@@ -530,20 +552,19 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
                 const bool lv = is_ins ? gen_in : (gen_sd && (m != 3 || rd.J >= 3));
                 if (!__any_sync(kFullMask, is_ins ? gen_in : gen_sd)) continue;
                 int e;
-                const float val = eval_mutation(R, g, s_emm, s_emi, is_ins ? word_in : word_sd, type,
-                                                is_ins ? q_in : q_sd, bl, lv, e);
-                double dll = dll_of(val, e, base_ll);
-                if (m == 3 && rd.J < 3) dll = -INFINITY;
+                float val = eval_mutation(R, g, s_emm, s_emi, is_ins ? word_in : word_sd, type,
+                                          is_ins ? q_in : q_sd, bl, lv, e);
+                if (m == 3 && rd.J < 3) val = 0.f;     // deleting one of two template bases leaves no template
                 const bool take = is_ins ? gen_in : gen_sd;
                 if (take) {
                     if (m < 3) {
 #pragma unroll
-                        for (int s2 = 0; s2 < 4; ++s2) if (s2 == bf) acc_sd[s2] += dll;
+                        for (int s2 = 0; s2 < 4; ++s2) if (s2 == bf) prod_mul(pr_sd[s2], px_sd[s2], val, e);
                     } else if (m == 3) {
-                        acc_sd[4] += dll;
+                        prod_mul(pr_sd[4], px_sd[4], val, e);
                     } else {
 #pragma unroll
-                        for (int s2 = 0; s2 < 4; ++s2) if (s2 == bf) acc_ia[s2] += dll;
+                        for (int s2 = 0; s2 < 4; ++s2) if (s2 == bf) prod_mul(pr_ia[s2], px_ia[s2], val, e);
                     }
                 }
             }
@@ -551,14 +572,15 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
     }
     if (have && g == 0) {
         double* out = delta + (size_t)(zm.delta_off + p) * kDeltaStride;
+        // slots nobody contributed to keep delta-LL 0 (product 1, exponent 0, no base term)
 #pragma unroll
-        for (int k = 0; k < 5; ++k) out[k] = acc_sd[k];
+        for (int k = 0; k < 5; ++k) out[k] = (k < 4 && k == tbase) ? 0.0 : prod_dll(pr_sd[k], px_sd[k], bs_sd);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) out[5 + k] = acc_ia[k];
+        for (int k = 0; k < 4; ++k) out[5 + k] = prod_dll(pr_ia[k], px_ia[k], bs_ia);
         // reverse-strand insertions before the local position are forward INS(p+1)
         double* nxt = out + kDeltaStride;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) nxt[9 + k] = acc_ib[k];
+        for (int k = 0; k < 4; ++k) nxt[9 + k] = prod_dll(pr_ib[k], px_ib[k], bs_ib);
         if (p == p_begin) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) out[9 + k] = 0.0;

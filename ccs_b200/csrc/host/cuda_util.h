@@ -42,7 +42,7 @@ struct DevBuf {
     // grow-only; contents are NOT preserved
     void ensure(size_t n, size_t budget = 0) {
         if (n <= cap) return;
-        size_t want = n + n / 8 + 64;
+        size_t want = n + n / 4 + 64;   // generous slack: a regrow frees + reallocates and stalls every lane
         if (budget && budget_used && *budget_used - cap * sizeof(T) + want * sizeof(T) > budget) want = n;
         if (budget && budget_used && *budget_used - cap * sizeof(T) + want * sizeof(T) > budget)
             throw OomError("device budget exceeded");
@@ -63,7 +63,7 @@ struct PinBuf {
     PinBuf& operator=(const PinBuf&) = delete;
     void ensure(size_t n) {
         if (n <= cap) return;
-        const size_t want = n + n / 8 + 64;
+        const size_t want = n + n / 4 + 64;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         CCS_CUDA(cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault));
