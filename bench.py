@@ -27,7 +27,7 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--zmws", type=int, default=1000, help="ZMWs per step per GPU")
@@ -35,7 +35,10 @@ def parse():
     ap.add_argument("--draft-error", type=float, default=0.02)
     ap.add_argument("--cpu-sample", type=int, default=0, help="ZMWs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=0, help="concurrent engine lanes per GPU (0 = library default)")
+    ap.add_argument("--lanes", type=int, default=3, help="concurrent engine lanes per context (0 = library default)")
+    ap.add_argument("--contexts", type=int, default=2,
+                    help="GPU contexts per rank; steps are dealt round-robin to the contexts and run concurrently "
+                         "(pipelined batches, as a reader thread feeding two stage instances would)")
     ap.add_argument("--stage", default="ccs", choices=["ccs", "polish"],
                     help="ccs = whole per-ZMW hot path (filter + SparsePoa draft + Arrow polish + QVs); "
                          "polish = Polish Stage only on corrupted-truth drafts")
@@ -206,10 +209,13 @@ def main():
     model = sim.synthetic_model()
     cfg = sim.get_config(args.config)
     threads = max(1, (os.cpu_count() or 8) // max(world, 1))
-    os.environ["CCS_B200_THREADS"] = str(threads)   # host threads of this rank's stage engines
-    ctx = api.Context(model, device=local)
+    # host threads of each stage context of this rank
+    os.environ["CCS_B200_THREADS"] = str(max(1, threads // max(1, args.contexts)))
+    ctxs = [api.Context(model, device=local) for _ in range(max(1, args.contexts))]
+    ctx = ctxs[0]
     if args.lanes > 0:
-        ctx.set_lanes(args.lanes)
+        for c in ctxs:
+            c.set_lanes(args.lanes)
     pcfg = ctx.default_polish_cfg()
 
     def barrier():
@@ -225,35 +231,58 @@ def main():
 
     dcfg = ctx.default_draft_cfg()
 
-    def run_step(b):
-        return ctx.ccs(b, dcfg, pcfg) if args.stage == "ccs" else ctx.polish(b, pcfg)
+    def run_step(b, c=None):
+        c = c or ctx
+        return c.ccs(b, dcfg, pcfg) if args.stage == "ccs" else c.polish(b, pcfg)
 
     for w in range(args.warmup):
         b, _ = step_batch(w)
-        run_step(b)
+        for c in ctxs:
+            run_step(b, c)
     batches = [step_batch(args.warmup + k) for k in range(args.steps)]
-    ctx.stats(reset=True)
+    for c in ctxs:
+        c.stats(reset=True)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    results = []
-    step_s = []
-    for b, _ in batches:
-        ts = time.perf_counter()
-        results.append(run_step(b))
-        step_s.append(time.perf_counter() - ts)
+    results = [None] * len(batches)
+    step_s = [0.0] * len(batches)
+
+    next_step = [0]
+    qlock = threading.Lock()
+
+    def worker(ci):   # each context takes the next unprocessed step as soon as it is free
+        while True:
+            with qlock:
+                k = next_step[0]
+                next_step[0] += 1
+            if k >= len(batches):
+                return
+            ts = time.perf_counter()
+            results[k] = run_step(batches[k][0], ctxs[ci])
+            step_s[k] = time.perf_counter() - ts
+
+    if len(ctxs) == 1:
+        worker(0)
+    else:
+        ths = [threading.Thread(target=worker, args=(ci,)) for ci in range(len(ctxs))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     barrier()
-    st = ctx.stats()
+    sts = [c.stats() for c in ctxs]
+    st = {k: sum(x[k] for x in sts) for k in sts[0]}
     lanes = args.lanes if args.lanes > 0 else int(os.environ.get("CCS_B200_LANES", "4"))
-    t_e2e = st["ms_e2e"] / 1e3
+    t_e2e = wall if len(ctxs) > 1 else st["ms_e2e"] / 1e3   # overlapping contexts: wall clock of the K steps
     # `value`: same run with the batch upload taken out (inputs resident): the initial H2D of the packed
     # read codes / templates is the only input traffic; its CUDA-event span (per lane, lanes overlap) is
     # subtracted from the wall time of the calls
-    t_res = t_e2e - st["ms_h2d"] / 1e3 / max(lanes, 1)
+    t_res = t_e2e - st["ms_h2d"] / 1e3 / max(lanes * len(ctxs), 1)
     # per-kernel timing pass: one more step on a single lane (kernels strictly serial, no overlap), used
     # only for the roofline object and the kernel_ms breakdown
     ctx.set_lanes(1)
@@ -296,7 +325,7 @@ def main():
             "config": {"workload": WORKLOADS.get(args.config, str(args.config)), "zmws_per_step_per_gpu": args.zmws,
                        "stage": STAGE_DESC[args.stage],
                        "l2": "inputs larger than L2 (tens of GB of DP bands per step, new ZMWs every step)",
-                       "parallelism": f"zmw-range-shard x{world}, no collective", "lanes_per_gpu": lanes,
+                       "parallelism": f"zmw-range-shard x{world}, no collective", "lanes_per_gpu": lanes, "contexts_per_gpu": len(ctxs),
                        "value_def": "e2e wall time of the calls minus the batch-upload span (inputs resident)"},
             "hifi_zmws_per_s": n_hifi / t_res, "hifi_fraction": n_hifi / n_total,
             "e2e": {"value": n_total / t_e2e, "unit": "ZMW/s", "h2d_bytes_per_step": st["h2d_bytes"] / args.steps,
@@ -327,7 +356,8 @@ def main():
                                     "sample": f"first {n} ZMWs of step 0, {cores} threads, {dt:.1f} s",
                                     "consensus_identical": f"{same}/{n}"}
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -24,7 +26,7 @@ struct Options {
     std::string in, out, report;
     ccs_draft_cfg d;
     ccs_polish_cfg p;
-    int chunk_i = 1, chunk_n = 1, batch = 512, device = 0, log_level = 1;
+    int chunk_i = 1, chunk_n = 1, batch = 512, device = 0, log_level = 1, pipeline = 2;
 };
 
 void usage() {
@@ -41,6 +43,7 @@ void usage() {
                  "  --report-file FILE   Where to write the results report. [<out prefix>.ccs_report.txt]\n"
                  "  --batch-size INT     ZMWs per GPU batch. [512]\n"
                  "  --device INT         CUDA device. [0]\n"
+                 "  --pipeline INT       Batches in flight (GPU stage instances fed by the reader). [2]\n"
                  "  --log-level STR      Set log level: DEBUG INFO WARN. [WARN]\n");
 }
 
@@ -63,6 +66,7 @@ bool parse(int argc, char** argv, Options& o) {
         else if (a == "--report-file") o.report = val("--report-file");
         else if (a == "--batch-size") o.batch = std::max(1, std::atoi(val("--batch-size")));
         else if (a == "--device") o.device = std::atoi(val("--device"));
+        else if (a == "--pipeline") o.pipeline = std::max(1, std::min(4, std::atoi(val("--pipeline"))));
         else if (a == "-j" || a == "--num-threads") val("-j");     // accepted for drop-in compatibility; host threads follow the core count
         else if (a == "--log-level") { std::string l = val("--log-level"); o.log_level = l == "DEBUG" ? 3 : (l == "INFO" ? 2 : 1); }
         else if (a == "--chunk") {
@@ -167,9 +171,20 @@ int main(int argc, char** argv) {
     }
     std::vector<uint8_t> model(ccs_model_sizeof());
     ccs_model_synthetic(model.data());          // the only chemistry this build ships (DESIGN.md "Model")
-    int cerr = 0;
-    ccsgpu_ctx* ctx = ccsgpu_create(o.device, model.data(), 0, &cerr);
-    if (!ctx) { std::fprintf(stderr, "ccs: %s\n", ccsgpu_last_error(nullptr)); return 1; }
+    // `pipeline` stage instances (one ccsgpu_ctx each); the reader deals batches to them round-robin, they run
+    // concurrently, and results are written in input order (reader -> stages -> ordered writer, docs/img/ccs-impl.png)
+    std::vector<ccsgpu_ctx*> ctxs;
+    if (!std::getenv("CCS_B200_THREADS")) {   // split the host cores between the stage instances
+        const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
+        setenv("CCS_B200_THREADS", std::to_string(std::max(1u, hc / (unsigned)o.pipeline)).c_str(), 1);
+    }
+    for (int k = 0; k < o.pipeline; ++k) {
+        int cerr = 0;
+        ccsgpu_ctx* c = ccsgpu_create(o.device, model.data(), 0, &cerr);
+        if (!c) { std::fprintf(stderr, "ccs: %s\n", ccsgpu_last_error(nullptr)); return 1; }
+        if (o.pipeline > 1) ccsgpu_set_lanes(c, 3);
+        ctxs.push_back(c);
+    }
     std::string cl;
     for (int k = 0; k < argc; ++k) { if (k) cl += ' '; cl += argv[k]; }
     CcsBamWriter writer;
@@ -177,65 +192,84 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "ccs: cannot write %s\n", o.out.c_str());
         return 1;
     }
+    struct BatchIO {
+        std::vector<ZmwSubreads> zmws;
+        std::vector<int32_t> zmw_read_off, hole, status, npass, iters, napp, rstatus;
+        std::vector<int64_t> read_off, seq_off, ntest;
+        std::vector<uint8_t> codes, cx, seq, qv;
+        std::vector<float> snr, rq;
+        std::vector<double> rll;
+        std::string err;
+    };
+    auto process = [&](ccsgpu_ctx* ctx, BatchIO& B) -> int {
+        const int nz = (int)B.zmws.size();
+        B.zmw_read_off.assign(1, 0); B.read_off.assign(1, 0);
+        size_t maxlen = 1;
+        for (const auto& zz : B.zmws) {
+            for (const auto& rd : zz.reads) {
+                B.codes.insert(B.codes.end(), rd.codes.begin(), rd.codes.end());
+                B.read_off.push_back((int64_t)B.codes.size());
+                B.cx.push_back(rd.cx);
+                maxlen = std::max(maxlen, rd.codes.size());
+            }
+            B.zmw_read_off.push_back((int32_t)B.cx.size());
+            B.snr.insert(B.snr.end(), zz.snr, zz.snr + 4);
+            B.hole.push_back(zz.hole);
+        }
+        const int nr = (int)B.cx.size();
+        ccs_batch b{nz, nr, B.zmw_read_off.data(), B.read_off.data(), B.codes.data(), B.snr.data(), B.cx.data(), B.hole.data()};
+        int64_t cap = (int64_t)maxlen * 2 * nz + 1024;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            B.seq_off.assign(nz + 1, 0); B.seq.assign(cap, 0); B.qv.assign(cap, 0); B.rq.assign(nz, 0); B.status.assign(nz, 0);
+            B.npass.assign(nz, 0); B.iters.assign(nz, 0); B.napp.assign(nz, 0); B.ntest.assign(nz, 0);
+            B.rll.assign(nr, 0); B.rstatus.assign(nr, 0);
+            ccs_results r{cap, B.seq_off.data(), B.seq.data(), B.qv.data(), B.rq.data(), B.status.data(), B.npass.data(),
+                          B.iters.data(), B.napp.data(), B.ntest.data(), B.rll.data(), B.rstatus.data()};
+            const int rc = ccsgpu_ccs(ctx, &b, &o.d, &o.p, &r);
+            if (rc == CCS_ERR_CAPACITY) { cap = r.seq_cap + 1024; continue; }
+            if (rc != CCS_OK) { B.err = ccsgpu_last_error(ctx); return rc; }
+            return CCS_OK;
+        }
+        B.err = "result capacity";
+        return CCS_ERR_CAPACITY;
+    };
     Report rep;
     const auto t0 = std::chrono::steady_clock::now();
-    std::vector<ZmwSubreads> batch;
-    std::vector<int32_t> zmw_read_off, hole, status, npass, iters, napp, rstatus;
-    std::vector<int64_t> read_off, seq_off, ntest;
-    std::vector<uint8_t> codes, cx, seq, qv;
-    std::vector<float> snr, rq;
-    std::vector<double> rll;
     int64_t z_index = 0;
     bool more = true;
     while (more) {
-        batch.clear();
-        ZmwSubreads z;
-        while ((int)batch.size() < o.batch && (more = reader.next_zmw(z))) {
-            if (z_index >= z_begin && z_index < z_end) batch.push_back(std::move(z));
-            ++z_index;
-            if (z_index >= z_end) { more = false; break; }
-        }
-        if (batch.empty()) break;
-        const int nz = (int)batch.size();
-        zmw_read_off.assign(1, 0); read_off.assign(1, 0);
-        codes.clear(); cx.clear(); snr.clear(); hole.clear();
-        size_t maxlen = 1;
-        for (const auto& zz : batch) {
-            for (const auto& rd : zz.reads) {
-                codes.insert(codes.end(), rd.codes.begin(), rd.codes.end());
-                read_off.push_back((int64_t)codes.size());
-                cx.push_back(rd.cx);
-                maxlen = std::max(maxlen, rd.codes.size());
+        std::vector<BatchIO> wave(ctxs.size());
+        size_t n_wave = 0;
+        for (; n_wave < ctxs.size() && more; ++n_wave) {
+            BatchIO& B = wave[n_wave];
+            ZmwSubreads z;
+            while ((int)B.zmws.size() < o.batch && (more = reader.next_zmw(z))) {
+                if (z_index >= z_begin && z_index < z_end) B.zmws.push_back(std::move(z));
+                ++z_index;
+                if (z_index >= z_end) { more = false; break; }
             }
-            zmw_read_off.push_back((int32_t)cx.size());
-            snr.insert(snr.end(), zz.snr, zz.snr + 4);
-            hole.push_back(zz.hole);
+            if (B.zmws.empty()) break;
         }
-        const int nr = (int)cx.size();
-        ccs_batch b{nz, nr, zmw_read_off.data(), read_off.data(), codes.data(), snr.data(), cx.data(), hole.data()};
-        int64_t cap = (int64_t)maxlen * 2 * nz + 1024;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            seq_off.assign(nz + 1, 0); seq.assign(cap, 0); qv.assign(cap, 0); rq.assign(nz, 0); status.assign(nz, 0);
-            npass.assign(nz, 0); iters.assign(nz, 0); napp.assign(nz, 0); ntest.assign(nz, 0); rll.assign(nr, 0); rstatus.assign(nr, 0);
-            ccs_results r{cap, seq_off.data(), seq.data(), qv.data(), rq.data(), status.data(), npass.data(), iters.data(),
-                          napp.data(), ntest.data(), rll.data(), rstatus.data()};
-            const int rc = ccsgpu_ccs(ctx, &b, &o.d, &o.p, &r);
-            if (rc == CCS_ERR_CAPACITY) { cap = r.seq_cap + 1024; continue; }
-            if (rc != CCS_OK) { std::fprintf(stderr, "ccs: %s\n", ccsgpu_last_error(ctx)); return 1; }
-            break;
-        }
-        for (int zi = 0; zi < nz; ++zi) {
-            ++rep.input;
-            ++rep.counts[status[zi]];
-            if (status[zi] != CCS_ZMW_SUCCESS) continue;
-            ++rep.pass;
-            CcsRecord rec;
-            rec.hole = hole[zi]; rec.np = npass[zi]; rec.rq = rq[zi]; rec.ec = (float)(npass[zi] + 1);
-            std::memcpy(rec.snr, &snr[4 * zi], sizeof(rec.snr));
-            rec.seq = seq.data() + seq_off[zi]; rec.qv = qv.data() + seq_off[zi];
-            rec.len = (int32_t)(seq_off[zi + 1] - seq_off[zi]);
-            writer.write(rec);
-            rep.lens.push_back(rec.len); rep.nps.push_back(rec.np); rep.rqs.push_back(rec.rq);
+        if (n_wave == 0) break;
+        std::vector<std::future<int>> fut;
+        for (size_t k = 0; k < n_wave; ++k)
+            fut.push_back(std::async(std::launch::async, [&, k]() { return process(ctxs[k], wave[k]); }));
+        for (size_t k = 0; k < n_wave; ++k) {
+            if (fut[k].get() != CCS_OK) { std::fprintf(stderr, "ccs: %s\n", wave[k].err.c_str()); return 1; }
+            BatchIO& B = wave[k];
+            for (int zi = 0; zi < (int)B.zmws.size(); ++zi) {
+                ++rep.input;
+                ++rep.counts[B.status[zi]];
+                if (B.status[zi] != CCS_ZMW_SUCCESS) continue;
+                ++rep.pass;
+                CcsRecord rec;
+                rec.hole = B.hole[zi]; rec.np = B.npass[zi]; rec.rq = B.rq[zi]; rec.ec = (float)(B.npass[zi] + 1);
+                std::memcpy(rec.snr, &B.snr[4 * zi], sizeof(rec.snr));
+                rec.seq = B.seq.data() + B.seq_off[zi]; rec.qv = B.qv.data() + B.seq_off[zi];
+                rec.len = (int32_t)(B.seq_off[zi + 1] - B.seq_off[zi]);
+                writer.write(rec);
+                rep.lens.push_back(rec.len); rep.nps.push_back(rec.np); rep.rqs.push_back(rec.rq);
+            }
         }
         if (o.log_level >= 2) {
             const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -248,6 +282,6 @@ int main(int argc, char** argv) {
     if (o.log_level >= 1)
         std::fprintf(stderr, "ZMWs input: %lld  ZMWs pass filters: %lld  elapsed: %.2f s  (%.1f ZMW/s)\n", (long long)rep.input,
                      (long long)rep.pass, el, rep.input / std::max(el, 1e-9));
-    ccsgpu_destroy(ctx);
+    for (ccsgpu_ctx* c : ctxs) ccsgpu_destroy(c);
     return 0;
 }
