@@ -211,7 +211,9 @@ def main():
     threads = max(1, (os.cpu_count() or 8) // max(world, 1))
     # host threads of each stage context of this rank
     os.environ["CCS_B200_THREADS"] = str(max(1, threads // max(1, args.contexts)))
-    ctxs = [api.Context(model, device=local) for _ in range(max(1, args.contexts))]
+    free_b, _tot = torch.cuda.mem_get_info()
+    budget = int(free_b * 0.85 / max(1, args.contexts))          # device bytes each stage context may use
+    ctxs = [api.Context(model, device=local, budget_bytes=budget) for _ in range(max(1, args.contexts))]
     ctx = ctxs[0]
     if args.lanes > 0:
         for c in ctxs:

@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
         acol[0] = make_float4(v[0], v[1], v[2], v[3]);
         if (g == 0) cinfo[0] = ColInfo{0, 0};
     }
-    const int t0 = tp[0], t1 = tp[min(1, Jc - 1)];
-    int t2 = tp[min(2, Jc - 1)];
+    const int t0 = tp[0] & 3, t1 = tp[min(1, Jc - 1)] & 3;   // & 3: idle octets read whatever sits at the buffer start
+    int t2 = tp[min(2, Jc - 1)] & 3;
     int cm = kCtxStartRow + t0;          // match/deletion context of column 1: pinned first move
     int ci = 4 * t0 + t1;                // insertion context of column 1
     float4 tr_m = tr[cm];
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
         // prefetch next column's transition row and the template base after it
         const int ci_next = ((ci & 3) << 2) | t2;
         const float4 tr_next = tr[ci_next];
-        const int t3 = tp[min(j + 2, Jc - 1)];
+        const int t3 = tp[min(j + 2, Jc - 1)] & 3;
 
         octet_forward_column(v, g, d, rel, code, tr_m.x, tr_m.y, tr_i.z, tr_i.w, s_emm + cm * kEmStride,
                              s_emi + ci * kEmStride, (ci & 3) << 2);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
     const float fv = octet_max(final_val);
     if (valid) {
         if (g == 0) {
-            const int ctxl = 4 * tp[J - 2] + tp[J - 1];
+            const int ctxl = 4 * (tp[J - 2] & 3) + (tp[J - 1] & 3);
             const double a = (double)fv * (double)s_emm[(kCtxEndRow + ctxl) * kEmStride + rd.last_code];
             const double base = (a > 0.0) ? log(a) + 0.6931471805599453094 * (double)final_cum : -INFINITY;
             V.base_ll[r] = base;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
             // prologue at j == J-1
             s_cur = cinfo[j].start;
             s_next = s_cur;
-            t_hi = tp[j]; t_lo = tp[j - 1]; t_lo2 = tp[max(j - 2, 0)];
+            t_hi = tp[j] & 3; t_lo = tp[j - 1] & 3; t_lo2 = tp[max(j - 2, 0)] & 3;
             tr_c = tr[4 * t_lo + t_hi];
             tr_p = tr[4 * t_lo2 + t_lo];
             lap = s_cur >> 5;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
         for (int q = 0; q < 4; ++q) rel[q] = (4 * g + q - s_cur) & 31;
         // prefetch for column j-1
         const int s_prev = (alive && j >= 2) ? cinfo[j - 1].start : s_cur;
-        const int t_lo3 = (alive && j >= 3) ? tp[j - 3] : 0;
+        const int t_lo3 = (alive && j >= 3) ? (tp[j - 3] & 3) : 0;
         const float4 tr_pp = alive ? tr[4 * t_lo3 + t_lo2] : tr_p;
 
         float A[4], G[4];
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     const float fv = octet_max(first_val);
     if (valid) {
         if (g == 0) {
-            const double b = (double)fv * (double)s_emm[(kCtxStartRow + tp[0]) * kEmStride + rd.first_code];
+            const double b = (double)fv * (double)s_emm[(kCtxStartRow + (tp[0] & 3)) * kEmStride + rd.first_code];
             const double lb = (b > 0.0) ? log(b) + 0.6931471805599453094 * (double)first_cum - (double)I * V.log_cw : -INFINITY;
             V.ll_beta[r] = lb;
             const double la = V.ll_alpha[r];
@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_n_kernel(const ArrowBatc
         for (int k = 0; k < NW; ++k) acol[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         if (g == 0) cinfo[0] = ColInfo{0, 0};
     }
-    const int t0 = tp[0], t1 = tp[min(1, Jc - 1)];
-    int t2 = tp[min(2, Jc - 1)];
+    const int t0 = tp[0] & 3, t1 = tp[min(1, Jc - 1)] & 3;   // & 3: idle octets read whatever sits at the buffer start
+    int t2 = tp[min(2, Jc - 1)] & 3;
     int cm = kCtxStartRow + t0;
     int ci = 4 * t0 + t1;
     float4 tr_m = tr[cm];
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_n_kernel(const ArrowBatc
         const int rel0 = (CPL * g - s_new) & 31;
         const int ci_next = ((ci & 3) << 2) | t2;
         const float4 tr_next = tr[ci_next];
-        const int t3 = tp[min(j + 2, Jc - 1)];
+        const int t3 = tp[min(j + 2, Jc - 1)] & 3;
 
         const float* __restrict__ emm_row = s_emm + cm * kEmStride;
         const float* __restrict__ emi_row = s_emi + ci * kEmStride;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_n_kernel(const ArrowBatc
     const float fv = group_max<LPP>(final_val);
     if (valid) {
         if (g == 0) {
-            const int ctxl = 4 * tp[J - 2] + tp[J - 1];
+            const int ctxl = 4 * (tp[J - 2] & 3) + (tp[J - 1] & 3);
             const double a = (double)fv * (double)s_emm[(kCtxEndRow + ctxl) * kEmStride + rd.last_code];
             const double base = (a > 0.0) ? log(a) + 0.6931471805599453094 * (double)final_cum : -INFINITY;
             V.base_ll[r] = base;
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_n_kernel(const ArrowBatch
         if (alive && !started) {
             s_cur = cinfo[j].start;
             s_next = s_cur;
-            t_hi = tp[j]; t_lo = tp[j - 1]; t_lo2 = tp[max(j - 2, 0)];
+            t_hi = tp[j] & 3; t_lo = tp[j - 1] & 3; t_lo2 = tp[max(j - 2, 0)] & 3;
             tr_c = tr[4 * t_lo + t_hi];
             tr_p = tr[4 * t_lo2 + t_lo];
             lap = s_cur >> 5;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_n_kernel(const ArrowBatch
         lane_codes_n<CPL>(w0, w1, s_cur, g, code1);
         const int rel0 = (CPL * g - s_cur) & 31;
         const int s_prev = (alive && j >= 2) ? cinfo[j - 1].start : s_cur;
-        const int t_lo3 = (alive && j >= 3) ? tp[j - 3] : 0;
+        const int t_lo3 = (alive && j >= 3) ? (tp[j - 3] & 3) : 0;
         const float4 tr_pp = alive ? tr[4 * t_lo3 + t_lo2] : tr_p;
 
         const float* __restrict__ emm_row = s_emm + ci * kEmStride;
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_n_kernel(const ArrowBatch
     const float fv = group_max<LPP>(first_val);
     if (valid) {
         if (g == 0) {
-            const double b = (double)fv * (double)s_emm[(kCtxStartRow + tp[0]) * kEmStride + rd.first_code];
+            const double b = (double)fv * (double)s_emm[(kCtxStartRow + (tp[0] & 3)) * kEmStride + rd.first_code];
             const double lb = (b > 0.0) ? log(b) + 0.6931471805599453094 * (double)first_cum - (double)I * V.log_cw : -INFINITY;
             V.ll_beta[r] = lb;
             const double la = V.ll_alpha[r];

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
     int n_max = n_reads;
     n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 8));
     n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 16));
-    const int tbase = have ? V.tpl[zm.fwd_off + p] : 0;
+    const int tbase = have ? (V.tpl[zm.fwd_off + p] & 3) : 0;
 
     double acc[9];
 #pragma unroll
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
 #pragma unroll
             for (int x = 0; x < 8; ++x) {
                 const int j1 = q_sd - 3 + x, j2 = q_in - 3 + x;
-                const unsigned b1 = (cov_sd && j1 >= 0 && j1 < rd.J) ? R.tp[j1] : 0u;
-                const unsigned b2 = (cov_in && j2 >= 0 && j2 < rd.J) ? R.tp[j2] : 0u;
+                const unsigned b1 = (cov_sd && j1 >= 0 && j1 < rd.J) ? (R.tp[j1] & 3u) : 0u;
+                const unsigned b2 = (cov_in && j2 >= 0 && j2 < rd.J) ? (R.tp[j2] & 3u) : 0u;
                 word_sd |= b1 << (2 * x);
                 word_in |= b2 << (2 * x);
             }
@@ -305,7 +305,7 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const f
     const float4 b2v = R.bcol[(size_t)j2 * 8 + g];
     out.e_sd = cim1.cumexp + R.bexp[j2];
     out.e_in = cim1.cumexp + R.bexp[j1];
-    const int tm2 = R.tp[jm2], tm1 = R.tp[jm1], t0 = R.tp[j0], tp1 = R.tp[j1];
+    const int tm2 = R.tp[jm2] & 3, tm1 = R.tp[jm1] & 3, t0 = R.tp[j0] & 3, tp1 = R.tp[j1] & 3;   // & 3: idle octets read arbitrary bytes
 
     int rel1[4], rel2[4], codeU1[4], codeG1[4], codeU2[4], codeG2[4], codeL2[4], codeL1[4], codeLb1[4];
     float pvm2[4];
@@ -328,10 +328,11 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const f
         rel1[x] = (slot - s1) & 31;
         rel2[x] = (slot - s2) & 31;
         const int row1 = s1 + rel1[x], row2 = s2 + rel2[x];
-        const int c1 = R.rc[min(row1, code_max)];
-        const int c2 = R.rc[min(row2, code_max)];
-        const int c1n = R.rc[min(row1 + 1, code_max)];
-        const int c2n = R.rc[min(row2 + 1, code_max)];
+        // (idle octets run on whatever band starts sit in the first columns of the store: clamp both ways)
+        const int c1 = R.rc[min(max(row1, 0), code_max)];
+        const int c2 = R.rc[min(max(row2, 0), code_max)];
+        const int c1n = R.rc[min(max(row1 + 1, 0), code_max)];
+        const int c2n = R.rc[min(max(row2 + 1, 0), code_max)];
         const int rd1 = rel1[x] + d1, rd2 = rel2[x] + d2;
         const float pv = (rd1 < 32) ? v0[x] : 0.f;
         codeU1[x] = ((unsigned)(rd1 - 1) < 32u) ? c1 : kC4Sentinel;
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
     int n_max = n_reads;
     n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 8));
     n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 16));
-    const int tbase = have ? V.tpl[zm.fwd_off + p] : 0;
+    const int tbase = have ? (V.tpl[zm.fwd_off + p] & 3) : 0;
 
     // per-slot running products {SUB A,C,G,T, DEL}, {INS A,C,G,T}, {INS' A,C,G,T} and, per group, the sum of the
     // contributing reads' base log-likelihoods
@@ -535,8 +536,8 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
 #pragma unroll
             for (int x = 0; x < 8; ++x) {
                 const int j1 = q_sd - 3 + x, j2 = q_in - 3 + x;
-                const unsigned b1 = (cov_sd && j1 >= 0 && j1 < rd.J) ? R.tp[j1] : 0u;
-                const unsigned b2 = (cov_in && j2 >= 0 && j2 < rd.J) ? R.tp[j2] : 0u;
+                const unsigned b1 = (cov_sd && j1 >= 0 && j1 < rd.J) ? (R.tp[j1] & 3u) : 0u;
+                const unsigned b2 = (cov_in && j2 >= 0 && j2 < rd.J) ? (R.tp[j2] & 3u) : 0u;
                 word_sd |= b1 << (2 * x);
                 word_in |= b2 << (2 * x);
             }

@@ -30,7 +30,8 @@ struct ccsgpu_ctx {
     std::vector<Lane> extra;                 // lanes 1..n-1
     int n_lanes = 1;
     int host_threads = 8;
-    size_t budget = 0;
+    size_t budget = 0;           // device bytes this ctx may use (0 at create -> 85 % of the free memory then)
+    size_t lane_budget() const { return n_lanes > 0 ? budget / (size_t)n_lanes : budget; }
     bool generic_score = false;
     int fill_cpl = 4;
     bool reuse_scores = false;
@@ -95,6 +96,10 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
         if (const char* e = std::getenv("CCS_B200_REUSE_SCORES")) ctx->reuse_scores = (e[0] != '0');
         ctx->engine->reuse_scores = ctx->reuse_scores;
         ctx->budget = device_bytes_budget;
+        if (ctx->budget == 0) {
+            size_t fr = 0, tot = 0;
+            if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ctx->budget = fr - fr / 7;
+        }
         int lanes = 4;
         if (const char* e = std::getenv("CCS_B200_LANES")) lanes = std::max(1, std::min(8, std::atoi(e)));
         ccsgpu_set_lanes(ctx, lanes);
@@ -263,12 +268,20 @@ static void make_sub(const ccs_batch* in, const ccs_drafts* dr, int z0, int z1, 
     }
 }
 
-// contiguous chunks with ~equal numbers of read bases
-static std::vector<int> split_zmws(const ccs_batch* in, int n_chunks) {
+// Contiguous ZMW chunks with ~equal numbers of read bases: at least one per lane, and more (processed in
+// waves, lane k takes chunks k, k+n_lanes, ...) when a chunk's device footprint would exceed the lane's share of
+// the budget.  Footprint estimate per read base: two 128-B band columns + column info (alpha, beta), two row-code
+// copies, ~15 % growth room; plus the per-position delta rows -- ~330 B per read base, rounded up to 400.
+static std::vector<int> split_zmws(const ccs_batch* in, int n_lanes, size_t lane_budget_bytes) {
     std::vector<int> cut(1, 0);
     const int nz = in->n_zmws;
-    n_chunks = std::max(1, std::min(n_chunks, std::max(1, nz / 8)));
     const int64_t total = in->read_off[in->n_reads];
+    int n_chunks = std::max(1, std::min(n_lanes, std::max(1, nz / 8)));
+    if (lane_budget_bytes > 0) {
+        const int64_t per_chunk = (int64_t)(lane_budget_bytes / 400);
+        const int need = (int)std::min<int64_t>(nz, (total + per_chunk - 1) / std::max<int64_t>(per_chunk, 1));
+        if (need > n_chunks) n_chunks = ((need + n_lanes - 1) / n_lanes) * n_lanes;
+    }
     for (int c = 1; c < n_chunks; ++c) {
         const int64_t want = total * c / n_chunks;
         int z = cut.back();
@@ -312,13 +325,17 @@ static DraftEngine& lane_draft(ccsgpu_ctx* ctx, int k) { return k == 0 ? *ctx->d
 
 }  // extern "C"
 
-// Runs f(chunk) for every chunk on its own host thread; rethrows the first failure.
+// Runs f(lane, chunk) for every chunk: lane k (its own host thread) takes chunks k, k+n_lanes, ... in turn;
+// rethrows the first failure.
 template <class F>
-static void run_lanes(int n_chunks, F&& f) {
-    std::vector<std::exception_ptr> errs(n_chunks);
+static void run_lanes(int n_lanes, int n_chunks, F&& f) {
+    n_lanes = std::max(1, std::min(n_lanes, n_chunks));
+    std::vector<std::exception_ptr> errs(n_lanes);
     std::vector<std::thread> th;
-    auto body = [&](int k) { try { f(k); } catch (...) { errs[k] = std::current_exception(); } };
-    for (int k = 1; k < n_chunks; ++k) th.emplace_back(body, k);
+    auto body = [&](int lane) {
+        try { for (int c = lane; c < n_chunks; c += n_lanes) f(lane, c); } catch (...) { errs[lane] = std::current_exception(); }
+    };
+    for (int k = 1; k < n_lanes; ++k) th.emplace_back(body, k);
     body(0);
     for (auto& t : th) t.join();
     for (auto& e : errs) if (e) std::rethrow_exception(e);
@@ -331,13 +348,13 @@ int ccsgpu_polish(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_drafts* drafts
     return guarded(ctx, [&]() {
         const auto t_begin = std::chrono::steady_clock::now();
         const PolishParams pp = to_params(cfg);
-        const std::vector<int> cut = split_zmws(in, ctx->n_lanes);
+        const std::vector<int> cut = split_zmws(in, ctx->n_lanes, ctx->lane_budget());
         const int nc = (int)cut.size() - 1;
         std::vector<ChunkOut> cos(nc);
         std::vector<SubBatch> subs(nc);
-        run_lanes(nc, [&](int k) {
+        run_lanes(ctx->n_lanes, nc, [&](int lane, int k) {
             make_sub(in, drafts, cut[k], cut[k + 1], subs[k]);
-            ArrowEngine& E = lane_engine(ctx, k);
+            ArrowEngine& E = lane_engine(ctx, lane);
             E.load(make_input(&subs[k].b, &subs[k].d));
             E.polish(pp);
             collect_results(E, subs[k].b.n_zmws, subs[k].b.n_reads, subs[k].b.cx, pp, nullptr, cos[k]);
@@ -438,13 +455,13 @@ int ccsgpu_ccs(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_draft_cfg* dcfg, 
         const auto t_begin = std::chrono::steady_clock::now();
         const DraftParams dpar = to_draft_params(dcfg);
         const PolishParams pp = to_params(pcfg);
-        const std::vector<int> cut = split_zmws(in, ctx->n_lanes);
+        const std::vector<int> cut = split_zmws(in, ctx->n_lanes, ctx->lane_budget());
         const int nc = (int)cut.size() - 1;
         std::vector<ChunkOut> cos(nc);
         std::vector<SubBatch> subs(nc);
-        run_lanes(nc, [&](int k) {
+        run_lanes(ctx->n_lanes, nc, [&](int lane, int k) {
             make_sub(in, nullptr, cut[k], cut[k + 1], subs[k]);
-            ccs_chunk(ctx, k, &subs[k].b, dpar, pp, cos[k]);
+            ccs_chunk(ctx, lane, &subs[k].b, dpar, pp, cos[k]);
         });
         const int rc = merge_chunks(in, cut, cos, out);
         ctx->ms_e2e += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();

@@ -7,6 +7,8 @@
 // (/root/reference/docs/changelog.md:66).  Compute goes through the C ABI only (include/ccsgpu.h).
 #include "../../../include/ccsgpu.h"
 #include "bam_io.h"
+#include <cuda_runtime.h>
+#include <zlib.h>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -23,7 +25,7 @@ using namespace ccs;
 namespace {
 
 struct Options {
-    std::string in, out, report;
+    std::string in, out, report, metrics;
     ccs_draft_cfg d;
     ccs_polish_cfg p;
     int chunk_i = 1, chunk_n = 1, batch = 512, device = 0, log_level = 1, pipeline = 2;
@@ -41,6 +43,7 @@ void usage() {
                  "  --min-rq FLOAT       Minimum predicted accuracy in [0, 1]. [0.99]\n"
                  "  --chunk i/N          Operate on a single chunk. Format i/N, where i in [1,N].\n"
                  "  --report-file FILE   Where to write the results report. [<out prefix>.ccs_report.txt]\n"
+                 "  --metrics-json FILE  Where to write the zmw_metrics JSON (gzip). [<out prefix>.zmw_metrics.json.gz]\n"
                  "  --batch-size INT     ZMWs per GPU batch. [512]\n"
                  "  --device INT         CUDA device. [0]\n"
                  "  --pipeline INT       Batches in flight (GPU stage instances fed by the reader). [2]\n"
@@ -64,6 +67,7 @@ bool parse(int argc, char** argv, Options& o) {
         else if (a == "--max-length") o.d.max_length = o.p.max_length = std::atoi(val("--max-length"));
         else if (a == "--min-rq") o.p.min_rq = std::atof(val("--min-rq"));
         else if (a == "--report-file") o.report = val("--report-file");
+        else if (a == "--metrics-json") o.metrics = val("--metrics-json");
         else if (a == "--batch-size") o.batch = std::max(1, std::atoi(val("--batch-size")));
         else if (a == "--device") o.device = std::atoi(val("--device"));
         else if (a == "--pipeline") o.pipeline = std::max(1, std::min(4, std::atoi(val("--pipeline"))));
@@ -85,6 +89,12 @@ bool parse(int argc, char** argv, Options& o) {
         const size_t dot = pre.rfind(".bam");
         if (dot != std::string::npos) pre = pre.substr(0, dot);
         o.report = pre + ".ccs_report.txt";
+    }
+    if (o.metrics.empty()) {
+        std::string pre = o.out;
+        const size_t dot = pre.rfind(".bam");
+        if (dot != std::string::npos) pre = pre.substr(0, dot);
+        o.metrics = pre + ".zmw_metrics.json.gz";
     }
     return true;
 }
@@ -178,9 +188,13 @@ int main(int argc, char** argv) {
         const unsigned hc = std::max(1u, std::thread::hardware_concurrency());
         setenv("CCS_B200_THREADS", std::to_string(std::max(1u, hc / (unsigned)o.pipeline)).c_str(), 1);
     }
+    size_t free_b = 0, total_b = 0;
+    cudaSetDevice(o.device);
+    cudaMemGetInfo(&free_b, &total_b);                          // fails harmlessly without a device: budget 0
+    const size_t budget = (size_t)((double)free_b * 0.85 / o.pipeline);
     for (int k = 0; k < o.pipeline; ++k) {
         int cerr = 0;
-        ccsgpu_ctx* c = ccsgpu_create(o.device, model.data(), 0, &cerr);
+        ccsgpu_ctx* c = ccsgpu_create(o.device, model.data(), budget, &cerr);
         if (!c) { std::fprintf(stderr, "ccs: %s\n", ccsgpu_last_error(nullptr)); return 1; }
         if (o.pipeline > 1) ccsgpu_set_lanes(c, 3);
         ctxs.push_back(c);
@@ -233,6 +247,13 @@ int main(int argc, char** argv) {
         B.err = "result capacity";
         return CCS_ERR_CAPACITY;
     };
+    // <prefix>.zmw_metrics.json.gz: one entry per input ZMW (docs/faq/reports-aux-files.md:100-171)
+    static const char* kStatusName[17] = {"POOR_SNR", "NO_SUBREADS", "TOO_FEW_PASSES", "LOW_PASS_SHORTCUT", "HETERODUPLEXES",
+        "COVERAGE_DROPS", "INSUFFICIENT_SPANS", "TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT", "DRAFT_FAILURE", "TOO_LONG", "TOO_SHORT",
+        "TOO_MANY_UNUSABLE", "EMPTY_WINDOW_DURING_POLISHING", "NON_CONVERGENT", "POOR_QUALITY", "EXCEPTION_THROWN", "SUCCESS"};
+    gzFile mz = gzopen(o.metrics.c_str(), "wb");
+    if (mz) gzputs(mz, "{\n  \"zmws\": [");
+    bool first_metric = true;
     Report rep;
     const auto t0 = std::chrono::steady_clock::now();
     int64_t z_index = 0;
@@ -260,6 +281,23 @@ int main(int argc, char** argv) {
             for (int zi = 0; zi < (int)B.zmws.size(); ++zi) {
                 ++rep.input;
                 ++rep.counts[B.status[zi]];
+                if (mz) {
+                    const ZmwSubreads& zz = B.zmws[zi];
+                    int64_t poly = 0;
+                    std::vector<int32_t> ls;
+                    for (const auto& rd : zz.reads) { poly += (int64_t)rd.codes.size(); ls.push_back((int32_t)rd.codes.size()); }
+                    std::sort(ls.begin(), ls.end());
+                    const int64_t clen = B.seq_off[zi + 1] - B.seq_off[zi];
+                    const int64_t insert = clen > 0 ? clen : (ls.empty() ? 0 : ls[ls.size() / 2]);
+                    const bool has_rq = clen > 0;
+                    gzprintf(mz, "%s\n    {\"effective_coverage\": %d, \"has_tandem_repeat\": false, \"insert_size\": %lld, "
+                                 "\"num_full_passes\": %d, \"polymerase_length\": %lld, \"predicted_accuracy\": %.6f, "
+                                 "\"status\": \"%s\", \"zmw\": \"%s/%d\"}",
+                             first_metric ? "" : ",", B.npass[zi] + (B.npass[zi] > 0 ? 1 : 0), (long long)insert, B.npass[zi],
+                             (long long)poly, has_rq ? (double)B.rq[zi] : -1.0, kStatusName[B.status[zi]], reader.movie().c_str(),
+                             zz.hole);
+                    first_metric = false;
+                }
                 if (B.status[zi] != CCS_ZMW_SUCCESS) continue;
                 ++rep.pass;
                 CcsRecord rec;
@@ -277,6 +315,7 @@ int main(int argc, char** argv) {
         }
     }
     writer.close();
+    if (mz) { gzputs(mz, "\n  ]\n}\n"); gzclose(mz); }
     write_report(o.report, rep);
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (o.log_level >= 1)

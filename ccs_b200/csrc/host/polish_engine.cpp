@@ -242,6 +242,7 @@ void ArrowEngine::upload_templates_and_reads() {
     }
     if (toff > 0x7fffffffll) throw OomError("template buffer exceeds 2 GiB; use smaller batches");
     h_tpl_.ensure((size_t)toff + 16);
+    std::memset(h_tpl_.p, 0, 64);   // idle lanes of the kernels read the first bytes of the buffer
     // column offsets (serial prefix), then the per-ZMW copies in parallel
     for (int z = 0; z < nz; ++z) {
         const ZmwState& zs = zstate_[z];

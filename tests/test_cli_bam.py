@@ -106,6 +106,16 @@ def test_cli_end_to_end_matches_api(tmp_path):
     assert "ZMWs input                    : %d" % n in rep
     assert "ZMWs pass filters             : %d" % len(want) in rep
     assert "Below SNR threshold" in rep and "HiFi Reads                    : %d" % len(want) in rep
+    # zmw_metrics.json.gz: one entry per input ZMW, status names in the reference's vocabulary
+    import gzip
+    import json
+    met = json.loads(gzip.open(str(tmp_path / "m.hifi_reads.zmw_metrics.json.gz")).read())["zmws"]
+    assert len(met) == n and [m["zmw"] for m in met] == ["m64000_000000_000000/%d" % (i + 1) for i in range(n)]
+    assert sum(m["status"] == "SUCCESS" for m in met) == len(want)
+    assert {m["status"] for m in met} <= set(api.ZMW_STATUS)
+    for m in met:
+        assert (m["predicted_accuracy"] >= 0.99) if m["status"] == "SUCCESS" else True
+        assert m["insert_size"] > 0 and m["polymerase_length"] >= m["insert_size"]
     # chunked runs concatenate to the full run (docs/faq/parallelize.md:15-28)
     parts = []
     for i in (1, 2):
