@@ -35,9 +35,13 @@ int filter_reads(const int32_t* lens, const uint8_t* cx, int n, int top_passes, 
 struct KmerSet {
     std::vector<uint32_t> tab;
     uint32_t mask = 0;
+    // content sampling: only k-mers whose hash has its three top bits clear take part (1 in 8), on both the
+    // reference and the read side, so the table and the number of probes shrink 8x at the same vote statistic
+    static uint32_t hash(uint32_t k) { k *= 0x9E3779B1u; return k ^ (k >> 15); }
+    static bool sampled(uint32_t k) { return ((k * 0x9E3779B1u) >> 29) == 0u; }
     void build(const uint8_t* s, int n) {
-        size_t cap = 1024;
-        while (cap < (size_t)n * 4) cap <<= 1;
+        size_t cap = 256;
+        while (cap < (size_t)n) cap <<= 1;          // ~n/8 entries expected: load factor <= 1/8
         tab.assign(cap, 0u);
         mask = (uint32_t)cap - 1;
         if (n < kPoaKmer) return;
@@ -45,10 +49,9 @@ struct KmerSet {
         uint32_t k = 0;
         for (int i = 0; i < n; ++i) {
             k = ((k << 2) | s[i]) & kmask;
-            if (i >= kPoaKmer - 1) insert(k);
+            if (i >= kPoaKmer - 1 && sampled(k)) insert(k);
         }
     }
-    static uint32_t hash(uint32_t k) { k *= 0x9E3779B1u; return k ^ (k >> 15); }
     void insert(uint32_t k) {
         uint32_t h = hash(k) & mask;
         while (tab[h] != 0u && tab[h] != k + 1) h = (h + 1) & mask;
@@ -59,7 +62,7 @@ struct KmerSet {
         while (tab[h] != 0u) { if (tab[h] == k + 1) return true; h = (h + 1) & mask; }
         return false;
     }
-    // shared k-mers of seq (forward) and of its reverse complement
+    // sampled k-mers of seq (forward) and of its reverse complement that occur in the reference
     void count(const uint8_t* codes, int n, int64_t& fwd, int64_t& rev) const {
         fwd = rev = 0;
         if (n < kPoaKmer) return;
@@ -69,8 +72,10 @@ struct KmerSet {
             const uint32_t b = codes[i] & 3u;
             kf = ((kf << 2) | b) & kmask;
             kr = (kr >> 2) | ((3u - b) << (2 * (kPoaKmer - 1)));
-            // every 8th read k-mer votes (window start = 0 mod 8): plenty of signal, 8x fewer probes
-            if (i >= kPoaKmer - 1 && ((i - (kPoaKmer - 1)) & 7) == 0) { fwd += has(kf); rev += has(kr); }
+            if (i >= kPoaKmer - 1) {
+                if (sampled(kf)) fwd += has(kf);
+                if (sampled(kr)) rev += has(kr);
+            }
         }
     }
 };

@@ -218,6 +218,9 @@ static void kmers(const uint8_t* s, int n, std::vector<uint32_t>& out) {
     }
 }
 
+// content sampling: a k-mer takes part iff the three top bits of k * 0x9E3779B1 (mod 2^32) are clear
+static bool kmer_sampled(uint32_t k) { return ((uint32_t)(k * 0x9E3779B1u) >> 29) == 0u; }
+
 bool kmer_vote_reverse(const uint8_t* ref, int nref, const uint8_t* read, int n) {
     std::vector<uint32_t> rk, fk, ck;
     kmers(ref, nref, rk);
@@ -227,14 +230,9 @@ bool kmer_vote_reverse(const uint8_t* ref, int nref, const uint8_t* read, int n)
     for (int i = 0; i < n; ++i) rc[i] = (uint8_t)(3 - read[n - 1 - i]);
     kmers(read, n, fk);
     kmers(rc.data(), n, ck);
-    // every 8th window of the read votes (window start = 0 mod 8 in forward coordinates); the reverse
-    // complement of forward window w is window (nk-1-w) of the reverse-complemented read
     long long f = 0, c = 0;
-    const size_t nk = fk.size();
-    for (size_t w = 0; w < nk; w += 8) {
-        f += std::binary_search(rk.begin(), rk.end(), fk[w]);
-        c += std::binary_search(rk.begin(), rk.end(), ck[nk - 1 - w]);
-    }
+    for (uint32_t k : fk) if (kmer_sampled(k)) f += std::binary_search(rk.begin(), rk.end(), k);
+    for (uint32_t k : ck) if (kmer_sampled(k)) c += std::binary_search(rk.begin(), rk.end(), k);
     return c > f;
 }
 
