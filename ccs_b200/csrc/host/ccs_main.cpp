@@ -25,7 +25,7 @@ using namespace ccs;
 namespace {
 
 struct Options {
-    std::string in, out, report, metrics;
+    std::string in, out, report, metrics, model_path;
     ccs_draft_cfg d;
     ccs_polish_cfg p;
     int chunk_i = 1, chunk_n = 1, batch = 512, device = 0, log_level = 1, pipeline = 2;
@@ -44,6 +44,7 @@ void usage() {
                  "  --chunk i/N          Operate on a single chunk. Format i/N, where i in [1,N].\n"
                  "  --report-file FILE   Where to write the results report. [<out prefix>.ccs_report.txt]\n"
                  "  --metrics-json FILE  Where to write the zmw_metrics JSON (gzip). [<out prefix>.zmw_metrics.json.gz]\n"
+                 "  --model-path FILE    Arrow model JSON (else $SMRT_CHEMISTRY_BUNDLE_DIR/arrow/model.json, else built-in synthetic).\n"
                  "  --batch-size INT     ZMWs per GPU batch. [512]\n"
                  "  --device INT         CUDA device. [0]\n"
                  "  --pipeline INT       Batches in flight (GPU stage instances fed by the reader). [2]\n"
@@ -68,6 +69,7 @@ bool parse(int argc, char** argv, Options& o) {
         else if (a == "--min-rq") o.p.min_rq = std::atof(val("--min-rq"));
         else if (a == "--report-file") o.report = val("--report-file");
         else if (a == "--metrics-json") o.metrics = val("--metrics-json");
+        else if (a == "--model-path") o.model_path = val("--model-path");
         else if (a == "--batch-size") o.batch = std::max(1, std::atoi(val("--batch-size")));
         else if (a == "--device") o.device = std::atoi(val("--device"));
         else if (a == "--pipeline") o.pipeline = std::max(1, std::min(4, std::atoi(val("--pipeline"))));
@@ -181,6 +183,17 @@ int main(int argc, char** argv) {
     }
     std::vector<uint8_t> model(ccs_model_sizeof());
     ccs_model_synthetic(model.data());          // the only chemistry this build ships (DESIGN.md "Model")
+    {   // model injection: --model-path, or the chemistry bundle directory (docs/faq/chemistry.md:28-56)
+        std::string mp = o.model_path;
+        if (mp.empty()) if (const char* b = std::getenv("SMRT_CHEMISTRY_BUNDLE_DIR")) {
+            const std::string cand = std::string(b) + "/arrow/model.json";
+            if (FILE* t = std::fopen(cand.c_str(), "rb")) { std::fclose(t); mp = cand; }
+        }
+        if (!mp.empty() && ccs_model_load_json(mp.c_str(), model.data()) != CCS_OK) {
+            std::fprintf(stderr, "ccs: cannot load the Arrow model from %s\n", mp.c_str());
+            return 1;
+        }
+    }
     // `pipeline` stage instances (one ccsgpu_ctx each); the reader deals batches to them round-robin, they run
     // concurrently, and results are written in input order (reader -> stages -> ordered writer, docs/img/ccs-impl.png)
     std::vector<ccsgpu_ctx*> ctxs;

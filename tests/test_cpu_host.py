@@ -131,3 +131,20 @@ def test_filter_reads_rule():
     assert d2["status"] == 2
     # SNR below --min-snr -> POOR_SNR (status 0)
     assert O.draft_zmw(np.array([2.0, 9, 9, 9], np.float32), reads, z.cx)["status"] == 0
+
+
+def test_model_json_round_trip(tmp_path):
+    """chemistry-bundle style model injection: save -> load reproduces the parameter blob bit for bit"""
+    L = lib()
+    m = sim.synthetic_model()
+    p = str(tmp_path / "model.json").encode()
+    assert L.ccs_model_save_json(m.ctypes.data_as(C.c_void_p), p) == 0
+    import json
+    j = json.load(open(p.decode()))
+    assert j["ModelForm"] == "PwSnr" and len(j["TransitionParameters"]) == 16 and len(j["EmissionParameters"]) == 3
+    back = np.zeros_like(m)
+    assert L.ccs_model_load_json(p, back.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(back, m)
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"ModelForm": "Marginal"}')
+    assert L.ccs_model_load_json(str(bad).encode(), back.ctypes.data_as(C.c_void_p)) == -7     # CCS_ERR_CHEMISTRY
