@@ -73,10 +73,10 @@ def main():
                               "max_ms": round(max(v), 2)} for n, v in agg.items()}
     json.dump(res, open("profiles/r1_summary.json", "w"), indent=1)
     with open("profiles/r1_summary.md", "w") as f:
-        f.write("# Round-1 ncu summary (B200, config 2: 1000 ZMWs, 10 kb x 10 passes, `bench.py --lanes 1`)\n\n")
+        f.write("# Round-1 ncu summary (B200, config 2: 1000 ZMWs, 10 kb x 10 passes, full captures with `bench.py --lanes 1 --contexts 1`)\n\n")
         f.write("Source: `gpurun_out/r1_full_*.ncu-rep` (`ncu --set full --clock-control none --import-source on`, first launch of "
                 "each kernel = the full-population launch) and `profiles/r1_launches_bench.csv` (`ncu --metrics "
-                "gpu__time_duration.sum --clock-control none` over `python bench.py --steps 1 --warmup 1`; per-launch times "
+                "gpu__time_duration.sum --clock-control none` over `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`; per-launch times "
                 "are cold-cache and serialised, compare shares). Regenerate with `python scripts/summarize_profiles.py`.\n\n")
         f.write("| kernel | duration ms | DRAM read GB | DRAM write GB | DRAM %peak | issue-active % | warp-instr | regs | warps active % | top stalls (% of samples) |\n|---|---|---|---|---|---|---|---|---|---|\n")
         for k in KERNELS:
