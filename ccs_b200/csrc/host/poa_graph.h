@@ -21,7 +21,7 @@ public:
         base_.assign(seq, seq + n);
         nreads_.assign(n, 1);
         next_.resize(n); prev_.resize(n);
-        in_.assign((size_t)n * kPoaMaxPred, -1);
+        in_.resize((size_t)n * kPoaMaxPred);      // only the first nin_ entries of a vertex are ever read
         nin_.assign(n, 0);
         for (int i = 0; i < n; ++i) {
             prev_[i] = i - 1; next_[i] = (i + 1 < n) ? i + 1 : -1;
@@ -42,17 +42,23 @@ public:
     // to this graph's list); preds[n_edges] = predecessor ranks, ascending per vertex.
     void export_topo(std::vector<int32_t>& order, uint8_t* base, int32_t* pred_off, int32_t* preds) const {
         const int V = size();
-        order.clear(); order.reserve(V);
-        rank_.assign(V, -1);
-        for (int x = head_; x >= 0; x = next_[x]) { rank_[x] = (int)order.size(); order.push_back(x); }
+        order.resize(V);
+        rank_.resize(V);
+        int t = 0;
+        for (int x = head_; x >= 0; x = next_[x]) { rank_[x] = t; order[t++] = x; }
         int32_t np = 0;
-        for (int t = 0; t < V; ++t) {
+        for (t = 0; t < V; ++t) {
             const int x = order[t];
             base[t] = base_[x];
             pred_off[t] = np;
-            const int b = np;
-            for (int k = 0; k < nin_[x]; ++k) preds[np++] = rank_[in_[(size_t)x * kPoaMaxPred + k]];
-            std::sort(preds + b, preds + np);
+            const int n = nin_[x];
+            const int32_t* e = &in_[(size_t)x * kPoaMaxPred];
+            if (n == 1) preds[np++] = rank_[e[0]];                 // the common case: a chain vertex
+            else if (n > 1) {
+                const int b = np;
+                for (int k = 0; k < n; ++k) preds[np++] = rank_[e[k]];
+                std::sort(preds + b, preds + np);
+            }
         }
         pred_off[V] = np;
     }
@@ -95,10 +101,9 @@ public:
     // FindConsensus: score(v) = 2*nReads - max(spanning, minCov); best-scoring path
     void consensus(int min_cov, std::vector<uint8_t>& out) const {
         const int V = size();
-        std::vector<int32_t> order;
-        order.reserve(V);
-        rank_.assign(V, -1);
-        for (int x = head_; x >= 0; x = next_[x]) { rank_[x] = (int)order.size(); order.push_back(x); }
+        std::vector<int32_t> order(V);
+        rank_.resize(V);
+        { int t = 0; for (int x = head_; x >= 0; x = next_[x]) { rank_[x] = t; order[t++] = x; } }
         std::vector<int32_t> cov(V + 1, 0);
         for (auto& s : spans_) { cov[rank_[s.first]]++; cov[rank_[s.second] + 1]--; }
         for (int t = 1; t <= V; ++t) cov[t] += cov[t - 1];
@@ -128,7 +133,7 @@ private:
     int new_vertex_after(int after, uint8_t b) {
         const int id = size();
         base_.push_back(b); nreads_.push_back(1); nin_.push_back(0);
-        in_.resize(in_.size() + kPoaMaxPred, -1);
+        in_.resize(in_.size() + kPoaMaxPred);
         if (after < 0) { prev_.push_back(-1); next_.push_back(head_); if (head_ >= 0) prev_[head_] = id; head_ = id; }
         else {
             prev_.push_back(after); next_.push_back(next_[after]);
