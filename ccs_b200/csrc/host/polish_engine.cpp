@@ -56,8 +56,6 @@ ArrowEngine::ArrowEngine(int device, const ArrowModelParams& model, size_t budge
         budget_ = fr - fr / 10;
     }
     CCS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    CCS_CUDA(cudaEventCreate(&ev0_));
-    CCS_CUDA(cudaEventCreate(&ev1_));
     CCS_CUDA(cudaEventCreate(&evA_));
     CCS_CUDA(cudaEventCreate(&evB_));
     build_emission_tables(model_, em_);
@@ -76,8 +74,6 @@ ArrowEngine::ArrowEngine(int device, const ArrowModelParams& model, size_t budge
 ArrowEngine::~ArrowEngine() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
-    if (ev0_) cudaEventDestroy(ev0_);
-    if (ev1_) cudaEventDestroy(ev1_);
     if (evA_) cudaEventDestroy(evA_);
     if (evB_) cudaEventDestroy(evB_);
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);

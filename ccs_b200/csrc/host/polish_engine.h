@@ -132,7 +132,7 @@ private:
     ArrowModelParams model_;
     EmissionTables em_;
     cudaStream_t stream_ = nullptr;
-    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, evA_ = nullptr, evB_ = nullptr;
+    cudaEvent_t evA_ = nullptr, evB_ = nullptr;   // bracket polish() (resident-input time)
 
     // host state of the current batch
     std::vector<ZmwState> zstate_;
