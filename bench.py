@@ -185,10 +185,23 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": "ZMW/s", "cores": cores, "kind": "port",
                              "sample": f"{n} ZMWs of the same workload per step, {cores} threads"},
             "e2e": {"value": val, "unit": "ZMW/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the real stdout"""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    global _REAL_STDOUT
+    # libraries (NCCL's version banner, ...) print to stdout: keep fd 1 for the JSON line only
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -357,7 +370,7 @@ def main():
             line["cpu_baseline"] = {"value": n / dt, "unit": "ZMW/s", "cores": cores, "kind": "port",
                                     "sample": f"first {n} ZMWs of step 0, {cores} threads, {dt:.1f} s",
                                     "consensus_identical": f"{same}/{n}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     for c in ctxs:
         c.close()
     if world > 1:
