@@ -3,17 +3,23 @@
 // SURVEY.md 8a rows a8-a10; /root/reference/docs/how-does-ccs-work.md:94-96,
 // /root/reference/docs/faq/revio.md:20-25 "filling out matrices at its core").
 //
-// Mapping: one warp octet per (read, template) pair, 16 pairs per 128-thread CTA, pairs sorted
-// by length so the four octets of a warp finish together.  Per column an octet reads one
-// template base + one 16-byte transition row (L1-resident), looks the emissions up in shared
-// memory, and writes one 128-byte line of fp32 cells -- the kernel is HBM-write bound:
-// algorithmic bytes per pair = 4*32*(J-1) cells + 8 (alpha) or 4 (beta) bytes of column info
-// per column + I + J input bytes (DESIGN.md "Roofline").
+// Mapping: one CTA (128 threads) per group of <= 16 reads of ONE ZMW, one warp octet (8 lanes x 4
+// cells) per (read, template) pair.  Per column an octet reads one template byte, looks its four
+// cells' folded factors up in shared memory (one 8-byte load per cell) and writes one 128-byte line
+// of fp32 cells -- the kernel is HBM-write bound by construction: algorithmic bytes per pair =
+// 4*32*(J-1) cells + 8 (alpha) or 4 (beta) bytes of column info per column + I + J input bytes
+// (DESIGN.md "Roofline").
 //
-// Row codes: a lane's four slots hold rows 32*lap + 4g + {0..3}; one aligned 32-bit word of the
-// row-code array carries exactly those four codes, so a lane keeps the words of the current
-// and next lap (plus one prefetched) and assembles its codes with a single byte-permute; a
-// new word is loaded once every 32 columns (coalesced 32 B per octet).
+// What keeps the per-column instruction count low (DESIGN.md "Kernels"):
+//  * the band start only moves in steps of 4 rows (spec: quantised slide), so band bookkeeping is
+//    per LANE, not per cell: the lane that leaves the band at the bottom re-enters at the top, one
+//    predicate zeroes it, one predicate marks the band-start lane, and the leading-edge test looks
+//    at three cells of the top lane only;
+//  * the CTA's ZMW has its transition factors folded into the emission tables once per CTA:
+//    alpha indexes one row per template TRINUCLEOTIDE (t[j-2], t[j-1], t[j]) holding
+//    {match factor of context (t[j-2],t[j-1]), insertion factor of context (t[j-1],t[j])} per
+//    code, plus the deletion transition in a spare code slot -- the template byte IS the row index;
+//  * row codes: a lane's four slots are one aligned 32-bit word of the row-code array.
 #include "arrow_octet.cuh"
 #include "arrow_launch.h"
 
@@ -21,31 +27,61 @@ namespace ccs {
 
 namespace {
 
-__device__ __forceinline__ void load_emissions(const ArrowBatchView& V, float* s_emm, float* s_emi) {
-    for (int k = threadIdx.x; k < 36 * kEmStride; k += blockDim.x) s_emm[k] = V.em_match[k];
-    for (int k = threadIdx.x; k < 17 * kEmStride; k += blockDim.x) s_emi[k] = V.em_ins[k];
-    __syncthreads();
+constexpr int kT3Rows = 80;        // 64 trinucleotide rows + 16 pinned-first-move rows (64 + 4*t0 + t1)
+constexpr int kT2Rows = 16;        // beta: one row per dinucleotide context
+constexpr int kDSlot = 13;         // unused code slot of a row: {deletion transition of the row's match context, 0}
+
+__device__ __forceinline__ float2 lds_f2(const unsigned addr) {
+    float2 r;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float lds_f1(const unsigned addr) {
+    float r;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
 }
 
-// codes of this lane's four slots for band start s: slots below the start slot are one lap ahead
-__device__ __forceinline__ void lane_codes(const unsigned w_lo, const unsigned w_hi, const int s, const int g, int code[4]) {
-    const int t = min(max((s & 31) - 4 * g, 0), 4);          // how many of the lane's slots are in the next lap
-    const unsigned sel = 0x3210u | (0x4444u & ((1u << (4 * t)) - 1u));
-    const unsigned cw = __byte_perm(w_lo, w_hi, sel);
-    code[0] = (int)(cw & 0xffu);
-    code[1] = (int)__byte_perm(cw, 0u, 0x4441u);
-    code[2] = (int)__byte_perm(cw, 0u, 0x4442u);
-    code[3] = (int)(cw >> 24);
+// Folded per-ZMW factors (the model, DESIGN.md "Arrow model"): one fp32 product each, identical to the
+// oracle's Tables::mm / Tables::gg.
+__device__ __forceinline__ float2 folded_entry(const ArrowBatchView& V, const float4* __restrict__ tr, const int cm,
+                                               const int ci, const int code) {
+    const float4 tm = tr[cm], ti = tr[ci];
+    if (code == kDSlot) return make_float2(tm.y, 0.f);
+    const float mm = __fmul_rn(V.em_match[cm * kEmStride + code], tm.x);
+    const bool cognate = (code & 3) == (ci & 3);
+    const float gg = __fmul_rn(V.em_ins[ci * kEmStride + code], cognate ? ti.z : ti.w);
+    return make_float2(mm, gg);
+}
+
+// A loop-invariant value the compiler must keep in a register: ptxas otherwise re-derives lane constants from %tid
+// inside the column loop (S2R + integer ops per column).  An identity shuffle is opaque to it.  Call converged.
+__device__ __forceinline__ int pinned(const int x) { return __shfl_sync(kFullMask, x, (int)(threadIdx.x & 31)); }
+
+__device__ __forceinline__ unsigned vmax_oct(unsigned key) {
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) key = __vmaxu2(key, __shfl_xor_sync(kFullMask, key, off, 8));
+    return key;
 }
 
 __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
                                                                const int n_items) {
-    __shared__ float s_emm[36 * kEmStride];
-    __shared__ float s_emi[17 * kEmStride];
-    load_emissions(V, s_emm, s_emi);
+    __shared__ __align__(128) float2 s_t3[kT3Rows * kEmStride];
+    {
+        const int r0 = order[blockIdx.x * 16];                 // a group's first slot is always a real read
+        const int zmw = (r0 >= 0) ? V.reads[r0].zmw : 0;
+        const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)zmw * 36;
+        for (int idx = threadIdx.x; idx < kT3Rows * kEmStride; idx += blockDim.x) {
+            const int row = idx >> 4, code = idx & 15;
+            const int cm = (row < 64) ? (row >> 2) : kCtxStartRow + ((row - 64) >> 2);
+            const int ci = row & 15;
+            s_t3[idx] = folded_entry(V, tr, cm, ci, code);
+        }
+    }
+    __syncthreads();
 
     const int item = blockIdx.x * 16 + (threadIdx.x >> 3);
-    const int g = threadIdx.x & 7;
+    const int g = pinned(threadIdx.x & 7);
     int r = -1;
     if (item < n_items) r = order[item];
     DevRead rd;
@@ -53,8 +89,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
     rd.active = 0;
     if (r >= 0) rd = V.reads[r];
     const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
-    const int J = valid ? rd.J : 0;
-    const int Jc = valid ? rd.J : 2;      // clamp bound for harmless loads of idle octets
+    const int J = pinned(valid ? rd.J : 0);
     const int I = rd.I;
     int Jmax = J;
 #pragma unroll
@@ -63,76 +98,101 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
     const unsigned* __restrict__ rc32 = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off);
     const int wmax = (rd.code_stride >> 2) - 1;
     const uint8_t* __restrict__ tp = V.tpl + rd.tpl_off;
-    const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
     float4* __restrict__ acol = reinterpret_cast<float4*>(V.alpha) + (size_t)rd.col_off * 8 + g;
     ColInfo* __restrict__ cinfo = V.colinfo + rd.col_off;
+    const unsigned t3_base = (unsigned)pinned((int)__cvta_generic_to_shared(s_t3));
+    const int src_up = pinned((g + 7) & 7), src_up2 = pinned((g + 6) & 7), src_up4 = pinned((g + 4) & 7);
+    const int g4 = pinned(4 * g);
+    const float thr = __uint_as_float((unsigned)(127 + kEdgeLog2) << 23);
 
     // column 0: alpha(0,0) = 1
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (g == 0) v[0] = 1.f;
-    int s = 0, cum = 0, edge = 0, lap = 0;
+    float v0 = (g == 0) ? 1.f : 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    int s = 0, cum = 0, lap = 0;
+    bool slid = false;                   // band start moved by 4 rows between the previous column and this one
     unsigned w0 = rc32[min(g, wmax)], w1 = rc32[min(8 + g, wmax)], w2 = rc32[min(16 + g, wmax)];
     if (valid) {
-        acol[0] = make_float4(v[0], v[1], v[2], v[3]);
+        acol[0] = make_float4(v0, v1, v2, v3);
         if (g == 0) cinfo[0] = ColInfo{0, 0};
     }
-    const int t0 = tp[0] & 3, t1 = tp[min(1, Jc - 1)] & 3;   // & 3: idle octets read whatever sits at the buffer start
-    int t2 = tp[min(2, Jc - 1)] & 3;
-    int cm = kCtxStartRow + t0;          // match/deletion context of column 1: pinned first move
-    int ci = 4 * t0 + t1;                // insertion context of column 1
-    float4 tr_m = tr[cm];
-    float4 tr_i = tr[ci];
-    float final_val = 0.f;
-    int final_cum = 0;
+    // template bytes carry the trinucleotide index 16*t[j-2] + 4*t[j-1] + t[j]; column 1 uses the pinned-first-move rows
+    int x_cur = valid ? 64 + (tp[1] & 15) : 0;
+    int x_nxt = (2 < J) ? tp[2] : 0;
 
     for (int j = 1; j < Jmax; ++j) {
         const bool alive = j < J;
-        const int s_new = max(s, edge + 2 + kBandMargin - kBandW);
-        const int d = s_new - s;
-        if ((s_new >> 5) != lap) {       // octet-uniform, once every 32 columns
-            lap = s_new >> 5;
+        int x_pre = 0;
+        if (j + 2 < J) x_pre = tp[j + 2];          // prefetch, two columns ahead
+        const int ss = s & 31;
+        const unsigned cw = (g4 < ss) ? w1 : w0;   // lanes below the start slot hold rows of the next lap
+        const int r0 = (g4 - s) & 31;              // band-relative row of this lane's first cell
+        const bool startl = r0 == 0, topl = r0 == 28;
+        float up0 = __shfl_sync(kFullMask, v3, src_up, 8);   // alpha(row-1, j-1) of the lane's first cell
+        if (startl && !slid) up0 = 0.f;            // row s-1 is outside the previous band
+        if (topl && slid) { v0 = 0.f; v1 = 0.f; v2 = 0.f; v3 = 0.f; }   // this lane just re-entered at the top: new rows
+        const unsigned row = t3_base + ((unsigned)x_cur << 7);
+        const float2 e0 = lds_f2(row + ((cw & 0xffu) << 1));
+        const float2 e1 = lds_f2(row + (__byte_perm(cw, 0u, 0x4441u) << 1));
+        const float2 e2 = lds_f2(row + (__byte_perm(cw, 0u, 0x4442u) << 1));
+        const float2 e3 = lds_f2(row + ((cw >> 24) << 1));
+        const float D = lds_f1(row + kDSlot * 8);
+        float A0 = fmaf(e0.x, up0, D * v0);
+        float A1 = fmaf(e1.x, v0, D * v1);
+        float A2 = fmaf(e2.x, v1, D * v2);
+        float A3 = fmaf(e3.x, v2, D * v3);
+        float G0 = startl ? 0.f : e0.y;            // band start: no in-band predecessor (makes the ring scan exact)
+        float G1 = e1.y, G2 = e2.y, G3 = e3.y;
+        // a_i = A_i + G_i * a_{i-1}: serial inside the lane, Kogge-Stone ring over the octet
+        A1 = fmaf(G1, A0, A1); G1 *= G0;
+        A2 = fmaf(G2, A1, A2); G2 *= G1;
+        A3 = fmaf(G3, A2, A3); G3 *= G2;
+        float At = A3, Gt = G3;
+        {
+            float As = __shfl_sync(kFullMask, At, src_up, 8), Gs = __shfl_sync(kFullMask, Gt, src_up, 8);
+            At = fmaf(Gt, As, At); Gt *= Gs;
+            As = __shfl_sync(kFullMask, At, src_up2, 8); Gs = __shfl_sync(kFullMask, Gt, src_up2, 8);
+            At = fmaf(Gt, As, At); Gt *= Gs;
+            As = __shfl_sync(kFullMask, At, src_up4, 8);
+            At = fmaf(Gt, As, At);
+        }
+        const float xin = __shfl_sync(kFullMask, At, src_up, 8);
+        v0 = fmaf(G0, xin, A0); v1 = fmaf(G1, xin, A1); v2 = fmaf(G2, xin, A2); v3 = fmaf(G3, xin, A3);
+
+        // column maximum (power-of-two scaling) + leading edge: does one of the band's last three rows reach 2^-60?
+        const float m3 = fmaxf(fmaxf(v1, v2), v3);
+        const float mx = fmaxf(m3, v0);
+        unsigned key = (__float_as_uint(mx) & 0xffff0000u) | ((topl && m3 >= thr) ? 1u : 0u);
+        key = vmax_oct(key);
+        // the sign bit of a maximum is 0, so key >> 23 is its biased exponent e: scale by 2^(127-e) (an all-zero or
+        // denormal column gives e = 0 -- the read is dead or about to be, and its LL ends up -inf either way)
+        const int ebits = (int)(key >> 23);
+        const float sc = __uint_as_float(0x7f000000u - ((key >> 23) << 23));
+        v0 *= sc; v1 *= sc; v2 *= sc; v3 *= sc;
+        cum += ebits - 127;
+        if (alive) {
+            acol[(size_t)j * 8] = make_float4(v0, v1, v2, v3);
+            if (g == 0) cinfo[j] = ColInfo{s, cum};
+        }
+        slid = (key & 1u) != 0u;
+        s += slid ? 4 : 0;
+        if ((s >> 5) != lap) {           // octet-uniform, once every 32 rows
+            lap = s >> 5;
             w0 = w1; w1 = w2;
             w2 = rc32[min(8 * (lap + 2) + g, wmax)];
         }
-        int rel[4], code[4];
-        lane_codes(w0, w1, s_new, g, code);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rel[q] = (4 * g + q - s_new) & 31;
-        // prefetch next column's transition row and the template base after it
-        const int ci_next = ((ci & 3) << 2) | t2;
-        const float4 tr_next = tr[ci_next];
-        const int t3 = tp[min(j + 2, Jc - 1)] & 3;
-
-        octet_forward_column(v, g, d, rel, code, tr_m.x, tr_m.y, tr_i.z, tr_i.w, s_emm + cm * kEmStride,
-                             s_emi + ci * kEmStride, (ci & 3) << 2);
-        int edge_rel;
-        bool dead;
-        const int k = octet_scale_column(v, rel, edge_rel, dead);
-        cum += k;
-        edge = s_new + edge_rel - 1;
-        s = s_new;
-        if (alive) {
-            acol[(size_t)j * 8] = make_float4(v[0], v[1], v[2], v[3]);
-            if (g == 0) cinfo[j] = ColInfo{s_new, cum};
-            if (j == J - 1) {   // alpha(I-1, J-1) lives in slot (I-1) mod 32 if it is inside the band
-                const int slot = (I - 1) & 31;
-                const int rrel = (slot - s_new) & 31;
-                const bool inband = (s_new + rrel) == (I - 1);
-                float x = 0.f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) x = (4 * g + q == slot && inband) ? v[q] : x;
-                final_val = x;
-                final_cum = cum;
-            }
-        }
-        cm = ci; ci = ci_next; tr_m = tr_i; tr_i = tr_next; t2 = t3;
+        x_cur = x_nxt; x_nxt = x_pre;
     }
-    // gather the final cell from whichever lane owns it, then the pinned last match
-    const float fv = octet_max(final_val);
+    // alpha(I-1, J-1) lives in slot (I-1) mod 32 of the last column if it is inside the band; lane 0 of the octet reads
+    // it back from the column line the octet just wrote (ordered by __syncwarp), then applies the pinned last match
+    __syncwarp();
     if (valid) {
         if (g == 0) {
-            const int ctxl = 4 * (tp[J - 2] & 3) + (tp[J - 1] & 3);
-            const double a = (double)fv * (double)s_emm[(kCtxEndRow + ctxl) * kEmStride + rd.last_code];
+            const ColInfo cl = cinfo[J - 1];
+            const int slot = (I - 1) & 31;
+            const bool inband = (cl.start + ((slot - cl.start) & 31)) == (I - 1);
+            const float fv = inband ? V.alpha[((size_t)rd.col_off + (J - 1)) * 32 + slot] : 0.f;
+            const int final_cum = cl.cumexp;
+            const int ctxl = tp[J - 1] & 15;
+            const double a = (double)fv * (double)V.em_match[(kCtxEndRow + ctxl) * kEmStride + rd.last_code];
             const double base = (a > 0.0) ? log(a) + 0.6931471805599453094 * (double)final_cum : -INFINITY;
             V.base_ll[r] = base;
             V.ll_alpha[r] = base - (double)I * V.log_cw;
@@ -145,12 +205,20 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
 
 __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
                                                               const int n_items) {
-    __shared__ float s_emm[36 * kEmStride];
-    __shared__ float s_emi[17 * kEmStride];
-    load_emissions(V, s_emm, s_emi);
+    __shared__ __align__(128) float2 s_t2[kT2Rows * kEmStride];
+    {
+        const int r0 = order[blockIdx.x * 16];
+        const int zmw = (r0 >= 0) ? V.reads[r0].zmw : 0;
+        const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)zmw * 36;
+        for (int idx = threadIdx.x; idx < kT2Rows * kEmStride; idx += blockDim.x) {
+            const int row = idx >> 4, code = idx & 15;
+            s_t2[idx] = folded_entry(V, tr, row, row, code);
+        }
+    }
+    __syncthreads();
 
     const int item = blockIdx.x * 16 + (threadIdx.x >> 3);
-    const int g = threadIdx.x & 7;
+    const int g = pinned(threadIdx.x & 7);
     int r = -1;
     if (item < n_items) r = order[item];
     DevRead rd;
@@ -158,7 +226,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     rd.code_stride = 64; rd.active = 0;
     if (r >= 0) rd = V.reads[r];
     const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
-    const int J = valid ? rd.J : 0;
+    const int J = pinned(valid ? rd.J : 0);
     const int I = rd.I;
     int Jmax = J;
 #pragma unroll
@@ -168,31 +236,32 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     const unsigned* __restrict__ rc32 = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off + rd.code_stride);
     const int wmax = (rd.code_stride >> 2) - 1;
     const uint8_t* __restrict__ tp = V.tpl + rd.tpl_off;
-    const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
     float4* __restrict__ bcol = reinterpret_cast<float4*>(V.beta) + (size_t)rd.col_off * 8 + g;
     const ColInfo* __restrict__ cinfo = V.colinfo + rd.col_off;
     int32_t* __restrict__ bexp = V.beta_exp + rd.col_off;
+    const unsigned t2_base = (unsigned)pinned((int)__cvta_generic_to_shared(s_t2));
+    const int src_dn = pinned((g + 1) & 7), src_dn2 = pinned((g + 2) & 7), src_dn4 = pinned((g + 4) & 7);
+    const int g4 = pinned(4 * g);
 
     // The warp walks columns from (Jmax-1) down to 1; an octet is alive once j <= J-1.
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    int s_next = 0, cum = 0, lap = 0;
-    int s_cur = 0;   // band start of column j (prefetched)
-    int t_hi = 0, t_lo = 0, t_lo2 = 0;   // template bases j, j-1, j-2
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    int cum = 0, lap = 0;
+    int s_cur = 0, s_nxt = 0;            // band starts of columns j and j+1
+    int s_p1 = 0, s_p2 = 0;              // prefetched band starts of columns j-1 and j-2
+    int x_cur = 0, x_p1 = 0, x_p2 = 0;   // dinucleotide contexts of columns j, j-1, j-2
     unsigned w0 = 0x30303030u, w1 = 0x30303030u, wm = 0x30303030u;   // laps L, L+1, L-1 (sentinels)
-    float4 tr_c = make_float4(0.f, 0.f, 0.f, 0.f), tr_p = tr_c;
-    float first_val = 0.f;
-    int first_cum = 0;
     bool started = false;
 
     for (int j = Jmax - 1; j >= 1; --j) {
         const bool alive = j <= J - 1;
-        if (alive && !started) {
+        const bool init_col = alive && !started;
+        if (init_col) {
             // prologue at j == J-1
             s_cur = cinfo[j].start;
-            s_next = s_cur;
-            t_hi = tp[j] & 3; t_lo = tp[j - 1] & 3; t_lo2 = tp[max(j - 2, 0)] & 3;
-            tr_c = tr[4 * t_lo + t_hi];
-            tr_p = tr[4 * t_lo2 + t_lo];
+            s_nxt = s_cur;
+            s_p1 = cinfo[max(j - 1, 0)].start;
+            x_cur = tp[j] & 15;
+            x_p1 = tp[max(j - 1, 0)] & 15;
             lap = s_cur >> 5;
             w0 = rc32[min(8 * lap + g, wmax)];
             w1 = rc32[min(8 * (lap + 1) + g, wmax)];
@@ -203,57 +272,76 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
             w1 = w0; w0 = wm;
             wm = rc32[min(8 * max(lap - 1, 0) + g, wmax)];
         }
-        const int ci = 4 * t_lo + t_hi;              // context of column j (= match context of j+1)
-        const int d = s_next - s_cur;
-        int rel[4], code1[4];
-        lane_codes(w0, w1, s_cur, g, code1);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rel[q] = (4 * g + q - s_cur) & 31;
-        // prefetch for column j-1
-        const int s_prev = (alive && j >= 2) ? cinfo[j - 1].start : s_cur;
-        const int t_lo3 = (alive && j >= 3) ? (tp[j - 3] & 3) : 0;
-        const float4 tr_pp = alive ? tr[4 * t_lo3 + t_lo2] : tr_p;
+        // prefetch for column j-2
+        if (alive && j >= 3) { s_p2 = cinfo[j - 2].start; x_p2 = tp[j - 2] & 15; }
 
-        float A[4], G[4];
-        octet_backward_terms(v, g, d, rel, code1, tr_c.x, tr_c.y, tr_c.z, tr_c.w, s_emm + ci * kEmStride,
-                             s_emi + ci * kEmStride, (ci & 3) << 2, A, G);
-        if (alive && !started) {
+        const bool slid = s_nxt != s_cur;          // band start of column j+1 is 4 rows further
+        const int ss = s_cur & 31;
+        const unsigned cw = (g4 < ss) ? w1 : w0;
+        const int r0 = (g4 - s_cur) & 31;
+        const bool startl = r0 == 0, topl = r0 == 28;
+        float dn3 = __shfl_sync(kFullMask, v0, src_dn, 8);   // beta(row+1, j+1) of the lane's last cell
+        if (topl && !slid) dn3 = 0.f;              // row s+32 is outside the band of column j+1
+        if (startl && slid) { v0 = 0.f; v1 = 0.f; v2 = 0.f; v3 = 0.f; }   // rows below the band of column j+1
+        const unsigned row = t2_base + ((unsigned)x_cur << 7);
+        const float2 e0 = lds_f2(row + ((cw & 0xffu) << 1));
+        const float2 e1 = lds_f2(row + (__byte_perm(cw, 0u, 0x4441u) << 1));
+        const float2 e2 = lds_f2(row + (__byte_perm(cw, 0u, 0x4442u) << 1));
+        const float2 e3 = lds_f2(row + ((cw >> 24) << 1));
+        const float D = lds_f1(row + kDSlot * 8);
+        float A0 = fmaf(e0.x, v1, D * v0);
+        float A1 = fmaf(e1.x, v2, D * v1);
+        float A2 = fmaf(e2.x, v3, D * v2);
+        float A3 = fmaf(e3.x, dn3, D * v3);
+        float G0 = e0.y, G1 = e1.y, G2 = e2.y;
+        float G3 = topl ? 0.f : e3.y;              // band end: no in-band successor
+        if (init_col) {
             // last column: beta(I-1, J-1) = pinned last match; rows above it by insertions
-            const float endv = s_emm[(kCtxEndRow + ci) * kEmStride + rd.last_code];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) A[q] = (s_cur + rel[q] == I - 1) ? endv : 0.f;
+            const float endv = V.em_match[(kCtxEndRow + x_cur) * kEmStride + rd.last_code];
+            const int row0 = s_cur + r0;
+            A0 = (row0 == I - 1) ? endv : 0.f;
+            A1 = (row0 + 1 == I - 1) ? endv : 0.f;
+            A2 = (row0 + 2 == I - 1) ? endv : 0.f;
+            A3 = (row0 + 3 == I - 1) ? endv : 0.f;
         }
-        if (!alive) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { A[q] = 0.f; G[q] = 0.f; }
+        if (!alive) { A0 = A1 = A2 = A3 = 0.f; G0 = G1 = G2 = G3 = 0.f; }
+        // b_i = A_i + G_i * b_{i+1}
+        A2 = fmaf(G2, A3, A2); G2 *= G3;
+        A1 = fmaf(G1, A2, A1); G1 *= G2;
+        A0 = fmaf(G0, A1, A0); G0 *= G1;
+        float At = A0, Gt = G0;
+        {
+            float As = __shfl_sync(kFullMask, At, src_dn, 8), Gs = __shfl_sync(kFullMask, Gt, src_dn, 8);
+            At = fmaf(Gt, As, At); Gt *= Gs;
+            As = __shfl_sync(kFullMask, At, src_dn2, 8); Gs = __shfl_sync(kFullMask, Gt, src_dn2, 8);
+            At = fmaf(Gt, As, At); Gt *= Gs;
+            As = __shfl_sync(kFullMask, At, src_dn4, 8);
+            At = fmaf(Gt, As, At);
         }
-        octet_backward_scan(A, G, g, v);
-        int edge_rel;
-        bool dead;
-        const int k = octet_scale_column(v, rel, edge_rel, dead);
+        const float xin = __shfl_sync(kFullMask, At, src_dn, 8);
+        v0 = fmaf(G0, xin, A0); v1 = fmaf(G1, xin, A1); v2 = fmaf(G2, xin, A2); v3 = fmaf(G3, xin, A3);
+
+        const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+        unsigned key = vmax_oct(__float_as_uint(mx) & 0xffff0000u);
+        const int ebits = (int)(key >> 23);
+        const float sc = __uint_as_float(0x7f000000u - ((key >> 23) << 23));
+        v0 *= sc; v1 *= sc; v2 *= sc; v3 *= sc;
         if (alive) {
-            cum += k;
-            bcol[(size_t)j * 8] = make_float4(v[0], v[1], v[2], v[3]);
+            cum += ebits - 127;
+            bcol[(size_t)j * 8] = make_float4(v0, v1, v2, v3);
             if (g == 0) bexp[j] = cum;
-            if (j == 1) {   // beta(1,1) lives in slot 1 if row 1 is inside the band
-                const int rrel = (1 - s_cur) & 31;
-                const bool inband = (s_cur + rrel) == 1;
-                float x = 0.f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) x = (4 * g + q == 1 && inband) ? v[q] : x;
-                first_val = x;
-                first_cum = cum;
-            }
             started = true;
-            s_next = s_cur; s_cur = s_prev;
-            t_hi = t_lo; t_lo = t_lo2; t_lo2 = t_lo3;
-            tr_c = tr_p; tr_p = tr_pp;
+            s_nxt = s_cur; s_cur = s_p1; s_p1 = s_p2;
+            x_cur = x_p1; x_p1 = x_p2;
         }
     }
-    const float fv = octet_max(first_val);
+    // the warp's last iteration is column 1 of every live octet: beta(1,1) is cell 1 of lane 0 if row 1 is in the band
     if (valid) {
         if (g == 0) {
-            const double b = (double)fv * (double)s_emm[(kCtxStartRow + (tp[0] & 3)) * kEmStride + rd.first_code];
+            const bool inband = s_nxt <= 1;        // after the last column s_nxt holds the band start of column 1
+            const float fv = inband ? v1 : 0.f;
+            const int first_cum = cum;
+            const double b = (double)fv * (double)V.em_match[(kCtxStartRow + (tp[0] & 3)) * kEmStride + rd.first_code];
             const double lb = (b > 0.0) ? log(b) + 0.6931471805599453094 * (double)first_cum - (double)I * V.log_cw : -INFINITY;
             V.ll_beta[r] = lb;
             const double la = V.ll_alpha[r];
@@ -268,385 +356,18 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// Generalised lane mapping: CPL cells per lane, LPP = 32 / CPL lanes per pair, CPL pairs per warp.
-// More cells per lane amortise the per-column bookkeeping (band slide, prefetch, reductions, loop)
-// and shorten the ring scan; fewer lanes per pair need more pairs in flight to fill the machine.
-// The memory layout is the same for every CPL (slot = row mod 32 inside the 128-B column line).
-// ---------------------------------------------------------------------------------------------
-template <int LPP>
-__device__ __forceinline__ float shfl_grp(float x, int src) { return __shfl_sync(kFullMask, x, src, LPP); }
-
-template <int CPL>
-struct LaneWords {   // row-code words of this lane for laps L, L+1 and (prefetched) L+2 / L-1
-    unsigned w[3][CPL / 4];
-};
-
-template <int CPL>
-__device__ __forceinline__ void lane_codes_n(const unsigned* lo, const unsigned* hi, const int s, const int g, int code[CPL]) {
-#pragma unroll
-    for (int k = 0; k < CPL / 4; ++k) {
-        const int t = min(max((s & 31) - (CPL * g + 4 * k), 0), 4);
-        const unsigned sel = 0x3210u | (0x4444u & ((1u << (4 * t)) - 1u));
-        const unsigned cw = __byte_perm(lo[k], hi[k], sel);
-        code[4 * k + 0] = (int)(cw & 0xffu);
-        code[4 * k + 1] = (int)__byte_perm(cw, 0u, 0x4441u);
-        code[4 * k + 2] = (int)__byte_perm(cw, 0u, 0x4442u);
-        code[4 * k + 3] = (int)(cw >> 24);
-    }
-}
-
-// column normalisation + leading edge over a group of LPP lanes
-template <int CPL>
-__device__ __forceinline__ int group_scale_column(float v[CPL], const int rel0, int& edge_rel) {
-    constexpr int LPP = 32 / CPL;
-    const float thr = __uint_as_float((unsigned)(127 + kEdgeLog2) << 23);
-    float mx = 0.f;
-    int er = 0;
-#pragma unroll
-    for (int q = 0; q < CPL; ++q) {
-        mx = fmaxf(mx, v[q]);
-        const int rl = (rel0 + q) & 31;
-        er = (v[q] >= thr) ? max(er, rl + 1) : er;
-    }
-    unsigned key = (__float_as_uint(mx) & 0xffff0000u) | (unsigned)er;
-#pragma unroll
-    for (int off = 1; off < LPP; off <<= 1) key = __vmaxu2(key, __shfl_xor_sync(kFullMask, key, off, LPP));
-    edge_rel = (int)(key & 0xffffu);
-    const int ebits = (int)((key >> 23) & 255u);
-    const int k = ((key >> 16) == 0u) ? 0 : ebits - 127;
-    const float sc = __uint_as_float((unsigned)(127 - k) << 23);
-#pragma unroll
-    for (int q = 0; q < CPL; ++q) v[q] *= sc;
-    return k;
-}
-
-template <int LPP>
-__device__ __forceinline__ float group_max(float x) {
-#pragma unroll
-    for (int off = 1; off < LPP; off <<= 1) x = fmaxf(x, __shfl_xor_sync(kFullMask, x, off, LPP));
-    return x;
-}
-
-template <int CPL>
-__global__ void __launch_bounds__(128) arrow_fill_alpha_n_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
-                                                                 const int n_items) {
-    constexpr int LPP = 32 / CPL;          // lanes per pair
-    constexpr int PPC = 128 / LPP;         // pairs per CTA
-    constexpr int NW = CPL / 4;            // row-code words per lane and lap
-    __shared__ float s_emm[36 * kEmStride];
-    __shared__ float s_emi[17 * kEmStride];
-    load_emissions(V, s_emm, s_emi);
-
-    const int item = blockIdx.x * PPC + (threadIdx.x / LPP);
-    const int g = threadIdx.x % LPP;
-    int r = -1;
-    if (item < n_items) r = order[item];
-    DevRead rd;
-    rd.J = 0; rd.I = 0; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0; rd.zmw = 0; rd.last_code = 0; rd.code_stride = 256;
-    rd.active = 0;
-    if (r >= 0) rd = V.reads[r];
-    const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
-    const int J = valid ? rd.J : 0;
-    const int Jc = valid ? rd.J : 2;
-    const int I = rd.I;
-    int Jmax = J;
-#pragma unroll
-    for (int off = LPP; off < 32; off <<= 1) Jmax = max(Jmax, __shfl_xor_sync(kFullMask, Jmax, off));
-
-    const unsigned* __restrict__ rc32 = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off);
-    const int wmax = (rd.code_stride >> 2) - 1;
-    const uint8_t* __restrict__ tp = V.tpl + rd.tpl_off;
-    const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
-    float4* __restrict__ acol = reinterpret_cast<float4*>(V.alpha) + (size_t)rd.col_off * 8 + NW * g;
-    ColInfo* __restrict__ cinfo = V.colinfo + rd.col_off;
-
-    float v[CPL];
-#pragma unroll
-    for (int q = 0; q < CPL; ++q) v[q] = 0.f;
-    if (g == 0) v[0] = 1.f;
-    int s = 0, cum = 0, edge = 0, lap = 0;
-    unsigned w0[NW], w1[NW], w2[NW];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) {
-        w0[k] = rc32[min(NW * g + k, wmax)];
-        w1[k] = rc32[min(8 + NW * g + k, wmax)];
-        w2[k] = rc32[min(16 + NW * g + k, wmax)];
-    }
-    if (valid) {
-#pragma unroll
-        for (int k = 0; k < NW; ++k) acol[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        if (g == 0) cinfo[0] = ColInfo{0, 0};
-    }
-    const int t0 = tp[0] & 3, t1 = tp[min(1, Jc - 1)] & 3;   // & 3: idle octets read whatever sits at the buffer start
-    int t2 = tp[min(2, Jc - 1)] & 3;
-    int cm = kCtxStartRow + t0;
-    int ci = 4 * t0 + t1;
-    float4 tr_m = tr[cm];
-    float4 tr_i = tr[ci];
-    float final_val = 0.f;
-    int final_cum = 0;
-
-    for (int j = 1; j < Jmax; ++j) {
-        const bool alive = j < J;
-        const int s_new = max(s, edge + 2 + kBandMargin - kBandW);
-        const int d = s_new - s;
-        if ((s_new >> 5) != lap) {
-            lap = s_new >> 5;
-#pragma unroll
-            for (int k = 0; k < NW; ++k) { w0[k] = w1[k]; w1[k] = w2[k]; w2[k] = rc32[min(8 * (lap + 2) + NW * g + k, wmax)]; }
-        }
-        int code[CPL];
-        lane_codes_n<CPL>(w0, w1, s_new, g, code);
-        const int rel0 = (CPL * g - s_new) & 31;
-        const int ci_next = ((ci & 3) << 2) | t2;
-        const float4 tr_next = tr[ci_next];
-        const int t3 = tp[min(j + 2, Jc - 1)] & 3;
-
-        const float* __restrict__ emm_row = s_emm + cm * kEmStride;
-        const float* __restrict__ emi_row = s_emi + ci * kEmStride;
-        const int cb4 = (ci & 3) << 2;
-        const float M = tr_m.x, D = tr_m.y, B = tr_i.z, S = tr_i.w;
-        // terms + serial scan inside the lane
-        float A[CPL], G[CPL];
-        float up = shfl_grp<LPP>(v[CPL - 1], (g + LPP - 1) % LPP);
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) {
-            const int rl = (rel0 + q) & 31;
-            const int rdd = rl + d;
-            const float old = v[q];
-            const float pv = (rdd < 32) ? old : 0.f;
-            const float uv = ((unsigned)(rdd - 1) < 32u) ? up : 0.f;
-            const float a = fmaf(M, ldtab(emm_row, code[q]) * uv, D * pv);
-            float gi = ldtab(emi_row, code[q]) * (((code[q] & 12) == cb4) ? B : S);
-            gi = (rl == 0) ? 0.f : gi;
-            if (q == 0) { A[0] = a; G[0] = gi; }
-            else { A[q] = fmaf(gi, A[q - 1], a); G[q] = gi * G[q - 1]; }
-            up = old;
-        }
-        float At = A[CPL - 1], Gt = G[CPL - 1];
-#pragma unroll
-        for (int off = 1; off < LPP; off <<= 1) {
-            const float As = shfl_grp<LPP>(At, (g + LPP - off) % LPP);
-            const float Gs = shfl_grp<LPP>(Gt, (g + LPP - off) % LPP);
-            At = fmaf(Gt, As, At);
-            Gt *= Gs;
-        }
-        const float x = shfl_grp<LPP>(At, (g + LPP - 1) % LPP);
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) v[q] = fmaf(G[q], x, A[q]);
-
-        int edge_rel;
-        const int k = group_scale_column<CPL>(v, rel0, edge_rel);
-        cum += k;
-        edge = s_new + edge_rel - 1;
-        s = s_new;
-        if (alive) {
-#pragma unroll
-            for (int kk = 0; kk < NW; ++kk)
-                acol[(size_t)j * 8 + kk] = make_float4(v[4 * kk], v[4 * kk + 1], v[4 * kk + 2], v[4 * kk + 3]);
-            if (g == 0) cinfo[j] = ColInfo{s_new, cum};
-            if (j == J - 1) {
-                const int slot = (I - 1) & 31;
-                const int rrel = (slot - s_new) & 31;
-                const bool inband = (s_new + rrel) == (I - 1);
-                float xx = 0.f;
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) xx = (CPL * g + q == slot && inband) ? v[q] : xx;
-                final_val = xx;
-                final_cum = cum;
-            }
-        }
-        cm = ci; ci = ci_next; tr_m = tr_i; tr_i = tr_next; t2 = t3;
-    }
-    const float fv = group_max<LPP>(final_val);
-    if (valid) {
-        if (g == 0) {
-            const int ctxl = 4 * (tp[J - 2] & 3) + (tp[J - 1] & 3);
-            const double a = (double)fv * (double)s_emm[(kCtxEndRow + ctxl) * kEmStride + rd.last_code];
-            const double base = (a > 0.0) ? log(a) + 0.6931471805599453094 * (double)final_cum : -INFINITY;
-            V.base_ll[r] = base;
-            V.ll_alpha[r] = base - (double)I * V.log_cw;
-        }
-    } else if (r >= 0 && g == 0) {
-        V.base_ll[r] = -INFINITY;
-        V.ll_alpha[r] = -INFINITY;
-    }
-}
-
-template <int CPL>
-__global__ void __launch_bounds__(128) arrow_fill_beta_n_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
-                                                                const int n_items) {
-    constexpr int LPP = 32 / CPL;
-    constexpr int PPC = 128 / LPP;
-    constexpr int NW = CPL / 4;
-    __shared__ float s_emm[36 * kEmStride];
-    __shared__ float s_emi[17 * kEmStride];
-    load_emissions(V, s_emm, s_emi);
-
-    const int item = blockIdx.x * PPC + (threadIdx.x / LPP);
-    const int g = threadIdx.x % LPP;
-    int r = -1;
-    if (item < n_items) r = order[item];
-    DevRead rd;
-    rd.J = 0; rd.I = 0; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0; rd.zmw = 0; rd.last_code = 0; rd.first_code = 0;
-    rd.code_stride = 256; rd.active = 0;
-    if (r >= 0) rd = V.reads[r];
-    const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
-    const int J = valid ? rd.J : 0;
-    const int I = rd.I;
-    int Jmax = J;
-#pragma unroll
-    for (int off = LPP; off < 32; off <<= 1) Jmax = max(Jmax, __shfl_xor_sync(kFullMask, Jmax, off));
-
-    const unsigned* __restrict__ rc32 = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off + rd.code_stride);
-    const int wmax = (rd.code_stride >> 2) - 1;
-    const uint8_t* __restrict__ tp = V.tpl + rd.tpl_off;
-    const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
-    float4* __restrict__ bcol = reinterpret_cast<float4*>(V.beta) + (size_t)rd.col_off * 8 + NW * g;
-    const ColInfo* __restrict__ cinfo = V.colinfo + rd.col_off;
-    int32_t* __restrict__ bexp = V.beta_exp + rd.col_off;
-
-    float v[CPL];
-#pragma unroll
-    for (int q = 0; q < CPL; ++q) v[q] = 0.f;
-    int s_next = 0, cum = 0, lap = 0, s_cur = 0;
-    int t_hi = 0, t_lo = 0, t_lo2 = 0;
-    unsigned w0[NW], w1[NW], wm[NW];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) { w0[k] = 0x30303030u; w1[k] = 0x30303030u; wm[k] = 0x30303030u; }
-    float4 tr_c = make_float4(0.f, 0.f, 0.f, 0.f), tr_p = tr_c;
-    float first_val = 0.f;
-    int first_cum = 0;
-    bool started = false;
-
-    for (int j = Jmax - 1; j >= 1; --j) {
-        const bool alive = j <= J - 1;
-        if (alive && !started) {
-            s_cur = cinfo[j].start;
-            s_next = s_cur;
-            t_hi = tp[j] & 3; t_lo = tp[j - 1] & 3; t_lo2 = tp[max(j - 2, 0)] & 3;
-            tr_c = tr[4 * t_lo + t_hi];
-            tr_p = tr[4 * t_lo2 + t_lo];
-            lap = s_cur >> 5;
-#pragma unroll
-            for (int k = 0; k < NW; ++k) {
-                w0[k] = rc32[min(8 * lap + NW * g + k, wmax)];
-                w1[k] = rc32[min(8 * (lap + 1) + NW * g + k, wmax)];
-                wm[k] = rc32[min(8 * max(lap - 1, 0) + NW * g + k, wmax)];
-            }
-        }
-        if (alive && (s_cur >> 5) != lap) {
-            lap = s_cur >> 5;
-#pragma unroll
-            for (int k = 0; k < NW; ++k) { w1[k] = w0[k]; w0[k] = wm[k]; wm[k] = rc32[min(8 * max(lap - 1, 0) + NW * g + k, wmax)]; }
-        }
-        const int ci = 4 * t_lo + t_hi;
-        const int d = s_next - s_cur;
-        int code1[CPL];
-        lane_codes_n<CPL>(w0, w1, s_cur, g, code1);
-        const int rel0 = (CPL * g - s_cur) & 31;
-        const int s_prev = (alive && j >= 2) ? cinfo[j - 1].start : s_cur;
-        const int t_lo3 = (alive && j >= 3) ? (tp[j - 3] & 3) : 0;
-        const float4 tr_pp = alive ? tr[4 * t_lo3 + t_lo2] : tr_p;
-
-        const float* __restrict__ emm_row = s_emm + ci * kEmStride;
-        const float* __restrict__ emi_row = s_emi + ci * kEmStride;
-        const int cb4 = (ci & 3) << 2;
-        const float M = tr_c.x, D = tr_c.y, B = tr_c.z, S = tr_c.w;
-        const bool init_col = alive && !started;
-        const float endv = s_emm[(kCtxEndRow + ci) * kEmStride + rd.last_code];
-        float A[CPL], G[CPL];
-        float dn = shfl_grp<LPP>(v[0], (g + 1) % LPP);
-#pragma unroll
-        for (int q = CPL - 1; q >= 0; --q) {
-            const int rl = (rel0 + q) & 31;
-            const float old = v[q];
-            const float nx = (rl >= d) ? old : 0.f;
-            const float nd = (rl >= d - 1 && rl <= d + 30) ? dn : 0.f;
-            float a = fmaf(M, ldtab(emm_row, code1[q]) * nd, D * nx);
-            if (init_col) a = (s_cur + rl == I - 1) ? endv : 0.f;
-            float gi = ldtab(emi_row, code1[q]) * (((code1[q] & 12) == cb4) ? B : S);
-            gi = (rl == 31) ? 0.f : gi;
-            if (!alive) { a = 0.f; gi = 0.f; }
-            if (q == CPL - 1) { A[q] = a; G[q] = gi; }
-            else { A[q] = fmaf(gi, A[q + 1], a); G[q] = gi * G[q + 1]; }
-            dn = old;
-        }
-        float At = A[0], Gt = G[0];
-#pragma unroll
-        for (int off = 1; off < LPP; off <<= 1) {
-            const float As = shfl_grp<LPP>(At, (g + off) % LPP);
-            const float Gs = shfl_grp<LPP>(Gt, (g + off) % LPP);
-            At = fmaf(Gt, As, At);
-            Gt *= Gs;
-        }
-        const float x = shfl_grp<LPP>(At, (g + 1) % LPP);
-#pragma unroll
-        for (int q = 0; q < CPL; ++q) v[q] = fmaf(G[q], x, A[q]);
-        int edge_rel;
-        const int k = group_scale_column<CPL>(v, rel0, edge_rel);
-        if (alive) {
-            cum += k;
-#pragma unroll
-            for (int kk = 0; kk < NW; ++kk)
-                bcol[(size_t)j * 8 + kk] = make_float4(v[4 * kk], v[4 * kk + 1], v[4 * kk + 2], v[4 * kk + 3]);
-            if (g == 0) bexp[j] = cum;
-            if (j == 1) {
-                const int rrel = (1 - s_cur) & 31;
-                const bool inband = (s_cur + rrel) == 1;
-                float xx = 0.f;
-#pragma unroll
-                for (int q = 0; q < CPL; ++q) xx = (CPL * g + q == 1 && inband) ? v[q] : xx;
-                first_val = xx;
-                first_cum = cum;
-            }
-            started = true;
-            s_next = s_cur; s_cur = s_prev;
-            t_hi = t_lo; t_lo = t_lo2; t_lo2 = t_lo3;
-            tr_c = tr_p; tr_p = tr_pp;
-        }
-    }
-    const float fv = group_max<LPP>(first_val);
-    if (valid) {
-        if (g == 0) {
-            const double b = (double)fv * (double)s_emm[(kCtxStartRow + (tp[0] & 3)) * kEmStride + rd.first_code];
-            const double lb = (b > 0.0) ? log(b) + 0.6931471805599453094 * (double)first_cum - (double)I * V.log_cw : -INFINITY;
-            V.ll_beta[r] = lb;
-            const double la = V.ll_alpha[r];
-            int st = 0;
-            if (!(la > -INFINITY) || !(lb > -INFINITY)) st = 3;
-            else if (!(fabs(1.0 - la / lb) <= V.ab_tol)) st = 1;
-            V.status[r] = st;
-        }
-    } else if (r >= 0 && g == 0) {
-        V.ll_beta[r] = -INFINITY;
-        V.status[r] = (rd.active && (rd.J < 2 || rd.I < 2)) ? 2 : (rd.active ? 3 : 4);
-    }
-}
-
 }  // namespace
 
-// cells_per_lane: 4 (octet kernels above), 8, 16 or 32
-void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream, int cells_per_lane) {
+// order[n_items]: n_items is a multiple of 16; every aligned group of 16 entries holds reads of ONE ZMW
+// (longest template first), padded with -1; a group's first entry is a real read.
+void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream) {
     if (n_items <= 0) return;
-    switch (cells_per_lane) {
-        case 8: arrow_fill_alpha_n_kernel<8><<<(n_items + 31) / 32, 128, 0, stream>>>(V, order, n_items); break;
-        case 16: arrow_fill_alpha_n_kernel<16><<<(n_items + 63) / 64, 128, 0, stream>>>(V, order, n_items); break;
-        case 32: arrow_fill_alpha_n_kernel<32><<<(n_items + 127) / 128, 128, 0, stream>>>(V, order, n_items); break;
-        default: arrow_fill_alpha_kernel<<<(n_items + 15) / 16, 128, 0, stream>>>(V, order, n_items);
-    }
+    arrow_fill_alpha_kernel<<<(n_items + 15) / 16, 128, 0, stream>>>(V, order, n_items);
 }
 
-void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream, int cells_per_lane) {
+void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream) {
     if (n_items <= 0) return;
-    switch (cells_per_lane) {
-        case 8: arrow_fill_beta_n_kernel<8><<<(n_items + 31) / 32, 128, 0, stream>>>(V, order, n_items); break;
-        case 16: arrow_fill_beta_n_kernel<16><<<(n_items + 63) / 64, 128, 0, stream>>>(V, order, n_items); break;
-        case 32: arrow_fill_beta_n_kernel<32><<<(n_items + 127) / 128, 128, 0, stream>>>(V, order, n_items); break;
-        default: arrow_fill_beta_kernel<<<(n_items + 15) / 16, 128, 0, stream>>>(V, order, n_items);
-    }
+    arrow_fill_beta_kernel<<<(n_items + 15) / 16, 128, 0, stream>>>(V, order, n_items);
 }
 
 }  // namespace ccs

@@ -5,10 +5,10 @@
 
 namespace ccs {
 
-// order[n_items]: read indices, longest template first (keeps a warp's four octets in step)
-// cells_per_lane selects the lane mapping: 4 = octet (8 lanes per pair) ... 32 = one lane per pair
-void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream, int cells_per_lane = 4);
-void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream, int cells_per_lane = 4);
+// order[n_items]: n_items is a multiple of 16; every aligned group of 16 entries (one CTA) holds reads of ONE ZMW,
+// longest template first, padded with -1; a group's first entry is a real read
+void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
+void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
 
 // delta[(zmw.delta_off + p) * kDeltaStride + slot]; INS total = slot[5+b] + slot[9+b].
 // Ranges of one ZMW must be disjoint and non-touching.  generic = reference kernel (every mutation

@@ -607,8 +607,8 @@ __global__ void __launch_bounds__(256) arrow_pick_kernel(const ArrowBatchView V,
     const int p = rg.p_begin + (int)(item - rg.first);
     const DevZmw zm = V.zmws[z];
     const uint8_t* t = V.tpl + zm.fwd_off;
-    const int tb = t[p];
-    const int tprev = (p > 0) ? t[p - 1] : -1;
+    const int tb = t[p] & 3;                       // template bytes carry context bits above the base
+    const int tprev = (p > 0) ? (t[p - 1] & 3) : -1;
     const double* d = delta + (size_t)(zm.delta_off + p) * kDeltaStride;
 #pragma unroll 1
     for (int s = 0; s < 9; ++s) {
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(256) arrow_qv_kernel(const ArrowBatchView V, c
     const int z = rg.zmw;
     const int p = rg.p_begin + (int)(item - rg.first);
     const DevZmw zm = V.zmws[z];
-    const int tb = V.tpl[zm.fwd_off + p];
+    const int tb = V.tpl[zm.fwd_off + p] & 3;
     const double* d = delta + (size_t)(zm.delta_off + p) * kDeltaStride;
     double s = 0.0;
 #pragma unroll

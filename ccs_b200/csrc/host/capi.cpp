@@ -33,7 +33,6 @@ struct ccsgpu_ctx {
     size_t budget = 0;           // device bytes this ctx may use (0 at create -> 85 % of the free memory then)
     size_t lane_budget() const { return n_lanes > 0 ? budget / (size_t)n_lanes : budget; }
     bool generic_score = false;
-    int fill_cpl = 4;
     bool reuse_scores = false;
     double ms_e2e = 0;
     int64_t n_zmws = 0;
@@ -91,8 +90,6 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
           ctx->host_threads = hc; ctx->engine->host_threads = hc; ctx->draft->host_threads = hc; }
         if (const char* e = std::getenv("CCS_B200_GENERIC_SCORE")) ctx->generic_score = (e[0] == '1');
         ctx->engine->generic_score = ctx->generic_score;
-        if (const char* e = std::getenv("CCS_B200_FILL_CPL")) ctx->fill_cpl = std::atoi(e);
-        ctx->engine->fill_cells_per_lane = ctx->fill_cpl;
         if (const char* e = std::getenv("CCS_B200_REUSE_SCORES")) ctx->reuse_scores = (e[0] != '0');
         ctx->engine->reuse_scores = ctx->reuse_scores;
         ctx->budget = device_bytes_budget;
@@ -122,7 +119,6 @@ int ccsgpu_set_lanes(ccsgpu_ctx* ctx, int n_lanes) {
             l.engine.reset(new ArrowEngine(ctx->device, ctx->model, ctx->budget));
             l.draft.reset(new DraftEngine(ctx->device, 0));
             l.engine->generic_score = ctx->generic_score;
-            l.engine->fill_cells_per_lane = ctx->fill_cpl;
             l.engine->reuse_scores = ctx->reuse_scores;
             ctx->extra.push_back(std::move(l));
         }

@@ -259,8 +259,15 @@ void ArrowEngine::upload_templates_and_reads() {
         const int J = dz.J;
         uint8_t* f = h_tpl_.p + dz.fwd_off;
         uint8_t* rv = h_tpl_.p + dz.rev_off;
-        std::memcpy(f, zs.tpl.data(), (size_t)J);
-        for (int j = 0; j < J; ++j) rv[j] = (uint8_t)(3 - zs.tpl[J - 1 - j]);
+        // template bytes carry the trinucleotide index 16*t[j-2] + 4*t[j-1] + t[j] (the base is byte & 3): the fill
+        // kernels use the byte as the row index of their folded factor tables
+        unsigned hf = 0, hr = 0;
+        for (int j = 0; j < J; ++j) {
+            hf = ((hf << 2) | zs.tpl[j]) & 63u;
+            hr = ((hr << 2) | (3u - zs.tpl[J - 1 - j])) & 63u;
+            f[j] = (uint8_t)hf;
+            rv[j] = (uint8_t)hr;
+        }
         for (int r = zs.read_begin; r < zs.read_end; ++r) {
             DevRead& rd = reads_[r];
             rd.tpl_off = rd.strand ? dz.rev_off + (J - rd.te) : dz.fwd_off + rd.ts;
@@ -269,24 +276,38 @@ void ArrowEngine::upload_templates_and_reads() {
     total_cols_ = cols;
     total_delta_rows_ = drows;
     // reads to (re)fill: every active read of a ZMW whose template changed since its last fill
+    // fill work list: groups of 16 slots (one CTA each) holding reads of ONE ZMW, longest template first, padded
+    // with -1; groups ordered longest first
     order_.clear();
-    for (int z = 0; z < nz; ++z) {
-        if (!zstate_[z].dirty) continue;
-        for (int r = zstate_[z].read_begin; r < zstate_[z].read_end; ++r) if (reads_[r].active) order_.push_back(r);
+    {
+        std::vector<std::pair<int, int>> groups;   // (longest J, first slot in `slots`)
+        std::vector<int32_t> slots, zr;
+        for (int z = 0; z < nz; ++z) {
+            if (!zstate_[z].dirty) continue;
+            zr.clear();
+            for (int r = zstate_[z].read_begin; r < zstate_[z].read_end; ++r) if (reads_[r].active) zr.push_back(r);
+            std::stable_sort(zr.begin(), zr.end(), [&](int a, int b) { return reads_[a].J > reads_[b].J; });
+            for (size_t k = 0; k < zr.size(); k += 16) {
+                groups.emplace_back(reads_[zr[k]].J, (int)slots.size());
+                for (size_t x = 0; x < 16; ++x) slots.push_back(k + x < zr.size() ? zr[k + x] : -1);
+            }
+        }
+        std::stable_sort(groups.begin(), groups.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+        order_.reserve(slots.size());
+        for (const auto& gp : groups) order_.insert(order_.end(), slots.begin() + gp.second, slots.begin() + gp.second + 16);
     }
-    std::stable_sort(order_.begin(), order_.end(), [&](int a, int b) { return reads_[a].J > reads_[b].J; });
 
     d_tpl_.ensure((size_t)toff + 16, budget_);
     d_reads_.ensure((size_t)nr + 1);
     d_zmws_.ensure((size_t)nz + 1);
-    d_order_.ensure((size_t)nr + 1);
+    d_order_.ensure(order_.size() + 16);
     d_status_.ensure((size_t)nr + 1);
     d_ll_alpha_.ensure((size_t)nr + 1); d_ll_beta_.ensure((size_t)nr + 1); d_base_ll_.ensure((size_t)nr + 1);
     d_alpha_.ensure((size_t)(cols + 2) * 32, budget_);
     d_beta_.ensure((size_t)(cols + 2) * 32, budget_);
     d_colinfo_.ensure((size_t)cols + 2, budget_);
     d_bexp_.ensure((size_t)cols + 2, budget_);
-    h_reads_.ensure((size_t)nr + 1); h_zmws_.ensure((size_t)nz + 1); h_order_.ensure((size_t)nr + 1);
+    h_reads_.ensure((size_t)nr + 1); h_zmws_.ensure((size_t)nz + 1); h_order_.ensure(order_.size() + 16);
     h_status_.ensure((size_t)nr + 1);
     std::memcpy(h_reads_.p, reads_.data(), sizeof(DevRead) * nr);
     std::memcpy(h_zmws_.p, zmws_.data(), sizeof(DevZmw) * nz);
@@ -305,12 +326,12 @@ void ArrowEngine::fill() {
     const ArrowBatchView V = view();
     const int n = (int)order_.size();
     int64_t cells = 0, in_bytes = 0;
-    for (int r : order_) { cells += 32ll * (reads_[r].J - 1); in_bytes += reads_[r].I + reads_[r].J; }
+    for (int r : order_) if (r >= 0) { cells += 32ll * (reads_[r].J - 1); in_bytes += reads_[r].I + reads_[r].J; }
     span_begin(&stats.ms_fill_alpha, 4 * cells + 8 * (cells / 32) + in_bytes, &stats.top_fill_alpha_bytes, &stats.top_fill_alpha_ms);
-    launch_fill_alpha(V, d_order_.p, n, stream_, fill_cells_per_lane);
+    launch_fill_alpha(V, d_order_.p, n, stream_);
     span_end();
     span_begin(&stats.ms_fill_beta);
-    launch_fill_beta(V, d_order_.p, n, stream_, fill_cells_per_lane);
+    launch_fill_beta(V, d_order_.p, n, stream_);
     span_end();
     CCS_CUDA(cudaGetLastError());
     for (auto& zs : zstate_) zs.dirty = false;

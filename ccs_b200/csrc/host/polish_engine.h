@@ -107,7 +107,6 @@ public:
     // re-scoring the whole template (-35 % scoring work).  NOT exact: in repeats an edit reaches further, measured
     // 28 of 1.66 M positions off by more than 1 QV, so it is off by default (CCS_B200_REUSE_SCORES=1 enables it).
     bool reuse_scores = false;
-    int fill_cells_per_lane = 4;  // lane mapping of the fill kernels (4, 8, 16, 32)
     bool generic_score = false;   // use the unfactored reference scoring kernel (tests)
 
 private:
@@ -138,7 +137,7 @@ private:
     std::vector<ZmwState> zstate_;
     std::vector<DevRead> reads_;
     std::vector<DevZmw> zmws_;
-    std::vector<int32_t> order_;             // active reads, longest template first
+    std::vector<int32_t> order_;             // fill work list: 16-slot groups of one ZMW's reads, -1 padded
     std::vector<int32_t> status_;
     std::vector<std::vector<uint8_t>> qv_;
     std::vector<int64_t> col_base_;          // fixed first column of each read's band slot

@@ -45,6 +45,18 @@ void Tables::build(const ccs::ArrowModelParams& m, const float snr[4]) {
         for (int code = 0; code < 12; ++code)
             em_match[CTX_START + b][code] = (double)(float)(m.counter_weight * m.emission[ccs::MOVE_MATCH][5 * b][code]);
     for (int r = CTX_START; r < N_MROWS; ++r) tr[r][0] = 1.0;
+    // folded factors: one fp32 multiply of the fp32 table values (no contraction: -ffp-contract=off)
+    for (int r = 0; r < N_MROWS; ++r)
+        for (int code = 0; code < CODE_STRIDE; ++code) {
+            const float p = (float)em_match[r][code] * (float)tr[r][0];
+            mm[r][code] = (double)p;
+        }
+    for (int ctx = 0; ctx < 16; ++ctx)
+        for (int code = 0; code < CODE_STRIDE; ++code) {
+            const bool cognate = (code & 3) == (ctx & 3);
+            const float p = (float)em_ins[ctx][code] * (float)(cognate ? tr[ctx][2] : tr[ctx][3]);
+            gg[ctx][code] = (double)p;
+        }
 }
 
 // Column normalisation + band tracking (DESIGN.md "Band rule").
@@ -100,7 +112,9 @@ void Recursor<Real>::fill_alpha() {
     alpha.at(0, 0) = Real(1);
     int edge = 0;   // leading edge of column 0 is row 0
     for (int j = 1; j < Jn; ++j) {
-        const int s = std::max(alpha.start[j - 1], edge + 2 + margin - W);
+        // the start advances by one `slide` step whenever the leading edge comes within `margin` + 1 rows of the
+        // band's last row (quantised slide: band starts stay multiples of `slide`)
+        const int s = alpha.start[j - 1] + ((edge + 2 + margin - W > alpha.start[j - 1]) ? slide : 0);
         alpha.start[j] = s;
         const int cm = (j == 1) ? CTX_START + tpl[0] : 4 * tpl[j - 2] + tpl[j - 1];
         const int ci = 4 * tpl[j - 1] + tpl[j];
@@ -109,9 +123,8 @@ void Recursor<Real>::fill_alpha() {
             const int i = s + rel;
             const int code = code_at_row(i);
             const Real up = alpha.get(j - 1, i - 1), pv = alpha.get(j - 1, i);
-            const Real C = (Real)T.em_match[cm][code] * up * (Real)T.tr[cm][0] + (Real)T.tr[cm][1] * pv;
-            const bool cognate = (code & 3) == (ci & 3);
-            const Real g = (Real)T.em_ins[ci][code] * (Real)(cognate ? T.tr[ci][2] : T.tr[ci][3]);
+            const Real C = (Real)T.mm[cm][code] * up + (Real)T.tr[cm][1] * pv;
+            const Real g = (Real)T.gg[ci][code];
             run = C + g * (rel == 0 ? Real(0) : run);
             alpha.at(j, i) = run;
         }
@@ -147,10 +160,9 @@ void Recursor<Real>::fill_beta() {
                 C = (i == In - 1) ? (Real)T.em_match[CTX_END + ci][codes[In - 1]] : Real(0);
             } else {
                 const Real nd = beta.get(j + 1, i + 1), nx = beta.get(j + 1, i);
-                C = (Real)T.em_match[ci][code1] * nd * (Real)T.tr[ci][0] + (Real)T.tr[ci][1] * nx;
+                C = (Real)T.mm[ci][code1] * nd + (Real)T.tr[ci][1] * nx;
             }
-            const bool cognate = (code1 & 3) == (ci & 3);
-            const Real g = (Real)T.em_ins[ci][code1] * (Real)(cognate ? T.tr[ci][2] : T.tr[ci][3]);
+            const Real g = (Real)T.gg[ci][code1];
             run = C + g * (rel == W - 1 ? Real(0) : run);
             beta.at(j, i) = run;
         }
@@ -197,9 +209,8 @@ double Recursor<Real>::ll_mutated(const Mutation& mu) const {
         for (int rel = 0; rel < W; ++rel) {
             const int i = S + rel;
             const int code = code_at_row(i);
-            const Real C = (Real)T.em_match[cm][code] * getp(i - 1) * (Real)T.tr[cm][0] + (Real)T.tr[cm][1] * getp(i);
-            const bool cognate = (code & 3) == (ci & 3);
-            const Real g = (Real)T.em_ins[ci][code] * (Real)(cognate ? T.tr[ci][2] : T.tr[ci][3]);
+            const Real C = (Real)T.mm[cm][code] * getp(i - 1) + (Real)T.tr[cm][1] * getp(i);
+            const Real g = (Real)T.gg[ci][code];
             run = C + g * (rel == 0 ? Real(0) : run);
             cur[rel] = run;
         }
@@ -217,8 +228,7 @@ double Recursor<Real>::ll_mutated(const Mutation& mu) const {
     for (int rel = 0; rel < W; ++rel) {
         const int i = sprev + rel;
         const int code1 = code_at_row(i + 1);
-        const Real w = (Real)T.em_match[cmL][code1] * beta.get(borig, i + 1) * (Real)T.tr[cmL][0] +
-                       (Real)T.tr[cmL][1] * beta.get(borig, i);
+        const Real w = (Real)T.mm[cmL][code1] * beta.get(borig, i + 1) + (Real)T.tr[cmL][1] * beta.get(borig, i);
         sum += prev[rel] * w;
     }
     if (!((double)sum > 0.0)) return NEG_INF;

@@ -41,9 +41,13 @@ struct Tables {
     double em_ins[N_IROWS][CODE_STRIDE];
     double tr[N_MROWS][4];   // match, deletion, branch, stick
     double log_cw;
+    // The model the recursion uses (DESIGN.md "Arrow model"): per-ZMW FOLDED factors, each one fp32 product of
+    // the fp32 emission and the fp32 transition, rounded once to fp32 and held in double:
+    //   mm[row][code] = fl32(em_match[row][code] * match[row])          (start/end rows: match = 1)
+    //   gg[ctx][code] = fl32(em_ins[ctx][code] * (cognate ? branch[ctx] : stick[ctx]))
+    double mm[N_MROWS][CODE_STRIDE];
+    double gg[N_IROWS][CODE_STRIDE];
     void build(const ccs::ArrowModelParams& m, const float snr[4]);
-    // combined factors
-    inline double mfac(int row, int code) const { return em_match[row][code] * tr[row][0]; }
 };
 
 template <class Real>
@@ -69,6 +73,7 @@ struct Recursor {
     int W = 32;
     int margin = 2;               // band rule: rows kept beyond the leading edge
     int edge_log2 = -60;          // band rule: leading-edge threshold 2^edge_log2 on unscaled cells
+    int slide = 4;                // band rule: the band start advances in steps of `slide` rows (one lane of an octet)
     Banded<Real> alpha, beta;
     double ll_alpha = 0, ll_beta = 0;
     int status = READ_VALID;

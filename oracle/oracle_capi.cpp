@@ -115,6 +115,14 @@ void oracle_get_tables(const void* model, const float* snr, double* em_match, do
     *log_cw = t.log_cw;
 }
 
+// folded factors the recursion uses: mm[36*16] = fl32(em_match * match), gg[17*16] = fl32(em_ins * (branch|stick))
+void oracle_get_folded(const void* model, const float* snr, double* mm, double* gg) {
+    Tables t;
+    t.build(*(const ccs::ArrowModelParams*)model, snr);
+    std::memcpy(mm, t.mm, sizeof(t.mm));
+    std::memcpy(gg, t.gg, sizeof(t.gg));
+}
+
 
 // Recursor::FillAlphaBeta of one (read, template) pair.  precision: 0 = double, 1 = float cells.
 // Optional dumps (may be NULL): alpha/beta cells [J*W] (slot = row mod W), start[J], cumexp[J].

@@ -43,6 +43,14 @@ def tables(model, snr):
     return em_match, em_ins, tr, lcw.value
 
 
+def folded(model, snr):
+    """The factors the recursion multiplies by: mm = fl32(em_match * match), gg = fl32(em_ins * (branch | stick))."""
+    snr = np.ascontiguousarray(snr, np.float32)
+    mm = np.zeros((36, 16)); gg = np.zeros((17, 16))
+    olib().oracle_get_folded(_vp(model), _p(snr, C.c_float), _p(mm, C.c_double), _p(gg, C.c_double))
+    return mm, gg
+
+
 def fill(model, snr, tpl, codes, W=32, precision=0, dump=False):
     snr = np.ascontiguousarray(snr, np.float32)
     tpl = np.ascontiguousarray(tpl, np.uint8); codes = np.ascontiguousarray(codes, np.uint8)

@@ -46,11 +46,21 @@ def test_tables_match_numpy_restatement():
             assert em_ins[ctx][code] == np.float32(cw * em[1 if cognate else 2][ctx][code])
     # each emission pmf sums to 1
     assert np.allclose(em.sum(axis=2), 1.0)
+    # the folded factors are single fp32 products of the fp32 tables (DESIGN.md "Arrow model")
+    mm, gg = O.folded(MODEL, SNR)
+    for ctx in range(16):
+        for code in range(12):
+            assert mm[ctx][code] == np.float32(em_match[ctx][code]) * np.float32(tr[ctx][0])
+            assert mm[20 + ctx][code] == em_match[20 + ctx][code]
+            cognate = (code & 3) == (ctx & 3)
+            assert gg[ctx][code] == np.float32(em_ins[ctx][code]) * np.float32(tr[ctx][2 if cognate else 3])
+    assert np.all(mm[:, 12:] == 0) and np.all(gg[:, 12:] == 0)
 
 
 def brute_force_ll(tpl, codes):
     """Sum over every path, no dynamic programming (SURVEY.md A.4 written as a recursion over moves)."""
     em_match, em_ins, tr, lcw = O.tables(MODEL, SNR)
+    mm, gg = O.folded(MODEL, SNR)
     J, I = len(tpl), len(codes)
 
     def ctx(j):
@@ -64,12 +74,11 @@ def brute_force_ll(tpl, codes):
         c = ctx(j)
         if i + 1 <= I - 1:                                            # insertion (branch / stick) in column j
             e = codes[i]
-            t = tr[c][2] if (e & 3) == (c & 3) else tr[c][3]
-            total += em_ins[c][e] * t * rec(i + 1, j)
+            total += gg[c][e] * rec(i + 1, j)
         if j + 1 <= J - 1:
             total += tr[c][1] * rec(i, j + 1)                         # deletion of t_j
             if i + 1 <= I - 1:
-                total += tr[c][0] * em_match[c][codes[i]] * rec(i + 1, j + 1)   # match
+                total += mm[c][codes[i]] * rec(i + 1, j + 1)   # match
         return total
 
     p = em_match[16 + tpl[0]][codes[0]] * rec(1, 1)                   # pinned first match
