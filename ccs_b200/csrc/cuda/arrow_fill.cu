@@ -29,34 +29,6 @@ namespace {
 
 constexpr int kT3Rows = 80;        // 64 trinucleotide rows + 16 pinned-first-move rows (64 + 4*t0 + t1)
 constexpr int kT2Rows = 16;        // beta: one row per dinucleotide context
-constexpr int kDSlot = 13;         // unused code slot of a row: {deletion transition of the row's match context, 0}
-
-__device__ __forceinline__ float2 lds_f2(const unsigned addr) {
-    float2 r;
-    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ float lds_f1(const unsigned addr) {
-    float r;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
-    return r;
-}
-
-// Folded per-ZMW factors (the model, DESIGN.md "Arrow model"): one fp32 product each, identical to the
-// oracle's Tables::mm / Tables::gg.
-__device__ __forceinline__ float2 folded_entry(const ArrowBatchView& V, const float4* __restrict__ tr, const int cm,
-                                               const int ci, const int code) {
-    const float4 tm = tr[cm], ti = tr[ci];
-    if (code == kDSlot) return make_float2(tm.y, 0.f);
-    const float mm = __fmul_rn(V.em_match[cm * kEmStride + code], tm.x);
-    const bool cognate = (code & 3) == (ci & 3);
-    const float gg = __fmul_rn(V.em_ins[ci * kEmStride + code], cognate ? ti.z : ti.w);
-    return make_float2(mm, gg);
-}
-
-// A loop-invariant value the compiler must keep in a register: ptxas otherwise re-derives lane constants from %tid
-// inside the column loop (S2R + integer ops per column).  An identity shuffle is opaque to it.  Call converged.
-__device__ __forceinline__ int pinned(const int x) { return __shfl_sync(kFullMask, x, (int)(threadIdx.x & 31)); }
 
 __device__ __forceinline__ unsigned vmax_oct(unsigned key) {
 #pragma unroll
@@ -75,7 +47,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
             const int row = idx >> 4, code = idx & 15;
             const int cm = (row < 64) ? (row >> 2) : kCtxStartRow + ((row - 64) >> 2);
             const int ci = row & 15;
-            s_t3[idx] = folded_entry(V, tr, cm, ci, code);
+            s_t3[idx] = folded_entry(V.em_match, V.em_ins, tr, cm, ci, code);
         }
     }
     __syncthreads();
@@ -212,7 +184,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
         const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)zmw * 36;
         for (int idx = threadIdx.x; idx < kT2Rows * kEmStride; idx += blockDim.x) {
             const int row = idx >> 4, code = idx & 15;
-            s_t2[idx] = folded_entry(V, tr, row, row, code);
+            s_t2[idx] = folded_entry(V.em_match, V.em_ins, tr, row, row, code);
         }
     }
     __syncthreads();

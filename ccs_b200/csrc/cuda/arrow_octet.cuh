@@ -40,6 +40,38 @@ __device__ __forceinline__ int shfl_oct_i(int x, int src_lane_in_octet) {
     return __shfl_sync(kFullMask, x, src_lane_in_octet, 8);
 }
 
+// ---- folded per-ZMW factor tables in shared memory -------------------------------------------
+// The model (DESIGN.md "Arrow model"): mm[ctx][code] = fl32(em_match * match), gg[ctx][code] =
+// fl32(em_ins * (cognate ? branch : stick)) -- one fp32 product each, identical to the oracle's
+// Tables::mm / Tables::gg.  Kernels build the rows they need once per CTA (a CTA works on one ZMW).
+constexpr int kDSlot = 13;         // unused code slot: carries {deletion transition of the match context, 0}
+
+__device__ __forceinline__ float2 lds_f2(const unsigned addr) {
+    float2 r;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float lds_f1(const unsigned addr) {
+    float r;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+
+// {match factor of context cm, insertion factor of context ci} for one emission code
+__device__ __forceinline__ float2 folded_entry(const float* __restrict__ em_match, const float* __restrict__ em_ins,
+                                               const float4* __restrict__ tr, const int cm, const int ci, const int code) {
+    const float4 tm = tr[cm], ti = tr[ci];
+    if (code == kDSlot) return make_float2(tm.y, 0.f);
+    const float mm = __fmul_rn(em_match[cm * kEmStride + code], tm.x);
+    const bool cognate = (code & 3) == (ci & 3);
+    const float gg = __fmul_rn(em_ins[ci * kEmStride + code], cognate ? ti.z : ti.w);
+    return make_float2(mm, gg);
+}
+
+// A loop-invariant value the compiler must keep in a register: ptxas otherwise re-derives lane constants from %tid
+// inside hot loops (S2R + integer ops every iteration).  An identity shuffle is opaque to it.  Call converged.
+__device__ __forceinline__ int pinned(const int x) { return __shfl_sync(0xffffffffu, x, (int)(threadIdx.x & 31)); }
+
 // All shuffles below use the full-warp mask: callers must keep the warp converged around them
 // (idle octets run the same instruction stream on zeros).
 

@@ -20,6 +20,9 @@ namespace {
 
 struct ReadCtx {
     const uint8_t* rc;
+    const unsigned* rcA;     // row-code words: word k = codes of rows 4k..4k+3
+    const unsigned* rcB;     // shifted copy: word k = codes of rows 4k+1..4k+4
+    int wmax;
     const uint8_t* tp;
     const float4* tr;
     const float4* acol;
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
 
     const long long item = (long long)blockIdx.x * 16 + (threadIdx.x >> 3);
     const int g = threadIdx.x & 7;
-    const bool have = item < n_items;
+    bool have = item < n_items;
     int z = 0, p = 0;
     if (have) {
         int lo = 0, hi = n_ranges - 1;
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
         const ScoreRange rg = ranges[lo];
         z = rg.zmw;
         p = rg.p_begin + (int)(item - rg.first);
+        have = p < rg.p_end;             // ranges are padded to multiples of 16 items
     }
     DevZmw zm;
     zm.read_begin = zm.read_end = 0; zm.fwd_off = 0; zm.J = 0; zm.delta_off = 0;
@@ -272,143 +276,168 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
 //   * the first extension column X_b per new base b (SUB(q,b), INS(before q,b) and, for
 //     b = t[q+1], DEL(q) all start with context (t[q-1], b)),
 //   * the match/deletion terms of the second extension column per b.
-// => 4 + 7 in-column scans and 8 links per (read, position) instead of 14 + 8 with every
-//    operand reloaded.  Reverse-strand reads compute the insertion BEFORE their local q, which
-//    is forward INS(p+1): those sums go to slots 9..12 of row p+1 (combined by the consumers).
+// => 4 + 8 in-column scans and 9 links per (read, position).  Band starts are multiples of 4
+// (quantised slide), so every band mask is a per-LANE predicate, a lane's four row codes are one
+// aligned word of the row-code array, and the per-ZMW folded factors sit in shared memory in
+// CODE-MAJOR order [code][context]: a cell's table address is (cell base + context offset), with
+// the part of the context that depends on the unrolled base b as an immediate.
+// Reverse-strand reads compute the insertion BEFORE their local q, which is forward INS(p+1):
+// those sums go to slots 9..12 of row p+1 (combined by the consumers).
 // -------------------------------------------------------------------------------------------
-struct FastOut { float sub[4]; float del; float ins[4]; int e_sd; int e_in; };
+struct FastOut { float sub[4]; float del; float ins[4]; int e_sd; int e_in; };   // per-lane partial link sums
 
-__device__ __forceinline__ float link_dot(const float y[4], const float bx[4], const float bd[4], const int codeL[4],
-                                          const float4 trl, const float* __restrict__ emm_row) {
-    float acc = 0.f;
-#pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        const float wv = fmaf(trl.x, ldtab(emm_row, codeL[x]) * bd[x], trl.y * bx[x]);
-        acc = fmaf(y[x], wv, acc);
-    }
-    return octet_sum(acc);
+// Code-major table geometry: one code = 16 contexts x {mm, gg} = 32 words, padded to 33 so that the lanes of a warp
+// (same context per octet, different codes) fall into different shared-memory banks.
+constexpr int kTcCodeWords = 33;
+constexpr int kTcCodeBytes = 4 * kTcCodeWords;
+
+// byte address of code x of a row-code word (codes are stored x4) in the code-major table: tc + code * 132
+__device__ __forceinline__ unsigned code_base(const unsigned tc, const unsigned w, const int x) {
+    const unsigned byte = (x == 0) ? (w & 0xffu) : (x == 3) ? (w >> 24) : __byte_perm(w, 0u, 0x4440u + x);
+    return byte * (kTcCodeBytes / 4) + tc;
 }
 
-__device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g, const float* s_emm, const float* s_emi,
-                                          const int q_in, const bool live, FastOut& out) {
-    const int J = R.J, I = R.I;
+// a_i = A_i + G_i * a_{i-1} around the octet ring (G of the band-start cell is 0)
+__device__ __forceinline__ void ring_scan(float A[4], float G[4], const int src1, const int src2, const int src4, float v[4]) {
+    A[1] = fmaf(G[1], A[0], A[1]); G[1] *= G[0];
+    A[2] = fmaf(G[2], A[1], A[2]); G[2] *= G[1];
+    A[3] = fmaf(G[3], A[2], A[3]); G[3] *= G[2];
+    float At = A[3], Gt = G[3];
+    float As = __shfl_sync(kFullMask, At, src1, 8), Gs = __shfl_sync(kFullMask, Gt, src1, 8);
+    At = fmaf(Gt, As, At); Gt *= Gs;
+    As = __shfl_sync(kFullMask, At, src2, 8); Gs = __shfl_sync(kFullMask, Gt, src2, 8);
+    At = fmaf(Gt, As, At); Gt *= Gs;
+    As = __shfl_sync(kFullMask, At, src4, 8);
+    At = fmaf(Gt, As, At);
+    const float x = __shfl_sync(kFullMask, At, src1, 8);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = fmaf(G[q], x, A[q]);
+}
+
+// beta column masked onto the rows of an extension band: own = this lane's rows coincide, nxt = the next lane's first
+// row is this lane's last row + 1
+__device__ __forceinline__ void link_operands(const float4 b, const bool own, const bool nxt, const int src_dn,
+                                              float bx[4], float dn[4]) {
+    const float dn3 = __shfl_sync(kFullMask, b.x, src_dn, 8);
+    bx[0] = own ? b.x : 0.f; bx[1] = own ? b.y : 0.f; bx[2] = own ? b.z : 0.f; bx[3] = own ? b.w : 0.f;
+    dn[0] = bx[1]; dn[1] = bx[2]; dn[2] = bx[3]; dn[3] = nxt ? dn3 : 0.f;
+}
+
+// per-lane partial of sum_i y_i * (mm[ctx][code(i+1)] * beta(i+1) + D[ctx] * beta(i))
+__device__ __forceinline__ float link_partial(const float y[4], const float bx[4], const float dn[4], const unsigned a0,
+                                              const unsigned a1, const unsigned a2, const unsigned a3, const int imm,
+                                              const float D) {
+    float acc = y[0] * fmaf(lds_f1(a0 + imm), dn[0], D * bx[0]);
+    acc = fmaf(y[1], fmaf(lds_f1(a1 + imm), dn[1], D * bx[1]), acc);
+    acc = fmaf(y[2], fmaf(lds_f1(a2 + imm), dn[2], D * bx[2]), acc);
+    acc = fmaf(y[3], fmaf(lds_f1(a3 + imm), dn[3], D * bx[3]), acc);
+    return acc;
+}
+
+// tc = shared-memory byte address of the code-major folded table [16 codes][16 contexts] of {mm, gg}
+__device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g4, const int src_up, const int src_up2,
+                                          const int src_up4, const int src_dn, const unsigned tc, const int q_in,
+                                          const bool live, FastOut& out) {
+    const int J = R.J;
     const int q = live ? q_in : 2;
-    const int jm2 = min(max(q - 2, 0), J - 1), jm1 = min(max(q - 1, 0), J - 1), j0 = min(q, J - 1);
-    const int j1 = min(q + 1, J - 1), j2 = min(q + 2, J - 1);
-    const int code_max = I + kRowCodePad - 1;
+    const int jm1 = min(max(q - 1, 0), J - 1), j0 = min(q, J - 1), j1 = min(q + 1, J - 1), j2 = min(q + 2, J - 1);
     const ColInfo cim1 = R.cinfo[jm1];
-    const int s0 = cim1.start;
-    const int sq0 = R.cinfo[j0].start, sq1 = R.cinfo[j1].start, sq2 = R.cinfo[j2].start;
-    const int s1 = max(s0, sq0), s2 = max(s1, sq1);
-    const float4 a0 = R.acol[(size_t)jm1 * 8 + g];
-    const float4 b1v = R.bcol[(size_t)j1 * 8 + g];
-    const float4 b2v = R.bcol[(size_t)j2 * 8 + g];
+    const int s0 = cim1.start, s1 = R.cinfo[j0].start, s2 = R.cinfo[j1].start, s3 = R.cinfo[j2].start;
+    const float4 a0 = R.acol[(size_t)jm1 * 8];
+    const float4 b1 = R.bcol[(size_t)j1 * 8];
+    const float4 b2 = R.bcol[(size_t)j2 * 8];
     out.e_sd = cim1.cumexp + R.bexp[j2];
     out.e_in = cim1.cumexp + R.bexp[j1];
-    const int tm2 = R.tp[jm2] & 3, tm1 = R.tp[jm1] & 3, t0 = R.tp[j0] & 3, tp1 = R.tp[j1] & 3;   // & 3: idle octets read arbitrary bytes
+    // template bytes carry 16*t[j-2] + 4*t[j-1] + t[j]
+    const int x0 = R.tp[j0], x1 = R.tp[j1];
+    const int t0 = x0 & 3, tm1 = (x0 >> 2) & 3, cmq = (x0 >> 2) & 15, tp1 = x1 & 3;
 
-    int rel1[4], rel2[4], codeU1[4], codeG1[4], codeU2[4], codeG2[4], codeL2[4], codeL1[4], codeLb1[4];
-    float pvm2[4];
-    const float v0[4] = {a0.x, a0.y, a0.z, a0.w};
-    const int d1 = s1 - s0, d2 = s2 - s1;
-    float up1[4];
-    up1[0] = shfl_oct(v0[3], (g + 7) & 7); up1[1] = v0[0]; up1[2] = v0[1]; up1[3] = v0[2];
-    // beta columns, masked onto the rows of the extension bands
-    float bx2[4], bd2[4], bx1[4], bd1[4], bxD[4], bdD[4];
-    const float be2[4] = {b2v.x, b2v.y, b2v.z, b2v.w}, be1[4] = {b1v.x, b1v.y, b1v.z, b1v.w};
-    float dn2[4], dn1[4];
-    dn2[3] = shfl_oct(be2[0], (g + 1) & 7); dn2[0] = be2[1]; dn2[1] = be2[2]; dn2[2] = be2[3];
-    dn1[3] = shfl_oct(be1[0], (g + 1) & 7); dn1[0] = be1[1]; dn1[1] = be1[2]; dn1[2] = be1[3];
+    // lane geometry: first row of this lane in each band (band starts are multiples of 4)
+    const int rb0 = s0 + ((g4 - s0) & 31), rb1 = s1 + ((g4 - s1) & 31), rb2 = s2 + ((g4 - s2) & 31);
+    const int rb3 = s3 + ((g4 - s3) & 31);
+    const int g4n = (g4 + 4) & 31;
+    const int rb2n = s2 + ((g4n - s2) & 31), rb3n = s3 + ((g4n - s3) & 31);
+    // row codes: word k of copy A = rows 4k..4k+3, of copy B = rows 4k+1..4k+4
+    const unsigned wA1 = R.rcA[min(max(rb1 >> 2, 0), R.wmax)], wA2 = R.rcA[min(max(rb2 >> 2, 0), R.wmax)];
+    const unsigned wB1 = R.rcB[min(max(rb1 >> 2, 0), R.wmax)], wB2 = R.rcB[min(max(rb2 >> 2, 0), R.wmax)];
+
+    // ---- first extension column (band s1) from alpha column q-1 (band s0): shared match/deletion terms
+    const bool start1 = rb1 == s1, start2 = rb2 == s2;
+    float up = __shfl_sync(kFullMask, a0.w, src_up, 8);
+    if (start1 && s1 == s0) up = 0.f;                        // row s1-1 is outside band s0
+    const bool keep1 = rb1 == rb0;                           // false: the lane re-entered at the top, new rows
+    const float v0[4] = {keep1 ? a0.x : 0.f, keep1 ? a0.y : 0.f, keep1 ? a0.z : 0.f, keep1 ? a0.w : 0.f};
+    const unsigned c1[4] = {code_base(tc, wA1, 0), code_base(tc, wA1, 1), code_base(tc, wA1, 2), code_base(tc, wA1, 3)};
+    const unsigned c2[4] = {code_base(tc, wA2, 0), code_base(tc, wA2, 1), code_base(tc, wA2, 2), code_base(tc, wA2, 3)};
+    const unsigned n1[4] = {code_base(tc, wB1, 0), code_base(tc, wB1, 1), code_base(tc, wB1, 2), code_base(tc, wB1, 3)};
+    const unsigned n2[4] = {code_base(tc, wB2, 0), code_base(tc, wB2, 1), code_base(tc, wB2, 2), code_base(tc, wB2, 3)};
+    const unsigned dbase = tc + kDSlot * kTcCodeBytes;       // deletion transitions ride in code slot 13
     float A1[4];
-    const int cmq = 4 * tm2 + tm1;
-    const float4 trq = R.tr[cmq];
-#pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        const int slot = 4 * g + x;
-        rel1[x] = (slot - s1) & 31;
-        rel2[x] = (slot - s2) & 31;
-        const int row1 = s1 + rel1[x], row2 = s2 + rel2[x];
-        // (idle octets run on whatever band starts sit in the first columns of the store: clamp both ways)
-        const int c1 = R.rc[min(max(row1, 0), code_max)];
-        const int c2 = R.rc[min(max(row2, 0), code_max)];
-        const int c1n = R.rc[min(max(row1 + 1, 0), code_max)];
-        const int c2n = R.rc[min(max(row2 + 1, 0), code_max)];
-        const int rd1 = rel1[x] + d1, rd2 = rel2[x] + d2;
-        const float pv = (rd1 < 32) ? v0[x] : 0.f;
-        codeU1[x] = ((unsigned)(rd1 - 1) < 32u) ? c1 : kC4Sentinel;
-        codeG1[x] = (rel1[x] == 0) ? kC4Sentinel : c1;
-        codeU2[x] = ((unsigned)(rd2 - 1) < 32u) ? c2 : kC4Sentinel;
-        codeG2[x] = (rel2[x] == 0) ? kC4Sentinel : c2;
-        pvm2[x] = (rd2 < 32) ? 1.f : 0.f;
-        A1[x] = fmaf(trq.x, ldtab(s_emm + cmq * kEmStride, codeU1[x]) * up1[x], trq.y * pv);
-        // link operands: beta(i, c) / beta(i+1, c) at the rows of the extension band
-        bx2[x] = (row2 >= sq2 && row2 < sq2 + 32) ? be2[x] : 0.f;
-        bd2[x] = dn2[x];
-        codeL2[x] = (row2 + 1 >= sq2 && row2 + 1 < sq2 + 32) ? c2n : kC4Sentinel;
-        bx1[x] = (row2 >= sq1 && row2 < sq1 + 32) ? be1[x] : 0.f;
-        bd1[x] = dn1[x];
-        codeLb1[x] = (row2 + 1 >= sq1 && row2 + 1 < sq1 + 32) ? c2n : kC4Sentinel;
-        bxD[x] = (row1 >= sq2 && row1 < sq2 + 32) ? be2[x] : 0.f;
-        bdD[x] = dn2[x];
-        codeL1[x] = (row1 + 1 >= sq2 && row1 + 1 < sq2 + 32) ? c1n : kC4Sentinel;
+    {
+        const float Dq = lds_f1(dbase + cmq * 8);
+        A1[0] = fmaf(lds_f1(c1[0] + cmq * 8), up, Dq * v0[0]);
+        A1[1] = fmaf(lds_f1(c1[1] + cmq * 8), v0[0], Dq * v0[1]);
+        A1[2] = fmaf(lds_f1(c1[2] + cmq * 8), v0[1], Dq * v0[2]);
+        A1[3] = fmaf(lds_f1(c1[3] + cmq * 8), v0[2], Dq * v0[3]);
     }
+    // ---- link operands
+    float bxS[4], dnS[4], bxI[4], dnI[4], bxD[4], dnD[4];
+    link_operands(b2, rb3 == rb2, rb3n == rb2 + 4, src_dn, bxS, dnS);     // band s2 -> beta column q+2 (band s3)
+    link_operands(b1, true, rb2n == rb2 + 4, src_dn, bxI, dnI);           // band s2 -> beta column q+1 (band s2)
+    link_operands(b2, rb3 == rb1, rb3n == rb1 + 4, src_dn, bxD, dnD);     // band s1 -> beta column q+2 (band s3)
+    // per-cell table bases with the runtime part of the context folded in; the unrolled base b adds an immediate
+    const int o_m1 = tm1 * 32, o_p1 = tp1 * 8, o_t0 = t0 * 8;
+    const unsigned g1a[4] = {c1[0] + o_m1, c1[1] + o_m1, c1[2] + o_m1, c1[3] + o_m1};   // (tm1, b): + 8 b
+    const unsigned m2a[4] = {c2[0] + o_m1, c2[1] + o_m1, c2[2] + o_m1, c2[3] + o_m1};   // (tm1, b): + 8 b
+    const unsigned s2a[4] = {c2[0] + o_p1, c2[1] + o_p1, c2[2] + o_p1, c2[3] + o_p1};   // (b, tp1): + 32 b
+    const unsigned i2a[4] = {c2[0] + o_t0, c2[1] + o_t0, c2[2] + o_t0, c2[3] + o_t0};   // (b, t0):  + 32 b
+    const unsigned sla[4] = {n2[0] + o_p1, n2[1] + o_p1, n2[2] + o_p1, n2[3] + o_p1};   // link (b, tp1)
+    const unsigned ila[4] = {n2[0] + o_t0, n2[1] + o_t0, n2[2] + o_t0, n2[3] + o_t0};   // link (b, t0)
+    const unsigned d_m1 = dbase + o_m1, d_p1 = dbase + o_p1, d_t0 = dbase + o_t0;
+    const bool keep2 = rb2 == rb1;
+    const bool upok2 = !(start2 && s2 == s1);
     float Xdel[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        const int ci = 4 * tm1 + b;
-        const float4 tri = R.tr[ci];
-        const float* emi_row = s_emi + ci * kEmStride;
-        const float* emm_row = s_emm + ci * kEmStride;
         float A[4], G[4], X[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            A[x] = A1[x];
-            G[x] = ldtab(emi_row, codeG1[x]) * (((codeG1[x] & 12) == (b << 2)) ? tri.z : tri.w);
-        }
-        octet_forward_scan(A, G, g, X);
+        for (int x = 0; x < 4; ++x) { A[x] = A1[x]; G[x] = lds_f1(g1a[x] + 8 * b + 4); }
+        if (start1) G[0] = 0.f;
+        ring_scan(A, G, src_up, src_up2, src_up4, X);
         if (b == tp1) {
 #pragma unroll
             for (int x = 0; x < 4; ++x) Xdel[x] = X[x];
         }
-        // second extension column: match/deletion terms shared by SUB(b) and INS(b)
-        float up2[4], A2[4];
-        up2[0] = shfl_oct(X[3], (g + 7) & 7); up2[1] = X[0]; up2[2] = X[1]; up2[3] = X[2];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) A2[x] = fmaf(tri.x, ldtab(emm_row, codeU2[x]) * up2[x], tri.y * (X[x] * pvm2[x]));
+        // second extension column (band s2): match/deletion terms shared by SUB(b) and INS(b)
+        float up2 = __shfl_sync(kFullMask, X[3], src_up, 8);
+        if (!upok2) up2 = 0.f;
+        const float Xm[4] = {keep2 ? X[0] : 0.f, keep2 ? X[1] : 0.f, keep2 ? X[2] : 0.f, keep2 ? X[3] : 0.f};
+        const float Dm = lds_f1(d_m1 + 8 * b);
+        float A2[4];
+        A2[0] = fmaf(lds_f1(m2a[0] + 8 * b), up2, Dm * Xm[0]);
+        A2[1] = fmaf(lds_f1(m2a[1] + 8 * b), Xm[0], Dm * Xm[1]);
+        A2[2] = fmaf(lds_f1(m2a[2] + 8 * b), Xm[1], Dm * Xm[2]);
+        A2[3] = fmaf(lds_f1(m2a[3] + 8 * b), Xm[2], Dm * Xm[3]);
         {   // SUB(q, b): insertion context (b, t[q+1]); link into beta column q+2
-            const int c2 = 4 * b + tp1;
-            const float4 tr2 = R.tr[c2];
-            const float* e2 = s_emi + c2 * kEmStride;
             float Aa[4], Ga[4], Y[4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                Aa[x] = A2[x];
-                Ga[x] = ldtab(e2, codeG2[x]) * (((codeG2[x] & 12) == (tp1 << 2)) ? tr2.z : tr2.w);
-            }
-            octet_forward_scan(Aa, Ga, g, Y);
-            const float v = link_dot(Y, bx2, bd2, codeL2, tr2, s_emm + c2 * kEmStride);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (k == b) out.sub[k] = v;
+            for (int x = 0; x < 4; ++x) { Aa[x] = A2[x]; Ga[x] = lds_f1(s2a[x] + 32 * b + 4); }
+            if (start2) Ga[0] = 0.f;
+            ring_scan(Aa, Ga, src_up, src_up2, src_up4, Y);
+            out.sub[b] = link_partial(Y, bxS, dnS, sla[0], sla[1], sla[2], sla[3], 32 * b, lds_f1(d_p1 + 32 * b));
         }
         {   // INS(before q, b): insertion context (b, t[q]); link into beta column q+1
-            const int c3 = 4 * b + t0;
-            const float4 tr3 = R.tr[c3];
-            const float* e3 = s_emi + c3 * kEmStride;
             float Aa[4], Ga[4], Z[4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                Aa[x] = A2[x];
-                Ga[x] = ldtab(e3, codeG2[x]) * (((codeG2[x] & 12) == (t0 << 2)) ? tr3.z : tr3.w);
-            }
-            octet_forward_scan(Aa, Ga, g, Z);
-            const float v = link_dot(Z, bx1, bd1, codeLb1, tr3, s_emm + c3 * kEmStride);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (k == b) out.ins[k] = v;
+            for (int x = 0; x < 4; ++x) { Aa[x] = A2[x]; Ga[x] = lds_f1(i2a[x] + 32 * b + 4); }
+            if (start2) Ga[0] = 0.f;
+            ring_scan(Aa, Ga, src_up, src_up2, src_up4, Z);
+            out.ins[b] = link_partial(Z, bxI, dnI, ila[0], ila[1], ila[2], ila[3], 32 * b, lds_f1(d_t0 + 32 * b));
         }
     }
     {   // DEL(q): X_{t[q+1]} links straight into beta column q+2 with context (t[q-1], t[q+1])
-        const int cd = 4 * tm1 + tp1;
-        out.del = link_dot(Xdel, bxD, bdD, codeL1, R.tr[cd], s_emm + cd * kEmStride);
+        const int od = o_m1 + o_p1;
+        out.del = link_partial(Xdel, bxD, dnD, n1[0] + od, n1[1] + od, n1[2] + od, n1[3] + od, 0, lds_f1(dbase + od));
     }
 }
 
@@ -431,34 +460,52 @@ __device__ __forceinline__ double prod_dll(const float prod, const int pexp, con
     return (prod > 0.f) ? (double)logf(prod) + 0.6931471805599453094 * (double)pexp - base_sum : -INFINITY;
 }
 
-__device__ __forceinline__ double dll_of(const float val, const int e, const double base_ll) {
-    return (val > 0.f) ? (double)logf(val) + 0.6931471805599453094 * (double)e - base_ll : -INFINITY;
-}
-
+// Work items are (ZMW, position); `first` of every range is a multiple of 16, so the 16 octets of a CTA belong to one
+// ZMW and share its folded factor table.  The octet loops over the ZMW's reads in index order.  The eight mutation
+// slots of a position are spread over the octet's lanes: lane k < 4 owns SUB(forward base k) -- or DEL when k is the
+// template base, whose substitution is the identity -- and lane 4 + k owns INS(forward base k); per read the lanes'
+// partial link sums are transpose-reduced so that every lane ends up with the total of its own slot and keeps that
+// slot's running product.  The order of the reduction is fixed: results are deterministic.
 __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V, const ScoreRange* __restrict__ ranges,
                                                           const int n_ranges, const long long n_items,
                                                           double* __restrict__ delta) {
     __shared__ float s_emm[36 * kEmStride];
     __shared__ float s_emi[17 * kEmStride];
+    __shared__ __align__(16) float s_tc[16 * kTcCodeWords];  // code-major folded factors of the CTA's ZMW
     for (int k = threadIdx.x; k < 36 * kEmStride; k += blockDim.x) s_emm[k] = V.em_match[k];
     for (int k = threadIdx.x; k < 17 * kEmStride; k += blockDim.x) s_emi[k] = V.em_ins[k];
-    __syncthreads();
 
-    const long long item = (long long)blockIdx.x * 16 + (threadIdx.x >> 3);
-    const int g = threadIdx.x & 7;
-    const bool have = item < n_items;
-    int z = 0, p = 0, p_begin = 0;
-    if (have) {
+    const long long item0 = (long long)blockIdx.x * 16;
+    const long long item = item0 + (threadIdx.x >> 3);
+    const int g = pinned(threadIdx.x & 7);
+    ScoreRange rg;
+    {
         int lo = 0, hi = n_ranges - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (ranges[mid].first <= item) lo = mid; else hi = mid - 1;
+            if (ranges[mid].first <= item0) lo = mid; else hi = mid - 1;
         }
-        const ScoreRange rg = ranges[lo];
-        z = rg.zmw;
-        p = rg.p_begin + (int)(item - rg.first);
-        p_begin = rg.p_begin;
+        rg = ranges[lo];
     }
+    const int z = rg.zmw;
+    const int p = rg.p_begin + (int)(item - rg.first);
+    const int p_begin = rg.p_begin;
+    const bool have = item < n_items && p < rg.p_end;
+    {
+        const float4* __restrict__ tr = reinterpret_cast<const float4*>(V.trans) + (size_t)z * 36;
+        for (int idx = threadIdx.x; idx < 256; idx += blockDim.x) {
+            const int code = idx >> 4, ctx = idx & 15;
+            const float2 e = folded_entry(V.em_match, V.em_ins, tr, ctx, ctx, code);
+            s_tc[code * kTcCodeWords + 2 * ctx] = e.x;
+            s_tc[code * kTcCodeWords + 2 * ctx + 1] = e.y;
+        }
+    }
+    __syncthreads();
+    const unsigned tc = (unsigned)pinned((int)__cvta_generic_to_shared(s_tc));
+    const int g4 = pinned(4 * g);
+    const int src_up = pinned((g + 7) & 7), src_up2 = pinned((g + 6) & 7), src_up4 = pinned((g + 4) & 7);
+    const int src_dn = pinned((g + 1) & 7);
+
     DevZmw zm;
     zm.read_begin = zm.read_end = 0; zm.fwd_off = 0; zm.J = 0; zm.delta_off = 0;
     if (have) zm = V.zmws[z];
@@ -468,28 +515,23 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
     n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 16));
     const int tbase = have ? (V.tpl[zm.fwd_off + p] & 3) : 0;
 
-    // per-slot running products {SUB A,C,G,T, DEL}, {INS A,C,G,T}, {INS' A,C,G,T} and, per group, the sum of the
-    // contributing reads' base log-likelihoods
-    float pr_sd[5], pr_ia[4], pr_ib[4];
-    int px_sd[5], px_ia[4], px_ib[4];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) { pr_sd[k] = 1.f; px_sd[k] = 0; }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { pr_ia[k] = 1.f; px_ia[k] = 0; pr_ib[k] = 1.f; px_ib[k] = 0; }
+    // this lane's slot: running product(s) and the sums of the contributing reads' base log-likelihoods
+    float prA = 1.f, prB = 1.f;          // A: SUB / DEL / INS from forward reads;  B: INS' (reverse-strand share of row p+1)
+    int pxA = 0, pxB = 0;
     double bs_sd = 0.0, bs_ia = 0.0, bs_ib = 0.0;
 
     for (int k = 0; k < n_max; ++k) {
         const bool has_read = k < n_reads;
         DevRead rd;
         rd.active = 0; rd.ts = rd.te = 0; rd.strand = 0; rd.I = 2; rd.J = 2; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0;
-        rd.zmw = 0; rd.last_code = 0;
+        rd.zmw = 0; rd.last_code = 0; rd.code_stride = 16;
         int st = 1;
         const int r = zm.read_begin + k;
         if (has_read) { rd = V.reads[r]; st = V.status[r]; }
         const bool usable = has_read && rd.active && st == 0;
         if (!usable) {   // idle octets still execute the shared instruction stream: give them harmless operands
             rd.ts = rd.te = 0; rd.strand = 0; rd.I = 2; rd.J = 2; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0;
-            rd.zmw = 0; rd.last_code = 0;
+            rd.zmw = 0; rd.last_code = 0; rd.code_stride = 16;
         }
         const bool cov_sd = usable && p >= rd.ts && p < rd.te;       // SUB / DEL
         const bool cov_in = usable && p > rd.ts && p < rd.te;        // INS (before p)
@@ -497,10 +539,13 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
 
         ReadCtx R;
         R.rc = V.rowcode + rd.code_off;
+        R.rcA = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off);
+        R.rcB = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off + rd.code_stride);
+        R.wmax = max((rd.code_stride >> 2) - 1, 0);
         R.tp = V.tpl + rd.tpl_off;
         R.tr = reinterpret_cast<const float4*>(V.trans) + (size_t)rd.zmw * 36;
-        R.acol = reinterpret_cast<const float4*>(V.alpha) + (size_t)rd.col_off * 8;
-        R.bcol = reinterpret_cast<const float4*>(V.beta) + (size_t)rd.col_off * 8;
+        R.acol = reinterpret_cast<const float4*>(V.alpha) + (size_t)rd.col_off * 8 + g;
+        R.bcol = reinterpret_cast<const float4*>(V.beta) + (size_t)rd.col_off * 8 + g;
         R.cinfo = V.colinfo + rd.col_off;
         R.bexp = V.beta_exp + rd.col_off;
         R.I = rd.I; R.J = rd.J; R.last_code = rd.last_code;
@@ -513,21 +558,36 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
 
         if (__any_sync(kFullMask, interior)) {
             FastOut fo;
+            fast_eval(R, g4, src_up, src_up2, src_up4, src_dn, tc, q_sd, interior, fo);
+            // Q[k] = this lane's partial of the slot lane k owns (forward-strand base k & 3; reverse reads see 3 - base)
+            const bool rv = rd.strand != 0;
+            float Q[8];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) { fo.sub[b] = 0.f; fo.ins[b] = 0.f; }
-            fo.del = 0.f; fo.e_sd = 0; fo.e_in = 0;
-            fast_eval(R, g, s_emm, s_emi, q_sd, interior, fo);
+            for (int b = 0; b < 4; ++b) {
+                const float sb = rv ? fo.sub[3 - b] : fo.sub[b];
+                Q[b] = (b == tbase) ? fo.del : sb;
+                Q[4 + b] = rv ? fo.ins[3 - b] : fo.ins[b];
+            }
+            // transpose-reduce over the octet: after the three steps lane k holds the octet-wide sum of Q[k]
+            const bool h4 = (g & 4) != 0, h2 = (g & 2) != 0, h1 = (g & 1) != 0;
+            float R4[4], R2[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float send = h4 ? Q[i] : Q[i + 4], keep = h4 ? Q[i + 4] : Q[i];
+                R4[i] = keep + __shfl_xor_sync(kFullMask, send, 4, 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float send = h2 ? R4[i] : R4[i + 2], keep = h2 ? R4[i + 2] : R4[i];
+                R2[i] = keep + __shfl_xor_sync(kFullMask, send, 2, 8);
+            }
+            const float send = h1 ? R2[0] : R2[1], keep = h1 ? R2[1] : R2[0];
+            const float tot = keep + __shfl_xor_sync(kFullMask, send, 1, 8);
             if (interior) {
                 bs_sd += base_ll;
-                if (rd.strand) bs_ib += base_ll; else bs_ia += base_ll;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {                        // b = forward-strand base of the slot
-                    const float vs = rd.strand ? fo.sub[3 - b] : fo.sub[b];
-                    const float vi = rd.strand ? fo.ins[3 - b] : fo.ins[b];
-                    if (b != tbase) prod_mul(pr_sd[b], px_sd[b], vs, fo.e_sd);
-                    if (rd.strand) prod_mul(pr_ib[b], px_ib[b], vi, fo.e_in); else prod_mul(pr_ia[b], px_ia[b], vi, fo.e_in);
-                }
-                prod_mul(pr_sd[4], px_sd[4], fo.del, fo.e_sd);
+                if (rv) bs_ib += base_ll; else bs_ia += base_ll;
+                const int e = (g < 4) ? fo.e_sd : fo.e_in;
+                if (g >= 4 && rv) prod_mul(prB, pxB, tot, e); else prod_mul(prA, pxA, tot, e);
             }
         }
         if (__any_sync(kFullMask, gen_sd) || __any_sync(kFullMask, gen_in)) {
@@ -543,6 +603,7 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
             }
             if (gen_sd) bs_sd += base_ll;
             if (gen_in) bs_ia += base_ll;
+            R.acol -= g; R.bcol -= g;    // the generic evaluator indexes the lane itself
 #pragma unroll 1
             for (int m = 0; m < 8; ++m) {
                 // m = 0..2 SUB, 3 DEL, 4..7 INS
@@ -557,34 +618,22 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
                                           is_ins ? q_in : q_sd, bl, lv, e);
                 if (m == 3 && rd.J < 3) val = 0.f;     // deleting one of two template bases leaves no template
                 const bool take = is_ins ? gen_in : gen_sd;
-                if (take) {
-                    if (m < 3) {
-#pragma unroll
-                        for (int s2 = 0; s2 < 4; ++s2) if (s2 == bf) prod_mul(pr_sd[s2], px_sd[s2], val, e);
-                    } else if (m == 3) {
-                        prod_mul(pr_sd[4], px_sd[4], val, e);
-                    } else {
-#pragma unroll
-                        for (int s2 = 0; s2 < 4; ++s2) if (s2 == bf) prod_mul(pr_ia[s2], px_ia[s2], val, e);
-                    }
-                }
+                const int owner = (m < 3) ? bf : ((m == 3) ? tbase : 4 + bf);
+                if (take && g == owner) prod_mul(prA, pxA, val, e);
             }
         }
     }
-    if (have && g == 0) {
+    if (have) {
         double* out = delta + (size_t)(zm.delta_off + p) * kDeltaStride;
         // slots nobody contributed to keep delta-LL 0 (product 1, exponent 0, no base term)
-#pragma unroll
-        for (int k = 0; k < 5; ++k) out[k] = (k < 4 && k == tbase) ? 0.0 : prod_dll(pr_sd[k], px_sd[k], bs_sd);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) out[5 + k] = prod_dll(pr_ia[k], px_ia[k], bs_ia);
-        // reverse-strand insertions before the local position are forward INS(p+1)
-        double* nxt = out + kDeltaStride;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) nxt[9 + k] = prod_dll(pr_ib[k], px_ib[k], bs_ib);
-        if (p == p_begin) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out[9 + k] = 0.0;
+        if (g < 4) {
+            const double v = prod_dll(prA, pxA, bs_sd);
+            if (g == tbase) { out[4] = v; out[g] = 0.0; } else out[g] = v;
+        } else {
+            out[5 + (g - 4)] = prod_dll(prA, pxA, bs_ia);
+            // reverse-strand insertions before the local position are forward INS(p+1)
+            out[kDeltaStride + 9 + (g - 4)] = prod_dll(prB, pxB, bs_ib);
+            if (p == p_begin) out[9 + (g - 4)] = 0.0;
         }
     }
 }
@@ -605,6 +654,7 @@ __global__ void __launch_bounds__(256) arrow_pick_kernel(const ArrowBatchView V,
     const ScoreRange rg = ranges[lo];
     const int z = rg.zmw;
     const int p = rg.p_begin + (int)(item - rg.first);
+    if (p >= rg.p_end) return;           // padding item (ranges start at multiples of 16)
     const DevZmw zm = V.zmws[z];
     const uint8_t* t = V.tpl + zm.fwd_off;
     const int tb = t[p] & 3;                       // template bytes carry context bits above the base
@@ -643,6 +693,7 @@ __global__ void __launch_bounds__(256) arrow_qv_kernel(const ArrowBatchView V, c
     const ScoreRange rg = ranges[lo];
     const int z = rg.zmw;
     const int p = rg.p_begin + (int)(item - rg.first);
+    if (p >= rg.p_end) return;           // padding item (ranges start at multiples of 16)
     const DevZmw zm = V.zmws[z];
     const int tb = V.tpl[zm.fwd_off + p] & 3;
     const double* d = delta + (size_t)(zm.delta_off + p) * kDeltaStride;

@@ -389,6 +389,10 @@ void ArrowEngine::dump_pair(int r, float* alpha, float* beta, int32_t* start, in
 // ---------------------------------------------------------------------------------------------
 // scoring
 // ---------------------------------------------------------------------------------------------
+// Ranges start at multiples of 16 in the flattened work list: the 16 octets of a scoring CTA then belong to one ZMW
+// (the kernels skip the padding items past a range's end).
+static inline int64_t pad16(int64_t n) { return (n + 15) & ~15ll; }
+
 void ArrowEngine::score_ranges(const std::vector<ScoreRange>& ranges, int64_t n_items) {
     if (ranges.empty() || n_items == 0) return;
     d_ranges_.ensure(ranges.size());
@@ -403,7 +407,7 @@ void ArrowEngine::score_ranges(const std::vector<ScoreRange>& ranges, int64_t n_
     span_end();
     CCS_CUDA(cudaGetLastError());
     ++stats.n_score;
-    stats.score_items += n_items;
+    for (const ScoreRange& r : ranges) stats.score_items += r.p_end - r.p_begin;
     n_ranges_ = (int)ranges.size();
     n_range_items_ = n_items;
 }
@@ -415,7 +419,7 @@ void ArrowEngine::score_all_positions() {
         const ZmwState& zs = zstate_[z];
         if (zs.failed || zs.tpl.empty()) continue;
         ranges.push_back(ScoreRange{z, 0, (int32_t)zs.tpl.size(), 0, first});
-        first += (int64_t)zs.tpl.size();
+        first += pad16((int64_t)zs.tpl.size());
     }
     score_ranges(ranges, first);
 }
@@ -492,7 +496,7 @@ void ArrowEngine::polish(const PolishParams& pp) {
             zs.iterations = it + 1;
             if (it == 0) {
                 ranges.push_back(ScoreRange{z, 0, J, 0, first});
-                first += J;
+                first += pad16(J);
                 zs.n_tested += count_canonical(zs.tpl, 0, J);
             } else {
                 // union of +-neighborhood around the last-applied sites
@@ -505,7 +509,7 @@ void ArrowEngine::polish(const PolishParams& pp) {
                         const int e = std::min(ce, J);
                         if (e > cb) {
                             ranges.push_back(ScoreRange{z, cb, e, 0, first});
-                            first += e - cb;
+                            first += pad16(e - cb);
                             zs.n_tested += count_canonical(zs.tpl, cb, e);
                         }
                     }
@@ -650,12 +654,12 @@ void ArrowEngine::consensus_qvs() {
         const ZmwState& zs = zstate_[z];
         if (zs.failed || zs.tpl.empty()) continue;
         ranges.push_back(ScoreRange{z, 0, (int32_t)zs.tpl.size(), 0, first});
-        first += (int64_t)zs.tpl.size();
+        first += pad16((int64_t)zs.tpl.size());
         // every position was last scored after all edits within `neighborhood` of it had been applied, unless the
         // ZMW stopped without converging or lost a read after scoring began: only those are scored again
         if (!reuse_scores || !zs.converged || zs.stale_scores) {
             rescoring.push_back(ScoreRange{z, 0, (int32_t)zs.tpl.size(), 0, first_rs});
-            first_rs += (int64_t)zs.tpl.size();
+            first_rs += pad16((int64_t)zs.tpl.size());
         }
     }
     for (int z = 0; z < nz; ++z) qv_[z].clear();
