@@ -286,6 +286,8 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
 // -------------------------------------------------------------------------------------------
 struct FastOut { float sub[4]; float del; float ins[4]; int e_sd; int e_in; };   // per-lane partial link sums
 
+constexpr int kReadCache = 48;     // read descriptors of the CTA's ZMW kept in shared memory (more reads: global loads)
+
 // Code-major table geometry: one code = 16 contexts x {mm, gg} = 32 words, padded to 33 so that the lanes of a warp
 // (same context per octet, different codes) fall into different shared-memory banks.
 constexpr int kTcCodeWords = 33;
@@ -466,12 +468,15 @@ __device__ __forceinline__ double prod_dll(const float prod, const int pexp, con
 // template base, whose substitution is the identity -- and lane 4 + k owns INS(forward base k); per read the lanes'
 // partial link sums are transpose-reduced so that every lane ends up with the total of its own slot and keeps that
 // slot's running product.  The order of the reduction is fixed: results are deterministic.
-__global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V, const ScoreRange* __restrict__ ranges,
+__global__ void __launch_bounds__(128, 4) arrow_score_kernel(const ArrowBatchView V, const ScoreRange* __restrict__ ranges,
                                                           const int n_ranges, const long long n_items,
                                                           double* __restrict__ delta) {
     __shared__ float s_emm[36 * kEmStride];
     __shared__ float s_emi[17 * kEmStride];
     __shared__ __align__(16) float s_tc[16 * kTcCodeWords];  // code-major folded factors of the CTA's ZMW
+    __shared__ DevRead s_rd[kReadCache];                     // the ZMW's read descriptors, statuses, base LLs
+    __shared__ int s_st[kReadCache];
+    __shared__ double s_bl[kReadCache];
     for (int k = threadIdx.x; k < 36 * kEmStride; k += blockDim.x) s_emm[k] = V.em_match[k];
     for (int k = threadIdx.x; k < 17 * kEmStride; k += blockDim.x) s_emi[k] = V.em_ins[k];
 
@@ -498,6 +503,17 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
             const float2 e = folded_entry(V.em_match, V.em_ins, tr, ctx, ctx, code);
             s_tc[code * kTcCodeWords + 2 * ctx] = e.x;
             s_tc[code * kTcCodeWords + 2 * ctx + 1] = e.y;
+        }
+    }
+    int nrc = 0;
+    if (item0 < n_items) {
+        const DevZmw zc = V.zmws[z];
+        nrc = min(zc.read_end - zc.read_begin, kReadCache);
+        const int* src = reinterpret_cast<const int*>(V.reads + zc.read_begin);
+        for (int idx = threadIdx.x; idx < nrc * (int)(sizeof(DevRead) / 4); idx += blockDim.x) reinterpret_cast<int*>(s_rd)[idx] = src[idx];
+        for (int idx = threadIdx.x; idx < nrc; idx += blockDim.x) {
+            s_st[idx] = V.status[zc.read_begin + idx];
+            s_bl[idx] = V.base_ll[zc.read_begin + idx];
         }
     }
     __syncthreads();
@@ -527,7 +543,22 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
         rd.zmw = 0; rd.last_code = 0; rd.code_stride = 16;
         int st = 1;
         const int r = zm.read_begin + k;
-        if (has_read) { rd = V.reads[r]; st = V.status[r]; }
+        if (has_read) {
+            if (k < nrc) { rd = s_rd[k]; st = s_st[k]; } else { rd = V.reads[r]; st = V.status[r]; }
+        }
+        // start the next read's three column lines (and its column info) on their way from HBM to L2 while this one
+        // is being scored: lanes 0..3 of the octet take one line each
+        if (have && k + 1 < nrc) {
+            const DevRead& nx = s_rd[k + 1];
+            if (nx.active && p >= nx.ts && p < nx.te) {
+                const int qn = nx.strand ? nx.te - 1 - p : p - nx.ts;
+                const int col = min(max((g == 0) ? qn - 1 : ((g == 1) ? qn + 1 : ((g == 2) ? qn + 2 : qn - 1)), 0), nx.J - 1);
+                const void* a = (g == 0) ? (const void*)(V.alpha + ((size_t)nx.col_off + col) * 32)
+                              : (g == 3) ? (const void*)(V.colinfo + nx.col_off + col)
+                                         : (const void*)(V.beta + ((size_t)nx.col_off + col) * 32);
+                if (g < 4) asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+            }
+        }
         const bool usable = has_read && rd.active && st == 0;
         if (!usable) {   // idle octets still execute the shared instruction stream: give them harmless operands
             rd.ts = rd.te = 0; rd.strand = 0; rd.I = 2; rd.J = 2; rd.code_off = 0; rd.col_off = 0; rd.tpl_off = 0;
@@ -549,7 +580,7 @@ __global__ void __launch_bounds__(128) arrow_score_kernel(const ArrowBatchView V
         R.cinfo = V.colinfo + rd.col_off;
         R.bexp = V.beta_exp + rd.col_off;
         R.I = rd.I; R.J = rd.J; R.last_code = rd.last_code;
-        const double base_ll = cov_sd ? V.base_ll[r] : 0.0;
+        const double base_ll = cov_sd ? ((k < nrc) ? s_bl[k] : V.base_ll[r]) : 0.0;
         const int q_sd = cov_sd ? (rd.strand ? rd.te - 1 - p : p - rd.ts) : 0;
         const bool interior = cov_sd && q_sd >= 2 && q_sd <= rd.J - 4;
         const bool gen_sd = cov_sd && !interior;
