@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--draft-error", type=float, default=0.02)
     ap.add_argument("--cpu-sample", type=int, default=0, help="ZMWs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=3, help="concurrent engine lanes per context (0 = library default)")
+    ap.add_argument("--lanes", type=int, default=4, help="concurrent engine lanes per context (0 = library default)")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank (0 = 2 x cpu count / world)")
     ap.add_argument("--contexts", type=int, default=2,
                     help="GPU contexts per rank; steps are dealt round-robin to the contexts and run concurrently "
                          "(pipelined batches, as a reader thread feeding two stage instances would)")
@@ -221,7 +222,9 @@ def main():
     from ccs_b200 import sim, api
     model = sim.synthetic_model()
     cfg = sim.get_config(args.config)
-    threads = max(1, (os.cpu_count() or 8) // max(world, 1))
+    # host threads of this rank: twice its share of the cores -- the stage threads spend much of their time blocked on
+    # stream synchronisation, and 2x measured +6 % e2e over 1x on a 16-core box (profiles/r1_lanes_matrix.txt)
+    threads = args.host_threads if args.host_threads > 0 else max(1, 2 * (os.cpu_count() or 8) // max(world, 1))
     # host threads of each stage context of this rank
     os.environ["CCS_B200_THREADS"] = str(max(1, threads // max(1, args.contexts)))
     free_b, _tot = torch.cuda.mem_get_info()
@@ -360,7 +363,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            n = args.cpu_sample or max(cores, 4)
+            n = min(args.zmws, args.cpu_sample or max(6 * cores, 24))   # ~10 s of CPU work on the oracle
             _, arrays = batches[0]
             dt, ores = oracle_sample(model, arrays, list(range(n)), cores, args.stage)
             # the sample doubles as a parity spot check at full size

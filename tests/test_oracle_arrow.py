@@ -127,6 +127,21 @@ def test_alpha_beta_agree_and_band_is_lossless():
         assert f["ll_alpha"] == pytest.approx(a["ll_alpha"], abs=1e-4)   # fp32 cells stay inside the north-star bound
 
 
+def test_band_slides_in_steps_of_four_and_stays_lossless_at_10kb():
+    """Quantised slide (DESIGN.md "Band rule"): starts are multiples of 4, move by 0 or 4 per column, and the
+    32-row band still loses nothing against a 256-row band on long reads."""
+    for snr, t, r in _pairs(1, 10000, insert_sd=0, snr_sd=1.5)[:4]:
+        a = O.fill(MODEL, snr, t, r, W=32, dump=True)
+        assert a["status"] == 0
+        st = a["start"]
+        assert np.all(st % 4 == 0)
+        d = np.diff(st)
+        assert set(np.unique(d)).issubset({0, 4})
+        w = O.fill(MODEL, snr, t, r, W=256)
+        assert abs(a["ll_alpha"] - w["ll_alpha"]) < 1e-9
+        assert abs(a["ll_alpha"] - a["ll_beta"]) < 1e-7
+
+
 def all_mutations(tpl, positions):
     J = len(tpl)
     muts = []
