@@ -1,6 +1,7 @@
 // extern "C" boundary of libccsgpu.so (include/ccsgpu.h).  No exception crosses it.
 #include "../../../include/ccsgpu.h"
 #include "polish_engine.h"
+#include "parallel.h"
 #include "draft_engine.h"
 #include <cmath>
 #include <cstring>
@@ -414,7 +415,7 @@ static void ccs_chunk(ccsgpu_ctx* ctx, int lane, const ccs_batch* in, const Draf
                       ChunkOut& co) {
     const auto t0 = std::chrono::steady_clock::now();
     DraftOutput d;
-    lane_draft(ctx, lane).run(to_draft_input(in), dpar, d);
+    { HostPhase hp("ccs.draft total"); lane_draft(ctx, lane).run(to_draft_input(in), dpar, d); }
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (lane == 0) ctx->ms_draft += ms; else ctx->extra[lane - 1].ms_draft += ms;
     // ZMWs that failed the draft get an empty template and no reads
@@ -442,6 +443,7 @@ static void ccs_chunk(ccsgpu_ctx* ctx, int lane, const ccs_batch* in, const Draf
     ArrowEngine& E = lane_engine(ctx, lane);
     E.load(p);
     E.polish(pp);
+    HostPhase hp("ccs.collect_results");
     collect_results(E, nz, nr, in->cx, pp, d.status.data(), co);
 }
 
@@ -455,11 +457,15 @@ int ccsgpu_ccs(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_draft_cfg* dcfg, 
         const int nc = (int)cut.size() - 1;
         std::vector<ChunkOut> cos(nc);
         std::vector<SubBatch> subs(nc);
+        { HostPhase hp("ccs.lanes total");
         run_lanes(ctx->n_lanes, nc, [&](int lane, int k) {
-            make_sub(in, nullptr, cut[k], cut[k + 1], subs[k]);
+            { HostPhase hp2("ccs.make_sub"); make_sub(in, nullptr, cut[k], cut[k + 1], subs[k]); }
             ccs_chunk(ctx, lane, &subs[k].b, dpar, pp, cos[k]);
         });
-        const int rc = merge_chunks(in, cut, cos, out);
+        }
+        int rc;
+        { HostPhase hp("ccs.merge_chunks"); rc = merge_chunks(in, cut, cos, out); }
+        HostProf::dump();
         ctx->ms_e2e += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         ctx->n_zmws += in->n_zmws;
         return rc;

@@ -130,7 +130,7 @@ void DraftEngine::align_tasks(int nt, bool any_dag, bool want_paths, int64_t row
         CCS_CUDA(cudaMemcpyAsync(h_paths_.p, d_paths_.p, (size_t)path_bytes, cudaMemcpyDeviceToHost, stream_));
         stats.d2h_bytes += path_bytes;
     }
-    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
     CCS_CUDA(cudaGetLastError());
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0_, ev1_);
@@ -161,6 +161,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
         bool alive = false;
     };
     std::vector<ZmwWork> work(nz);
+    { HostPhase hp("draft.a1 filter+seed+kmer");
     parallel_for(nz, host_threads, [&](int z) {
         const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
         const int n = r1 - r0;
@@ -186,6 +187,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
         }
         w.alive = true;
     });
+    }
 
     // ---- a2: SparsePoa rounds: round k aligns the k-th POA read of every ZMW on the GPU ----
     std::vector<int> task_zmw;
@@ -216,6 +218,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
             h_preds_.ensure((size_t)n_preds + 16); h_reads_.ensure((size_t)n_reads + 16);
             std::memcpy(h_tasks_.p, tl.data(), sizeof(PoaTask) * nt);
             // pass 2 (parallel): export graphs and orient reads straight into pinned memory
+            { HostPhase hp("draft.a2 export");
             parallel_for(nt, host_threads, [&](int k) {
                 ZmwWork& w = work[task_zmw[k]];
                 const PoaTask& t = tl[k];
@@ -223,7 +226,11 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
                 const int rd = w.poa_reads[round];
                 orient(in.codes + in.read_off[rd], lens[rd], w.poa_rev[round], h_reads_.p + t.read_off);
             });
+            }
+            { HostPhase hp("draft.a2 gpu align (wait)");
             align_tasks(nt, true, true, rows, path_bytes, (size_t)rows, (size_t)n_poff, (size_t)n_preds, (size_t)n_reads);
+            }
+            HostPhase hp2("draft.a2 commit");
             parallel_for(nt, host_threads, [&](int k) {
                 ZmwWork& w = work[task_zmw[k]];
                 const PoaTask& t = tl[k];
@@ -237,6 +244,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
 
     // ---- a4: consensus + length gates; a3: orientation of every kept read against the draft ----
     std::vector<std::vector<uint8_t>> rev_flag(nz);
+    { HostPhase hp("draft.a4 consensus+kmer");
     parallel_for(nz, host_threads, [&](int z) {
         ZmwWork& w = work[z];
         if (!w.alive) return;
@@ -259,6 +267,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
             rev_flag[z][r - r0] = c > f;
         }
     });
+    }
 
     // ---- a5: subread -> draft mapping of every kept read (linear graphs on the same kernel) ---
     {
@@ -291,6 +300,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
             if (nt == 0) break;
             h_tasks_.ensure(nt); h_vbase_.ensure((size_t)n_vbase + 16); h_reads_.ensure((size_t)n_reads + 16);
             std::memcpy(h_tasks_.p, tl.data(), sizeof(PoaTask) * nt);
+            { HostPhase hp("draft.a5 map pack");
             parallel_for(nt, host_threads, [&](int k) {
                 const PoaTask& t = tl[k];
                 const int r = task_read[k], zz = t.pad_;
@@ -298,7 +308,10 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
                     std::memcpy(h_vbase_.p + t.vert_off, out.draft[zz].data(), out.draft[zz].size());
                 orient(in.codes + in.read_off[r], lens[r], rev_flag[zz][r - in.zmw_read_off[zz]], h_reads_.p + t.read_off);
             });
+            }
+            { HostPhase hp("draft.a5 gpu map (wait)");
             align_tasks(nt, false, false, rows, 0, (size_t)n_vbase, 0, 0, (size_t)n_reads);
+            }
             for (int k = 0; k < nt; ++k) {
                 const PoaResult& pr = h_results_.p[k];
                 ReadMap& m = out.maps[task_read[k]];

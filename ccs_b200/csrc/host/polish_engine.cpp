@@ -68,7 +68,7 @@ ArrowEngine::ArrowEngine(int device, const ArrowModelParams& model, size_t budge
     CCS_CUDA(cudaMemcpyAsync(d_emi_.p, em_.em_ins, sizeof(em_.em_ins), cudaMemcpyHostToDevice, stream_));
     d_counter_.ensure(4);
     h_counter_.ensure(4);
-    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
 }
 
 ArrowEngine::~ArrowEngine() {
@@ -130,6 +130,7 @@ ArrowBatchView ArrowEngine::view() const {
 // (ModelConfig::Populate, row a6).
 // ---------------------------------------------------------------------------------------------
 void ArrowEngine::load(const PolishInput& in) {
+    HostPhase hp("polish.load pack");
     CCS_CUDA(cudaSetDevice(device_));
     const int nz = in.n_zmws, nr = in.n_reads;
     zstate_.assign(nz, ZmwState());
@@ -223,6 +224,7 @@ void ArrowEngine::load(const PolishInput& in) {
 // (Re)derive DevRead / DevZmw / template buffer / column offsets from the host state and push
 // them.  Called after load() and after every round that edited templates.
 void ArrowEngine::upload_templates_and_reads() {
+    HostPhase hp("polish.upload templates+reads");
     const int nz = (int)zstate_.size(), nr = (int)reads_.size();
     int64_t toff = 0, cols = 0, drows = 0;
     for (int z = 0; z < nz; ++z) {
@@ -343,9 +345,10 @@ void ArrowEngine::fill() {
 }
 
 void ArrowEngine::sync_statuses() {
+    HostPhase hp("polish.fill (wait)");
     const int nr = (int)reads_.size();
     CCS_CUDA(cudaMemcpyAsync(h_status_.p, d_status_.p, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, stream_));
-    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
     resolve_spans();
     stats.d2h_bytes += 4ll * nr;
     for (int r = 0; r < nr; ++r) {
@@ -363,7 +366,7 @@ void ArrowEngine::read_lls(double* ll_alpha, double* ll_beta, int32_t* status) {
     h_ll_.ensure((size_t)2 * nr + 2);
     CCS_CUDA(cudaMemcpyAsync(h_ll_.p, d_ll_alpha_.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream_));
     CCS_CUDA(cudaMemcpyAsync(h_ll_.p + nr, d_ll_beta_.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream_));
-    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
     stats.d2h_bytes += 16ll * nr;
     for (int r = 0; r < nr; ++r) {
         const bool filled = status_[r] == 0 || status_[r] == 1 || status_[r] == 3;
@@ -378,7 +381,7 @@ void ArrowEngine::dump_pair(int r, float* alpha, float* beta, int32_t* start, in
     const int J = rd.J;
     if (J <= 0) return;
     std::vector<ColInfo> ci(J);
-    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
     if (alpha) CCS_CUDA(cudaMemcpy(alpha, d_alpha_.p + rd.col_off * 32, sizeof(float) * 32 * J, cudaMemcpyDeviceToHost));
     if (beta) CCS_CUDA(cudaMemcpy(beta, d_beta_.p + rd.col_off * 32, sizeof(float) * 32 * J, cudaMemcpyDeviceToHost));
     CCS_CUDA(cudaMemcpy(ci.data(), d_colinfo_.p + rd.col_off, sizeof(ColInfo) * J, cudaMemcpyDeviceToHost));
@@ -436,7 +439,7 @@ int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
         launch_pick(V, d_ranges_.p, n_ranges_, n_range_items_, d_delta_.p, d_cand_.p, (int)d_cand_.cap, d_counter_.p, stream_);
         span_end();
         CCS_CUDA(cudaMemcpyAsync(h_counter_.p, d_counter_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-        CCS_CUDA(cudaStreamSynchronize(stream_));
+        CCS_CUDA(stream_sync_blocking(stream_));
         resolve_spans();
         ++stats.n_pick;
         const int64_t n = h_counter_.p[0];
@@ -444,7 +447,7 @@ int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
             h_cand_.ensure((size_t)n + 1);
             if (n > 0) {
                 CCS_CUDA(cudaMemcpyAsync(h_cand_.p, d_cand_.p, sizeof(Candidate) * n, cudaMemcpyDeviceToHost, stream_));
-                CCS_CUDA(cudaStreamSynchronize(stream_));
+                CCS_CUDA(stream_sync_blocking(stream_));
                 stats.d2h_bytes += (int64_t)sizeof(Candidate) * n;
                 out.assign(h_cand_.p, h_cand_.p + n);
             }
@@ -457,7 +460,7 @@ int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
 
 void ArrowEngine::download_delta(int z, double* out) {
     const DevZmw& dz = zmws_[z];
-    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
     std::vector<double> tmp((size_t)dz.J * kDeltaStride);
     CCS_CUDA(cudaMemcpy(tmp.data(), d_delta_.p + dz.delta_off * kDeltaStride, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
     for (int p = 0; p < dz.J; ++p)
@@ -524,7 +527,8 @@ void ArrowEngine::polish(const PolishParams& pp) {
         if (ranges.empty()) break;
         ++stats.rounds;
         score_ranges(ranges, first);
-        pick(cands);
+        { HostPhase hp("polish.score+pick (wait)"); pick(cands); }
+        HostPhase hp_round("polish.round select+apply");
         // group candidates per ZMW
         std::vector<std::vector<HostMutation>> per(nz);
         for (const Candidate& c : cands) per[c.zmw].push_back(HostMutation{c.type, c.pos, c.base, c.score});
@@ -591,14 +595,17 @@ void ArrowEngine::polish(const PolishParams& pp) {
             applied_flag.store(1, std::memory_order_relaxed);
         });
         const bool any_applied = applied_flag.load() != 0;
+        hp_round.~HostPhase();
+        new (&hp_round) HostPhase("polish.round tail");
         if (!any_applied) break;
         upload_templates_and_reads();
         if (reuse_scores) remap_deltas();
         fill();
         for (int z = 0; z < nz; ++z) if (!zstate_[z].done) check_usable(z);
     }
-    consensus_qvs();
+    { HostPhase hp("polish.qv (wait)"); consensus_qvs(); }
     CCS_CUDA(cudaEventRecord(evB_, stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
     CCS_CUDA(cudaEventSynchronize(evB_));
     float ms = 0;
     cudaEventElapsedTime(&ms, evA_, evB_);
@@ -630,7 +637,7 @@ void ArrowEngine::remap_deltas() {
     CCS_CUDA(cudaMemcpyAsync(d_remap_jobs_.p, jobs.data(), sizeof(RemapJob) * jobs.size(), cudaMemcpyHostToDevice, stream_));
     CCS_CUDA(cudaMemcpyAsync(d_remap_sites_.p, sites.data(), 4 * sites.size(), cudaMemcpyHostToDevice, stream_));
     CCS_CUDA(cudaMemcpyAsync(d_remap_shifts_.p, shifts.data(), 4 * shifts.size(), cudaMemcpyHostToDevice, stream_));
-    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
     launch_remap_delta(d_remap_jobs_.p, (int)jobs.size(), d_remap_sites_.p, d_remap_shifts_.p, d_delta_.p,
                        d_delta_scratch_.p, stream_);
 }
@@ -678,7 +685,7 @@ void ArrowEngine::consensus_qvs() {
     launch_qv(V, d_delta_.p, d_qv_.p, first, d_ranges_.p, (int)ranges.size(), stream_);
     span_end();
     CCS_CUDA(cudaMemcpyAsync(h_qv_.p, d_qv_.p, (size_t)total_delta_rows_, cudaMemcpyDeviceToHost, stream_));
-    CCS_CUDA(cudaStreamSynchronize(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
     resolve_spans();
     CCS_CUDA(cudaGetLastError());
     ++stats.n_qv;
