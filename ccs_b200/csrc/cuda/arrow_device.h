@@ -14,6 +14,7 @@ namespace ccs {
 constexpr int kBandW = 32;            // band rows per column (spec)
 constexpr int kBandMargin = 2;        // rows kept beyond the leading edge (spec)
 constexpr int kEdgeLog2 = -60;        // leading-edge threshold 2^-60 on unscaled cells (spec)
+constexpr int kScaleEvery = 4;        // columns j with j % 4 == 0 are rescaled by the power of two of their maximum (spec)
 constexpr int kRowCodePad = 96;
 constexpr int kDeltaStride = 16;       // doubles per template position in the delta store:
                                       // {SUB A,C,G,T, DEL, INS A,C,G,T, INS' A,C,G,T (reverse-strand share), pad x3}       // sentinel codes after the last real row code

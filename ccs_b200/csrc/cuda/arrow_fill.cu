@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
     const int src_up = pinned((g + 7) & 7), src_up2 = pinned((g + 6) & 7), src_up4 = pinned((g + 4) & 7);
     const int g4 = pinned(4 * g);
     const float thr = __uint_as_float((unsigned)(127 + kEdgeLog2) << 23);
+    const int oct_shift = pinned((int)(threadIdx.x & 24));
 
     // column 0: alpha(0,0) = 1
     float v0 = (g == 0) ? 1.f : 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
@@ -129,22 +130,23 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
         const float xin = __shfl_sync(kFullMask, At, src_up, 8);
         v0 = fmaf(G0, xin, A0); v1 = fmaf(G1, xin, A1); v2 = fmaf(G2, xin, A2); v3 = fmaf(G3, xin, A3);
 
-        // column maximum (power-of-two scaling) + leading edge: does one of the band's last three rows reach 2^-60?
+        // leading edge: does one of the band's last three rows reach 2^-60?  Only the top lane can say so; one ballot
+        // tells the whole octet
         const float m3 = fmaxf(fmaxf(v1, v2), v3);
-        const float mx = fmaxf(m3, v0);
-        unsigned key = (__float_as_uint(mx) & 0xffff0000u) | ((topl && m3 >= thr) ? 1u : 0u);
-        key = vmax_oct(key);
-        // the sign bit of a maximum is 0, so key >> 23 is its biased exponent e: scale by 2^(127-e) (an all-zero or
-        // denormal column gives e = 0 -- the read is dead or about to be, and its LL ends up -inf either way)
-        const int ebits = (int)(key >> 23);
-        const float sc = __uint_as_float(0x7f000000u - ((key >> 23) << 23));
-        v0 *= sc; v1 *= sc; v2 *= sc; v3 *= sc;
-        cum += ebits - 127;
+        const unsigned bal = __ballot_sync(kFullMask, topl && m3 >= thr);
+        if ((j & (kScaleEvery - 1)) == 0) {        // warp-uniform: every 4th column is rescaled (spec)
+            // the sign bit of a maximum is 0, so key >> 23 is its biased exponent e: scale by 2^(127-e) (an all-zero
+            // or denormal column gives e = 0 -- the read is dead or about to be, and its LL ends up -inf either way)
+            const unsigned key = vmax_oct(__float_as_uint(fmaxf(m3, v0)) & 0xffff0000u);
+            const float sc = __uint_as_float(0x7f000000u - ((key >> 23) << 23));
+            v0 *= sc; v1 *= sc; v2 *= sc; v3 *= sc;
+            cum += (int)(key >> 23) - 127;
+        }
         if (alive) {
             acol[(size_t)j * 8] = make_float4(v0, v1, v2, v3);
             if (g == 0) cinfo[j] = ColInfo{s, cum};
         }
-        slid = (key & 1u) != 0u;
+        slid = ((bal >> oct_shift) & 0xffu) != 0u;
         s += slid ? 4 : 0;
         if ((s >> 5) != lap) {           // octet-uniform, once every 32 rows
             lap = s >> 5;
@@ -293,13 +295,16 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
         const float xin = __shfl_sync(kFullMask, At, src_dn, 8);
         v0 = fmaf(G0, xin, A0); v1 = fmaf(G1, xin, A1); v2 = fmaf(G2, xin, A2); v3 = fmaf(G3, xin, A3);
 
-        const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-        unsigned key = vmax_oct(__float_as_uint(mx) & 0xffff0000u);
-        const int ebits = (int)(key >> 23);
-        const float sc = __uint_as_float(0x7f000000u - ((key >> 23) << 23));
-        v0 *= sc; v1 *= sc; v2 *= sc; v3 *= sc;
+        int kcol = 0;
+        if ((j & (kScaleEvery - 1)) == 0) {        // warp-uniform: every 4th column is rescaled (spec)
+            const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+            const unsigned key = vmax_oct(__float_as_uint(mx) & 0xffff0000u);
+            const float sc = __uint_as_float(0x7f000000u - ((key >> 23) << 23));
+            v0 *= sc; v1 *= sc; v2 *= sc; v3 *= sc;
+            kcol = (int)(key >> 23) - 127;
+        }
         if (alive) {
-            cum += ebits - 127;
+            cum += kcol;
             bcol[(size_t)j * 8] = make_float4(v0, v1, v2, v3);
             if (g == 0) bexp[j] = cum;
             started = true;

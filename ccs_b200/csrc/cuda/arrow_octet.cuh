@@ -7,8 +7,10 @@
 // recycled in place and no cell moves between lanes.
 //
 //   column step (forward):  a_i = C_i + g_i * a_{i-1},
-//       C_i = M * emM[code_i] * prev_{i-1} + D * prev_i        (match + deletion from column j-1)
-//       g_i = emI[code_i] * (cognate ? B : S)                  (branch / stick inside column j)
+//       C_i = mm[code_i] * prev_{i-1} + D * prev_i             (match + deletion from column j-1)
+//       g_i = gg[code_i]                                       (branch / stick inside column j)
+//   (mm, gg = the folded per-ZMW factors below; the generic evaluator of arrow_score.cu computes the same
+//   products from the unfolded tables)
 //   The in-column first-order recurrence is solved by a 4-cell serial scan per lane plus a
 //   3-step Kogge-Stone ring scan over the octet (pairs (g, C) under (g2 g1, g2 C1 + C2)); the
 //   band start is a slot with g = 0, which is what makes the ring scan exact.
@@ -113,76 +115,6 @@ __device__ __forceinline__ void octet_forward_scan(float A[4], float G[4], const
     const float x = shfl_oct(At, (g + 7) & 7);     // final value of slot 4g-1
 #pragma unroll
     for (int q = 0; q < 4; ++q) v[q] = fmaf(G[q], x, A[q]);
-}
-
-__device__ __forceinline__ void octet_forward_column(float v[4], const int g, const int d, const int rel[4],
-                                                     const int code[4], const float M, const float D, const float B,
-                                                     const float S, const float* __restrict__ emm_row,
-                                                     const float* __restrict__ emi_row, const int cur_base4) {
-    float A[4], G[4];
-    octet_forward_terms(v, g, d, rel, code, M, D, B, S, emm_row, emi_row, cur_base4, A, G);
-    octet_forward_scan(A, G, g, v);
-}
-
-// Backward column terms: v[] = column j+1 (scaled); d = s_{j+1} - s_j; rel[q] = (slot - s_j) & 31;
-// code1[q] = code of row (row_q + 1).
-__device__ __forceinline__ void octet_backward_terms(const float v[4], const int g, const int d, const int rel[4],
-                                                     const int code1[4], const float M, const float D, const float B,
-                                                     const float S, const float* __restrict__ emm_row,
-                                                     const float* __restrict__ emi_row, const int cur_base4 /* (base of the context's current template base) << 2 */,
-                                                     float A[4], float G[4]) {
-    float dn[4];
-    dn[3] = shfl_oct(v[0], (g + 1) & 7);
-    dn[0] = v[1]; dn[1] = v[2]; dn[2] = v[3];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float nx = (rel[q] >= d) ? v[q] : 0.f;                            // beta(i, j+1)
-        const float nd = (rel[q] >= d - 1 && rel[q] <= d + 30) ? dn[q] : 0.f;   // beta(i+1, j+1)
-        const float em = ldtab(emm_row, code1[q]);
-        A[q] = fmaf(M, em * nd, D * nx);
-        const float gi = ldtab(emi_row, code1[q]) * (((code1[q] & 12) == cur_base4) ? B : S);
-        G[q] = (rel[q] == 31) ? 0.f : gi;          // band end: no in-band successor
-    }
-}
-
-__device__ __forceinline__ void octet_backward_scan(float A[4], float G[4], const int g, float v[4]) {
-    A[2] = fmaf(G[2], A[3], A[2]); G[2] *= G[3];
-    A[1] = fmaf(G[1], A[2], A[1]); G[1] *= G[2];
-    A[0] = fmaf(G[0], A[1], A[0]); G[0] *= G[1];
-    float At = A[0], Gt = G[0];
-#pragma unroll
-    for (int off = 1; off < 8; off <<= 1) {
-        const float As = shfl_oct(At, (g + off) & 7);
-        const float Gs = shfl_oct(Gt, (g + off) & 7);
-        At = fmaf(Gt, As, At);
-        Gt *= Gs;
-    }
-    const float x = shfl_oct(At, (g + 1) & 7);     // final value of slot 4g+4
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = fmaf(G[q], x, A[q]);
-}
-
-// Column normalisation + leading edge.  Returns the power-of-two exponent k of the column
-// maximum (values are multiplied by 2^-k) and writes edge_rel = 1 + largest rel whose
-// unscaled value >= 2^kEdgeLog2 (0 if none).  One packed reduction: high half = top 16 bits
-// of the max's fp32 pattern, low half = edge_rel, combined with a per-halfword max.
-__device__ __forceinline__ int octet_scale_column(float v[4], const int rel[4], int& edge_rel, bool& dead) {
-    const float thr = __uint_as_float((unsigned)(127 + kEdgeLog2) << 23);
-    float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
-    int er = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) er = (v[q] >= thr) ? max(er, rel[q] + 1) : er;
-    unsigned key = (__float_as_uint(mx) & 0xffff0000u) | (unsigned)er;
-#pragma unroll
-    for (int off = 1; off < 8; off <<= 1) key = __vmaxu2(key, __shfl_xor_sync(kFullMask, key, off, 8));
-    edge_rel = (int)(key & 0xffffu);
-    const int ebits = (int)((key >> 23) & 255u);
-    dead = (key >> 16) == 0u;
-    const int k = dead ? 0 : ebits - 127;
-    const float sc = __uint_as_float((unsigned)(127 - k) << 23);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] *= sc;
-    return k;
 }
 
 __device__ __forceinline__ float octet_max(float x) {

@@ -64,8 +64,11 @@ void Tables::build(const ccs::ArrowModelParams& m, const float snr[4]) {
 //  * edge:  largest row whose UNSCALED value is >= 2^edge_log2 (the leading edge of the
 //           probability mass; the forward mass trails behind the true path inside insertion
 //           bursts, so the band is anchored at its leading edge, not at its maximum).
+//  * schedule: only columns j with j % kScaleEvery == 0 are rescaled (k = 0 elsewhere): the values stay far inside
+//           the fp32 range over three unscaled columns, and the kernels save the octet-wide maximum on those columns.
+constexpr int kScaleEvery = 4;
 template <class Real>
-static void scale_column(Real* col, int W, int s, int edge_log2, int& edge_row, int& k_out, bool& dead) {
+static void scale_column(Real* col, int W, int s, int edge_log2, int& edge_row, int& k_out, bool& dead, bool rescale) {
     double best_val = 0.0;
     const double thr = std::ldexp(1.0, edge_log2);
     edge_row = s - 1;
@@ -77,7 +80,7 @@ static void scale_column(Real* col, int W, int s, int edge_log2, int& edge_row, 
     }
     dead = !(best_val > 0.0);
     int k = 0;
-    if (!dead) {
+    if (!dead && rescale) {
         float f = (float)best_val;
         uint32_t u;
         std::memcpy(&u, &f, 4);
@@ -130,7 +133,7 @@ void Recursor<Real>::fill_alpha() {
         }
         int k;
         bool dead;
-        scale_column(&alpha.v[(size_t)j * W], W, s, edge_log2, edge, k, dead);
+        scale_column(&alpha.v[(size_t)j * W], W, s, edge_log2, edge, k, dead, j % kScaleEvery == 0);
         alpha.cumexp[j] = alpha.cumexp[j - 1] + k;
         cells += W;
         if (dead) { status = READ_DEAD; return; }
@@ -168,7 +171,7 @@ void Recursor<Real>::fill_beta() {
         }
         int k, m;
         bool dead;
-        scale_column(&beta.v[(size_t)j * W], W, s, edge_log2, m, k, dead);
+        scale_column(&beta.v[(size_t)j * W], W, s, edge_log2, m, k, dead, j % kScaleEvery == 0);
         beta.cumexp[j] = (j == Jn - 1 ? 0 : beta.cumexp[j + 1]) + k;
         if (dead) { status = READ_DEAD; return; }
     }
