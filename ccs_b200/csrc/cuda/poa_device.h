@@ -14,6 +14,7 @@ constexpr int kPoaBand = 64;
 constexpr int kPoaMatch = 3, kPoaMismatch = -5, kPoaIns = -4, kPoaDel = -4;
 constexpr int kPoaMaxPred = 8;
 constexpr int kPoaKmer = 11;
+constexpr int kPoaVoteBases = 2048;   // orientation vote: k-mers of the read's first 2048 bases (spec)
 
 struct PoaTask {
     int64_t vert_off;     // this graph's vertices in base[]

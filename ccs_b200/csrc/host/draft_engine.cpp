@@ -182,7 +182,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
         w.poa_rev.assign(w.poa_reads.size(), 0);
         for (size_t k = 1; k < w.poa_reads.size(); ++k) {
             int64_t f, c;
-            ks.count(in.codes + in.read_off[w.poa_reads[k]], lens[w.poa_reads[k]], f, c);
+            ks.count(in.codes + in.read_off[w.poa_reads[k]], std::min(lens[w.poa_reads[k]], kPoaVoteBases), f, c);
             w.poa_rev[k] = c > f;
         }
         w.alive = true;
@@ -263,7 +263,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
         for (int r = r0; r < r1; ++r) {
             if (!out.keep[r]) continue;
             int64_t f, c;
-            ks.count(in.codes + in.read_off[r], lens[r], f, c);
+            ks.count(in.codes + in.read_off[r], std::min(lens[r], kPoaVoteBases), f, c);
             rev_flag[z][r - r0] = c > f;
         }
     });

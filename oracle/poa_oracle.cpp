@@ -221,7 +221,9 @@ static void kmers(const uint8_t* s, int n, std::vector<uint32_t>& out) {
 // content sampling: a k-mer takes part iff the three top bits of k * 0x9E3779B1 (mod 2^32) are clear
 static bool kmer_sampled(uint32_t k) { return ((uint32_t)(k * 0x9E3779B1u) >> 29) == 0u; }
 
-bool kmer_vote_reverse(const uint8_t* ref, int nref, const uint8_t* read, int n) {
+// only the first POA_VOTE_BASES bases of the read vote (hundreds of sampled k-mers: the decision is not close)
+bool kmer_vote_reverse(const uint8_t* ref, int nref, const uint8_t* read, int n_read) {
+    const int n = std::min(n_read, POA_VOTE_BASES);
     std::vector<uint32_t> rk, fk, ck;
     kmers(ref, nref, rk);
     std::sort(rk.begin(), rk.end());

@@ -14,6 +14,7 @@ namespace oracle {
 constexpr int POA_MATCH = 3, POA_MISMATCH = -5, POA_INS = -4, POA_DEL = -4;
 constexpr int POA_BAND = 64;
 constexpr int POA_KMER = 11;
+constexpr int POA_VOTE_BASES = 2048;   // orientation vote: k-mers of the read's first 2048 bases (DESIGN.md "Draft stage")
 
 enum PoaMove : uint8_t { PM_STOP = 0, PM_MATCH = 1, PM_DEL = 2, PM_INS = 3 };
 
