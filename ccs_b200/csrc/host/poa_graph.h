@@ -44,11 +44,12 @@ public:
         const int V = size();
         order.resize(V);
         rank_.resize(V);
-        int t = 0;
-        for (int x = head_; x >= 0; x = next_[x]) { rank_[x] = t; order[t++] = x; }
+        // one pass in list (= topological) order: a vertex's predecessors precede it, so their ranks are already known
         int32_t np = 0;
-        for (t = 0; t < V; ++t) {
-            const int x = order[t];
+        int t = 0;
+        for (int x = head_; x >= 0; x = next_[x], ++t) {
+            rank_[x] = t;
+            order[t] = x;
             base[t] = base_[x];
             pred_off[t] = np;
             const int n = nin_[x];
