@@ -158,11 +158,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
         srow[2 * lane] = H0; srow[2 * lane + 1] = H1;
         if (store_h) *reinterpret_cast<int2*>(h_r + (size_t)t * kPoaBand + 2 * lane) = make_int2(H0, H1);
         // best cell of the row: largest value, smallest read prefix on ties
+        // one reduction: key = value * 64 + (63 - cell) -- the maximum key is the largest value and, among equals,
+        // the smallest cell (scores are >= 0 and < 2^25)
         const int hv = max(H0, H1);
-        const int rmax = __reduce_max_sync(kFull, hv);
-        const unsigned who = __ballot_sync(kFull, hv == rmax);
-        const int wl = __ffs(who) - 1;
-        const int wc = __shfl_sync(kFull, (H0 == rmax) ? 2 * lane : 2 * lane + 1, wl);
+        const int cell = (H0 >= H1) ? 2 * lane : 2 * lane + 1;
+        const int rkey = __reduce_max_sync(kFull, hv * kPoaBand + (kPoaBand - 1 - cell));
+        static_assert(kPoaBand == 64, "key packing assumes 64 cells per row");
+        const int rmax = rkey >> 6;
+        const int wc = kPoaBand - 1 - (rkey & (kPoaBand - 1));
         const int besti = (rmax > 0) ? lo + wc : lo;
         if (lane == 0) { lo_r[t] = lo; bi_r[t] = besti; }
         if (rmax > gbest) { gbest = rmax; gt = t; gi = besti; }

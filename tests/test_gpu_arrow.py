@@ -135,3 +135,23 @@ def test_polish_matches_oracle(ctx, insert, n_zmw, cfg_id):
         assert res["n_tested"][zi] == o["n_tested"]
         assert abs(res["rq"][zi] - o["rq"]) < 2e-3
         assert (res["status"][zi] == api.ZMW_SUCCESS) == (o["converged"] and o["rq"] >= 0.99)
+
+
+def test_polish_many_passes_matches_oracle(ctx):
+    """55 passes per ZMW: more reads than one fill group (16) and than the scoring kernel's shared-memory read cache
+    (48) -- both overflow paths must give the oracle's answer."""
+    cfg = sim.get_config(1, insert_mean=300, passes_min=55, passes_max=55, frac_low_snr=0.0, frac_few_passes=0.0)
+    zs = [sim.simulate_zmw(MODEL, cfg, i) for i in range(2)]
+    assert min(z.n_reads for z in zs) > 48
+    batch, drafts = _zmw_batch(zs)
+    res = ctx.polish(batch)
+    for zi, z in enumerate(zs):
+        d, reads, strand, ts, te = _oracle_inputs(z, drafts[zi])
+        o = O.polish(MODEL, z.snr, d, reads, strand, ts, te)
+        s0, s1 = res["seq_off"][zi], res["seq_off"][zi + 1]
+        assert np.array_equal(res["seq"][s0:s1], o["consensus"])
+        assert np.max(np.abs(res["qv"][s0:s1].astype(int) - o["qv"].astype(int))) <= 1
+        r0, r1 = batch.zmw_read_off[zi], batch.zmw_read_off[zi + 1]
+        assert np.array_equal(res["read_status"][r0:r1], o["read_status"])
+        assert np.nanmax(np.abs(res["read_ll"][r0:r1] - o["read_ll"])) < LL_TOL
+        assert res["n_applied"][zi] == o["n_applied"]
