@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     unsigned w0 = 0x30303030u, w1 = 0x30303030u, wm = 0x30303030u;   // laps L, L+1, L-1 (sentinels)
     bool started = false;
 
+#pragma unroll 2
     for (int j = Jmax - 1; j >= 1; --j) {
         const bool alive = j <= J - 1;
         const bool init_col = alive && !started;
@@ -278,7 +279,8 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
             A2 = (row0 + 2 == I - 1) ? endv : 0.f;
             A3 = (row0 + 3 == I - 1) ? endv : 0.f;
         }
-        if (!alive) { A0 = A1 = A2 = A3 = 0.f; G0 = G1 = G2 = G3 = 0.f; }
+        // (an octet that has not started yet holds an all-zero column: its terms A are zero whatever the table row
+        //  says, the scan returns zeros, and nothing is stored -- no masking needed)
         // b_i = A_i + G_i * b_{i+1}
         A2 = fmaf(G2, A3, A2); G2 *= G3;
         A1 = fmaf(G1, A2, A1); G1 *= G2;
