@@ -148,3 +148,21 @@ def test_model_json_round_trip(tmp_path):
     bad = tmp_path / "bad.json"
     bad.write_text('{"ModelForm": "Marginal"}')
     assert L.ccs_model_load_json(str(bad).encode(), back.ctypes.data_as(C.c_void_p)) == -7     # CCS_ERR_CHEMISTRY
+
+
+def test_host_poa_graph_matches_oracle(tmp_path):
+    """Host logic of the Draft Stage (CommitAdd threading, topological export, FindConsensus in
+    ccs_b200/csrc/host/poa_graph.h) against the oracle's independent graph, driven by the oracle's CPU
+    alignments re-encoded in the kernel's traceback format -- no device involved."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "poa_graph_parity")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", exe,
+                           os.path.join(ROOT, "tests", "host", "poa_graph_parity.cpp"),
+                           os.path.join(ROOT, "oracle", "poa_oracle.cpp")])
+    out = subprocess.run([exe, "30"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert out.stdout.startswith("ok:")
