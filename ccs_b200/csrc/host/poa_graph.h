@@ -4,9 +4,17 @@
 // aligned read into the graph (CommitAdd), keeping the vertex list in topological order, and
 // the consensus path (FindConsensus).
 //
-// Order maintenance: vertices live in a doubly linked list that is always a topological order;
+// Order maintenance: vertices live in a singly linked list that is always a topological order;
 // a new vertex is linked immediately after its predecessor on the read's path, so no re-sort is
 // ever needed (DESIGN.md "Draft stage").
+//
+// Layout: one 20-byte node per vertex {next, nreads, first predecessor, block, base, in-degree};
+// almost every vertex is a chain vertex with exactly one predecessor, so export, CommitAdd and
+// consensus touch one cache line per 3 vertices; further predecessors (up to kPoaMaxPred) live in
+// 7-int blocks of a pool that only branch points own.  Per-call scratch (path steps, ranks, the
+// consensus DP arrays) is thread-local and reused across graphs: a fresh graph per ZMW would
+// otherwise page-fault a few hundred KB of temporaries on every call.  This host code is the
+// multi-GPU scaling limit of the whole path (DESIGN.md "Multi-GPU"), hence the care.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -18,24 +26,28 @@ namespace ccs {
 class HostPoaGraph {
 public:
     void init(const uint8_t* seq, int n) {
-        base_.assign(seq, seq + n);
-        nreads_.assign(n, 1);
-        next_.resize(n); prev_.resize(n);
-        in_.resize((size_t)n * kPoaMaxPred);      // only the first nin_ entries of a vertex are ever read
-        nin_.assign(n, 0);
+        node_.clear();
+        node_.reserve((size_t)n + (size_t)n / 2 + 64);   // four more reads add ~10 % new vertices each
+        node_.resize((size_t)n);
         for (int i = 0; i < n; ++i) {
-            prev_[i] = i - 1; next_[i] = (i + 1 < n) ? i + 1 : -1;
-            if (i > 0) { in_[(size_t)i * kPoaMaxPred] = i - 1; nin_[i] = 1; }
+            Node& v = node_[i];
+            v.next = (i + 1 < n) ? i + 1 : -1;
+            v.nreads = 1;
+            v.in0 = i - 1;
+            v.more = -1;
+            v.base = seq[i];
+            v.nin = i > 0 ? 1 : 0;
+            v.pad_ = 0;
         }
+        pool_.clear();
         head_ = n ? 0 : -1;
         n_edges_ = n ? n - 1 : 0;
         spans_.clear();
         if (n) spans_.push_back({0, n - 1});
         n_reads_ = 1;
     }
-    int size() const { return (int)base_.size(); }
+    int size() const { return (int)node_.size(); }
     int n_reads() const { return n_reads_; }
-
     int n_edges() const { return n_edges_; }
 
     // Topological export into caller buffers: order[t] = vertex id; base[V]; pred_off[V+1] (relative
@@ -43,23 +55,26 @@ public:
     void export_topo(std::vector<int32_t>& order, uint8_t* base, int32_t* pred_off, int32_t* preds) const {
         const int V = size();
         order.resize(V);
+        std::vector<int32_t>& rank_ = scratch().rank;
         rank_.resize(V);
         // one pass in list (= topological) order: a vertex's predecessors precede it, so their ranks are already known
         int32_t np = 0;
         int t = 0;
-        for (int x = head_; x >= 0; x = next_[x], ++t) {
+        for (int x = head_; x >= 0; ++t) {
+            const Node& v = node_[x];
             rank_[x] = t;
             order[t] = x;
-            base[t] = base_[x];
+            base[t] = v.base;
             pred_off[t] = np;
-            const int n = nin_[x];
-            const int32_t* e = &in_[(size_t)x * kPoaMaxPred];
-            if (n == 1) preds[np++] = rank_[e[0]];                 // the common case: a chain vertex
-            else if (n > 1) {
+            if (v.nin == 1) preds[np++] = rank_[v.in0];            // the common case: a chain vertex
+            else if (v.nin > 1) {
                 const int b = np;
-                for (int k = 0; k < n; ++k) preds[np++] = rank_[e[k]];
+                preds[np++] = rank_[v.in0];
+                const int32_t* e = &pool_[(size_t)v.more * kMore];
+                for (int k = 0; k + 1 < v.nin; ++k) preds[np++] = rank_[e[k]];
                 std::sort(preds + b, preds + np);
             }
+            x = v.next;
         }
         pred_off[V] = np;
     }
@@ -68,7 +83,8 @@ public:
     // topology and thread the read.  order/pred_off/preds are this graph's export of the round.
     void commit(const uint8_t* moves_rev, int len, int end_t, int end_i, const std::vector<int32_t>& order,
                 const int32_t* pred_off, const int32_t* preds, const uint8_t* seq) {
-        // rebuild the path start -> end: (vertex id or -1, read position or -1)
+        // rebuild the path start -> end: (vertex id or -1, read position)
+        std::vector<std::pair<int32_t, int32_t>>& steps_ = scratch().steps;
         steps_.clear();
         int t = end_t, i = end_i;
         for (int k = 0; k < len; ++k) {
@@ -88,7 +104,7 @@ public:
         for (size_t k = steps_.size(); k-- > 0;) {
             const int vx = steps_[k].first, rp = steps_[k].second;
             int cur;
-            if (vx >= 0 && base_[vx] == seq[rp]) { nreads_[vx]++; cur = vx; }
+            if (vx >= 0 && node_[vx].base == seq[rp]) { node_[vx].nreads++; cur = vx; }
             else cur = new_vertex_after(prevV, seq[rp]);
             add_edge(prevV, cur);
             prevV = cur;
@@ -99,63 +115,81 @@ public:
         ++n_reads_;
     }
 
-    // FindConsensus: score(v) = 2*nReads - max(spanning, minCov); best-scoring path
+    // FindConsensus: score(v) = 2*nReads - max(spanning, minCov); best-scoring path, ties to the lowest rank
     void consensus(int min_cov, std::vector<uint8_t>& out) const {
         const int V = size();
-        std::vector<int32_t> order(V);
+        Scratch& S = scratch();
+        std::vector<int32_t>& order_ = S.order; std::vector<int32_t>& rank_ = S.rank;
+        std::vector<int32_t>& cov_ = S.cov; std::vector<int32_t>& bp_ = S.bp;
+        std::vector<int64_t>& reach_ = S.reach;
+        order_.resize(V);
         rank_.resize(V);
-        { int t = 0; for (int x = head_; x >= 0; x = next_[x]) { rank_[x] = t; order[t++] = x; } }
-        std::vector<int32_t> cov(V + 1, 0);
-        for (auto& s : spans_) { cov[rank_[s.first]]++; cov[rank_[s.second] + 1]--; }
-        for (int t = 1; t <= V; ++t) cov[t] += cov[t - 1];
-        std::vector<int64_t> reach(V, 0);
-        std::vector<int32_t> bp(V, -1);
+        { int t = 0; for (int x = head_; x >= 0; x = node_[x].next) { rank_[x] = t; order_[t++] = x; } }
+        cov_.assign((size_t)V + 1, 0);
+        for (auto& s : spans_) { cov_[rank_[s.first]]++; cov_[rank_[s.second] + 1]--; }
+        for (int t = 1; t <= V; ++t) cov_[t] += cov_[t - 1];
+        reach_.resize((size_t)V);
+        bp_.resize((size_t)V);
         int64_t best = 0;
         int bt = -1;
         for (int t = 0; t < V; ++t) {
-            const int x = order[t];
-            const int64_t sc = 2ll * nreads_[x] - std::max(cov[t], min_cov);
+            const int x = order_[t];
+            const Node& v = node_[x];
+            const int64_t sc = 2ll * v.nreads - std::max(cov_[t], min_cov);
             int64_t m = 0;
             int mp = -1;
-            for (int k = 0; k < nin_[x]; ++k) {
-                const int p = rank_[in_[(size_t)x * kPoaMaxPred + k]];
-                if (reach[p] > m || (reach[p] == m && mp >= 0 && p < mp && reach[p] > 0)) { m = reach[p]; mp = p; }
+            if (v.nin >= 1) {
+                const int p = rank_[v.in0];
+                if (reach_[p] > 0) { m = reach_[p]; mp = p; }
+                const int32_t* e = pool_.data() + (size_t)(v.nin > 1 ? v.more : 0) * kMore;
+                for (int k = 0; k + 1 < v.nin; ++k) {
+                    const int q = rank_[e[k]];
+                    if (reach_[q] > m || (reach_[q] == m && mp >= 0 && q < mp && reach_[q] > 0)) { m = reach_[q]; mp = q; }
+                }
             }
-            reach[t] = sc + m;
-            bp[t] = mp;
-            if (bt < 0 || reach[t] > best) { best = reach[t]; bt = t; }
+            reach_[t] = sc + m;
+            bp_[t] = mp;
+            if (bt < 0 || reach_[t] > best) { best = reach_[t]; bt = t; }
         }
         out.clear();
-        for (int t = bt; t >= 0; t = bp[t]) out.push_back(base_[order[t]]);
+        for (int t = bt; t >= 0; t = bp_[t]) out.push_back(node_[order_[t]].base);
         std::reverse(out.begin(), out.end());
     }
 
 private:
+    struct Node { int32_t next; int32_t nreads; int32_t in0; int32_t more; uint8_t base; uint8_t nin; uint16_t pad_; };
+    static_assert(sizeof(Node) == 20, "Node layout");
+    static constexpr int kMore = kPoaMaxPred - 1;     // predecessors beyond the first: one pool block per branch point
+    struct Scratch {
+        std::vector<std::pair<int32_t, int32_t>> steps;
+        std::vector<int32_t> rank, order, cov, bp;
+        std::vector<int64_t> reach;
+    };
+    static Scratch& scratch() { static thread_local Scratch s; return s; }
+
     int new_vertex_after(int after, uint8_t b) {
         const int id = size();
-        base_.push_back(b); nreads_.push_back(1); nin_.push_back(0);
-        in_.resize(in_.size() + kPoaMaxPred);
-        if (after < 0) { prev_.push_back(-1); next_.push_back(head_); if (head_ >= 0) prev_[head_] = id; head_ = id; }
-        else {
-            prev_.push_back(after); next_.push_back(next_[after]);
-            if (next_[after] >= 0) prev_[next_[after]] = id;
-            next_[after] = id;
-        }
+        Node v;
+        v.nreads = 1; v.in0 = -1; v.more = -1; v.base = b; v.nin = 0; v.pad_ = 0;
+        if (after < 0) { v.next = head_; head_ = id; }
+        else { v.next = node_[after].next; node_[after].next = id; }
+        node_.push_back(v);
         return id;
     }
     void add_edge(int u, int w) {
         if (u < 0) return;
-        int32_t* e = &in_[(size_t)w * kPoaMaxPred];
-        for (int k = 0; k < nin_[w]; ++k) if (e[k] == u) return;
-        if (nin_[w] < kPoaMaxPred) { e[nin_[w]++] = u; ++n_edges_; }
+        Node& v = node_[w];
+        if (v.nin == 0) { v.in0 = u; v.nin = 1; ++n_edges_; return; }
+        if (v.in0 == u) return;
+        if (v.more < 0) { v.more = (int32_t)(pool_.size() / kMore); pool_.resize(pool_.size() + kMore); }
+        int32_t* e = &pool_[(size_t)v.more * kMore];
+        for (int k = 0; k + 1 < v.nin; ++k) if (e[k] == u) return;
+        if (v.nin < kPoaMaxPred) { e[v.nin - 1] = u; ++v.nin; ++n_edges_; }
     }
-    std::vector<uint8_t> base_;
-    std::vector<int32_t> nreads_, next_, prev_, in_;
-    std::vector<uint8_t> nin_;
+    std::vector<Node> node_;
+    std::vector<int32_t> pool_;        // blocks of kMore ints: predecessors 2..kPoaMaxPred of the branch points
     int head_ = -1, n_reads_ = 0, n_edges_ = 0;
     std::vector<std::pair<int32_t, int32_t>> spans_;
-    mutable std::vector<int32_t> rank_;
-    std::vector<std::pair<int32_t, int32_t>> steps_;
 };
 
 }  // namespace ccs
