@@ -166,3 +166,22 @@ def test_host_poa_graph_matches_oracle(tmp_path):
     out = subprocess.run([exe, "30"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr + out.stdout
     assert out.stdout.startswith("ok:")
+
+
+def test_draft_host_helpers_match_oracle(tmp_path):
+    """FilterReads, the hashed k-mer orientation vote and orient() of ccs_b200/csrc/host/draft_host.h against the
+    oracle's restatements (sorted k-mer lists), on ragged read sets, both strands and unrelated reads."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "draft_host_parity")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", exe,
+                           os.path.join(ROOT, "tests", "host", "draft_host_parity.cpp"),
+                           os.path.join(ROOT, "oracle", "pipeline_oracle.cpp"),
+                           os.path.join(ROOT, "oracle", "poa_oracle.cpp"),
+                           os.path.join(ROOT, "oracle", "arrow_oracle.cpp")])
+    out = subprocess.run([exe, "150"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert out.stdout.startswith("ok:")
