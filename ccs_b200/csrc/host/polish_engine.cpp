@@ -1,5 +1,6 @@
 // Polish Stage host engine -- see polish_engine.h.
 #include "polish_engine.h"
+#include "polish_host.h"
 #include "../cuda/arrow_launch.h"
 #include "parallel.h"
 #include <algorithm>
@@ -10,37 +11,6 @@
 #include <atomic>
 
 namespace ccs {
-
-namespace {
-
-inline uint64_t tpl_hash(const std::vector<uint8_t>& t) {
-    uint64_t h = 1469598103934665603ull;
-    for (uint8_t b : t) { h ^= b; h *= 1099511628211ull; }
-    return h ^ ((uint64_t)t.size() * 0x9E3779B97F4A7C15ull);
-}
-
-inline int type_rank(int t) { return t == 2 ? 0 : (t == 1 ? 1 : 2); }   // DEL < INS < SUB
-
-// Template::ApplyMutations: muts sorted by position; at most one of SUB/DEL per position
-std::vector<uint8_t> apply_to_template(const std::vector<uint8_t>& tpl, const std::vector<HostMutation>& muts) {
-    std::vector<uint8_t> out;
-    out.reserve(tpl.size() + muts.size());
-    size_t k = 0;
-    const int J = (int)tpl.size();
-    for (int j = 0; j <= J; ++j) {
-        bool skip = false;
-        while (k < muts.size() && muts[k].pos == j) {
-            const HostMutation& m = muts[k++];
-            if (m.type == 1) out.push_back((uint8_t)m.base);
-            else if (m.type == 0) { out.push_back((uint8_t)m.base); skip = true; }
-            else skip = true;
-        }
-        if (j < J && !skip) out.push_back(tpl[j]);
-    }
-    return out;
-}
-
-}  // namespace
 
 ArrowEngine::ArrowEngine(int device, const ArrowModelParams& model, size_t budget_bytes)
     : device_(device), budget_(budget_bytes), model_(model) {
@@ -538,23 +508,9 @@ void ArrowEngine::polish(const PolishParams& pp) {
             if (zs.done) return;
             auto& sc = per[z];
             if (sc.empty()) { zs.converged = true; zs.done = true; return; }
-            std::sort(sc.begin(), sc.end(), [](const HostMutation& a, const HostMutation& b) {
-                if (a.score != b.score) return a.score > b.score;
-                if (a.pos != b.pos) return a.pos < b.pos;
-                if (a.type != b.type) return type_rank(a.type) < type_rank(b.type);
-                return a.base < b.base;
-            });
-            // BestMutations: greedy by score, chosen sites >= separation apart
+            // BestMutations: greedy by score, chosen sites >= separation apart (polish_host.h)
             const int J = (int)zs.tpl.size();
-            std::vector<uint8_t> blocked((size_t)J + 2, 0);
-            std::vector<HostMutation> best;
-            for (const auto& m : sc) {
-                if (blocked[m.pos]) continue;
-                best.push_back(m);
-                const int lo = std::max(0, m.pos - pp.separation + 1), hi = std::min(J + 1, m.pos + pp.separation - 1);
-                for (int x = lo; x <= hi; ++x) blocked[x] = 1;
-            }
-            std::sort(best.begin(), best.end(), [](const HostMutation& a, const HostMutation& b) { return a.pos < b.pos; });
+            std::vector<HostMutation> best = select_best_mutations(sc, J, pp.separation);
             std::vector<uint8_t> next = apply_to_template(zs.tpl, best);
             uint64_t h = tpl_hash(next);
             if (std::find(zs.seen.begin(), zs.seen.end(), h) != zs.seen.end()) {   // cycle guard
@@ -643,14 +599,7 @@ void ArrowEngine::remap_deltas() {
 }
 
 int64_t ArrowEngine::count_canonical(const std::vector<uint8_t>& t, int b, int e) const {
-    const int J = (int)t.size();
-    int64_t n = 0;
-    for (int p = b; p < e; ++p) {
-        n += 3;                                            // substitutions
-        if (!(p > 0 && t[p] == t[p - 1])) ++n;             // deletion
-        if (p >= 1 && p <= J - 1) n += 3;                  // insertions except the one equal to t[p-1]
-    }
-    return n;
+    return count_canonical_mutations(t, b, e);
 }
 
 void ArrowEngine::consensus_qvs() {

@@ -185,3 +185,20 @@ def test_draft_host_helpers_match_oracle(tmp_path):
     out = subprocess.run([exe, "150"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr + out.stdout
     assert out.stdout.startswith("ok:")
+
+
+def test_polish_host_helpers_match_oracle(tmp_path):
+    """Candidate order + BestMutations (separation), Template::ApplyMutations and the de-duplicated candidate count of
+    ccs_b200/csrc/host/polish_host.h against the oracle's best_mutations / apply_mutations / mutation_is_canonical."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "polish_host_parity")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", exe,
+                           os.path.join(ROOT, "tests", "host", "polish_host_parity.cpp"),
+                           os.path.join(ROOT, "oracle", "arrow_oracle.cpp")])
+    out = subprocess.run([exe, "300"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert out.stdout.startswith("ok:")
