@@ -115,27 +115,30 @@ public:
         ++n_reads_;
     }
 
-    // FindConsensus: score(v) = 2*nReads - max(spanning, minCov); best-scoring path, ties to the lowest rank
+    // FindConsensus: score(v) = 2*nReads - max(spanning, minCov); best-scoring path, ties to the lowest rank.
+    // One pass in list (= topological) order: ranks, the number of reads spanning each vertex (running count of span
+    // starts minus span ends, marked per vertex id) and the best-path DP together.
     void consensus(int min_cov, std::vector<uint8_t>& out) const {
         const int V = size();
         Scratch& S = scratch();
         std::vector<int32_t>& order_ = S.order; std::vector<int32_t>& rank_ = S.rank;
-        std::vector<int32_t>& cov_ = S.cov; std::vector<int32_t>& bp_ = S.bp;
+        std::vector<int32_t>& mark_ = S.cov; std::vector<int32_t>& bp_ = S.bp;
         std::vector<int64_t>& reach_ = S.reach;
         order_.resize(V);
         rank_.resize(V);
-        { int t = 0; for (int x = head_; x >= 0; x = node_[x].next) { rank_[x] = t; order_[t++] = x; } }
-        cov_.assign((size_t)V + 1, 0);
-        for (auto& s : spans_) { cov_[rank_[s.first]]++; cov_[rank_[s.second] + 1]--; }
-        for (int t = 1; t <= V; ++t) cov_[t] += cov_[t - 1];
         reach_.resize((size_t)V);
         bp_.resize((size_t)V);
+        mark_.assign((size_t)2 * V, 0);                    // [2x] span starts at vertex x, [2x+1] span ends at x
+        for (auto& s : spans_) { mark_[2 * (size_t)s.first]++; mark_[2 * (size_t)s.second + 1]++; }
         int64_t best = 0;
-        int bt = -1;
-        for (int t = 0; t < V; ++t) {
-            const int x = order_[t];
+        int bt = -1, t = 0, running = 0;
+        for (int x = head_; x >= 0; ++t) {
             const Node& v = node_[x];
-            const int64_t sc = 2ll * v.nreads - std::max(cov_[t], min_cov);
+            rank_[x] = t;
+            order_[t] = x;
+            running += mark_[2 * (size_t)x];
+            const int64_t sc = 2ll * v.nreads - std::max(running, min_cov);
+            running -= mark_[2 * (size_t)x + 1];
             int64_t m = 0;
             int mp = -1;
             if (v.nin >= 1) {
@@ -150,9 +153,10 @@ public:
             reach_[t] = sc + m;
             bp_[t] = mp;
             if (bt < 0 || reach_[t] > best) { best = reach_[t]; bt = t; }
+            x = v.next;
         }
         out.clear();
-        for (int t = bt; t >= 0; t = bp_[t]) out.push_back(node_[order_[t]].base);
+        for (int k = bt; k >= 0; k = bp_[k]) out.push_back(node_[order_[k]].base);
         std::reverse(out.begin(), out.end());
     }
 
