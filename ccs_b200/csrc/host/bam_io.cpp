@@ -1,9 +1,12 @@
 // See bam_io.h.  BGZF: RFC1952 gzip members with a 'BC' extra field carrying the block size;
 // BAM: little-endian records (SAM spec section 4).  PacBio conventions per SURVEY.md Appendix C.
 #include "bam_io.h"
+#include "parallel.h"
 #include <zlib.h>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <thread>
 
 namespace ccs {
 
@@ -67,88 +70,128 @@ std::string header_field(const std::string& line, const std::string& key) {   //
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+static int default_io_threads(int threads) {
+    if (threads > 0) return threads;
+    int hc = (int)std::thread::hardware_concurrency();
+    if (hc < 1) hc = 1;
+    return std::min(8, hc);
+}
+constexpr size_t kReadBatch = 64;        // compressed blocks per parallel inflate (<= 4 MiB of payload)
+
 BgzfReader::~BgzfReader() { if (f_) std::fclose(f_); }
 
-bool BgzfReader::open(const std::string& path) {
+bool BgzfReader::open(const std::string& path, int threads) {
     f_ = std::fopen(path.c_str(), "rb");
-    block_.clear(); pos_ = 0;
+    threads_ = default_io_threads(threads);
+    blocks_.assign(kReadBatch, {}); comp_.assign(kReadBatch, {});
+    n_batch_ = 0; cur_ = 0; pos_ = 0;
+    failed_ = false;
     return f_ != nullptr;
 }
 
-bool BgzfReader::fill() {
+bool BgzfReader::refill_batch() {
+    if (failed_) return false;
+    size_t n = 0;
+    std::vector<uint32_t> isize(kReadBatch, 0);
+    std::vector<size_t> clen(kReadBatch, 0);
     uint8_t h[18];
-    for (;;) {
-        if (std::fread(h, 1, 18, f_) != 18) return false;
-        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || rd16(h + 10) != 6 || h[12] != 'B' || h[13] != 'C') return false;
+    while (n < kReadBatch) {
+        if (std::fread(h, 1, 18, f_) != 18) break;                       // end of file
+        // a malformed or truncated block ends the stream AFTER the complete blocks in front of it have been delivered
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || rd16(h + 10) != 6 || h[12] != 'B' || h[13] != 'C') { failed_ = true; break; }
         const size_t bsize = (size_t)rd16(h + 16) + 1;
-        const size_t clen = bsize - 18 - 8;
-        comp_.resize(clen + 8);
-        if (std::fread(comp_.data(), 1, clen + 8, f_) != clen + 8) return false;
-        const uint32_t isize = rd32(comp_.data() + clen + 4);
-        block_.resize(isize);
-        pos_ = 0;
-        if (isize == 0) continue;                 // empty block (EOF marker or flush point)
+        if (bsize < 18 + 8) { failed_ = true; break; }
+        clen[n] = bsize - 18 - 8;
+        comp_[n].resize(clen[n] + 8);
+        if (std::fread(comp_[n].data(), 1, clen[n] + 8, f_) != clen[n] + 8) { failed_ = true; break; }
+        isize[n] = rd32(comp_[n].data() + clen[n] + 4);
+        ++n;
+    }
+    if (n == 0) return false;
+    std::atomic<int> bad(0);
+    parallel_for((int)n, threads_, [&](int k) {
+        blocks_[k].resize(isize[k]);
+        if (isize[k] == 0) return;                                        // empty block (EOF marker or flush point)
         z_stream zs;
         std::memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) return false;
-        zs.next_in = comp_.data(); zs.avail_in = (uInt)clen;
-        zs.next_out = block_.data(); zs.avail_out = (uInt)isize;
+        if (inflateInit2(&zs, -15) != Z_OK) { bad.store(1); return; }
+        zs.next_in = comp_[k].data(); zs.avail_in = (uInt)clen[k];
+        zs.next_out = blocks_[k].data(); zs.avail_out = (uInt)isize[k];
         const int rc = inflate(&zs, Z_FINISH);
         inflateEnd(&zs);
-        if (rc != Z_STREAM_END) return false;
-        return true;
+        if (rc != Z_STREAM_END) bad.store(1);
+    }, /*min_items_per_thread=*/1);
+    if (bad.load()) return false;
+    n_batch_ = n;
+    return true;
+}
+
+bool BgzfReader::fill() {
+    for (;;) {
+        if (cur_ + 1 < n_batch_) ++cur_;
+        else { if (!refill_batch()) { n_batch_ = 0; cur_ = 0; pos_ = 0; return false; } cur_ = 0; }
+        pos_ = 0;
+        if (!blocks_[cur_].empty()) return true;
     }
 }
 
 bool BgzfReader::read(void* dst, size_t n) {
     uint8_t* d = (uint8_t*)dst;
     while (n > 0) {
-        if (pos_ == block_.size() && !fill()) return false;
-        const size_t k = std::min(n, block_.size() - pos_);
-        std::memcpy(d, block_.data() + pos_, k);
+        if ((n_batch_ == 0 || pos_ == blocks_[cur_].size()) && !fill()) return false;
+        const std::vector<uint8_t>& blk = blocks_[cur_];
+        const size_t k = std::min(n, blk.size() - pos_);
+        std::memcpy(d, blk.data() + pos_, k);
         pos_ += k; d += k; n -= k;
     }
     return true;
 }
 
 bool BgzfReader::eof() {
-    if (pos_ < block_.size()) return false;
+    if (n_batch_ != 0 && pos_ < blocks_[cur_].size()) return false;
     return !fill();
 }
 
 BgzfWriter::~BgzfWriter() { close(); }
 
-bool BgzfWriter::open(const std::string& path, int level) {
+bool BgzfWriter::open(const std::string& path, int level, int threads) {
     f_ = std::fopen(path.c_str(), "wb");
     level_ = level;
+    threads_ = default_io_threads(threads);
     buf_.clear();
     return f_ != nullptr;
 }
 
 void BgzfWriter::flush_block() {
     if (buf_.empty() || !f_) return;
-    size_t done = 0;
-    while (done < buf_.size()) {
+    const size_t nb = (buf_.size() + kBlockData - 1) / kBlockData;
+    if (comp_.size() < nb) comp_.resize(nb);
+    std::vector<size_t> clen(nb, 0);
+    std::vector<uint32_t> crc(nb, 0);
+    parallel_for((int)nb, threads_, [&](int k) {
+        const size_t done = (size_t)k * kBlockData;
         const size_t n = std::min(kBlockData, buf_.size() - done);
-        comp_.resize(compressBound((uLong)n) + 64);
+        comp_[k].resize(compressBound((uLong)n) + 64);
         z_stream zs;
         std::memset(&zs, 0, sizeof(zs));
         deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
         zs.next_in = buf_.data() + done; zs.avail_in = (uInt)n;
-        zs.next_out = comp_.data(); zs.avail_out = (uInt)comp_.size();
+        zs.next_out = comp_[k].data(); zs.avail_out = (uInt)comp_[k].size();
         deflate(&zs, Z_FINISH);
-        const size_t clen = zs.total_out;
+        clen[k] = zs.total_out;
         deflateEnd(&zs);
-        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf_.data() + done, (uInt)n);
+        crc[k] = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf_.data() + done, (uInt)n);
+    }, /*min_items_per_thread=*/1);
+    for (size_t k = 0; k < nb; ++k) {
+        const size_t n = std::min(kBlockData, buf_.size() - k * kBlockData);
         uint8_t h[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
-        const uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1);
+        const uint16_t bsize = (uint16_t)(clen[k] + 18 + 8 - 1);
         h[16] = bsize & 255; h[17] = bsize >> 8;
         std::fwrite(h, 1, 18, f_);
-        std::fwrite(comp_.data(), 1, clen, f_);
+        std::fwrite(comp_[k].data(), 1, clen[k], f_);
         uint8_t t[8];
-        for (int k = 0; k < 4; ++k) { t[k] = (crc >> (8 * k)) & 255; t[4 + k] = ((uint32_t)n >> (8 * k)) & 255; }
+        for (int b = 0; b < 4; ++b) { t[b] = (crc[k] >> (8 * b)) & 255; t[4 + b] = ((uint32_t)n >> (8 * b)) & 255; }
         std::fwrite(t, 1, 8, f_);
-        done += n;
     }
     buf_.clear();
 }
@@ -156,7 +199,7 @@ void BgzfWriter::flush_block() {
 void BgzfWriter::write(const void* src, size_t n) {
     const uint8_t* s = (const uint8_t*)src;
     buf_.insert(buf_.end(), s, s + n);
-    if (buf_.size() >= 16 * kBlockData) flush_block();
+    if (buf_.size() >= 64 * kBlockData) flush_block();
 }
 
 void BgzfWriter::close() {
@@ -168,8 +211,8 @@ void BgzfWriter::close() {
 }
 
 // ---------------------------------------------------------------------------------------------
-bool SubreadBamReader::open(const std::string& path, std::string& err) {
-    if (!in_.open(path)) { err = "cannot open " + path; return false; }
+bool SubreadBamReader::open(const std::string& path, std::string& err, int threads) {
+    if (!in_.open(path, threads)) { err = "cannot open " + path; return false; }
     uint8_t magic[4];
     if (!in_.read(magic, 4) || std::memcmp(magic, "BAM\1", 4) != 0) { err = path + " is not a BAM file"; return false; }
     uint8_t b4[4];
@@ -205,7 +248,8 @@ bool SubreadBamReader::open(const std::string& path, std::string& err) {
 bool SubreadBamReader::next_record(Subread& s) {
     uint8_t b4[4];
     if (!in_.read(b4, 4)) return false;
-    std::vector<uint8_t> rec(rd32(b4));
+    std::vector<uint8_t>& rec = rec_;            // reused across records: no 26 KB allocation per subread
+    rec.resize(rd32(b4));
     if (rec.size() < 32 || !in_.read(rec.data(), rec.size())) return false;
     const uint8_t* r = rec.data();
     const int l_name = r[8];
@@ -216,8 +260,11 @@ bool SubreadBamReader::next_record(Subread& s) {
     p += l_name + 4 * n_cigar;
     const uint8_t* seq = p;
     p += (l_seq + 1) / 2 + l_seq;               // packed bases + qualities
-    s = Subread();
-    std::vector<uint8_t> pw;
+    s.hole = 0; s.qs = 0; s.qe = 0; s.cx = 0;
+    s.snr[0] = s.snr[1] = s.snr[2] = s.snr[3] = 0.f;
+    std::vector<uint8_t>& pw = pw_;               // only filled for 16-bit pulse widths
+    const uint8_t* pw8 = nullptr;                 // 8-bit pulse widths are used in place
+    uint32_t n_pw = 0;
     const uint8_t* end = r + rec.size();
     while (p + 3 <= end) {
         const char t0 = (char)p[0], t1 = (char)p[1], ty = (char)p[2];
@@ -235,8 +282,13 @@ bool SubreadBamReader::next_record(Subread& s) {
                 const size_t es = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
                 if (is("sn") && sub == 'f' && n == 4) for (int k = 0; k < 4; ++k) { uint32_t u = rd32(p + 5 + 4 * k); std::memcpy(&s.snr[k], &u, 4); }
                 if (is("pw")) {
-                    pw.resize(n);
-                    for (uint32_t k = 0; k < n; ++k) pw[k] = (es == 1) ? p[5 + k] : (uint8_t)std::min<uint32_t>(255, rd16(p + 5 + 2 * k));
+                    n_pw = n;
+                    if (es == 1) pw8 = p + 5;
+                    else {
+                        pw.resize(n);
+                        for (uint32_t k = 0; k < n; ++k) pw[k] = (uint8_t)std::min<uint32_t>(255, es == 2 ? rd16(p + 5 + 2 * k) : rd32(p + 5 + 4 * k));
+                        pw8 = pw.data();
+                    }
                 }
                 sz = 5 + es * n;
                 break;
@@ -259,13 +311,32 @@ bool SubreadBamReader::next_record(Subread& s) {
         const size_t a = name.find('/'), b = name.find('/', a + 1);
         if (a != std::string::npos && b != std::string::npos) s.hole = std::atoi(name.substr(a + 1, b - a - 1).c_str());
     }
-    static const int8_t dec[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1};
+    // Recursor::EncodeRead: code = 4 * (min(max(pw, 1), 3) - 1) + base; two bases per packed byte through a table
+    struct Lut {
+        uint8_t hi[256], lo[256], w4[256];
+        Lut() {
+            static const int8_t dec[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1};   // =ACMGRSVTWYHKDBN
+            for (int v = 0; v < 256; ++v) {
+                hi[v] = (uint8_t)(dec[v >> 4] < 0 ? 0 : dec[v >> 4]);
+                lo[v] = (uint8_t)(dec[v & 15] < 0 ? 0 : dec[v & 15]);
+                w4[v] = (uint8_t)(4 * (std::min(std::max(v, 1), 3) - 1));
+            }
+        }
+    };
+    static const Lut lut;
     s.codes.resize(l_seq);
-    for (int32_t i = 0; i < l_seq; ++i) {
-        const int nibble = (i & 1) ? (seq[i >> 1] & 15) : (seq[i >> 1] >> 4);
-        const int b = dec[nibble] < 0 ? 0 : dec[nibble];
-        const int w = (i < (int32_t)pw.size()) ? std::min<int>(std::max<int>(pw[i], 1), 3) : 1;
-        s.codes[i] = (uint8_t)(4 * (w - 1) + b);     // Recursor::EncodeRead
+    uint8_t* out = s.codes.data();
+    const int32_t n_w = (int32_t)std::min<uint32_t>(n_pw, (uint32_t)l_seq);   // bases beyond the pw array: width 1
+    int32_t i = 0;
+    for (; i + 1 < n_w; i += 2) {
+        const uint8_t v = seq[i >> 1];
+        out[i] = (uint8_t)(lut.w4[pw8[i]] + lut.hi[v]);
+        out[i + 1] = (uint8_t)(lut.w4[pw8[i + 1]] + lut.lo[v]);
+    }
+    for (; i < l_seq; ++i) {
+        const uint8_t v = seq[i >> 1];
+        const uint8_t b = (i & 1) ? lut.lo[v] : lut.hi[v];
+        out[i] = (uint8_t)((i < n_w ? lut.w4[pw8[i]] : 0) + b);
     }
     return true;
 }
@@ -329,8 +400,8 @@ void CcsBamWriter::write(const CcsRecord& r) {
 
 void CcsBamWriter::close() { out_.close(); }
 
-bool SubreadBamWriter::open(const std::string& path, const std::string& movie, bool with_chemistry) {
-    if (!out_.open(path)) return false;
+bool SubreadBamWriter::open(const std::string& path, const std::string& movie, bool with_chemistry, int threads) {
+    if (!out_.open(path, 1, threads)) return false;
     movie_ = movie; rg_ = "b200sim0";
     std::string ds = "READTYPE=SUBREAD;Ipd:CodecV1=ip;PulseWidth:CodecV1=pw";
     if (with_chemistry) ds += ";BINDINGKIT=000-000-000;SEQUENCINGKIT=000-000-001;BASECALLERVERSION=0.0.0;FRAMERATEHZ=100.000000";

@@ -10,30 +10,38 @@
 
 namespace ccs {
 
+// BGZF blocks are independent gzip members: the reader pulls a batch of compressed blocks off the file and inflates
+// them in parallel (host worker pool, parallel.h), the writer deflates the blocks of a flush in parallel and writes
+// them in order -- at 3 k ZMW/s one GPU consumes ~0.8 GB/s of uncompressed subread records, about three zlib threads.
 class BgzfReader {
 public:
     ~BgzfReader();
-    bool open(const std::string& path);
+    bool open(const std::string& path, int threads = 0);   // threads: 0 = min(8, hardware concurrency)
     bool read(void* dst, size_t n);          // false on EOF / error before n bytes
     bool eof();
 private:
-    bool fill();
+    bool fill();                             // advance to the next non-empty block
+    bool refill_batch();                     // read + inflate the next batch of blocks
     FILE* f_ = nullptr;
-    std::vector<uint8_t> block_, comp_;
+    int threads_ = 1;
+    std::vector<std::vector<uint8_t>> blocks_, comp_;
+    size_t n_batch_ = 0, cur_ = 0;           // blocks in the batch, index of the current one
     size_t pos_ = 0;
+    bool failed_ = false;                    // a malformed block was seen: stop after the blocks before it
 };
 
 class BgzfWriter {
 public:
     ~BgzfWriter();
-    bool open(const std::string& path, int level = 1);
+    bool open(const std::string& path, int level = 1, int threads = 0);
     void write(const void* src, size_t n);
     void close();                             // flushes and appends the BGZF EOF marker
 private:
     void flush_block();
     FILE* f_ = nullptr;
-    int level_ = 1;
-    std::vector<uint8_t> buf_, comp_;
+    int level_ = 1, threads_ = 1;
+    std::vector<uint8_t> buf_;
+    std::vector<std::vector<uint8_t>> comp_;
 };
 
 struct Subread {
@@ -53,7 +61,7 @@ class SubreadBamReader {
 public:
     // Opens and parses the header.  Fails (chemistry_ok() == false) if the read group lacks the
     // chemistry triple -- fatal in the reference too (docs/changelog.md:66, docs/faq/chemistry.md:7-10).
-    bool open(const std::string& path, std::string& err);
+    bool open(const std::string& path, std::string& err, int threads = 0);   // threads: BGZF inflate workers
     bool next_zmw(ZmwSubreads& z);            // records of one hole number (consecutive in the file)
     const std::string& header_text() const { return header_; }
     const std::string& movie() const { return movie_; }
@@ -65,6 +73,7 @@ private:
     std::string header_, movie_, rg_id_;
     bool chem_ok_ = false, have_pending_ = false;
     Subread pending_;
+    std::vector<uint8_t> rec_, pw_;           // record / 16-bit pulse-width scratch, reused across records
 };
 
 struct CcsRecord {
@@ -92,7 +101,7 @@ private:
 struct SubreadOut { int32_t hole, qs, qe; const float* snr; uint8_t cx; const uint8_t* codes; int32_t len; };
 class SubreadBamWriter {
 public:
-    bool open(const std::string& path, const std::string& movie, bool with_chemistry = true);
+    bool open(const std::string& path, const std::string& movie, bool with_chemistry = true, int threads = 0);
     void write(const SubreadOut& s);
     void close();
 private:

@@ -71,10 +71,12 @@ private:
     std::deque<std::shared_ptr<Job>> q_;
 };
 
+// min_items_per_thread: small items (per-ZMW host logic) are not worth a helper for fewer than 8 of them; heavy items
+// (a 64 KB zlib block) are.
 template <class F>
-inline void parallel_for(int n, int n_threads, F&& f) {
+inline void parallel_for(int n, int n_threads, F&& f, int min_items_per_thread = 8) {
     if (n <= 0) return;
-    n_threads = std::max(1, std::min(n_threads, (n + 7) / 8));
+    n_threads = std::max(1, std::min(n_threads, (n + min_items_per_thread - 1) / min_items_per_thread));
     if (n_threads == 1) { for (int i = 0; i < n; ++i) f(i); return; }
     auto job = std::make_shared<HostPool::Job>();
     job->n = n;
