@@ -147,6 +147,17 @@ bool BgzfReader::read(void* dst, size_t n) {
     return true;
 }
 
+bool BgzfReader::seek(uint64_t voffset) {
+    if (!f_) return false;
+    if (fseeko(f_, (off_t)(voffset >> 16), SEEK_SET) != 0) return false;
+    n_batch_ = 0; cur_ = 0; pos_ = 0; failed_ = false;
+    const size_t within = (size_t)(voffset & 0xffff);
+    if (!fill()) return within == 0;          // seeking to the very end is fine
+    if (within > blocks_[cur_].size()) return false;
+    pos_ = within;
+    return true;
+}
+
 bool BgzfReader::eof() {
     if (n_batch_ != 0 && pos_ < blocks_[cur_].size()) return false;
     return !fill();
@@ -159,7 +170,16 @@ bool BgzfWriter::open(const std::string& path, int level, int threads) {
     level_ = level;
     threads_ = default_io_threads(threads);
     buf_.clear();
+    uflushed_ = 0; cpos_ = 0; blocks_.clear();
     return f_ != nullptr;
+}
+
+uint64_t BgzfWriter::voffset_of(uint64_t upos) const {
+    // last block whose first uncompressed byte is <= upos
+    size_t lo = 0, hi = blocks_.size();
+    while (lo + 1 < hi) { const size_t mid = (lo + hi) / 2; if (blocks_[mid].first <= upos) lo = mid; else hi = mid; }
+    if (blocks_.empty()) return 0;
+    return (blocks_[lo].second << 16) | (upos - blocks_[lo].first);
 }
 
 void BgzfWriter::flush_block() {
@@ -187,12 +207,15 @@ void BgzfWriter::flush_block() {
         uint8_t h[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
         const uint16_t bsize = (uint16_t)(clen[k] + 18 + 8 - 1);
         h[16] = bsize & 255; h[17] = bsize >> 8;
+        blocks_.push_back({uflushed_ + k * kBlockData, cpos_});
         std::fwrite(h, 1, 18, f_);
         std::fwrite(comp_[k].data(), 1, clen[k], f_);
         uint8_t t[8];
         for (int b = 0; b < 4; ++b) { t[b] = (crc[k] >> (8 * b)) & 255; t[4 + b] = ((uint32_t)n >> (8 * b)) & 255; }
         std::fwrite(t, 1, 8, f_);
+        cpos_ += 18 + clen[k] + 8;
     }
+    uflushed_ += buf_.size();
     buf_.clear();
 }
 
@@ -205,6 +228,7 @@ void BgzfWriter::write(const void* src, size_t n) {
 void BgzfWriter::close() {
     if (!f_) return;
     flush_block();
+    blocks_.push_back({uflushed_, cpos_});        // the EOF marker block: where a position at the very end maps to
     std::fwrite(kBgzfEof, 1, sizeof(kBgzfEof), f_);
     std::fclose(f_);
     f_ = nullptr;
@@ -341,6 +365,39 @@ bool SubreadBamReader::next_record(Subread& s) {
     return true;
 }
 
+bool SubreadBamReader::seek_record(uint64_t voffset) {
+    have_pending_ = false;
+    return in_.seek(voffset);
+}
+
+bool select_chunk(SubreadBamReader& reader, const std::string& path, int chunk_i, int chunk_n, int64_t& z_begin,
+                  int64_t& z_end, bool& used_index, std::string& err) {
+    used_index = false;
+    if (chunk_n < 1 || chunk_i < 1 || chunk_i > chunk_n) { err = "--chunk expects i/N with i in [1,N]"; return false; }
+    PbiIndex pbi;
+    if (pbi.read(path + ".pbi") && pbi.size() > 0) {
+        const std::vector<int64_t> st = pbi.zmw_starts();
+        const int64_t total = (int64_t)st.size() - 1;
+        const int64_t zb = total * (chunk_i - 1) / chunk_n, ze = total * chunk_i / chunk_n;
+        z_begin = 0;
+        z_end = ze - zb;
+        if (ze > zb && !reader.seek_record((uint64_t)pbi.file_offset[st[zb]])) {
+            err = path + ".pbi does not match " + path;
+            return false;
+        }
+        used_index = true;
+        return true;
+    }
+    SubreadBamReader counter;
+    if (!counter.open(path, err)) return false;
+    ZmwSubreads z;
+    int64_t total = 0;
+    while (counter.next_zmw(z)) ++total;
+    z_begin = total * (chunk_i - 1) / chunk_n;
+    z_end = total * chunk_i / chunk_n;
+    return true;
+}
+
 bool SubreadBamReader::next_zmw(ZmwSubreads& z) {
     z.reads.clear();
     if (!have_pending_) {
@@ -402,6 +459,7 @@ void CcsBamWriter::close() { out_.close(); }
 
 bool SubreadBamWriter::open(const std::string& path, const std::string& movie, bool with_chemistry, int threads) {
     if (!out_.open(path, 1, threads)) return false;
+    path_ = path; pbi_ = PbiIndex();
     movie_ = movie; rg_ = "b200sim0";
     std::string ds = "READTYPE=SUBREAD;Ipd:CodecV1=ip;PulseWidth:CodecV1=pw";
     if (with_chemistry) ds += ";BINDINGKIT=000-000-000;SEQUENCINGKIT=000-000-001;BASECALLERVERSION=0.0.0;FRAMERATEHZ=100.000000";
@@ -434,9 +492,61 @@ void SubreadBamWriter::write(const SubreadOut& s) {
     rec_.push_back('p'); rec_.push_back('w'); rec_.push_back('B'); rec_.push_back('C'); wr32(rec_, (uint32_t)s.len);
     for (int32_t i = 0; i < s.len; ++i) rec_.push_back((uint8_t)((s.codes[i] >> 2) + 1));
     end_record(rec_, at);
+    pbi_.rg_id.push_back(0x0b200510);             // numeric form of the read-group id
+    pbi_.q_start.push_back(s.qs); pbi_.q_end.push_back(s.qe); pbi_.hole.push_back(s.hole);
+    pbi_.read_qual.push_back(0.8f); pbi_.ctxt.push_back(s.cx);
+    pbi_.file_offset.push_back((int64_t)out_.upos());
     out_.write(rec_.data(), rec_.size());
 }
 
-void SubreadBamWriter::close() { out_.close(); }
+void SubreadBamWriter::close() {
+    if (path_.empty()) return;
+    out_.close();
+    for (auto& o : pbi_.file_offset) o = (int64_t)out_.voffset_of((uint64_t)o);
+    pbi_.write(path_ + ".pbi");
+    path_.clear();
+}
+
+// ---------------------------------------------------------------------------------------------
+bool PbiIndex::write(const std::string& path) const {
+    BgzfWriter w;
+    if (!w.open(path, 1, 1)) return false;
+    std::vector<uint8_t> h;
+    wrs(h, std::string("PBI\1", 4));
+    wr32(h, 0x00030001u);                          // 3.0.1
+    wr16(h, 0);                                    // basic section only
+    wr32(h, (uint32_t)size());
+    h.resize(h.size() + 18, 0);
+    w.write(h.data(), h.size());
+    const size_t n = size();
+    if (n) {
+        w.write(rg_id.data(), 4 * n); w.write(q_start.data(), 4 * n); w.write(q_end.data(), 4 * n);
+        w.write(hole.data(), 4 * n); w.write(read_qual.data(), 4 * n); w.write(ctxt.data(), n);
+        w.write(file_offset.data(), 8 * n);
+    }
+    w.close();
+    return true;
+}
+
+bool PbiIndex::read(const std::string& path) {
+    BgzfReader r;
+    if (!r.open(path, 1)) return false;
+    uint8_t h[32];
+    if (!r.read(h, 32) || std::memcmp(h, "PBI\1", 4) != 0) return false;
+    const uint32_t n = rd32(h + 10);
+    rg_id.resize(n); q_start.resize(n); q_end.resize(n); hole.resize(n); read_qual.resize(n); ctxt.resize(n);
+    file_offset.resize(n);
+    if (n == 0) return true;
+    return r.read(rg_id.data(), 4 * (size_t)n) && r.read(q_start.data(), 4 * (size_t)n) && r.read(q_end.data(), 4 * (size_t)n) &&
+           r.read(hole.data(), 4 * (size_t)n) && r.read(read_qual.data(), 4 * (size_t)n) && r.read(ctxt.data(), n) &&
+           r.read(file_offset.data(), 8 * (size_t)n);
+}
+
+std::vector<int64_t> PbiIndex::zmw_starts() const {
+    std::vector<int64_t> st;
+    for (size_t k = 0; k < size(); ++k) if (k == 0 || hole[k] != hole[k - 1]) st.push_back((int64_t)k);
+    st.push_back((int64_t)size());
+    return st;
+}
 
 }  // namespace ccs

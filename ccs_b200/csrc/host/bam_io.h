@@ -19,6 +19,7 @@ public:
     bool open(const std::string& path, int threads = 0);   // threads: 0 = min(8, hardware concurrency)
     bool read(void* dst, size_t n);          // false on EOF / error before n bytes
     bool eof();
+    bool seek(uint64_t voffset);             // BGZF virtual offset: compressed block start << 16 | offset in block
 private:
     bool fill();                             // advance to the next non-empty block
     bool refill_batch();                     // read + inflate the next batch of blocks
@@ -36,13 +37,35 @@ public:
     bool open(const std::string& path, int level = 1, int threads = 0);
     void write(const void* src, size_t n);
     void close();                             // flushes and appends the BGZF EOF marker
+    uint64_t upos() const { return uflushed_ + buf_.size(); }   // uncompressed bytes written so far
+    // virtual offset of an uncompressed position (valid after close(); blocks are recorded as they are written)
+    uint64_t voffset_of(uint64_t upos) const;
 private:
     void flush_block();
     FILE* f_ = nullptr;
     int level_ = 1, threads_ = 1;
     std::vector<uint8_t> buf_;
     std::vector<std::vector<uint8_t>> comp_;
+    uint64_t uflushed_ = 0, cpos_ = 0;        // uncompressed / compressed bytes already written to the file
+    std::vector<std::pair<uint64_t, uint64_t>> blocks_;   // (first uncompressed byte, compressed offset) of every block
 };
+
+// PacBio BAM index (*.pbi), basic section only: per record the read group id, query start / end, hole number, read
+// quality, local-context flags and the BGZF virtual offset -- what `ccs --chunk i/N` needs to jump to its share of the
+// ZMWs without inflating the rest (/root/reference/docs/faq/parallelize.md:8-13).  Layout as published with the PacBio
+// BAM format 3.0.1 (magic "PBI\1", version, flags, n_reads, 18 reserved bytes, then one column per field), BGZF-wrapped.
+struct PbiIndex {
+    std::vector<int32_t> rg_id, q_start, q_end, hole;
+    std::vector<float> read_qual;
+    std::vector<uint8_t> ctxt;
+    std::vector<int64_t> file_offset;
+    size_t size() const { return hole.size(); }
+    bool write(const std::string& path) const;
+    bool read(const std::string& path);
+    // first record of every ZMW (runs of equal hole numbers), plus size() as the end sentinel
+    std::vector<int64_t> zmw_starts() const;
+};
+
 
 struct Subread {
     int32_t hole = 0, qs = 0, qe = 0;
@@ -63,6 +86,7 @@ public:
     // chemistry triple -- fatal in the reference too (docs/changelog.md:66, docs/faq/chemistry.md:7-10).
     bool open(const std::string& path, std::string& err, int threads = 0);   // threads: BGZF inflate workers
     bool next_zmw(ZmwSubreads& z);            // records of one hole number (consecutive in the file)
+    bool seek_record(uint64_t voffset);       // continue with the record that starts at this BGZF virtual offset
     const std::string& header_text() const { return header_; }
     const std::string& movie() const { return movie_; }
     const std::string& read_group_id() const { return rg_id_; }
@@ -75,6 +99,12 @@ private:
     Subread pending_;
     std::vector<uint8_t> rec_, pw_;           // record / 16-bit pulse-width scratch, reused across records
 };
+
+// `--chunk i/N`: positions `reader` (already opened on `path`) so that the caller, reading ZMW after ZMW from there and
+// counting them from 0, keeps exactly those with index in [z_begin, z_end).  With <path>.pbi the reader is moved to the
+// chunk's first record and nothing before it is inflated; without it the ZMWs are counted in a separate first pass.
+bool select_chunk(SubreadBamReader& reader, const std::string& path, int chunk_i, int chunk_n, int64_t& z_begin,
+                  int64_t& z_end, bool& used_index, std::string& err);
 
 struct CcsRecord {
     int32_t hole = 0, np = 0;
@@ -103,11 +133,12 @@ class SubreadBamWriter {
 public:
     bool open(const std::string& path, const std::string& movie, bool with_chemistry = true, int threads = 0);
     void write(const SubreadOut& s);
-    void close();
+    void close();                             // also writes <path>.pbi
 private:
     BgzfWriter out_;
-    std::string movie_, rg_;
+    std::string path_, movie_, rg_;
     std::vector<uint8_t> rec_;
+    PbiIndex pbi_;                            // file_offset holds uncompressed positions until close()
 };
 
 }  // namespace ccs

@@ -170,16 +170,15 @@ int main(int argc, char** argv) {
                              "read group of %s; cannot select an Arrow model\n", o.in.c_str());
         return 1;
     }
-    // chunking without a .pbi: count the ZMWs in a first pass
+    // --chunk i/N (docs/faq/parallelize.md:8-28): the ZMWs with index in [z_begin, z_end) counted from where the reader
+    // stands after select_chunk() -- the chunk's first record when <in>.pbi exists, the file start otherwise
     int64_t z_begin = 0, z_end = INT64_MAX;
     if (o.chunk_n > 1) {
-        SubreadBamReader counter;
-        if (!counter.open(o.in, err)) return 1;
-        ZmwSubreads z;
-        int64_t total = 0;
-        while (counter.next_zmw(z)) ++total;
-        z_begin = total * (o.chunk_i - 1) / o.chunk_n;
-        z_end = total * o.chunk_i / o.chunk_n;
+        bool used_index = false;
+        if (!select_chunk(reader, o.in, o.chunk_i, o.chunk_n, z_begin, z_end, used_index, err)) {
+            std::fprintf(stderr, "ccs: %s\n", err.c_str());
+            return 1;
+        }
     }
     std::vector<uint8_t> model(ccs_model_sizeof());
     ccs_model_synthetic(model.data());          // the only chemistry this build ships (DESIGN.md "Model")

@@ -94,6 +94,62 @@ int main(int argc, char** argv) {
         }
         if (k == 0 || k >= zs.size()) { std::fprintf(stderr, "MISMATCH: truncated stream delivered %zu of %zu ZMWs\n", k, zs.size()); return 1; }
     }
+    // .pbi: one entry per record, ZMW runs, and seeking to the first record of any ZMW continues the stream there
+    {
+        PbiIndex pbi;
+        if (!pbi.read(p8 + ".pbi")) { std::fprintf(stderr, "MISMATCH: cannot read the .pbi\n"); return 1; }
+        size_t n_rec = 0;
+        for (const Z& z : zs) n_rec += z.reads.size();
+        if (pbi.size() != n_rec) { std::fprintf(stderr, "MISMATCH: .pbi has %zu records, file has %zu\n", pbi.size(), n_rec); return 1; }
+        const std::vector<int64_t> st = pbi.zmw_starts();
+        if (st.size() != zs.size() + 1) { std::fprintf(stderr, "MISMATCH: .pbi ZMW runs\n"); return 1; }
+        size_t rec = 0;
+        for (size_t k = 0; k < zs.size(); ++k)
+            for (size_t r = 0; r < zs[k].reads.size(); ++r, ++rec)
+                if (pbi.hole[rec] != zs[k].hole || pbi.q_start[rec] != zs[k].qs[r] || pbi.q_end[rec] != zs[k].qe[r] || pbi.ctxt[rec] != zs[k].cx[r]) { std::fprintf(stderr, "MISMATCH: .pbi record %zu\n", rec); return 1; }
+        SubreadBamReader rd;
+        std::string err;
+        if (!rd.open(p8, err, 4)) return 1;
+        for (size_t k : {zs.size() - 1, (size_t)0, zs.size() / 2, (size_t)1, zs.size() / 3}) {
+            if (!rd.seek_record((uint64_t)pbi.file_offset[st[k]])) { std::fprintf(stderr, "MISMATCH: seek to ZMW %zu\n", k); return 1; }
+            ZmwSubreads got;
+            for (size_t j = k; j < std::min(zs.size(), k + 3); ++j) {
+                if (!rd.next_zmw(got) || got.hole != zs[j].hole || got.reads.size() != zs[j].reads.size()) { std::fprintf(stderr, "MISMATCH: ZMW %zu after seeking to %zu\n", j, k); return 1; }
+                for (size_t r = 0; r < zs[j].reads.size(); ++r) if (got.reads[r].codes != zs[j].reads[r]) { std::fprintf(stderr, "MISMATCH: read after seek\n"); return 1; }
+            }
+        }
+    }
+    // --chunk i/N through select_chunk(): the chunks concatenate to the whole file, with the index and without it
+    {
+        auto chunk_holes = [&](const std::string& path, int i, int n, bool expect_index, std::vector<int>& holes) -> bool {
+            SubreadBamReader rd;
+            std::string err;
+            if (!rd.open(path, err, 2)) return false;
+            int64_t zb = 0, ze = 0;
+            bool used = false;
+            if (!select_chunk(rd, path, i, n, zb, ze, used, err) || used != expect_index) return false;
+            // the loop of ccs_main.cpp
+            ZmwSubreads z;
+            int64_t z_index = 0;
+            if (ze <= zb) return true;
+            while (rd.next_zmw(z)) {
+                if (z_index >= zb && z_index < ze) holes.push_back(z.hole);
+                ++z_index;
+                if (z_index >= ze) break;
+            }
+            return true;
+        };
+        const std::string pn = dir + "/rt_noindex.subreads.bam";
+        { std::ofstream f(pn, std::ios::binary); f.write((const char*)b8.data(), (std::streamsize)b8.size()); }
+        for (int n : {1, 2, 3, 7, 149, 150, 400}) {
+            std::vector<int> with_idx, without_idx;
+            for (int i = 1; i <= n; ++i) {
+                if (!chunk_holes(p8, i, n, true, with_idx) || !chunk_holes(pn, i, n, false, without_idx)) { std::fprintf(stderr, "MISMATCH: chunk %d/%d failed\n", i, n); return 1; }
+            }
+            if (with_idx.size() != zs.size() || without_idx != with_idx) { std::fprintf(stderr, "MISMATCH: chunks of N=%d do not tile the file\n", n); return 1; }
+            for (size_t k = 0; k < zs.size(); ++k) if (with_idx[k] != zs[k].hole) { std::fprintf(stderr, "MISMATCH: chunk order N=%d\n", n); return 1; }
+        }
+    }
     std::printf("ok: %zu ZMWs, %ld bases round-tripped; %zu bytes on disk, identical for 1 and 8 threads\n", zs.size(), bases, b8.size());
     return 0;
 }
