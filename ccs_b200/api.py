@@ -64,7 +64,9 @@ class CStats(C.Structure):
                [("ms_poa_align", C.c_double)] + \
                [(n, C.c_int64) for n in ("launches_poa", "poa_tasks", "poa_rows", "bytes_poa_align")] + \
                [("ms_resident", C.c_double), ("ms_e2e", C.c_double), ("n_zmws", C.c_int64),
-                ("top_fill_alpha_bytes", C.c_int64), ("top_fill_alpha_ms", C.c_double)]
+                ("top_fill_alpha_bytes", C.c_int64), ("top_fill_alpha_ms", C.c_double),
+                ("ms_poa_map", C.c_double), ("ms_poa_graph", C.c_double), ("launches_poa_graph", C.c_int64),
+                ("bytes_poa_map", C.c_int64)]
 
 
 class Batch:

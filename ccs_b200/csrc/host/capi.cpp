@@ -489,7 +489,10 @@ int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset) {
             out->ms_resident += s.ms_resident;
             if (s.top_fill_alpha_bytes > out->top_fill_alpha_bytes) { out->top_fill_alpha_bytes = s.top_fill_alpha_bytes; out->top_fill_alpha_ms = s.top_fill_alpha_ms; }
             out->ms_poa_align += ds.ms_align; out->launches_poa += ds.n_align_launches; out->poa_tasks += ds.n_tasks;
-            out->poa_rows += ds.rows; out->bytes_poa_align += ds.bytes_align; out->launches_draft += ds.n_align_launches;
+            out->poa_rows += ds.rows; out->bytes_poa_align += ds.bytes_align;
+            out->launches_draft += ds.n_align_launches + ds.n_graph_launches;
+            out->ms_poa_map += ds.ms_map; out->ms_poa_graph += ds.ms_graph; out->launches_poa_graph += ds.n_graph_launches;
+            out->bytes_poa_map += ds.bytes_map;
             out->ms_draft += (k == 0 ? ctx->ms_draft : ctx->extra[k - 1].ms_draft);
         }
         out->ms_e2e = ctx->ms_e2e; out->n_zmws = ctx->n_zmws;

@@ -1,6 +1,5 @@
 // Draft Stage host engine -- see draft_engine.h.
 #include "draft_engine.h"
-#include "poa_graph.h"
 #include "draft_host.h"
 #include "parallel.h"
 #include "../cuda/poa_launch.h"
@@ -10,81 +9,94 @@
 
 namespace ccs {
 
+namespace {
+
+// Carves typed arrays out of one block, so that all descriptors of a pass go up in a single copy.
+struct Carver {
+    size_t off = 0;
+    template <class T>
+    size_t take(size_t n) {
+        off = (off + 15) & ~size_t(15);
+        const size_t o = off;
+        off += n * sizeof(T);
+        return o;
+    }
+};
+
+template <class T> T* at(uint8_t* base, size_t off) { return reinterpret_cast<T*>(base + off); }
+
+}  // namespace
+
 DraftEngine::DraftEngine(int device, size_t scratch_budget_bytes) : device_(device), budget_(scratch_budget_bytes) {
     CCS_CUDA(cudaSetDevice(device_));
     CCS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    CCS_CUDA(cudaEventCreate(&ev0_));
-    CCS_CUDA(cudaEventCreate(&ev1_));
     if (budget_ == 0) budget_ = 12ull << 30;
 }
 
 DraftEngine::~DraftEngine() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
-    if (ev0_) cudaEventDestroy(ev0_);
-    if (ev1_) cudaEventDestroy(ev1_);
+    for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
-// One GPU pass over the task list staged in the pinned buffers (already chunked to the scratch budget).
-void DraftEngine::align_tasks(int nt, bool any_dag, bool want_paths, int64_t rows, int64_t path_bytes, size_t n_vbase,
-                              size_t n_poff, size_t n_preds, size_t n_reads) {
-    if (nt == 0) return;
-    CCS_CUDA(cudaSetDevice(device_));
-    d_tasks_.ensure(nt); d_vbase_.ensure(n_vbase + 16); d_reads_.ensure(n_reads + 16);
-    d_poff_.ensure(n_poff + 16); d_preds_.ensure(n_preds + 16);
-    d_lo_.ensure((size_t)rows + 16); d_besti_.ensure((size_t)rows + 16); d_moves_.ensure((size_t)rows * kPoaBand + 16);
-    if (any_dag) d_hrows_.ensure((size_t)rows * kPoaBand + 16);
-    if (want_paths) { d_paths_.ensure((size_t)path_bytes + 16); h_paths_.ensure((size_t)path_bytes + 16); }
-    d_results_.ensure(nt);
-    h_results_.ensure(nt);
-    CCS_CUDA(cudaMemcpyAsync(d_tasks_.p, h_tasks_.p, sizeof(PoaTask) * nt, cudaMemcpyHostToDevice, stream_));
-    CCS_CUDA(cudaMemcpyAsync(d_vbase_.p, h_vbase_.p, n_vbase, cudaMemcpyHostToDevice, stream_));
-    CCS_CUDA(cudaMemcpyAsync(d_reads_.p, h_reads_.p, n_reads, cudaMemcpyHostToDevice, stream_));
-    if (n_poff) CCS_CUDA(cudaMemcpyAsync(d_poff_.p, h_poff_.p, n_poff * 4, cudaMemcpyHostToDevice, stream_));
-    if (n_preds) CCS_CUDA(cudaMemcpyAsync(d_preds_.p, h_preds_.p, n_preds * 4, cudaMemcpyHostToDevice, stream_));
-    stats.h2d_bytes += (int64_t)(sizeof(PoaTask) * nt + n_vbase + n_reads + 4 * (n_poff + n_preds));
-    CCS_CUDA(cudaEventRecord(ev0_, stream_));
-    launch_poa_align(d_tasks_.p, nt, d_vbase_.p, d_poff_.p, d_preds_.p, d_reads_.p, d_lo_.p, d_besti_.p, d_moves_.p,
-                     any_dag ? d_hrows_.p : nullptr, want_paths ? d_paths_.p : nullptr, d_results_.p, stream_);
-    CCS_CUDA(cudaEventRecord(ev1_, stream_));
-    CCS_CUDA(cudaMemcpyAsync(h_results_.p, d_results_.p, sizeof(PoaResult) * nt, cudaMemcpyDeviceToHost, stream_));
-    if (want_paths) {
-        CCS_CUDA(cudaMemcpyAsync(h_paths_.p, d_paths_.p, (size_t)path_bytes, cudaMemcpyDeviceToHost, stream_));
-        stats.d2h_bytes += path_bytes;
+void DraftEngine::span(double* acc) {
+    while (ev_used_ + 2 > ev_pool_.size()) {
+        cudaEvent_t e;
+        CCS_CUDA(cudaEventCreate(&e));
+        ev_pool_.push_back(e);
     }
-    CCS_CUDA(stream_sync_blocking(stream_));
-    CCS_CUDA(cudaGetLastError());
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev0_, ev1_);
-    stats.ms_align += ms;
-    stats.n_align_launches += 2;
-    stats.n_tasks += nt;
-    stats.rows += rows;
-    stats.d2h_bytes += (int64_t)sizeof(PoaResult) * nt;
-    stats.bytes_align += rows * (kPoaBand + 8 + (any_dag ? 4 * kPoaBand : 0)) + (int64_t)n_reads + (int64_t)n_vbase;
+    Span sp{ev_pool_[ev_used_], ev_pool_[ev_used_ + 1], acc};
+    ev_used_ += 2;
+    CCS_CUDA(cudaEventRecord(sp.a, stream_));
+    spans_.push_back(sp);
+}
+
+void DraftEngine::span_end() { CCS_CUDA(cudaEventRecord(spans_.back().b, stream_)); }
+
+void DraftEngine::resolve_spans() {   // call after a stream synchronisation
+    for (const Span& sp : spans_) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) *sp.acc += ms;
+    }
+    spans_.clear();
+    ev_used_ = 0;
 }
 
 void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& out) {
+    CCS_CUDA(cudaSetDevice(device_));
     const int nz = in.n_zmws, nr = in.n_reads;
     out.status.assign(nz, CCS_ZMW_EXCEPTION_THROWN);
     out.draft.assign(nz, {});
     out.maps.assign(nr, ReadMap());
     out.keep.assign(nr, 0);
+    if (nz == 0) return;
     std::vector<int32_t> lens(nr);
     for (int r = 0; r < nr; ++r) lens[r] = (int32_t)(in.read_off[r + 1] - in.read_off[r]);
 
-    // ---- a1: filtering, POA read selection, seed graph, orientation votes ------------------
-    struct ZmwWork {
-        std::vector<int32_t> poa_reads;   // global read indices, seed first
-        std::vector<uint8_t> poa_rev;     // orientation of each (vs the seed)
-        std::vector<uint8_t> seed;
-        HostPoaGraph graph;
-        std::vector<int32_t> order;       // export of the current round
-        bool alive = false;
-    };
-    std::vector<ZmwWork> work(nz);
-    { HostPhase hp("draft.a1 filter+seed+kmer");
+    // ---- the batch's read codes go up once and stay resident (the Polish Stage of this lane reads them too) ----
+    const int64_t code_base = nr ? in.read_off[0] : 0;
+    const int64_t code_total = nr ? in.read_off[nr] - code_base : 0;
+    {
+        HostPhase hp("draft.upload codes");
+        h_codes_.ensure((size_t)code_total + 64);
+        d_codes_.ensure((size_t)code_total + 64);
+        const int64_t piece = 1 << 20;
+        const int np = (int)((code_total + piece - 1) / piece);
+        parallel_for(np, host_threads, [&](int k) {
+            const int64_t b = k * piece, e = std::min<int64_t>(code_total, b + piece);
+            std::memcpy(h_codes_.p + b, in.codes + code_base + b, (size_t)(e - b));
+        });
+        if (code_total) CCS_CUDA(cudaMemcpyAsync(d_codes_.p, h_codes_.p, (size_t)code_total, cudaMemcpyHostToDevice, stream_));
+        d_rev_.ensure((size_t)nr + 64);
+        h_rev_.ensure((size_t)nr + 64);
+        CCS_CUDA(cudaMemsetAsync(d_rev_.p, 0, (size_t)nr + 64, stream_));
+        stats.h2d_bytes += code_total;
+    }
+
+    // ---- a1: filtering and POA read selection (host: a sort of a dozen lengths per ZMW) ----------------------
+    std::vector<Zw> work(nz);
+    { HostPhase hp("draft.a1 filter");
     parallel_for(nz, host_threads, [&](int z) {
         const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
         const int n = r1 - r0;
@@ -93,174 +105,269 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
         if (std::min(std::min(s[0], s[1]), std::min(s[2], s[3])) < dp.min_snr) { out.status[z] = CCS_ZMW_POOR_SNR; return; }
         const int nfull = filter_reads(lens.data() + r0, in.cx + r0, n, dp.top_passes, out.keep.data() + r0);
         if (nfull < dp.min_passes) { out.status[z] = CCS_ZMW_TOO_FEW_PASSES; return; }
-        ZmwWork& w = work[z];
-        for (int r = r0; r < r1 && (int)w.poa_reads.size() < dp.max_poa_reads; ++r)
+        Zw& w = work[z];
+        const int max_poa = std::max(1, std::min(dp.max_poa_reads, kPoaMaxReads));
+        for (int r = r0; r < r1 && (int)w.poa_reads.size() < max_poa; ++r)
             if (out.keep[r] && (in.cx[r] & 3) == 3) w.poa_reads.push_back(r);
-        const int sr = w.poa_reads[0];
-        w.seed.resize(lens[sr]);
-        orient(in.codes + in.read_off[sr], lens[sr], false, w.seed.data());
-        w.graph.init(w.seed.data(), lens[sr]);
-        KmerSet ks;
-        ks.build(w.seed.data(), lens[sr]);
-        w.poa_rev.assign(w.poa_reads.size(), 0);
-        for (size_t k = 1; k < w.poa_reads.size(); ++k) {
-            int64_t f, c;
-            ks.count(in.codes + in.read_off[w.poa_reads[k]], std::min(lens[w.poa_reads[k]], kPoaVoteBases), f, c);
-            w.poa_rev[k] = c > f;
-        }
+        // no full-length read (only reachable with --min-passes 0): no draft can be generated
+        if (w.poa_reads.empty()) { out.status[z] = CCS_ZMW_DRAFT_FAILURE; return; }
+        if (lens[w.poa_reads[0]] > kPoaMaxRefLen) { out.status[z] = CCS_ZMW_TOO_LONG; return; }
         w.alive = true;
     });
     }
 
-    // ---- a2: SparsePoa rounds: round k aligns the k-th POA read of every ZMW on the GPU ----
-    std::vector<int> task_zmw;
-    const int64_t row_bytes = kPoaBand * 5 + 8;   // moves + score row + lo/best per vertex
-    for (int round = 1; round < dp.max_poa_reads; ++round) {
-        int z = 0;
-        while (z < nz) {
-            // pass 1 (serial, cheap): lay out the chunk
-            task_zmw.clear();
-            int64_t rows = 0, path_bytes = 0, n_preds = 0, n_reads = 0, n_poff = 0;
-            std::vector<PoaTask> tl;
-            for (; z < nz; ++z) {
-                ZmwWork& w = work[z];
-                if (!w.alive || (int)w.poa_reads.size() <= round) continue;
-                const int V = w.graph.size();
-                const int rd = w.poa_reads[round];
-                if (!tl.empty() && (rows + V) * row_bytes > (int64_t)budget_) break;
-                PoaTask t;
-                t.vert_off = rows; t.poff_off = n_poff; t.pred_base = n_preds; t.read_off = n_reads;
-                t.row_off = rows; t.path_off = path_bytes; t.V = V; t.n = lens[rd]; t.linear = 0; t.pad_ = 0;
-                rows += V; n_poff += V + 1; n_preds += w.graph.n_edges(); n_reads += lens[rd]; path_bytes += V + lens[rd];
-                tl.push_back(t);
-                task_zmw.push_back(z);
-            }
-            const int nt = (int)tl.size();
-            if (nt == 0) break;
-            h_tasks_.ensure(nt); h_vbase_.ensure((size_t)rows + 16); h_poff_.ensure((size_t)n_poff + 16);
-            h_preds_.ensure((size_t)n_preds + 16); h_reads_.ensure((size_t)n_reads + 16);
-            std::memcpy(h_tasks_.p, tl.data(), sizeof(PoaTask) * nt);
-            // pass 2 (parallel): export graphs and orient reads straight into pinned memory
-            { HostPhase hp("draft.a2 export");
-            parallel_for(nt, host_threads, [&](int k) {
-                ZmwWork& w = work[task_zmw[k]];
-                const PoaTask& t = tl[k];
-                w.graph.export_topo(w.order, h_vbase_.p + t.vert_off, h_poff_.p + t.poff_off, h_preds_.p + t.pred_base);
-                const int rd = w.poa_reads[round];
-                orient(in.codes + in.read_off[rd], lens[rd], w.poa_rev[round], h_reads_.p + t.read_off);
-            });
-            }
-            { HostPhase hp("draft.a2 gpu align (wait)");
-            align_tasks(nt, true, true, rows, path_bytes, (size_t)rows, (size_t)n_poff, (size_t)n_preds, (size_t)n_reads);
-            }
-            HostPhase hp2("draft.a2 commit");
-            parallel_for(nt, host_threads, [&](int k) {
-                ZmwWork& w = work[task_zmw[k]];
-                const PoaTask& t = tl[k];
-                const PoaResult& r = h_results_.p[k];
-                if (r.score >= t.n && r.path_len > 0)   // placed: CommitAdd
-                    w.graph.commit(h_paths_.p + t.path_off, r.path_len, r.end_t, r.end_i, w.order,
-                                   h_poff_.p + t.poff_off, h_preds_.p + t.pred_base, h_reads_.p + t.read_off);
-            });
+    // ---- a2-a5 on the device, in chunks of ZMWs that fit the scratch budget -------------------------------------
+    std::vector<int> zlist;
+    int64_t bytes = 0;
+    auto flush = [&]() {
+        if (!zlist.empty()) poa_chunk(in, dp, out, lens, work, zlist);
+        zlist.clear();
+        bytes = 0;
+    };
+    for (int z = 0; z < nz; ++z) {
+        const Zw& w = work[z];
+        if (!w.alive) continue;
+        int64_t cap = lens[w.poa_reads[0]] + 8, nmax = 0;
+        for (size_t k = 1; k < w.poa_reads.size(); ++k) {
+            cap += poa_new_vertex_bound(lens[w.poa_reads[k]]);
+            nmax = std::max<int64_t>(nmax, lens[w.poa_reads[k]]);
+        }
+        const int64_t need = cap * 400 + nmax * 32;
+        if (!zlist.empty() && bytes + need > (int64_t)budget_) flush();
+        zlist.push_back(z);
+        bytes += need;
+    }
+    flush();
+}
+
+// One chunk of ZMWs through SparsePoa (rounds of align -> traceback -> CommitAdd), FindConsensus and the mapping.
+void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOutput& out, const std::vector<int32_t>& lens,
+                            std::vector<Zw>& work, const std::vector<int>& zlist) {
+    const int ng = (int)zlist.size();
+    const int64_t code_base = in.read_off[0];
+    auto coff = [&](int r) { return in.read_off[r] - code_base; };
+    // ---- layout ------------------------------------------------------------------------------------------------
+    std::vector<int64_t> voff(ng + 1, 0), soff(ng + 1, 0), stoff(ng + 1, 0);
+    int max_rounds = 0, max_ref = 0;
+    int64_t n_vote_reads = 0;
+    for (int g = 0; g < ng; ++g) {
+        const Zw& w = work[zlist[g]];
+        int64_t cap = lens[w.poa_reads[0]] + 8, nmax = 0;
+        for (size_t k = 1; k < w.poa_reads.size(); ++k) {
+            cap += poa_new_vertex_bound(lens[w.poa_reads[k]]);
+            nmax = std::max<int64_t>(nmax, lens[w.poa_reads[k]]);
+        }
+        cap = (cap + 15) & ~15ll;                          // rows stay 16-byte aligned in every pool
+        voff[g + 1] = voff[g] + cap;
+        soff[g + 1] = soff[g] + 5 * nmax + 4 * cap + 16;
+        stoff[g + 1] = stoff[g] + nmax;
+        max_rounds = std::max(max_rounds, (int)w.poa_reads.size() - 1);
+        max_ref = std::max(max_ref, lens[w.poa_reads[0]]);
+        n_vote_reads += (int64_t)w.poa_reads.size() - 1;
+    }
+    const int64_t pool = voff[ng];
+    std::vector<std::vector<int>> round_graphs(max_rounds);
+    for (int g = 0; g < ng; ++g)
+        for (int k = 1; k < (int)work[zlist[g]].poa_reads.size(); ++k) round_graphs[k - 1].push_back(g);
+
+    Carver cv;
+    const size_t o_hdr = cv.take<PoaGraphHdr>(ng), o_seed = cv.take<PoaTask>(ng), o_graphs = cv.take<int32_t>(ng);
+    const size_t o_soff = cv.take<int64_t>(ng), o_jobs = cv.take<PoaVoteJob>(ng), o_vreads = cv.take<PoaVoteRead>((size_t)n_vote_reads + 1);
+    std::vector<size_t> o_tasks(max_rounds);
+    for (int k = 0; k < max_rounds; ++k) o_tasks[k] = cv.take<PoaTask>(round_graphs[k].size());
+    const size_t desc_bytes = cv.off + 64;
+    h_desc_.ensure(desc_bytes);
+    d_desc_.ensure(desc_bytes);
+    uint8_t* hb = h_desc_.p;
+    { HostPhase hp("draft.a2 descriptors");
+    int64_t vr = 0;
+    for (int g = 0; g < ng; ++g) {
+        const Zw& w = work[zlist[g]];
+        const int sr = w.poa_reads[0];
+        PoaGraphHdr& H = at<PoaGraphHdr>(hb, o_hdr)[g];
+        std::memset(&H, 0, sizeof(H));
+        H.voff = voff[g]; H.cap = (int32_t)(voff[g + 1] - voff[g]);
+        PoaTask& S = at<PoaTask>(hb, o_seed)[g];
+        std::memset(&S, 0, sizeof(S));
+        S.codes_off = coff(sr); S.n = lens[sr]; S.graph = g; S.rev_idx = sr;
+        at<int32_t>(hb, o_graphs)[g] = g;
+        at<int64_t>(hb, o_soff)[g] = soff[g];
+        PoaVoteJob& J = at<PoaVoteJob>(hb, o_jobs)[g];
+        J.ref_off = coff(sr); J.ref_len = lens[sr]; J.ref_is_codes = 1; J.read_begin = (int32_t)vr;
+        for (size_t k = 1; k < w.poa_reads.size(); ++k) {
+            const int r = w.poa_reads[k];
+            at<PoaVoteRead>(hb, o_vreads)[vr++] = PoaVoteRead{coff(r), lens[r], r};
+        }
+        J.read_end = (int32_t)vr;
+    }
+    for (int k = 0; k < max_rounds; ++k)
+        for (size_t x = 0; x < round_graphs[k].size(); ++x) {
+            const int g = round_graphs[k][x];
+            const int r = work[zlist[g]].poa_reads[k + 1];
+            PoaTask& T = at<PoaTask>(hb, o_tasks[k])[x];
+            std::memset(&T, 0, sizeof(T));
+            T.codes_off = coff(r); T.row_off = voff[g]; T.step_off = stoff[g]; T.n = lens[r]; T.graph = g;
+            T.rev_idx = r; T.scratch_off = soff[g];
         }
     }
+    d_meta_.ensure((size_t)pool + 16); d_pred0_.ensure((size_t)pool + 16); d_predx_.ensure((size_t)pool * 7 + 16);
+    d_rank_.ensure((size_t)pool + 16); d_order_.ensure((size_t)pool * 2 + 16);
+    d_lo_.ensure((size_t)pool + 16); d_besti_.ensure((size_t)pool + 16);
+    d_moves_.ensure((size_t)pool * kPoaBand + 16); d_hrows_.ensure((size_t)pool * kPoaBand + 16);
+    d_scratch_.ensure((size_t)soff[ng] + 16); d_steps_.ensure((size_t)stoff[ng] + 16);
+    d_results_.ensure((size_t)ng + 1); d_draft_.ensure((size_t)pool + 16); d_draft_len_.ensure((size_t)ng + 1);
+    h_draft_.ensure((size_t)pool + 16); h_draft_len_.ensure((size_t)ng + 1);
+    CCS_CUDA(cudaMemcpyAsync(d_desc_.p, h_desc_.p, desc_bytes, cudaMemcpyHostToDevice, stream_));
+    stats.h2d_bytes += (int64_t)desc_bytes;
+    uint8_t* db = d_desc_.p;
+    PoaGraphView G;
+    G.hdr = at<PoaGraphHdr>(db, o_hdr); G.meta = d_meta_.p; G.pred0 = d_pred0_.p; G.predx = d_predx_.p; G.rank = d_rank_.p;
+    G.order[0] = d_order_.p; G.order[1] = d_order_.p + pool;
 
-    // ---- a4: consensus + length gates; a3: orientation of every kept read against the draft ----
-    std::vector<std::vector<uint8_t>> rev_flag(nz);
-    { HostPhase hp("draft.a4 consensus+kmer");
-    parallel_for(nz, host_threads, [&](int z) {
-        ZmwWork& w = work[z];
-        if (!w.alive) return;
-        const int n = w.graph.n_reads();
-        const int min_cov = n < 5 ? 1 : (n + 1) / 2 - 1;
-        w.graph.consensus(min_cov, out.draft[z]);
-        const int J = (int)out.draft[z].size();
-        if (J == 0) { out.status[z] = CCS_ZMW_DRAFT_FAILURE; w.alive = false; }
-        else if (J < dp.min_length) { out.status[z] = CCS_ZMW_TOO_SHORT; w.alive = false; }
-        else if (J > dp.max_length) { out.status[z] = CCS_ZMW_TOO_LONG; w.alive = false; }
-        if (!w.alive) return;
-        const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
-        KmerSet ks;
-        ks.build(out.draft[z].data(), J);
-        rev_flag[z].assign(r1 - r0, 0);
-        for (int r = r0; r < r1; ++r) {
-            if (!out.keep[r]) continue;
-            int64_t f, c;
-            ks.count(in.codes + in.read_off[r], std::min(lens[r], kPoaVoteBases), f, c);
-            rev_flag[z][r - r0] = c > f;
+    // ---- a3 (seeding): orientation of the POA reads against the seed; a2: seed chains + SparsePoa rounds ----------
+    span(&stats.ms_graph);
+    CCS_CUDA(launch_poa_kmer_vote(at<PoaVoteJob>(db, o_jobs), ng, max_ref, at<PoaVoteRead>(db, o_vreads), d_codes_.p,
+                                  d_draft_.p, d_rev_.p, stream_));
+    launch_poa_graph_init(G, at<PoaTask>(db, o_seed), ng, d_codes_.p, stream_);
+    span_end();
+    stats.n_graph_launches += 2;
+    for (int k = 0; k < max_rounds; ++k) {
+        const int nt = (int)round_graphs[k].size();
+        if (nt == 0) continue;
+        const PoaTask* tk = at<PoaTask>(db, o_tasks[k]);
+        span(&stats.ms_align);
+        launch_poa_align(tk, nt, G, d_draft_.p, d_codes_.p, d_rev_.p, d_lo_.p, d_besti_.p, d_moves_.p, d_hrows_.p,
+                         d_steps_.p, d_results_.p, stream_);
+        span_end();
+        span(&stats.ms_graph);
+        launch_poa_commit(G, tk, nt, d_codes_.p, d_rev_.p, d_steps_.p, d_results_.p, d_scratch_.p, stream_);
+        span_end();
+        stats.n_align_launches += 2; stats.n_graph_launches += 1; stats.n_tasks += nt;
+        for (int g : round_graphs[k]) {
+            // rows of round k: the graph has at most seed + bound(earlier reads) vertices; count the seed length
+            const int64_t rows = lens[work[zlist[g]].poa_reads[0]];
+            stats.rows += rows;
+            stats.bytes_align += rows * (kPoaBand + 8 + 4 * kPoaBand) + lens[work[zlist[g]].poa_reads[k + 1]] + rows;
         }
-    });
+    }
+    // ---- a4: consensus -------------------------------------------------------------------------------------------
+    span(&stats.ms_graph);
+    launch_poa_consensus(G, at<int32_t>(db, o_graphs), ng, at<int64_t>(db, o_soff), d_scratch_.p, d_draft_.p,
+                         d_draft_len_.p, stream_);
+    span_end();
+    stats.n_graph_launches += 1;
+    CCS_CUDA(cudaMemcpyAsync(h_draft_len_.p, d_draft_len_.p, sizeof(int32_t) * ng, cudaMemcpyDeviceToHost, stream_));
+    CCS_CUDA(cudaMemcpyAsync(h_draft_.p, d_draft_.p, (size_t)pool, cudaMemcpyDeviceToHost, stream_));
+    stats.d2h_bytes += pool + 4ll * ng;
+    { HostPhase hp("draft.a2-a4 gpu (wait)");
+    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(cudaGetLastError());
+    resolve_spans();
+    }
+    // length gates
+    std::vector<int> live;      // graph indices that go on to the mapping
+    for (int g = 0; g < ng; ++g) {
+        const int z = zlist[g];
+        const int J = h_draft_len_.p[g];
+        out.draft[z].assign(h_draft_.p + voff[g], h_draft_.p + voff[g] + J);
+        if (J == 0) out.status[z] = CCS_ZMW_DRAFT_FAILURE;
+        else if (J < dp.min_length) out.status[z] = CCS_ZMW_TOO_SHORT;
+        else if (dp.max_length > 0 && J > dp.max_length) out.status[z] = CCS_ZMW_TOO_LONG;
+        else { live.push_back(g); continue; }
+        work[z].alive = false;
     }
 
-    // ---- a5: subread -> draft mapping of every kept read (linear graphs on the same kernel) ---
-    {
-        int z = 0;
-        std::vector<int> task_read;
-        std::vector<PoaTask> tl;
-        while (z < nz) {
-            tl.clear(); task_read.clear();
-            int64_t rows = 0, n_vbase = 0, n_reads = 0;
-            for (; z < nz; ++z) {
-                ZmwWork& w = work[z];
-                if (!w.alive) continue;
-                const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
-                const int J = (int)out.draft[z].size();
-                int nk = 0;
-                for (int r = r0; r < r1; ++r) nk += out.keep[r];
-                if (!tl.empty() && (rows + (int64_t)nk * J) * (kPoaBand + 8) > (int64_t)budget_) break;
-                for (int r = r0; r < r1; ++r) {
-                    if (!out.keep[r]) continue;
-                    PoaTask t;
-                    t.vert_off = n_vbase; t.poff_off = 0; t.pred_base = 0; t.read_off = n_reads;
-                    t.row_off = rows; t.path_off = 0; t.V = J; t.n = lens[r]; t.linear = 1; t.pad_ = z;
-                    rows += J; n_reads += lens[r];
-                    tl.push_back(t);
-                    task_read.push_back(r);
+    // ---- a5: subread -> draft mapping of every kept read (orientation vote against the draft, then the same
+    //      aligner on the linear template), in passes that fit the scratch budget -------------------------------
+    size_t li = 0;
+    while (li < live.size()) {
+        std::vector<int> task_read, task_g;
+        int64_t rows = 0;
+        size_t lj = li;
+        int max_J = 0;
+        for (; lj < live.size(); ++lj) {
+            const int g = live[lj], z = zlist[g];
+            const int J = h_draft_len_.p[g];
+            int nk = 0;
+            for (int r = in.zmw_read_off[z]; r < in.zmw_read_off[z + 1]; ++r) nk += out.keep[r];
+            if (lj > li && (rows + (int64_t)nk * J) * (kPoaBand + 8) > (int64_t)budget_) break;
+            for (int r = in.zmw_read_off[z]; r < in.zmw_read_off[z + 1]; ++r)
+                if (out.keep[r]) { task_read.push_back(r); task_g.push_back(g); }
+            rows += (int64_t)nk * J;
+            max_J = std::max(max_J, J);
+        }
+        const int nt = (int)task_read.size(), nj = (int)(lj - li);
+        Carver c2;
+        const size_t o_j2 = c2.take<PoaVoteJob>(nj), o_v2 = c2.take<PoaVoteRead>((size_t)nt + 1), o_t2 = c2.take<PoaTask>((size_t)nt + 1);
+        const size_t bytes2 = c2.off + 64;
+        h_desc_.ensure(bytes2);
+        d_desc_.ensure(bytes2);
+        hb = h_desc_.p; db = d_desc_.p;
+        {
+            int64_t ro = 0;
+            int k = 0;
+            for (size_t x = li; x < lj; ++x) {
+                const int g = live[x];
+                const int J = h_draft_len_.p[g];
+                PoaVoteJob& Jb = at<PoaVoteJob>(hb, o_j2)[x - li];
+                Jb.ref_off = voff[g]; Jb.ref_len = J; Jb.ref_is_codes = 0; Jb.read_begin = k;
+                for (; k < nt && task_g[k] == g; ++k) {
+                    const int r = task_read[k];
+                    at<PoaVoteRead>(hb, o_v2)[k] = PoaVoteRead{coff(r), lens[r], r};
+                    PoaTask& T = at<PoaTask>(hb, o_t2)[k];
+                    std::memset(&T, 0, sizeof(T));
+                    T.codes_off = coff(r); T.row_off = ro; T.tpl_off = voff[g]; T.n = lens[r]; T.graph = -1; T.V = J;
+                    T.rev_idx = r;
+                    ro += J;
+                    stats.bytes_map += (int64_t)J * (kPoaBand + 8) + lens[r] + J;
                 }
-                n_vbase += J;
-            }
-            const int nt = (int)tl.size();
-            if (nt == 0) break;
-            h_tasks_.ensure(nt); h_vbase_.ensure((size_t)n_vbase + 16); h_reads_.ensure((size_t)n_reads + 16);
-            std::memcpy(h_tasks_.p, tl.data(), sizeof(PoaTask) * nt);
-            { HostPhase hp("draft.a5 map pack");
-            parallel_for(nt, host_threads, [&](int k) {
-                const PoaTask& t = tl[k];
-                const int r = task_read[k], zz = t.pad_;
-                if (k == 0 || tl[k - 1].pad_ != zz)   // first task of the ZMW copies the draft
-                    std::memcpy(h_vbase_.p + t.vert_off, out.draft[zz].data(), out.draft[zz].size());
-                orient(in.codes + in.read_off[r], lens[r], rev_flag[zz][r - in.zmw_read_off[zz]], h_reads_.p + t.read_off);
-            });
-            }
-            { HostPhase hp("draft.a5 gpu map (wait)");
-            align_tasks(nt, false, false, rows, 0, (size_t)n_vbase, 0, 0, (size_t)n_reads);
-            }
-            for (int k = 0; k < nt; ++k) {
-                const PoaResult& pr = h_results_.p[k];
-                ReadMap& m = out.maps[task_read[k]];
-                m.score = pr.score;
-                if (pr.first_t < 0) continue;
-                m.tstart = pr.first_t; m.tend = pr.last_t + 1;
-                m.rstart = pr.first_i; m.rend = pr.last_i + 1;
-                m.mapped = pr.score >= tl[k].n;
+                Jb.read_end = k;
             }
         }
-    }
-    parallel_for(nz, host_threads, [&](int z) {
-        ZmwWork& w = work[z];
-        if (!w.alive) return;
-        const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
-        int mapped_full = 0;
-        for (int r = r0; r < r1; ++r) {
-            if (!out.keep[r]) continue;
+        d_lo_.ensure((size_t)rows + 16); d_besti_.ensure((size_t)rows + 16); d_moves_.ensure((size_t)rows * kPoaBand + 16);
+        d_results_.ensure((size_t)nt + 1); h_results_.ensure((size_t)nt + 1);
+        CCS_CUDA(cudaMemcpyAsync(d_desc_.p, h_desc_.p, bytes2, cudaMemcpyHostToDevice, stream_));
+        stats.h2d_bytes += (int64_t)bytes2;
+        PoaGraphView G0 = G;     // linear tasks never touch the graph arrays
+        span(&stats.ms_graph);
+        CCS_CUDA(launch_poa_kmer_vote(at<PoaVoteJob>(db, o_j2), nj, max_J, at<PoaVoteRead>(db, o_v2), d_codes_.p, d_draft_.p,
+                                      d_rev_.p, stream_));
+        span_end();
+        span(&stats.ms_map);
+        launch_poa_align(at<PoaTask>(db, o_t2), nt, G0, d_draft_.p, d_codes_.p, d_rev_.p, d_lo_.p, d_besti_.p, d_moves_.p,
+                         nullptr, nullptr, d_results_.p, stream_);
+        span_end();
+        stats.n_graph_launches += 1; stats.n_align_launches += 2; stats.n_tasks += nt; stats.rows += rows;
+        CCS_CUDA(cudaMemcpyAsync(h_results_.p, d_results_.p, sizeof(PoaResult) * nt, cudaMemcpyDeviceToHost, stream_));
+        CCS_CUDA(cudaMemcpyAsync(h_rev_.p, d_rev_.p, (size_t)in.n_reads, cudaMemcpyDeviceToHost, stream_));
+        stats.d2h_bytes += (int64_t)sizeof(PoaResult) * nt + in.n_reads;
+        { HostPhase hp("draft.a5 gpu map (wait)");
+        CCS_CUDA(stream_sync_blocking(stream_));
+        CCS_CUDA(cudaGetLastError());
+        resolve_spans();
+        }
+        for (int k = 0; k < nt; ++k) {
+            const PoaResult& pr = h_results_.p[k];
+            const int r = task_read[k];
             ReadMap& m = out.maps[r];
-            m.strand = rev_flag[z][r - r0];
+            m.score = pr.score;
+            m.strand = h_rev_.p[r];
+            if (pr.first_t < 0) continue;
+            m.tstart = pr.first_t; m.tend = pr.last_t + 1;
+            m.rstart = pr.first_i; m.rend = pr.last_i + 1;
+            m.mapped = pr.score >= lens[r];
             if (m.strand) { const int rs = lens[r] - m.rend, re = lens[r] - m.rstart; m.rstart = rs; m.rend = re; }
             if (m.mapped && (m.tend - m.tstart < 2 || m.rend - m.rstart < 2)) m.mapped = 0;
-            if (m.mapped && (in.cx[r] & 3) == 3) ++mapped_full;
         }
-        out.status[z] = mapped_full < dp.min_passes ? CCS_ZMW_TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT : CCS_ZMW_SUCCESS;
-    });
+        for (size_t x = li; x < lj; ++x) {
+            const int z = zlist[live[x]];
+            int mapped_full = 0;
+            for (int r = in.zmw_read_off[z]; r < in.zmw_read_off[z + 1]; ++r)
+                if (out.keep[r] && out.maps[r].mapped && (in.cx[r] & 3) == 3) ++mapped_full;
+            out.status[z] = mapped_full < dp.min_passes ? CCS_ZMW_TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT : CCS_ZMW_SUCCESS;
+        }
+        li = lj;
+    }
 }
 
 }  // namespace ccs

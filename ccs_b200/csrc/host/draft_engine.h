@@ -1,7 +1,9 @@
-// Host side of the Draft Stage (the first GPU box of /root/reference/docs/img/ccs-impl.png):
-// initial filtering, k-mer orientation vote, SparsePoa rounds (GPU alignment + host graph
-// threading), consensus, and the subread -> draft mapping that feeds the Polish Stage
-// (/root/reference/docs/how-does-ccs-work.md:19-55).
+// Host side of the Draft Stage (the first GPU box of /root/reference/docs/img/ccs-impl.png).
+// The host only filters reads (a1) and lays out task descriptors; the k-mer orientation votes, the SparsePoa
+// rounds (alignment, traceback, CommitAdd on the device-resident graph), FindConsensus and the subread -> draft
+// mapping all run as kernels on one stream, with two synchronisation points per chunk: after the consensus
+// (draft lengths size the mapping pass) and after the mapping (SURVEY.md 8a rows a1-a5;
+// /root/reference/docs/how-does-ccs-work.md:19-55).
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -15,7 +17,7 @@ struct DraftParams {
     int32_t min_passes = 3;    // --min-passes
     int32_t top_passes = 60;   // --top-passes
     int32_t max_poa_reads = 5; // "draft consensus from a few subreads"
-    int32_t min_length = 10, max_length = 50000;
+    int32_t min_length = 10, max_length = 50000;   // max_length 0: unlimited
 };
 
 struct DraftInput {
@@ -37,9 +39,12 @@ struct DraftOutput {
 };
 
 struct DraftStats {
-    double ms_align = 0;        // CUDA-event time of poa_align + traceback launches
-    int64_t n_align_launches = 0, n_tasks = 0, rows = 0;
-    int64_t bytes_align = 0;    // algorithmic bytes
+    double ms_align = 0;        // CUDA-event time of the POA-round poa_align + traceback launches
+    double ms_map = 0;          // ... of the mapping launches (linear templates)
+    double ms_graph = 0;        // ... of the graph kernels (init, CommitAdd, consensus) and the k-mer votes
+    int64_t n_align_launches = 0, n_graph_launches = 0, n_tasks = 0, rows = 0;
+    int64_t bytes_align = 0;    // algorithmic bytes of the align launches
+    int64_t bytes_map = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
 };
 
@@ -50,23 +55,34 @@ public:
     void run(const DraftInput& in, const DraftParams& dp, DraftOutput& out);
     DraftStats stats;
     int host_threads = 8;
+    // The uploaded read codes of the last run() stay resident for the Polish Stage of the same lane.
+    const uint8_t* device_codes() const { return d_codes_.p; }
+    cudaStream_t stream() const { return stream_; }
 
 private:
-    struct TaskHost { int zmw; int read; int rev; int V; int n; const uint8_t* bases; };   // bases: oriented read
-    // staged in pinned memory by the caller: h_tasks_[0..nt), h_vbase_, h_poff_, h_preds_, h_reads_
-    void align_tasks(int nt, bool any_dag, bool want_paths, int64_t rows, int64_t path_bytes, size_t n_vbase,
-                     size_t n_poff, size_t n_preds, size_t n_reads);
+    struct Zw {                           // per-ZMW host state of one run
+        std::vector<int32_t> poa_reads;   // batch read indices, seed first
+        bool alive = false;
+    };
+    void poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOutput& out, const std::vector<int32_t>& lens,
+                   std::vector<Zw>& work, const std::vector<int>& zlist);
+    void span(double* acc);
+    void span_end();
+    void resolve_spans();
     int device_;
     size_t budget_;
     cudaStream_t stream_ = nullptr;
-    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
-    DevBuf<PoaTask> d_tasks_;
-    DevBuf<uint8_t> d_vbase_, d_reads_, d_moves_, d_paths_;
-    DevBuf<int32_t> d_poff_, d_preds_, d_lo_, d_besti_, d_hrows_;
+    struct Span { cudaEvent_t a, b; double* acc; };
+    std::vector<Span> spans_;
+    std::vector<cudaEvent_t> ev_pool_;
+    size_t ev_used_ = 0;
+    DevBuf<uint8_t> d_codes_, d_desc_, d_rev_, d_moves_, d_draft_;
+    DevBuf<uint32_t> d_meta_;
+    DevBuf<int32_t> d_pred0_, d_predx_, d_rank_, d_order_, d_lo_, d_besti_, d_hrows_, d_scratch_, d_draft_len_;
+    DevBuf<PoaStep> d_steps_;
     DevBuf<PoaResult> d_results_;
-    PinBuf<PoaTask> h_tasks_;
-    PinBuf<uint8_t> h_vbase_, h_reads_, h_paths_;
-    PinBuf<int32_t> h_poff_, h_preds_;
+    PinBuf<uint8_t> h_codes_, h_desc_, h_draft_, h_rev_;
+    PinBuf<int32_t> h_draft_len_;
     PinBuf<PoaResult> h_results_;
 };
 

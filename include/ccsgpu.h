@@ -212,8 +212,9 @@ typedef struct ccs_drafts_out {
 /* ------------------------------------------------------------------------------------
  * Stages
  * ---------------------------------------------------------------------------------- */
-/* Draft Stage: FilterReads -> SparsePoa (GPU sequence-to-DAG alignment, host graph threading) ->
- * FindConsensus -> subread-to-draft mapping (docs/how-does-ccs-work.md:19-55). */
+/* Draft Stage: FilterReads -> k-mer orientation votes -> SparsePoa (sequence-to-DAG alignment, traceback and
+ * CommitAdd on the device-resident graph) -> FindConsensus -> subread-to-draft mapping, all kernels
+ * (docs/how-does-ccs-work.md:19-55). */
 int ccsgpu_draft(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_draft_cfg* cfg, ccs_drafts_out* out);
 
 /* The whole per-ZMW hot path: Draft Stage + Polish Stage + final gates; per-ZMW status in the
@@ -255,6 +256,9 @@ typedef struct ccs_stats {
     int64_t n_zmws;        /* ZMWs processed */
     int64_t top_fill_alpha_bytes;   /* the largest single arrow_fill_alpha launch: algorithmic bytes */
     double  top_fill_alpha_ms;      /* and its duration (roofline numerator/denominator) */
+    double  ms_poa_map;    /* poa_align + traceback launches of the subread -> draft mapping (linear templates) */
+    double  ms_poa_graph;  /* graph kernels: seed chain, CommitAdd, FindConsensus, k-mer votes */
+    int64_t launches_poa_graph, bytes_poa_map;
 } ccs_stats;
 int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset);
 

@@ -150,22 +150,29 @@ def test_model_json_round_trip(tmp_path):
     assert L.ccs_model_load_json(str(bad).encode(), back.ctypes.data_as(C.c_void_p)) == -7     # CCS_ERR_CHEMISTRY
 
 
-def test_host_poa_graph_matches_oracle(tmp_path):
-    """Host logic of the Draft Stage (CommitAdd threading, topological export, FindConsensus in
-    ccs_b200/csrc/host/poa_graph.h) against the oracle's independent graph, driven by the oracle's CPU
-    alignments re-encoded in the kernel's traceback format -- no device involved."""
+def test_device_poa_graph_ops_match_oracle(tmp_path):
+    """Graph routines of the Draft Stage kernels (seed chain, CommitAdd on the id/order/rank layout, FindConsensus,
+    hashed k-mer vote: ccs_b200/csrc/cuda/poa_graph_ops.cuh -- the code the CUDA kernels run) instantiated over a host
+    execution context and checked against the oracle's independent graph, driven by the oracle's CPU alignments.
+    Runs single-threaded, as a team of 8 threads (barrier = __syncthreads), and as a team under ThreadSanitizer
+    (races between the phases of a routine would be races between the CTA's threads)."""
     import shutil
     import subprocess
     cxx = shutil.which("g++")
     if cxx is None:
         pytest.skip("no g++")
-    exe = str(tmp_path / "poa_graph_parity")
-    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", exe,
-                           os.path.join(ROOT, "tests", "host", "poa_graph_parity.cpp"),
-                           os.path.join(ROOT, "oracle", "poa_oracle.cpp")])
-    out = subprocess.run([exe, "30"], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr + out.stdout
-    assert out.stdout.startswith("ok:")
+    srcs = [os.path.join(ROOT, "tests", "host", "poa_device_graph_parity.cpp"), os.path.join(ROOT, "oracle", "poa_oracle.cpp")]
+    exe = str(tmp_path / "poa_device_graph_parity")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-pthread", "-o", exe] + srcs)
+    for team in ("1", "8"):
+        out = subprocess.run([exe, "30", team], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr + out.stdout
+        assert out.stdout.startswith("ok:")
+    tsan = str(tmp_path / "poa_device_graph_parity_tsan")
+    if subprocess.call([cxx, "-O1", "-g", "-fsanitize=thread", "-std=c++17", "-pthread", "-o", tsan] + srcs,
+                       stderr=subprocess.DEVNULL) == 0:
+        out = subprocess.run([tsan, "4", "6"], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "data race" not in out.stderr, out.stderr[-3000:] + out.stdout
 
 
 def test_draft_host_helpers_match_oracle(tmp_path):
