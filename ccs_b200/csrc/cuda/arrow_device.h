@@ -51,6 +51,9 @@ static_assert(sizeof(DevZmw) == 32, "DevZmw layout");
 // range's first position in the flattened work list.
 struct ScoreRange { int32_t zmw; int32_t p_begin; int32_t p_end; int32_t pad_; int64_t first; };
 
+// One read to encode into its two row-code copies (arrow_pack_rowcodes_kernel).
+struct PackJob { int64_t src_off; int64_t dst_off; int32_t I; int32_t stride; };
+
 // Delta rows of one edited ZMW to re-index (arrow_remap_delta_kernel).
 struct RemapJob { int64_t delta_off; int64_t scratch_off; int32_t J_old, J_new; int32_t site_off, n_sites; };
 

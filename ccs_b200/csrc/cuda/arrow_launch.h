@@ -10,6 +10,10 @@ namespace ccs {
 void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
 void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream);
 
+// Recursor::EncodeRead on the device: job k encodes codes[src_off .. src_off + I) into the two row-code copies at
+// rowcode[dst_off ..) (see arrow_pack.cu)
+void launch_pack_rowcodes(const PackJob* jobs, int n_jobs, const uint8_t* codes, uint8_t* rowcode, cudaStream_t stream);
+
 // delta[(zmw.delta_off + p) * kDeltaStride + slot]; INS total = slot[5+b] + slot[9+b].
 // Ranges of one ZMW must be disjoint and non-touching.  generic = reference kernel (every mutation
 // evaluated independently), used by the tests to cross-check the factored kernel.

@@ -85,7 +85,7 @@ bool BgzfReader::open(const std::string& path, int threads) {
     threads_ = default_io_threads(threads);
     blocks_.assign(kReadBatch, {}); comp_.assign(kReadBatch, {});
     n_batch_ = 0; cur_ = 0; pos_ = 0;
-    failed_ = false;
+    failed_ = false; last_block_empty_ = false; error_.clear();
     return f_ != nullptr;
 }
 
@@ -95,16 +95,24 @@ bool BgzfReader::refill_batch() {
     std::vector<uint32_t> isize(kReadBatch, 0);
     std::vector<size_t> clen(kReadBatch, 0);
     uint8_t h[18];
+    auto fail = [&](const char* why) { failed_ = true; if (error_.empty()) error_ = why; };
     while (n < kReadBatch) {
-        if (std::fread(h, 1, 18, f_) != 18) break;                       // end of file
+        const size_t got = std::fread(h, 1, 18, f_);
+        if (got == 0) {                                                   // physical end of the file
+            if (!last_block_empty_) fail("BGZF EOF marker missing: the file is truncated");
+            break;
+        }
         // a malformed or truncated block ends the stream AFTER the complete blocks in front of it have been delivered
-        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || rd16(h + 10) != 6 || h[12] != 'B' || h[13] != 'C') { failed_ = true; break; }
+        if (got != 18) { fail("truncated BGZF block header"); break; }
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || rd16(h + 10) != 6 || h[12] != 'B' || h[13] != 'C') { fail("malformed BGZF block header"); break; }
         const size_t bsize = (size_t)rd16(h + 16) + 1;
-        if (bsize < 18 + 8) { failed_ = true; break; }
+        if (bsize < 18 + 8) { fail("malformed BGZF block size"); break; }
         clen[n] = bsize - 18 - 8;
         comp_[n].resize(clen[n] + 8);
-        if (std::fread(comp_[n].data(), 1, clen[n] + 8, f_) != clen[n] + 8) { failed_ = true; break; }
+        if (std::fread(comp_[n].data(), 1, clen[n] + 8, f_) != clen[n] + 8) { fail("truncated BGZF block"); break; }
         isize[n] = rd32(comp_[n].data() + clen[n] + 4);
+        if (isize[n] > 65536u) { fail("BGZF block claims more than 64 KiB of payload"); break; }
+        last_block_empty_ = isize[n] == 0;
         ++n;
     }
     if (n == 0) return false;
@@ -118,10 +126,13 @@ bool BgzfReader::refill_batch() {
         zs.next_in = comp_[k].data(); zs.avail_in = (uInt)clen[k];
         zs.next_out = blocks_[k].data(); zs.avail_out = (uInt)isize[k];
         const int rc = inflate(&zs, Z_FINISH);
+        const bool full = zs.total_out == isize[k];
         inflateEnd(&zs);
-        if (rc != Z_STREAM_END) bad.store(1);
+        if (rc != Z_STREAM_END || !full) { bad.store(1); return; }
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), blocks_[k].data(), (uInt)isize[k]);
+        if (crc != rd32(comp_[k].data() + clen[k])) bad.store(2);
     }, /*min_items_per_thread=*/1);
-    if (bad.load()) return false;
+    if (bad.load()) { fail(bad.load() == 2 ? "BGZF block CRC32 mismatch" : "BGZF block does not inflate"); return false; }
     n_batch_ = n;
     return true;
 }
@@ -150,7 +161,7 @@ bool BgzfReader::read(void* dst, size_t n) {
 bool BgzfReader::seek(uint64_t voffset) {
     if (!f_) return false;
     if (fseeko(f_, (off_t)(voffset >> 16), SEEK_SET) != 0) return false;
-    n_batch_ = 0; cur_ = 0; pos_ = 0; failed_ = false;
+    n_batch_ = 0; cur_ = 0; pos_ = 0; failed_ = false; last_block_empty_ = false; error_.clear();
     const size_t within = (size_t)(voffset & 0xffff);
     if (!fill()) return within == 0;          // seeking to the very end is fine
     if (within > blocks_[cur_].size()) return false;
@@ -170,7 +181,7 @@ bool BgzfWriter::open(const std::string& path, int level, int threads) {
     level_ = level;
     threads_ = default_io_threads(threads);
     buf_.clear();
-    uflushed_ = 0; cpos_ = 0; blocks_.clear();
+    uflushed_ = 0; cpos_ = 0; blocks_.clear(); io_error_ = false;
     return f_ != nullptr;
 }
 
@@ -188,31 +199,32 @@ void BgzfWriter::flush_block() {
     if (comp_.size() < nb) comp_.resize(nb);
     std::vector<size_t> clen(nb, 0);
     std::vector<uint32_t> crc(nb, 0);
+    std::atomic<int> bad(0);
     parallel_for((int)nb, threads_, [&](int k) {
         const size_t done = (size_t)k * kBlockData;
         const size_t n = std::min(kBlockData, buf_.size() - done);
         comp_[k].resize(compressBound((uLong)n) + 64);
         z_stream zs;
         std::memset(&zs, 0, sizeof(zs));
-        deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+        if (deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad.store(1); return; }
         zs.next_in = buf_.data() + done; zs.avail_in = (uInt)n;
         zs.next_out = comp_[k].data(); zs.avail_out = (uInt)comp_[k].size();
-        deflate(&zs, Z_FINISH);
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) bad.store(1);
         clen[k] = zs.total_out;
         deflateEnd(&zs);
         crc[k] = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf_.data() + done, (uInt)n);
     }, /*min_items_per_thread=*/1);
+    if (bad.load()) io_error_ = true;
     for (size_t k = 0; k < nb; ++k) {
         const size_t n = std::min(kBlockData, buf_.size() - k * kBlockData);
         uint8_t h[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
         const uint16_t bsize = (uint16_t)(clen[k] + 18 + 8 - 1);
         h[16] = bsize & 255; h[17] = bsize >> 8;
         blocks_.push_back({uflushed_ + k * kBlockData, cpos_});
-        std::fwrite(h, 1, 18, f_);
-        std::fwrite(comp_[k].data(), 1, clen[k], f_);
         uint8_t t[8];
         for (int b = 0; b < 4; ++b) { t[b] = (crc[k] >> (8 * b)) & 255; t[4 + b] = ((uint32_t)n >> (8 * b)) & 255; }
-        std::fwrite(t, 1, 8, f_);
+        if (std::fwrite(h, 1, 18, f_) != 18 || std::fwrite(comp_[k].data(), 1, clen[k], f_) != clen[k] ||
+            std::fwrite(t, 1, 8, f_) != 8) io_error_ = true;
         cpos_ += 18 + clen[k] + 8;
     }
     uflushed_ += buf_.size();
@@ -225,13 +237,14 @@ void BgzfWriter::write(const void* src, size_t n) {
     if (buf_.size() >= 64 * kBlockData) flush_block();
 }
 
-void BgzfWriter::close() {
-    if (!f_) return;
+bool BgzfWriter::close() {
+    if (!f_) return !io_error_;
     flush_block();
     blocks_.push_back({uflushed_, cpos_});        // the EOF marker block: where a position at the very end maps to
-    std::fwrite(kBgzfEof, 1, sizeof(kBgzfEof), f_);
-    std::fclose(f_);
+    if (std::fwrite(kBgzfEof, 1, sizeof(kBgzfEof), f_) != sizeof(kBgzfEof)) io_error_ = true;
+    if (std::fclose(f_) != 0) io_error_ = true;
     f_ = nullptr;
+    return !io_error_;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -271,14 +284,24 @@ bool SubreadBamReader::open(const std::string& path, std::string& err, int threa
 
 bool SubreadBamReader::next_record(Subread& s) {
     uint8_t b4[4];
-    if (!in_.read(b4, 4)) return false;
+    if (!error_.empty()) return false;
+    if (in_.eof()) return false;                 // clean end of the data (or a damaged container: in_.error())
+    auto bad = [&](const char* why) { error_ = std::string("malformed BAM record: ") + why; return false; };
+    if (!in_.read(b4, 4)) return bad("truncated record length");
     std::vector<uint8_t>& rec = rec_;            // reused across records: no 26 KB allocation per subread
-    rec.resize(rd32(b4));
-    if (rec.size() < 32 || !in_.read(rec.data(), rec.size())) return false;
+    const uint32_t rec_size = rd32(b4);
+    constexpr uint32_t kMaxRecord = 64u << 20;   // a subread of 20 M bases: far beyond any real polymerase read
+    if (rec_size < 32 || rec_size > kMaxRecord) return bad("implausible record size");
+    rec.resize(rec_size);
+    if (!in_.read(rec.data(), rec.size())) return bad("truncated record");
     const uint8_t* r = rec.data();
     const int l_name = r[8];
     const int n_cigar = rd16(r + 12);
     const int32_t l_seq = (int32_t)rd32(r + 16);
+    if (l_seq < 0) return bad("negative l_seq");
+    // every length field is checked against the record before anything is decoded
+    const uint64_t fixed = 32ull + (uint64_t)l_name + 4ull * (uint64_t)n_cigar + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
+    if (fixed > rec.size()) return bad("name / cigar / sequence lengths exceed the record");
     const uint8_t* p = r + 32;
     const std::string name((const char*)p, l_name > 0 ? l_name - 1 : 0);
     p += l_name + 4 * n_cigar;
@@ -299,11 +322,18 @@ bool SubreadBamReader::next_record(Subread& s) {
             case 'A': case 'c': case 'C': sz = 1; break;
             case 's': case 'S': sz = 2; break;
             case 'i': case 'I': case 'f': sz = 4; break;
-            case 'Z': case 'H': sz = std::strlen((const char*)p) + 1; break;
+            case 'Z': case 'H': {
+                const void* z = std::memchr(p, 0, (size_t)(end - p));
+                if (!z) return bad("unterminated string tag");
+                sz = (size_t)((const uint8_t*)z - p) + 1;
+                break;
+            }
             case 'B': {
+                if (p + 5 > end) return bad("truncated array tag");
                 const char sub = (char)p[0];
                 const uint32_t n = rd32(p + 1);
                 const size_t es = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
+                if ((uint64_t)es * n + 5 > (uint64_t)(end - p)) return bad("array tag exceeds the record");
                 if (is("sn") && sub == 'f' && n == 4) for (int k = 0; k < 4; ++k) { uint32_t u = rd32(p + 5 + 4 * k); std::memcpy(&s.snr[k], &u, 4); }
                 if (is("pw")) {
                     n_pw = n;
@@ -317,8 +347,9 @@ bool SubreadBamReader::next_record(Subread& s) {
                 sz = 5 + es * n;
                 break;
             }
-            default: return false;
+            default: return bad("unknown tag type");
         }
+        if (sz > (size_t)(end - p)) return bad("tag exceeds the record");
         if (ty != 'B') {
             int32_t iv = 0;
             if (ty == 'i' || ty == 'I') iv = (int32_t)rd32(p);
@@ -410,6 +441,8 @@ bool SubreadBamReader::next_zmw(ZmwSubreads& z) {
         z.reads.push_back(std::move(pending_));
         have_pending_ = next_record(pending_);
     }
+    // a damaged file ends the stream with an error; the ZMW being assembled may be missing subreads and is dropped
+    if (!error().empty()) { z.reads.clear(); have_pending_ = false; return false; }
     return true;
 }
 
@@ -439,9 +472,9 @@ bool CcsBamWriter::open(const std::string& path, const std::string& in_header, c
     return true;
 }
 
-void CcsBamWriter::write(const CcsRecord& r) {
+void CcsBamWriter::write(const CcsRecord& r, const char* suffix) {
     rec_.clear();
-    const std::string name = movie_ + "/" + std::to_string(r.hole) + "/ccs";
+    const std::string name = movie_ + "/" + std::to_string(r.hole) + "/" + suffix;
     const size_t at = begin_record(rec_, name, r.len);
     put_seq(rec_, r.seq, r.len);
     rec_.insert(rec_.end(), r.qv, r.qv + r.len);
@@ -455,7 +488,7 @@ void CcsBamWriter::write(const CcsRecord& r) {
     out_.write(rec_.data(), rec_.size());
 }
 
-void CcsBamWriter::close() { out_.close(); }
+bool CcsBamWriter::close() { return out_.close(); }
 
 bool SubreadBamWriter::open(const std::string& path, const std::string& movie, bool with_chemistry, int threads) {
     if (!out_.open(path, 1, threads)) return false;

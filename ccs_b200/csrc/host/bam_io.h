@@ -20,6 +20,9 @@ public:
     bool read(void* dst, size_t n);          // false on EOF / error before n bytes
     bool eof();
     bool seek(uint64_t voffset);             // BGZF virtual offset: compressed block start << 16 | offset in block
+    // Empty while the stream is sound.  A malformed / truncated block, an inflate failure, a CRC32 or ISIZE mismatch, or
+    // a file that ends without the 28-byte BGZF EOF marker sets it: end of data and a damaged file are different things.
+    const std::string& error() const { return error_; }
 private:
     bool fill();                             // advance to the next non-empty block
     bool refill_batch();                     // read + inflate the next batch of blocks
@@ -29,6 +32,8 @@ private:
     size_t n_batch_ = 0, cur_ = 0;           // blocks in the batch, index of the current one
     size_t pos_ = 0;
     bool failed_ = false;                    // a malformed block was seen: stop after the blocks before it
+    bool last_block_empty_ = false;          // the last block read from the file was an empty one (the EOF marker)
+    std::string error_;
 };
 
 class BgzfWriter {
@@ -36,7 +41,8 @@ public:
     ~BgzfWriter();
     bool open(const std::string& path, int level = 1, int threads = 0);
     void write(const void* src, size_t n);
-    void close();                             // flushes and appends the BGZF EOF marker
+    bool close();                             // flushes and appends the BGZF EOF marker; false if any write failed
+    bool ok() const { return !io_error_; }    // false once an fwrite / deflate / fclose failed (e.g. disk full)
     uint64_t upos() const { return uflushed_ + buf_.size(); }   // uncompressed bytes written so far
     // virtual offset of an uncompressed position (valid after close(); blocks are recorded as they are written)
     uint64_t voffset_of(uint64_t upos) const;
@@ -46,6 +52,7 @@ private:
     int level_ = 1, threads_ = 1;
     std::vector<uint8_t> buf_;
     std::vector<std::vector<uint8_t>> comp_;
+    bool io_error_ = false;
     uint64_t uflushed_ = 0, cpos_ = 0;        // uncompressed / compressed bytes already written to the file
     std::vector<std::pair<uint64_t, uint64_t>> blocks_;   // (first uncompressed byte, compressed offset) of every block
 };
@@ -85,7 +92,9 @@ public:
     // Opens and parses the header.  Fails (chemistry_ok() == false) if the read group lacks the
     // chemistry triple -- fatal in the reference too (docs/changelog.md:66, docs/faq/chemistry.md:7-10).
     bool open(const std::string& path, std::string& err, int threads = 0);   // threads: BGZF inflate workers
-    bool next_zmw(ZmwSubreads& z);            // records of one hole number (consecutive in the file)
+    bool next_zmw(ZmwSubreads& z);            // records of one hole number (consecutive in the file); false at the end
+                                              // of the data AND on a damaged file: check error() afterwards
+    const std::string& error() const { return error_.empty() ? in_.error() : error_; }
     bool seek_record(uint64_t voffset);       // continue with the record that starts at this BGZF virtual offset
     const std::string& header_text() const { return header_; }
     const std::string& movie() const { return movie_; }
@@ -97,6 +106,7 @@ private:
     std::string header_, movie_, rg_id_;
     bool chem_ok_ = false, have_pending_ = false;
     Subread pending_;
+    std::string error_;
     std::vector<uint8_t> rec_, pw_;           // record / 16-bit pulse-width scratch, reused across records
 };
 
@@ -119,8 +129,8 @@ public:
     // header derived from the input header: @RG DS:READTYPE=CCS (docs/faq/mode-heteroduplex-filtering.md:49-51)
     bool open(const std::string& path, const std::string& in_header, const std::string& movie, const std::string& rg_id,
               const std::string& program_cl);
-    void write(const CcsRecord& r);           // name movie/zmw/ccs (docs/faq/mode-by-strand.md:11-14)
-    void close();
+    void write(const CcsRecord& r, const char* suffix = "ccs");   // name movie/zmw/ccs[/fwd|/rev] (docs/faq/mode-by-strand.md:11-14)
+    bool close();                             // false if the file could not be written completely
 private:
     BgzfWriter out_;
     std::string movie_, rg_;

@@ -440,6 +440,7 @@ static void ccs_chunk(ccsgpu_ctx* ctx, int lane, const ccs_batch* in, const Draf
     p.n_zmws = nz; p.n_reads = nr; p.zmw_read_off = in->zmw_read_off; p.read_off = in->read_off; p.codes = in->codes;
     p.snr = in->snr; p.tpl_off = tpl_off.data(); p.tpl = tpl.data(); p.strand = strand.data();
     p.tstart = ts.data(); p.tend = te.data(); p.rstart = rs.data(); p.rend = re.data();
+    p.d_codes = lane_draft(ctx, lane).device_codes();   // uploaded once by the Draft Stage of this lane, still resident
     ArrowEngine& E = lane_engine(ctx, lane);
     E.load(p);
     E.polish(pp);

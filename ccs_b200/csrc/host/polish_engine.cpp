@@ -110,15 +110,16 @@ void ArrowEngine::load(const PolishInput& in) {
     qv_.assign(nz, {});
     tpl_cap_.assign(nz, 0);
 
-    // row codes: two 16-byte aligned copies per read (row i, and row i+1 for the backward pass),
-    // pre-multiplied by 4 = byte offset into an emission-table row
+    // row codes: two 16-byte aligned copies per read (row i, and row i+1 for the backward pass), pre-multiplied by 4 =
+    // byte offset into an emission-table row -- encoded ON THE DEVICE from the resident codes (arrow_pack.cu)
     int64_t code_total = 0;
     auto rlen = [&](int r) -> int64_t { return in.rstart ? std::max(0, in.rend[r] - in.rstart[r]) : (in.read_off[r + 1] - in.read_off[r]); };
-    for (int r = 0; r < nr; ++r) code_total += 2 * ((rlen(r) + kRowCodePad + 1 + 15) & ~15ll);
-    h_rowcode_.ensure((size_t)code_total + 64);
     std::vector<int64_t> coffs(nr + 1, 0);
-    for (int r = 0; r < nr; ++r)
-        coffs[r + 1] = coffs[r] + 2 * ((rlen(r) + kRowCodePad + 1 + 15) & ~15ll);
+    for (int r = 0; r < nr; ++r) {
+        const bool mapped = in.tend[r] > in.tstart[r];        // unmapped reads are never touched: no row codes
+        coffs[r + 1] = coffs[r] + (mapped ? 2 * ((rlen(r) + kRowCodePad + 1 + 15) & ~15ll) : 0);
+    }
+    code_total = coffs[nr];
     for (int z = 0; z < nz; ++z) {
         ZmwState& zs = zstate_[z];
         zs.read_begin = in.zmw_read_off[z];
@@ -126,27 +127,25 @@ void ArrowEngine::load(const PolishInput& in) {
         zs.tpl.assign(in.tpl + in.tpl_off[z], in.tpl + in.tpl_off[z + 1]);
         zs.seen.assign(1, tpl_hash(zs.tpl));
     }
+    const int64_t raw_base = nr ? in.read_off[0] : 0;
+    h_pack_.ensure((size_t)nr + 1);
     parallel_for(nr, host_threads, [&](int r) {
         DevRead& rd = reads_[r];
         std::memset(&rd, 0, sizeof(rd));
         const int64_t I = rlen(r);
-        const uint8_t* src = in.codes + in.read_off[r] + (in.rstart ? in.rstart[r] : 0);
+        const int64_t soff = in.read_off[r] + (in.rstart ? in.rstart[r] : 0);
+        const uint8_t* src = in.codes + soff;
         const int64_t stride = (coffs[r + 1] - coffs[r]) / 2;
         rd.code_off = coffs[r];
-        rd.code_stride = (int32_t)stride;
+        rd.code_stride = (int32_t)std::max<int64_t>(stride, 16);
         rd.I = (int32_t)I;
         rd.strand = in.strand[r];
         rd.ts = in.tstart[r];
         rd.te = in.tend[r];
         rd.active = (rd.te > rd.ts) ? 1 : 0;
-        // copy A: A[i] = 4*code of DP row i: sentinel at row 0 and at rows >= I (the last read base
-        // is consumed only by the pinned final match); copy B[i] = A[i+1]
-        uint8_t* a = h_rowcode_.p + coffs[r];
-        uint8_t* b = a + stride;
-        std::memset(a, 4 * kCodeSentinel, (size_t)(2 * stride));
-        for (int64_t i = 1; i <= I - 1; ++i) { const uint8_t c = (uint8_t)(4 * src[i - 1]); a[i] = c; b[i - 1] = c; }
         rd.first_code = I >= 1 ? src[0] : 0;
         rd.last_code = I >= 1 ? src[I - 1] : 0;
+        h_pack_.p[r] = PackJob{soff - raw_base, coffs[r], (int32_t)I, (int32_t)stride};   // stride 0: nothing to write
     });
     for (int z = 0; z < nz; ++z) {
         ZmwState& zs = zstate_[z];
@@ -155,7 +154,8 @@ void ArrowEngine::load(const PolishInput& in) {
             if (reads_[r].active) ++zs.n_mapped;
         }
     }
-    d_rowcode_.ensure((size_t)code_total, budget_);
+    d_rowcode_.ensure((size_t)code_total + 64, budget_);
+    d_pack_.ensure((size_t)nr + 1);
     // transitions
     h_trans_.ensure((size_t)nz * 36 * 4);
     for (int z = 0; z < nz; ++z) {
@@ -165,9 +165,24 @@ void ArrowEngine::load(const PolishInput& in) {
     }
     d_trans_.ensure((size_t)nz * 36 * 4, budget_);
     span_begin(&stats.ms_h2d);
-    CCS_CUDA(cudaMemcpyAsync(d_rowcode_.p, h_rowcode_.p, (size_t)code_total, cudaMemcpyHostToDevice, stream_));
+    const uint8_t* d_raw = in.d_codes;
+    if (!d_raw) {     // stand-alone Polish Stage: the engine uploads the read codes itself
+        const int64_t raw_total = nr ? in.read_off[nr] - raw_base : 0;
+        h_rawcodes_.ensure((size_t)raw_total + 64);
+        d_rawcodes_.ensure((size_t)raw_total + 64);
+        const int64_t piece = 1 << 20;
+        parallel_for((int)((raw_total + piece - 1) / piece), host_threads, [&](int k) {
+            const int64_t b = k * piece, e = std::min<int64_t>(raw_total, b + piece);
+            std::memcpy(h_rawcodes_.p + b, in.codes + raw_base + b, (size_t)(e - b));
+        });
+        if (raw_total) CCS_CUDA(cudaMemcpyAsync(d_rawcodes_.p, h_rawcodes_.p, (size_t)raw_total, cudaMemcpyHostToDevice, stream_));
+        stats.h2d_bytes += raw_total;
+        d_raw = d_rawcodes_.p;
+    }
+    CCS_CUDA(cudaMemcpyAsync(d_pack_.p, h_pack_.p, sizeof(PackJob) * nr, cudaMemcpyHostToDevice, stream_));
     CCS_CUDA(cudaMemcpyAsync(d_trans_.p, h_trans_.p, (size_t)nz * 36 * 4 * sizeof(float), cudaMemcpyHostToDevice, stream_));
-    stats.h2d_bytes += code_total + (int64_t)nz * 36 * 4 * 4;
+    launch_pack_rowcodes(d_pack_.p, nr, d_raw, d_rowcode_.p, stream_);
+    stats.h2d_bytes += (int64_t)sizeof(PackJob) * nr + (int64_t)nz * 36 * 4 * 4;
     // template capacities: room for the template to grow during polishing
     for (int z = 0; z < nz; ++z) {
         const int J = (int)zstate_[z].tpl.size();

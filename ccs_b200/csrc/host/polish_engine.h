@@ -27,6 +27,9 @@ struct PolishInput {
     const int32_t* tend = nullptr;
     const int32_t* rstart = nullptr;         // optional clip of each read [rstart,rend), native orientation
     const int32_t* rend = nullptr;
+    // optional: the same codes already resident on this device (the lane's Draft Stage uploaded them);
+    // d_codes[k] is codes[read_off[0] + k].  NULL: the engine uploads them itself.
+    const uint8_t* d_codes = nullptr;
 };
 
 struct PolishParams {
@@ -150,7 +153,10 @@ private:
     int64_t n_range_items_ = 0;
 
     // device buffers
-    DevBuf<uint8_t> d_rowcode_, d_tpl_;
+    DevBuf<uint8_t> d_rowcode_, d_tpl_, d_rawcodes_;
+    DevBuf<PackJob> d_pack_;
+    PinBuf<PackJob> h_pack_;
+    PinBuf<uint8_t> h_rawcodes_;
     DevBuf<float> d_emm_, d_emi_, d_trans_, d_alpha_, d_beta_;
     DevBuf<DevRead> d_reads_;
     DevBuf<DevZmw> d_zmws_;
@@ -163,7 +169,7 @@ private:
     DevBuf<Candidate> d_cand_;
     DevBuf<uint8_t> d_qv_;
     // pinned staging
-    PinBuf<uint8_t> h_rowcode_, h_tpl_, h_qv_;
+    PinBuf<uint8_t> h_tpl_, h_qv_;
     PinBuf<float> h_trans_;
     PinBuf<DevRead> h_reads_;
     PinBuf<DevZmw> h_zmws_;

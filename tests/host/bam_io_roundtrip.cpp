@@ -74,8 +74,10 @@ int main(int argc, char** argv) {
             }
         }
         if (rd.next_zmw(got)) { std::fprintf(stderr, "MISMATCH: records after the last ZMW\n"); return 1; }
+        if (!rd.error().empty()) { std::fprintf(stderr, "MISMATCH: sound file reported '%s'\n", rd.error().c_str()); return 1; }
     }
-    // truncated copy: every ZMW delivered before the cut is intact, then the stream ends
+    // truncated copy: every ZMW delivered before the cut is COMPLETE, then the stream ends with an error (a cut file is
+    // not a short file: the BGZF EOF marker is missing and the last block is damaged)
     {
         const std::string pt = dir + "/rt_trunc.subreads.bam";
         std::ofstream f(pt, std::ios::binary);
@@ -88,11 +90,69 @@ int main(int argc, char** argv) {
         size_t k = 0;
         while (rd.next_zmw(got)) {
             if (k >= zs.size() || got.hole != zs[k].hole) { std::fprintf(stderr, "MISMATCH: truncated stream out of order\n"); return 1; }
-            // the last delivered ZMW may be cut short; all earlier ones must be complete
-            if (k > 0 && false) {}
+            if (got.reads.size() != zs[k].reads.size()) { std::fprintf(stderr, "MISMATCH: truncated stream delivered an incomplete ZMW\n"); return 1; }
             ++k;
         }
         if (k == 0 || k >= zs.size()) { std::fprintf(stderr, "MISMATCH: truncated stream delivered %zu of %zu ZMWs\n", k, zs.size()); return 1; }
+        if (rd.error().empty()) { std::fprintf(stderr, "MISMATCH: truncated file read without an error\n"); return 1; }
+    }
+    // cut exactly at a block boundary (complete blocks, no EOF marker): still an error
+    {
+        size_t pos = 0, last = 0;
+        while (pos + 18 <= b8.size()) { const size_t bs = (size_t)(b8[pos + 16] | (b8[pos + 17] << 8)) + 1; last = pos; pos += bs; }
+        const std::string pt = dir + "/rt_noeof.subreads.bam";
+        std::ofstream f(pt, std::ios::binary);
+        f.write((const char*)b8.data(), (std::streamsize)last);     // drops the final (EOF marker) block
+        f.close();
+        SubreadBamReader rd;
+        std::string err;
+        if (!rd.open(pt, err, 2)) return 1;
+        ZmwSubreads got;
+        while (rd.next_zmw(got)) {}
+        if (rd.error().find("EOF marker") == std::string::npos) { std::fprintf(stderr, "MISMATCH: missing EOF marker not reported ('%s')\n", rd.error().c_str()); return 1; }
+    }
+    // a corrupted payload byte fails the block's CRC32
+    {
+        std::vector<uint8_t> c = b8;
+        c[c.size() / 2] ^= 0x5a;
+        const std::string pt = dir + "/rt_crc.subreads.bam";
+        std::ofstream f(pt, std::ios::binary);
+        f.write((const char*)c.data(), (std::streamsize)c.size());
+        f.close();
+        SubreadBamReader rd;
+        std::string err;
+        if (rd.open(pt, err, 2)) {
+            ZmwSubreads got;
+            while (rd.next_zmw(got)) {}
+            if (rd.error().empty()) { std::fprintf(stderr, "MISMATCH: corrupted block read without an error\n"); return 1; }
+        }
+    }
+    // a record whose length fields lie (l_seq = 50 M in a 40-byte record) is rejected, not decoded
+    {
+        const std::string pt = dir + "/rt_badrec.subreads.bam";
+        {
+            BgzfWriter w;
+            if (!w.open(pt, 1, 1)) return 1;
+            const std::string text = "@HD\tVN:1.5\n@RG\tID:x\tPL:PACBIO\tDS:READTYPE=SUBREAD;BINDINGKIT=1;SEQUENCINGKIT=2;BASECALLERVERSION=3\tPU:m\n";
+            std::vector<uint8_t> h = {'B', 'A', 'M', 1};
+            auto w32 = [&](uint32_t x) { for (int b = 0; b < 4; ++b) h.push_back((x >> (8 * b)) & 255); };
+            w32((uint32_t)text.size()); h.insert(h.end(), text.begin(), text.end()); w32(0);
+            w32(40);                                   // block_size
+            w32(0xffffffffu); w32(0xffffffffu);        // refID, pos
+            h.push_back(2); h.push_back(255); h.push_back(0x48); h.push_back(0x12);   // l_read_name, mapq, bin
+            h.push_back(0); h.push_back(0); h.push_back(4); h.push_back(0);           // n_cigar, flag
+            w32(50000000u);                            // l_seq
+            w32(0xffffffffu); w32(0xffffffffu); w32(0);
+            h.push_back('a'); h.push_back(0);
+            for (int k = 0; k < 6; ++k) h.push_back(0);
+            w.write(h.data(), h.size());
+            if (!w.close()) return 1;
+        }
+        SubreadBamReader rd;
+        std::string err;
+        if (!rd.open(pt, err, 1)) { std::fprintf(stderr, "open badrec: %s\n", err.c_str()); return 1; }
+        ZmwSubreads got;
+        if (rd.next_zmw(got) || rd.error().find("malformed BAM record") == std::string::npos) { std::fprintf(stderr, "MISMATCH: lying record accepted ('%s')\n", rd.error().c_str()); return 1; }
     }
     // .pbi: one entry per record, ZMW runs, and seeking to the first record of any ZMW continues the stream there
     {
