@@ -80,4 +80,40 @@ inline void build_zmw_transitions(const ArrowModelParams& m, const float snr[4],
     for (int r = kCtxStart; r < kNumMatchRows; ++r) z.tr[r][0] = 1.0f;
 }
 
+// Expected log-likelihood moments of one template position under the generative HMM, for the POOR_ZSCORE read filter
+// (Integrator::AddRead; DESIGN.md "z-score filter"): at a position with context ctx the read emits a
+// geometric number N of insertions (probability q = branch + stick each) and then a match or a deletion, so
+//   E[L] = E[N] E[X] + E[Y],  Var[L] = E[N] Var[X] + Var[N] E[X]^2 + Var[Y],
+// X = log-probability of one insertion event, Y = log-probability of the closing match / deletion event.
+struct ZscoreMoments { double mean[kNumCtx], var[kNumCtx], first_mean[4], first_var[4]; };
+
+inline void zscore_moments(const ArrowModelParams& m, const float snr[4], ZscoreMoments& z) {
+    TransProb tp[kNumCtx];
+    transition_probs(m, snr, tp);
+    for (int ctx = 0; ctx < kNumCtx; ++ctx) {
+        const double q = tp[ctx].branch + tp[ctx].stick;
+        double sx = 0, sxx = 0, sy = 0, syy = 0;
+        auto acc = [](double p, double& s1, double& s2) { if (p > 0) { const double l = std::log(p); s1 += p * l; s2 += p * l * l; } };
+        for (int code = 0; code < kNumCodes; ++code) {
+            acc(tp[ctx].branch * m.emission[MOVE_BRANCH][ctx][code], sx, sxx);
+            acc(tp[ctx].stick * m.emission[MOVE_STICK][ctx][code], sx, sxx);
+            acc(tp[ctx].match * m.emission[MOVE_MATCH][ctx][code], sy, syy);
+        }
+        acc(tp[ctx].deletion, sy, syy);
+        const double ex = sx / q, ex2 = sxx / q, ey = sy / (1.0 - q), ey2 = syy / (1.0 - q);
+        const double en = q / (1.0 - q), vn = q / ((1.0 - q) * (1.0 - q));
+        z.mean[ctx] = en * ex + ey;
+        z.var[ctx] = en * (ex2 - ex * ex) + vn * ex * ex + (ey2 - ey * ey);
+    }
+    for (int b = 0; b < 4; ++b) {
+        double s1 = 0, s2 = 0;
+        for (int code = 0; code < kNumCodes; ++code) {
+            const double p = m.emission[MOVE_MATCH][5 * b][code];
+            if (p > 0) { const double l = std::log(p); s1 += p * l; s2 += p * l * l; }
+        }
+        z.first_mean[b] = s1;
+        z.first_var[b] = s2 - s1 * s1;
+    }
+}
+
 }  // namespace ccs

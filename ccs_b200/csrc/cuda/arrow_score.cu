@@ -662,8 +662,10 @@ __global__ void __launch_bounds__(128, 4) arrow_score_kernel(const ArrowBatchVie
             if (g == tbase) { out[4] = v; out[g] = 0.0; } else out[g] = v;
         } else {
             out[5 + (g - 4)] = prod_dll(prA, pxA, bs_ia);
-            // reverse-strand insertions before the local position are forward INS(p+1)
-            out[kDeltaStride + 9 + (g - 4)] = prod_dll(prB, pxB, bs_ib);
+            // reverse-strand insertions before the local position are forward INS(p+1); the last position of a range
+            // keeps them to itself (row p_end belongs to nobody here, or to an earlier launch whose row must stay
+            // self-consistent when stored delta-LLs are reused)
+            if (p + 1 < rg.p_end) out[kDeltaStride + 9 + (g - 4)] = prod_dll(prB, pxB, bs_ib);
             if (p == p_begin) out[9 + (g - 4)] = 0.0;
         }
     }

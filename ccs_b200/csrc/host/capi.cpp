@@ -35,6 +35,7 @@ struct ccsgpu_ctx {
     size_t lane_budget() const { return n_lanes > 0 ? budget / (size_t)n_lanes : budget; }
     bool generic_score = false;
     bool reuse_scores = false;
+    int qv_halo = 48;
     double ms_e2e = 0;
     int64_t n_zmws = 0;
     int device = 0;
@@ -93,6 +94,8 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
         ctx->engine->generic_score = ctx->generic_score;
         if (const char* e = std::getenv("CCS_B200_REUSE_SCORES")) ctx->reuse_scores = (e[0] != '0');
         ctx->engine->reuse_scores = ctx->reuse_scores;
+        if (const char* e = std::getenv("CCS_B200_QV_HALO")) ctx->qv_halo = std::max(0, std::atoi(e));
+        ctx->engine->qv_halo = ctx->qv_halo;
         ctx->budget = device_bytes_budget;
         if (ctx->budget == 0) {
             size_t fr = 0, tot = 0;
@@ -121,6 +124,7 @@ int ccsgpu_set_lanes(ccsgpu_ctx* ctx, int n_lanes) {
             l.draft.reset(new DraftEngine(ctx->device, 0));
             l.engine->generic_score = ctx->generic_score;
             l.engine->reuse_scores = ctx->reuse_scores;
+            l.engine->qv_halo = ctx->qv_halo;
             ctx->extra.push_back(std::move(l));
         }
     } catch (const std::exception& e) {
@@ -140,7 +144,7 @@ void ccs_polish_cfg_default(ccs_polish_cfg* c) {
     PolishParams p;
     c->max_iterations = p.max_iterations; c->separation = p.separation; c->neighborhood = p.neighborhood;
     c->min_length = p.min_length; c->max_length = p.max_length; c->min_rq = p.min_rq;
-    c->ab_mismatch_tol = p.ab_mismatch_tol; c->min_active_fraction = p.min_active_fraction;
+    c->ab_mismatch_tol = p.ab_mismatch_tol; c->min_active_fraction = p.min_active_fraction; c->min_zscore = p.min_zscore;
 }
 
 int ccsgpu_fill_alpha_beta(ccsgpu_ctx* ctx, int32_t n_pairs, const int64_t* tpl_off, const uint8_t* tpl,
@@ -182,7 +186,7 @@ static PolishParams to_params(const ccs_polish_cfg* cfg) {
     if (cfg) {
         pp.max_iterations = cfg->max_iterations; pp.separation = cfg->separation; pp.neighborhood = cfg->neighborhood;
         pp.min_length = cfg->min_length; pp.max_length = cfg->max_length; pp.min_rq = cfg->min_rq;
-        pp.ab_mismatch_tol = cfg->ab_mismatch_tol; pp.min_active_fraction = cfg->min_active_fraction;
+        pp.ab_mismatch_tol = cfg->ab_mismatch_tol; pp.min_active_fraction = cfg->min_active_fraction; pp.min_zscore = cfg->min_zscore;
     }
     return pp;
 }

@@ -164,6 +164,8 @@ void ArrowEngine::load(const PolishInput& in) {
         std::memcpy(h_trans_.p + (size_t)z * 36 * 4, zt.tr, sizeof(zt.tr));
     }
     d_trans_.ensure((size_t)nz * 36 * 4, budget_);
+    zs_mom_.resize((size_t)nz);
+    parallel_for(nz, host_threads, [&](int z) { zscore_moments(model_, in.snr + 4 * z, zs_mom_[z]); });
     span_begin(&stats.ms_h2d);
     const uint8_t* d_raw = in.d_codes;
     if (!d_raw) {     // stand-alone Polish Stage: the engine uploads the read codes itself
@@ -346,6 +348,54 @@ void ArrowEngine::sync_statuses() {
     }
 }
 
+// Integrator::AddRead: a read whose log-likelihood against the draft lies more than |min_zscore| standard deviations
+// below its expectation is dropped (CCS_READ_POOR_ZSCORE).  Checked once, after the first fill.  The expectation sums
+// per-position moments over the read's template slice: prefix sums over the ZMW's forward / reverse template.
+void ArrowEngine::zscore_filter(double min_zscore) {
+    if (!(min_zscore > -1e29)) return;
+    HostPhase hp("polish.zscore");
+    const int nr = (int)reads_.size(), nz = (int)zstate_.size();
+    h_ll_.ensure((size_t)2 * nr + 2);
+    CCS_CUDA(cudaMemcpyAsync(h_ll_.p, d_ll_alpha_.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream_));
+    CCS_CUDA(stream_sync_blocking(stream_));
+    stats.d2h_bytes += 8ll * nr;
+    std::atomic<int> dropped(0);
+    parallel_for(nz, host_threads, [&](int z) {
+        const ZmwState& zs = zstate_[z];
+        const ZscoreMoments& M = zs_mom_[z];
+        const int J = (int)zs.tpl.size();
+        bool any = false;
+        for (int r = zs.read_begin; r < zs.read_end; ++r) any |= reads_[r].active && status_[r] == 0;
+        if (!any || J < 2) return;
+        // pm[s][j] / pv[s][j] = sums over template positions 1..j of strand s (0 forward, 1 reverse complement)
+        std::vector<double> pm[2], pv[2];
+        for (int s = 0; s < 2; ++s) {
+            pm[s].assign((size_t)J, 0.0); pv[s].assign((size_t)J, 0.0);
+            for (int j = 1; j < J; ++j) {
+                const int a = s ? 3 - zs.tpl[J - j] : zs.tpl[j - 1], b = s ? 3 - zs.tpl[J - 1 - j] : zs.tpl[j];
+                pm[s][j] = pm[s][j - 1] + M.mean[4 * a + b];
+                pv[s][j] = pv[s][j - 1] + M.var[4 * a + b];
+            }
+        }
+        for (int r = zs.read_begin; r < zs.read_end; ++r) {
+            DevRead& rd = reads_[r];
+            if (!rd.active || status_[r] != 0) continue;
+            const int s = rd.strand ? 1 : 0;
+            const int b0 = s ? J - rd.te : rd.ts, b1 = s ? J - rd.ts : rd.te;      // slice [b0, b1) on strand s
+            const int t0 = s ? 3 - zs.tpl[J - 1 - b0] : zs.tpl[b0];
+            const double mean = M.first_mean[t0] + (pm[s][b1 - 1] - pm[s][b0]);
+            const double var = M.first_var[t0] + (pv[s][b1 - 1] - pv[s][b0]);
+            const double zsc = (h_ll_.p[r] - mean) / std::sqrt(var);
+            if (zsc < min_zscore) { rd.active = 0; status_[r] = 5; dropped.fetch_add(1, std::memory_order_relaxed); }
+        }
+    });
+    if (dropped.load() > 0) {      // the scoring kernel reads the statuses on the device
+        std::memcpy(h_status_.p, status_.data(), sizeof(int32_t) * nr);
+        CCS_CUDA(cudaMemcpyAsync(d_status_.p, h_status_.p, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, stream_));
+        stats.h2d_bytes += 4ll * nr;
+    }
+}
+
 void ArrowEngine::read_lls(double* ll_alpha, double* ll_beta, int32_t* status) {
     const int nr = (int)reads_.size();
     h_ll_.ensure((size_t)2 * nr + 2);
@@ -464,6 +514,7 @@ void ArrowEngine::polish(const PolishParams& pp) {
     score_mark_ = stats.n_score;
     CCS_CUDA(cudaEventRecord(evA_, stream_));   // inputs are resident: load() has been issued on this stream
     fill();
+    zscore_filter(pp.min_zscore);
     auto check_usable = [&](int z) {
         ZmwState& zs = zstate_[z];
         int act = 0;
@@ -512,6 +563,12 @@ void ArrowEngine::polish(const PolishParams& pp) {
         if (ranges.empty()) break;
         ++stats.rounds;
         score_ranges(ranges, first);
+        if (reuse_scores)      // these positions now carry delta-LLs of the current template
+            for (const ScoreRange& rg : ranges) {
+                std::vector<uint8_t>& st = zstate_[rg.zmw].stale;
+                if (st.size() != zstate_[rg.zmw].tpl.size()) st.assign(zstate_[rg.zmw].tpl.size(), 1);
+                std::fill(st.begin() + rg.p_begin, st.begin() + rg.p_end, (uint8_t)0);
+            }
         { HostPhase hp("polish.score+pick (wait)"); pick(cands); }
         HostPhase hp_round("polish.round select+apply");
         // group candidates per ZMW
@@ -560,6 +617,22 @@ void ArrowEngine::polish(const PolishParams& pp) {
                     else if (m.type == 2) { if (m.pos < rd.ts) --ds; if (m.pos < rd.te) --de; }
                 }
                 rd.ts += ds; rd.te += de;
+            }
+            if (reuse_scores) {
+                // carry the per-position "stale" marks over to the new coordinates (same shifts as remap_deltas) and
+                // mark everything within qv_halo of this round's edits
+                const int Jn = (int)next.size(), Jo = (int)zs.tpl.size();
+                std::vector<uint8_t> ns((size_t)Jn, 1);
+                size_t e = 0;
+                int shift = 0;
+                for (int q = 0; q < Jn; ++q) {
+                    while (e < zs.remap_sites.size() && zs.remap_sites[e] <= q) shift = zs.remap_shifts[e++];
+                    const int old = q - shift;
+                    if (old >= 0 && old < Jo && zs.stale.size() == (size_t)Jo) ns[q] = zs.stale[old];
+                }
+                for (int sx : zs.sites)
+                    std::fill(ns.begin() + std::max(0, sx - qv_halo), ns.begin() + std::min(Jn, sx + qv_halo + 1), (uint8_t)1);
+                zs.stale.swap(ns);
             }
             zs.tpl.swap(next);
             zs.dirty = true;
@@ -626,11 +699,22 @@ void ArrowEngine::consensus_qvs() {
         if (zs.failed || zs.tpl.empty()) continue;
         ranges.push_back(ScoreRange{z, 0, (int32_t)zs.tpl.size(), 0, first});
         first += pad16((int64_t)zs.tpl.size());
-        // every position was last scored after all edits within `neighborhood` of it had been applied, unless the
-        // ZMW stopped without converging or lost a read after scoring began: only those are scored again
-        if (!reuse_scores || !zs.converged || zs.stale_scores) {
-            rescoring.push_back(ScoreRange{z, 0, (int32_t)zs.tpl.size(), 0, first_rs});
-            first_rs += pad16((int64_t)zs.tpl.size());
+        // With reuse_scores only the positions whose stored delta-LLs predate an edit within qv_halo of them (or that
+        // were never scored) are scored again; a ZMW that lost a read after scoring began is scored again in full
+        const int J = (int)zs.tpl.size();
+        if (!reuse_scores || zs.stale_scores || zs.stale.size() != (size_t)J) {
+            rescoring.push_back(ScoreRange{z, 0, J, 0, first_rs});
+            first_rs += pad16((int64_t)J);
+        } else {
+            int p = 0;
+            while (p < J) {
+                if (!zs.stale[p]) { ++p; continue; }
+                int e = p + 1, last = p;                       // merge runs separated by short clean gaps
+                while (e < J && e - last <= 8) { if (zs.stale[e]) last = e; ++e; }
+                rescoring.push_back(ScoreRange{z, p, last + 1, 0, first_rs});
+                first_rs += pad16((int64_t)(last + 1 - p));
+                p = last + 2;                                  // ranges of one ZMW must not touch
+            }
         }
     }
     for (int z = 0; z < nz; ++z) qv_[z].clear();
@@ -638,9 +722,9 @@ void ArrowEngine::consensus_qvs() {
     if (!rescoring.empty()) score_ranges(rescoring, first_rs);
     // the QV kernel walks every position of every live ZMW
     d_ranges_.ensure(ranges.size());
-    h_ranges_.ensure(ranges.size());
-    std::memcpy(h_ranges_.p, ranges.data(), sizeof(ScoreRange) * ranges.size());
-    CCS_CUDA(cudaMemcpyAsync(d_ranges_.p, h_ranges_.p, sizeof(ScoreRange) * ranges.size(), cudaMemcpyHostToDevice, stream_));
+    h_ranges_qv_.ensure(ranges.size());
+    std::memcpy(h_ranges_qv_.p, ranges.data(), sizeof(ScoreRange) * ranges.size());
+    CCS_CUDA(cudaMemcpyAsync(d_ranges_.p, h_ranges_qv_.p, sizeof(ScoreRange) * ranges.size(), cudaMemcpyHostToDevice, stream_));
     d_delta_.ensure((size_t)(total_delta_rows_ + 2) * kDeltaStride, budget_);
     d_qv_.ensure((size_t)total_delta_rows_ + 16, budget_);
     h_qv_.ensure((size_t)total_delta_rows_ + 16);

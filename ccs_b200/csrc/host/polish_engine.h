@@ -41,6 +41,7 @@ struct PolishParams {
     int32_t min_length = 10;       // --min-length
     int32_t max_length = 50000;    // --max-length
     double min_active_fraction = 0.5;   // TOO_MANY_UNUSABLE below this share of mapped reads
+    double min_zscore = -3.4;           // POOR_ZSCORE: reads whose LL z-score against the draft is lower are dropped
 };
 
 struct HostMutation { int32_t type, pos, base; double score; };
@@ -50,6 +51,8 @@ struct ZmwState {
     int32_t read_begin = 0, read_end = 0;
     bool converged = false, failed = false, done = false;
     bool stale_scores = false;         // a read was dropped after scoring began: stored delta-LLs no longer add up
+    std::vector<uint8_t> stale;        // per template position: 1 = the stored delta-LLs predate an edit within qv_halo
+                                       // positions (or were never computed); only kept when reuse_scores is on
     std::vector<int32_t> remap_sites, remap_shifts;   // this round's edits (new coordinates, cumulative shift)
     int32_t J_before = 0;
     bool dirty = true;                 // template changed since the last alpha/beta fill of its reads
@@ -110,6 +113,7 @@ public:
     // re-scoring the whole template (-35 % scoring work).  NOT exact: in repeats an edit reaches further, measured
     // 28 of 1.66 M positions off by more than 1 QV, so it is off by default (CCS_B200_REUSE_SCORES=1 enables it).
     bool reuse_scores = false;
+    int qv_halo = 48;             // positions within this distance of an edit are re-scored before their QV is taken
     bool generic_score = false;   // use the unfactored reference scoring kernel (tests)
 
 private:
@@ -125,6 +129,7 @@ private:
     int64_t count_canonical(const std::vector<uint8_t>& t, int b, int e) const;
     void upload_templates_and_reads();       // (re)build DevRead/DevZmw/template buffer from host state
     void sync_statuses();
+    void zscore_filter(double min_zscore);   // Integrator::AddRead's POOR_ZSCORE check, after the first fill
     void remap_deltas();
     ArrowBatchView view() const;
 
@@ -146,6 +151,7 @@ private:
     std::vector<int64_t> col_base_;          // fixed first column of each read's band slot
     std::vector<int32_t> col_cap_;           // columns reserved for it
     std::vector<int32_t> tpl_cap_;           // per-ZMW template capacity in the device buffer
+    std::vector<ZscoreMoments> zs_mom_;      // per ZMW: expected-LL moments per context (POOR_ZSCORE filter)
     int64_t total_cols_ = 0, total_delta_rows_ = 0;
     double ab_tol_ = 1e-3;
     int64_t score_mark_ = 0;                 // stats.n_score when the current polish() began
@@ -175,7 +181,7 @@ private:
     PinBuf<DevZmw> h_zmws_;
     PinBuf<int32_t> h_order_, h_status_, h_counter_;
     PinBuf<double> h_ll_;
-    PinBuf<ScoreRange> h_ranges_;
+    PinBuf<ScoreRange> h_ranges_, h_ranges_qv_;   // two host lists: the QV list is staged while the scoring list's copy may still be in flight
     PinBuf<Candidate> h_cand_;
 };
 

@@ -64,7 +64,8 @@ typedef enum ccs_read_status {
     CCS_READ_ALPHA_BETA_MISMATCH = 1,
     CCS_READ_TEMPLATE_TOO_SMALL = 2,
     CCS_READ_DEAD = 3,          /* band lost the probability mass (LL = -inf) */
-    CCS_READ_UNMAPPED = 4       /* not placed on the draft / filtered before polishing */
+    CCS_READ_UNMAPPED = 4,      /* not placed on the draft / filtered before polishing */
+    CCS_READ_POOR_ZSCORE = 5    /* log-likelihood against the draft too far below its expectation (Integrator::AddRead) */
 } ccs_read_status;
 
 /* ------------------------------------------------------------------------------------
@@ -168,6 +169,7 @@ typedef struct ccs_polish_cfg {
     double  min_rq;               /* --min-rq (docs/how-does-ccs-work.md:111-112) */
     double  ab_mismatch_tol;      /* 1e-3: |1 - LL_alpha/LL_beta| above this drops the read */
     double  min_active_fraction;  /* 0.5: fewer usable reads -> TOO_MANY_UNUSABLE */
+    double  min_zscore;           /* -3.4: a read whose LL z-score against the draft is lower is dropped (POOR_ZSCORE) */
 } ccs_polish_cfg;
 void ccs_polish_cfg_default(ccs_polish_cfg* cfg);
 

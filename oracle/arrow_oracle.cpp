@@ -57,6 +57,43 @@ void Tables::build(const ccs::ArrowModelParams& m, const float snr[4]) {
             const float p = (float)em_ins[ctx][code] * (float)(cognate ? tr[ctx][2] : tr[ctx][3]);
             gg[ctx][code] = (double)p;
         }
+    // z-score moments from the model's own probabilities in double (no fp32 rounding, no counter weight)
+    for (int ctx = 0; ctx < 16; ++ctx) {
+        const int ch = ctx & 3;
+        double s = (double)snr[ch];
+        if (s < m.snr_lo[ch]) s = m.snr_lo[ch];
+        if (s > m.snr_hi[ch]) s = m.snr_hi[ch];
+        double x[3], denom = 1.0;
+        for (int t = 0; t < 3; ++t) {
+            const double* c = m.trans[ctx][t];
+            x[t] = std::exp(c[0] + s * (c[1] + s * (c[2] + s * c[3])));
+            denom += x[t];
+        }
+        const double pM = 1.0 / denom, pD = x[ccs::TR_DELETION] / denom, pB = x[ccs::TR_BRANCH] / denom, pS = x[ccs::TR_STICK] / denom;
+        const double q = pB + pS;                      // another insertion
+        double ex = 0, ex2 = 0, ey = 0, ey2 = 0;
+        for (int code = 0; code < 12; ++code) {
+            const double pb = pB * m.emission[ccs::MOVE_BRANCH][ctx][code], ps = pS * m.emission[ccs::MOVE_STICK][ctx][code];
+            const double pm = pM * m.emission[ccs::MOVE_MATCH][ctx][code];
+            if (pb > 0) { const double l = std::log(pb); ex += pb * l; ex2 += pb * l * l; }
+            if (ps > 0) { const double l = std::log(ps); ex += ps * l; ex2 += ps * l * l; }
+            if (pm > 0) { const double l = std::log(pm); ey += pm * l; ey2 += pm * l * l; }
+        }
+        { const double l = std::log(pD); ey += pD * l; ey2 += pD * l * l; }
+        ex /= q; ex2 /= q; ey /= (1.0 - q); ey2 /= (1.0 - q);
+        const double en = q / (1.0 - q), vn = q / ((1.0 - q) * (1.0 - q));
+        zs_mean[ctx] = en * ex + ey;
+        zs_var[ctx] = en * (ex2 - ex * ex) + vn * ex * ex + (ey2 - ey * ey);
+    }
+    for (int b = 0; b < 4; ++b) {
+        double e1 = 0, e2 = 0;
+        for (int code = 0; code < 12; ++code) {
+            const double p = m.emission[ccs::MOVE_MATCH][5 * b][code];
+            if (p > 0) { const double l = std::log(p); e1 += p * l; e2 += p * l * l; }
+        }
+        zs_first_mean[b] = e1;
+        zs_first_var[b] = e2 - e1 * e1;
+    }
 }
 
 // Column normalisation + band tracking (DESIGN.md "Band rule").
@@ -262,7 +299,21 @@ void Integrator<Real>::add_read(const MappedRead& r) {
     reads.push_back(r);
     recs.emplace_back();
     active.push_back(1);
-    refill(reads.size() - 1);
+    const size_t k = reads.size() - 1;
+    refill(k);
+    // POOR_ZSCORE: only when the read is added (its LL against the draft), never after later refills
+    if (active[k] && zscore(k) < cfg.min_zscore) { active[k] = 0; recs[k].status = READ_POOR_ZSCORE; }
+}
+
+template <class Real>
+double Integrator<Real>::zscore(size_t r) const {
+    const MappedRead& rd = reads[r];
+    const int J = (int)fwd.size();
+    const int len = rd.tend - rd.tstart;
+    const uint8_t* t = rd.strand ? rev.data() + (J - rd.tend) : fwd.data() + rd.tstart;
+    double mean = tab.zs_first_mean[t[0]], var = tab.zs_first_var[t[0]];
+    for (int j = 1; j < len; ++j) { const int ctx = 4 * t[j - 1] + t[j]; mean += tab.zs_mean[ctx]; var += tab.zs_var[ctx]; }
+    return (recs[r].ll() - mean) / std::sqrt(var);
 }
 
 template <class Real>

@@ -33,7 +33,8 @@ constexpr int CTX_START = 16, CTX_END = 20, N_MROWS = 36, N_IROWS = 17, CODE_STR
 enum MutType : int { MUT_SUB = 0, MUT_INS = 1, MUT_DEL = 2 };
 struct Mutation { int type; int pos; int base; };   // INS: inserted before pos
 
-enum ReadStatus : int { READ_VALID = 0, READ_ALPHA_BETA_MISMATCH = 1, READ_TEMPLATE_TOO_SMALL = 2, READ_DEAD = 3 };
+enum ReadStatus : int { READ_VALID = 0, READ_ALPHA_BETA_MISMATCH = 1, READ_TEMPLATE_TOO_SMALL = 2, READ_DEAD = 3,
+                        READ_POOR_ZSCORE = 5 };
 
 // per-ZMW tables; values are fp32-rounded (the spec says the tables are fp32) held in double
 struct Tables {
@@ -47,6 +48,10 @@ struct Tables {
     //   gg[ctx][code] = fl32(em_ins[ctx][code] * (cognate ? branch[ctx] : stick[ctx]))
     double mm[N_MROWS][CODE_STRIDE];
     double gg[N_IROWS][CODE_STRIDE];
+    // Expected log-likelihood moments of one template position under the generative HMM (DESIGN.md "z-score filter";
+    // Integrator's POOR_ZSCORE read filter): a geometric number of insertions, then a match or a
+    // deletion.  zs_*[ctx] for the positions 1..J-1, zs_first_*[base] for the pinned first match.
+    double zs_mean[16], zs_var[16], zs_first_mean[4], zs_first_var[4];
     void build(const ccs::ArrowModelParams& m, const float snr[4]);
 };
 
@@ -105,6 +110,7 @@ struct PolishConfig {
     int neighborhood = 20;
     int band_width = 32;
     double ab_mismatch_tol = 1e-3;
+    double min_zscore = -3.4;     // AddRead drops a read whose LL lies further below its expectation (POOR_ZSCORE)
 };
 
 struct PolishResult {
@@ -125,6 +131,7 @@ struct Integrator {
 
     void init(const ccs::ArrowModelParams& m, const float snr[4], const uint8_t* tpl, int J, const PolishConfig& c);
     void add_read(const MappedRead& r);
+    double zscore(size_t r) const;           // (LL - E[LL]) / sd[LL] of read r on its template slice
     void refill_all();
     void refill(size_t r);
     double ll() const;                       // sum over active reads

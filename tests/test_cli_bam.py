@@ -124,3 +124,64 @@ def test_cli_end_to_end_matches_api(tmp_path):
         assert rr.returncode == 0, rr.stderr
         parts += [(x["name"], x["seq"], x["qual"]) for x in read_bam(o)[1]]
     assert parts == [(x["name"], x["seq"], x["qual"]) for x in recs]
+
+
+@pytest.mark.gpu
+def test_cli_pipeline_by_strand_reports_and_damaged_input(tmp_path):
+    """The pipeline (reader -> queue -> stage workers -> ordered writer) gives the same bytes whatever the batch size,
+    the number of stage instances and -j; --by-strand emits one read per strand named .../ccs/fwd|rev
+    (docs/faq/mode-by-strand.md:10-24); --report-json / --hifi-summary-json are written; a cut input file or an
+    unwritable output is an error exit, not a short run."""
+    import json
+    cfg = sim.get_config(2, insert_mean=800, insert_sd=40, frac_low_snr=0.1, frac_few_passes=0.1)
+    n = 30
+    p = str(tmp_path / "m.subreads.bam")
+    write_subreads(p, cfg, 100, n)
+    outs = []
+    for k, extra in enumerate((["--batch-size", "7", "--pipeline", "1", "-j", "2"],
+                               ["--batch-size", "16", "--pipeline", "3", "--gpus", "1"],
+                               ["--batch-size", "256"])):
+        o = str(tmp_path / ("p%d.bam" % k))
+        r = subprocess.run([CCS, p, o, "--report-json", str(tmp_path / ("p%d.json" % k)),
+                            "--hifi-summary-json", str(tmp_path / ("h%d.json" % k))] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append([(x["name"], x["seq"], x["qual"], x["tags"]["np"]) for x in read_bam(o)[1]])
+    assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 0
+    rj = json.load(open(str(tmp_path / "p0.json")))
+    assert rj["input"] == n and rj["pass_filters"] == len(outs[0]) and rj["hifi"]["reads"] == len(outs[0])
+    assert sum(rj["exclusive_failed_counts"].values()) == rj["fail_filters"] == n - len(outs[0])
+    hs = json.load(open(str(tmp_path / "h0.json")))
+    assert hs["hifi_reads"] == len(outs[0]) and hs["hifi_yield_bp"] == sum(len(x[1]) for x in outs[0])
+    rep = open(str(tmp_path / "p0.ccs_report.txt")).read()
+    for label in ("<Q20 Reads", ">=Q30 Reads", "Base quality >=Q30 (bp)", "ZMWs with tandem repeats", "ZMWs missing adapters"):
+        assert label in rep                       # docs/faq/reports-aux-files.md:16-72
+    # --by-strand
+    ob = str(tmp_path / "bs.bam")
+    r = subprocess.run([CCS, p, ob, "--by-strand"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    recs = read_bam(ob)[1]
+    names = [x["name"] for x in recs]
+    assert names and all(nm.endswith("/ccs/fwd") or nm.endswith("/ccs/rev") for nm in names)
+    by_zmw = {}
+    for x in recs:
+        by_zmw.setdefault(x["tags"]["zm"], {})[x["name"].rsplit("/", 1)[1]] = x
+    both = [z for z, d in by_zmw.items() if len(d) == 2]
+    assert both                                    # 10 passes = 5 per strand >= --min-passes 3
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    for z in both:
+        f, rv = by_zmw[z]["fwd"]["seq"], by_zmw[z]["rev"]["seq"]
+        assert abs(len(f) - len(rv)) <= 0.02 * len(f)
+        rc = "".join(comp[c] for c in reversed(rv))
+        k = 12                                     # the two strands describe the same molecule
+        kf = {f[i:i + k] for i in range(len(f) - k)}
+        assert sum(rc[i:i + k] in kf for i in range(len(rc) - k)) > 0.8 * (len(rc) - k)
+        assert by_zmw[z]["fwd"]["tags"]["np"] <= 5 and by_zmw[z]["rev"]["tags"]["np"] <= 5
+    assert "Single-Strand Reads input" in open(str(tmp_path / "bs.ccs_report.txt")).read()
+    # damaged input: exit code 1 and a message, the ZMWs in front of the damage are still written
+    data = open(p, "rb").read()
+    cut = str(tmp_path / "cut.subreads.bam")
+    open(cut, "wb").write(data[:len(data) * 3 // 5])
+    r = subprocess.run([CCS, cut, str(tmp_path / "cut.bam")], capture_output=True, text=True)
+    assert r.returncode == 1 and ("BGZF" in r.stderr or "truncated" in r.stderr), r.stderr
+    r = subprocess.run([CCS, p, "/nonexistent-dir/out.bam"], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot write" in r.stderr

@@ -246,3 +246,50 @@ def test_polish_never_worse_than_truth_at_10_passes(index):
     # wherever the consensus departs from the truth the QV says so
     if not np.array_equal(res["consensus"], z.tpl):
         assert res["qv"].min() <= 10
+
+
+def logspace_forward_ll(snr, tpl, codes):
+    """Second, independent pin of the oracle's recursion: the UNBANDED forward algorithm in LOG space (numpy
+    logaddexp, no scaling, no band, no folded-table indexing tricks), written from the move semantics of the
+    brute-force enumeration above: state (i, j) = i read bases emitted, j template bases consumed."""
+    em_match, em_ins, tr, lcw = O.tables(MODEL, snr)
+    mm, gg = O.folded(MODEL, snr)
+    J, I = len(tpl), len(codes)
+    with np.errstate(divide="ignore"):
+        lmm, lgg, ldel, lem = np.log(mm), np.log(gg), np.log(tr[:, 1]), np.log(em_match)
+    ctx = lambda j: 4 * int(tpl[j - 1]) + int(tpl[j])
+    NEG = -np.inf
+    prev = np.full(I, NEG)                       # f(., j-1), rows 0..I-1 (row 0 unused)
+    cur = np.full(I, NEG)
+    cur[1] = lem[16 + int(tpl[0])][codes[0]]     # pinned first match: state (1, 1)
+    c1 = ctx(1)
+    for i in range(2, I):                        # insertions inside column 1
+        cur[i] = cur[i - 1] + lgg[c1][codes[i - 1]]
+    for j in range(2, J):
+        prev, cur = cur, np.full(I, NEG)
+        cp, cj = ctx(j - 1), ctx(j)
+        base = np.full(I, NEG)
+        base[1:] = prev[1:] + ldel[cp]                                                   # deletion of t_{j-1}
+        base[2:] = np.logaddexp(base[2:], prev[1:I - 1] + lmm[cp][codes[1:I - 1]])       # match emits codes[i-1]
+        gi = lgg[cj][codes[:I - 1]]                                                      # insertion emits codes[i-1]
+        cur[1] = base[1]
+        for i in range(2, I):
+            cur[i] = np.logaddexp(base[i], cur[i - 1] + gi[i - 1])
+    return cur[I - 1] + lem[20 + ctx(J - 1)][codes[I - 1]] - I * lcw
+
+
+def test_oracle_fill_equals_unbanded_logspace_numpy_forward():
+    """300-500 bp reads sampled from the HMM: the oracle's banded, scaled, probability-domain fill (the code the GPU
+    kernels are checked against) equals an unbanded log-space forward written independently in numpy."""
+    n = 0
+    for ins in (300, 420, 500):
+        for snr, t, r in _pairs(1, ins, insert_sd=0)[1:5]:
+            want = logspace_forward_ll(snr, t, r)
+            wide = O.fill(MODEL, snr, t, r, W=256)
+            band = O.fill(MODEL, snr, t, r, W=32)
+            assert wide["status"] == 0 and band["status"] == 0
+            assert wide["ll_alpha"] == pytest.approx(want, abs=1e-9)
+            assert wide["ll_beta"] == pytest.approx(want, abs=1e-9)
+            assert band["ll_alpha"] == pytest.approx(want, abs=1e-9)      # the 32-row leading-edge band loses nothing
+            n += 1
+    assert n == 12
