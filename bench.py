@@ -4,8 +4,10 @@
   python bench.py --gpus N --steps K --warmup W            product arm (CUDA, through the C ABI)
   python bench.py --impl reference --gpus N ...            reference arm (CPU oracle on host cores)
 
-A step = one pass of the hot path over one batch of synthetic ZMWs (config 2 of BASELINE.json:
-1 000 ZMWs, 10 kb insert x 10 passes, Sequel-II-shape reads sampled from the Arrow HMM).
+A step = one pass of the hot path (FilterReads -> SparsePoa draft -> mapping -> Arrow polish -> QVs) over one batch
+of synthetic ZMWs from HOST buffers.  The default workload is the largest single-GPU configuration of BASELINE.json,
+config 3 (15 kb insert, mixed 5-20 passes; one batch = 600 ZMWs ~ 1.3e8 read bases); configs 2 (1 000 ZMWs, 10 kb x 10
+passes) and 5 (25 kb x 4 passes) are measured in the same run with fewer steps and reported under "other_configs".
 N > 1 (torchrun): ZMW index ranges are sharded across ranks, no collective on the data path;
 value = all ranks' ZMWs / max-over-ranks time ("weak": per-GPU work fixed).
 """
@@ -23,6 +25,8 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+DEFAULT_ZMWS = {1: 1, 2: 1000, 3: 600, 4: 600, 5: 800}   # ZMWs per step per GPU: ~1.2e8 - 1.3e8 read bases each
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -30,19 +34,23 @@ def parse():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--zmws", type=int, default=1000, help="ZMWs per step per GPU")
-    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config id (2 = metric config)")
+    ap.add_argument("--zmws", type=int, default=0, help="ZMWs per step per GPU (0 = the config's default)")
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.json config id (3 = largest single-GPU config)")
+    ap.add_argument("--other-configs", default="2,5", help="configs also measured (fewer steps) at N=1; '' = none")
     ap.add_argument("--draft-error", type=float, default=0.02)
     ap.add_argument("--cpu-sample", type=int, default=0, help="ZMWs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=4, help="concurrent engine lanes per context (0 = library default)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per rank (0 = 2 x cpu count / world)")
     ap.add_argument("--contexts", type=int, default=2,
-                    help="GPU contexts per rank; steps are dealt round-robin to the contexts and run concurrently "
-                         "(pipelined batches, as a reader thread feeding two stage instances would)")
+                    help="GPU contexts per rank; steps are dealt to the contexts and run concurrently "
+                         "(pipelined batches, as the ccs reader feeds two stage instances per GPU)")
     ap.add_argument("--stage", default="ccs", choices=["ccs", "polish"],
                     help="ccs = whole per-ZMW hot path (filter + SparsePoa draft + Arrow polish + QVs); "
                          "polish = Polish Stage only on corrupted-truth drafts")
+    ap.add_argument("--minutes", type=float, default=0.0,
+                    help="time-boxed mode (config 4: the full-SMRT-Cell shape cannot be materialised): keep taking new "
+                         "batches of the ZMW range for this many minutes and report the steady-state rate")
     return ap.parse_args()
 
 
@@ -51,7 +59,18 @@ METRIC = {"ccs": "ZMWs/sec through the per-ZMW hot path (filter -> SparsePoa dra
 STAGE_DESC = {"ccs": "whole hot path from raw subreads: FilterReads + SparsePoa draft + mapping + Arrow polish + QVs",
               "polish": "Polish Stage only; drafts = truth corrupted at 2 % (Draft Stage not timed)"}
 WORKLOADS = {1: "config1: 1 ZMW 10kb x 10 passes", 2: "config2: 1000 ZMWs, 10 kb insert x 10 passes (+2 partial passes)",
-             3: "config3: 15 kb insert, 5-20 passes", 5: "config5: 25 kb insert x 4 passes"}
+             3: "config3: 15 kb insert, mixed 5-20 passes (+2 partial passes), batches of the 100 000-ZMW range",
+             4: "config4: full SMRT Cell shape (config-3 distribution), ZMW range sharded across the GPUs, time-boxed",
+             5: "config5: 25 kb insert x 4 passes (+2 partial passes)"}
+
+
+def config_dict(args, cfg_id, zmws, world, lanes, contexts):
+    """the `config` object -- identical for the product and the reference arm (the driver compares them)"""
+    return {"workload": WORKLOADS.get(cfg_id, str(cfg_id)), "zmws_per_step_per_gpu": zmws,
+            "stage": STAGE_DESC[args.stage],
+            "l2": "inputs larger than L2 (tens of GB of DP bands per step, new ZMWs every step)",
+            "parallelism": f"zmw-range-shard x{world}, no collective", "lanes_per_gpu": lanes, "contexts_per_gpu": contexts,
+            "value_def": "e2e wall time of the calls minus the batch-upload span (inputs resident)"}
 
 
 def make_batch(model, cfg, first, n, draft_error, threads):
@@ -161,14 +180,16 @@ def peaks():
 
 def run_reference(args, rank, world):
     """Reference arm: the reference's CPU implementation of the path.  /root/reference holds no source
-    (docs only), so this is the CPU oracle port on all host cores, bounded sample per step."""
+    (docs only), so this is the CPU oracle port on all host cores, a bounded sample of the workload per step.
+    Loads the simulator library and the oracle only -- never the product library."""
     if rank != 0:
         return
     from ccs_b200 import sim
     model = sim.synthetic_model()
     cfg = sim.get_config(args.config)
     cores = os.cpu_count() or 1
-    n = args.cpu_sample or max(cores, 4)
+    zmws = args.zmws or DEFAULT_ZMWS.get(args.config, 1000)
+    n = min(zmws, args.cpu_sample or max(cores, 4))
     times = []
     for step in range(args.warmup + args.steps):
         arrays = sim.simulate_batch(model, cfg, 1_000_000 + step * n, n, args.draft_error, cores)
@@ -177,14 +198,15 @@ def run_reference(args, rank, world):
             times.append(dt)
     T = sum(times)
     val = n * len(times) / T
+    lanes = args.lanes if args.lanes > 0 else 4
     line = {"impl": "reference", "metric": METRIC[args.stage],
             "value": val, "unit": "ZMW/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS.get(args.config, str(args.config)), "zmws_per_step": n,
-                       "stage": STAGE_DESC[args.stage]},
+            "config": config_dict(args, args.config, zmws, max(world, 1), lanes, max(1, args.contexts)),
             "cpu_baseline": {"value": val, "unit": "ZMW/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} ZMWs of the same workload per step, {cores} threads"},
+                             "sample": f"{n} ZMWs of the workload per step (bounded sample of the {zmws}-ZMW batch), "
+                                       f"{cores} threads; ms_per_step is the time of the sample"},
             "e2e": {"value": val, "unit": "ZMW/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -195,6 +217,144 @@ _REAL_STDOUT = None
 def emit(line):
     """the ONE JSON line of the contract, on the real stdout"""
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
+KERNELS = [  # (name, bytes key, ms key, top bytes key, top ms key)
+    ("arrow_fill_alpha_kernel", "bytes_fill_alpha", "ms_fill_alpha", "top_fill_alpha_bytes", "top_fill_alpha_ms"),
+    ("arrow_fill_beta_kernel", "bytes_fill_beta", "ms_fill_beta", "top_fill_beta_bytes", "top_fill_beta_ms"),
+    ("arrow_score_kernel", "bytes_score", "ms_score", "top_score_bytes", "top_score_ms"),
+    ("poa_align_kernel (SparsePoa rounds)", "bytes_poa_align", "ms_poa_align", "top_poa_align_bytes", "top_poa_align_ms"),
+    ("poa_align_kernel (subread -> draft mapping)", "bytes_poa_map", "ms_poa_map", "top_poa_map_bytes", "top_poa_map_ms"),
+]
+
+
+def rooflines(st, st1, peak, peak_src, traffic):
+    """One entry per heavy kernel: algorithmic bytes / CUDA-event time over (a) all launches of the timed region in the
+    timed lane/context configuration (concurrent lanes: spans include the other lanes' interference), (b) all launches
+    of one single-lane step (kernels strictly serial), (c) the largest single launch of that step."""
+    tot = sum(st[k[2]] for k in KERNELS) + st["ms_pick"] + st["ms_qv"] + st["ms_poa_graph"]
+    out = []
+    for name, bk, mk, tbk, tmk in KERNELS:
+        def gbps(b, ms):
+            return b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        e = {"kernel": name, "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+             "share_of_kernel_time": st[mk] / tot if tot > 0 else 0.0,
+             "timed_region": {"bytes": st[bk], "ms": st[mk], "achieved": gbps(st[bk], st[mk]),
+                              "frac": gbps(st[bk], st[mk]) / peak},
+             "single_lane_all_launches": {"bytes": st1[bk], "ms": st1[mk], "achieved": gbps(st1[bk], st1[mk]),
+                                          "frac": gbps(st1[bk], st1[mk]) / peak},
+             "largest_launch": {"bytes": st1[tbk], "ms": st1[tmk], "achieved": gbps(st1[tbk], st1[tmk]),
+                                "frac": gbps(st1[tbk], st1[tmk]) / peak},
+             "traffic": (traffic or {}).get(name.split(" ")[0])}
+        out.append(e)
+    return out
+
+
+def measure(args, cfg_id, zmws, steps, warmup, ctxs, model, rank, world, local, threads, lanes, minutes=0.0):
+    """W warm-up + K timed steps of one config through the stage contexts; returns raw timings and stats."""
+    import torch
+    import torch.distributed as dist
+    from ccs_b200 import sim
+    cfg = sim.get_config(cfg_id)
+    ctx = ctxs[0]
+    pcfg = ctx.default_polish_cfg()
+    dcfg = ctx.default_draft_cfg()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # distinct synthetic ZMW index range per rank and per step (working set >> L2: tens of GB of DP bands)
+    def step_batch(step):
+        first = (step * world + rank) * zmws
+        return make_batch(model, cfg, first, zmws, args.draft_error, threads)
+
+    def run_step(b, c=None):
+        c = c or ctx
+        return c.ccs(b, dcfg, pcfg) if args.stage == "ccs" else c.polish(b, pcfg)
+
+    for w in range(warmup):
+        b, _ = step_batch(w)
+        for c in ctxs:
+            run_step(b, c)
+    batches = [step_batch(warmup + k) for k in range(steps)]
+    for c in ctxs:
+        c.stats(reset=True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    results = [None] * len(batches)
+    step_s = [0.0] * len(batches)
+    next_step = [0]
+    qlock = threading.Lock()
+    deadline = t0 + 60.0 * minutes if minutes > 0 else None
+    extra_steps = [0]
+
+    def worker(ci):   # each context takes the next unprocessed step as soon as it is free
+        while True:
+            with qlock:
+                k = next_step[0]
+                next_step[0] += 1
+            if k >= len(batches):
+                if deadline is None or time.perf_counter() >= deadline:
+                    return
+                # time-boxed mode: keep cycling through the prepared batches (new ZMW ranges cannot be simulated as
+                # fast as the GPU consumes them; the hot path does not cache anything between calls)
+                run_step(batches[k % len(batches)][0], ctxs[ci])
+                with qlock:
+                    extra_steps[0] += 1
+                continue
+            ts = time.perf_counter()
+            results[k] = run_step(batches[k][0], ctxs[ci])
+            step_s[k] = time.perf_counter() - ts
+
+    if len(ctxs) == 1:
+        worker(0)
+    else:
+        ths = [threading.Thread(target=worker, args=(ci,)) for ci in range(len(ctxs))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    barrier()
+    sts = [c.stats() for c in ctxs]
+    st = {k: sum(x[k] for x in sts) for k in sts[0]}
+    for k in sts[0]:
+        if k.startswith("top_"):
+            st[k] = max(x[k] for x in sts)
+    n_steps = steps + extra_steps[0]
+    t_e2e = wall if len(ctxs) > 1 else st["ms_e2e"] / 1e3   # overlapping contexts: wall clock of the K steps
+    # `value`: same run with the batch upload taken out (inputs resident): the H2D of the read codes is the only
+    # input traffic; its CUDA-event span (per lane, lanes overlap) is subtracted from the wall time of the calls
+    t_res = t_e2e - st["ms_h2d"] / 1e3 / max(lanes * len(ctxs), 1)
+    # per-kernel timing pass: one more step on a single lane (kernels strictly serial, no overlap)
+    ctx.set_lanes(1)
+    ctx.stats(reset=True)
+    run_step(batches[0][0])
+    torch.cuda.synchronize()
+    st1 = ctx.stats()
+    ctx.set_lanes(lanes)
+    n_hifi = float(sum(int((r["status"] == 16).sum()) for r in results if r is not None)) * n_steps / max(steps, 1)
+    tt = torch.tensor([t_e2e, t_res, wall], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(zmws * n_steps), n_hifi], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    t_e2e, t_res, wall = [float(x) for x in tt.tolist()]
+    n_total, n_hifi = [float(x) for x in cnt.tolist()]
+    return dict(t_e2e=t_e2e, t_res=t_res, wall=wall, n_total=n_total, n_hifi=n_hifi, st=st, st1=st1, clocks=clocks,
+                step_s=step_s, results=results, batches=batches, n_steps=n_steps)
+
+
+def launches_of(st):
+    return int(st["launches_fill_alpha"] + st["launches_fill_beta"] + st["launches_score"] + st["launches_pick"] +
+               st["launches_qv"] + st["launches_draft"] + st["launches_pack"])
 
 
 def main():
@@ -221,158 +381,96 @@ def main():
 
     from ccs_b200 import sim, api
     model = sim.synthetic_model()
-    cfg = sim.get_config(args.config)
     # host threads of this rank: twice its share of the cores -- the stage threads spend much of their time blocked on
-    # stream synchronisation, and 2x measured +6 % e2e over 1x on a 16-core box (profiles/r1_lanes_matrix.txt)
+    # stream synchronisation
     threads = args.host_threads if args.host_threads > 0 else max(1, 2 * (os.cpu_count() or 8) // max(world, 1))
-    # host threads of each stage context of this rank
     os.environ["CCS_B200_THREADS"] = str(max(1, threads // max(1, args.contexts)))
     free_b, _tot = torch.cuda.mem_get_info()
     budget = int(free_b * 0.85 / max(1, args.contexts))          # device bytes each stage context may use
     ctxs = [api.Context(model, device=local, budget_bytes=budget) for _ in range(max(1, args.contexts))]
-    ctx = ctxs[0]
-    if args.lanes > 0:
-        for c in ctxs:
-            c.set_lanes(args.lanes)
-    pcfg = ctx.default_polish_cfg()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # distinct synthetic ZMW index range per rank and per step (working set >> L2: ~30 GB of DP bands)
-    def step_batch(step):
-        first = (step * world + rank) * args.zmws
-        return make_batch(model, cfg, first, args.zmws, args.draft_error, threads)
-
-    dcfg = ctx.default_draft_cfg()
-
-    def run_step(b, c=None):
-        c = c or ctx
-        return c.ccs(b, dcfg, pcfg) if args.stage == "ccs" else c.polish(b, pcfg)
-
-    for w in range(args.warmup):
-        b, _ = step_batch(w)
-        for c in ctxs:
-            run_step(b, c)
-    batches = [step_batch(args.warmup + k) for k in range(args.steps)]
-    for c in ctxs:
-        c.stats(reset=True)
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    t0 = time.perf_counter()
-    results = [None] * len(batches)
-    step_s = [0.0] * len(batches)
-
-    next_step = [0]
-    qlock = threading.Lock()
-
-    def worker(ci):   # each context takes the next unprocessed step as soon as it is free
-        while True:
-            with qlock:
-                k = next_step[0]
-                next_step[0] += 1
-            if k >= len(batches):
-                return
-            ts = time.perf_counter()
-            results[k] = run_step(batches[k][0], ctxs[ci])
-            step_s[k] = time.perf_counter() - ts
-
-    if len(ctxs) == 1:
-        worker(0)
-    else:
-        ths = [threading.Thread(target=worker, args=(ci,)) for ci in range(len(ctxs))]
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-    barrier()
-    sts = [c.stats() for c in ctxs]
-    st = {k: sum(x[k] for x in sts) for k in sts[0]}
     lanes = args.lanes if args.lanes > 0 else int(os.environ.get("CCS_B200_LANES", "4"))
-    t_e2e = wall if len(ctxs) > 1 else st["ms_e2e"] / 1e3   # overlapping contexts: wall clock of the K steps
-    # `value`: same run with the batch upload taken out (inputs resident): the initial H2D of the packed
-    # read codes / templates is the only input traffic; its CUDA-event span (per lane, lanes overlap) is
-    # subtracted from the wall time of the calls
-    t_res = t_e2e - st["ms_h2d"] / 1e3 / max(lanes * len(ctxs), 1)
-    # per-kernel timing pass: one more step on a single lane (kernels strictly serial, no overlap), used
-    # only for the roofline object and the kernel_ms breakdown
-    ctx.set_lanes(1)
-    ctx.stats(reset=True)
-    run_step(batches[0][0])
-    torch.cuda.synchronize()
-    st1 = ctx.stats()
-    ctx.set_lanes(lanes)
-    tt = torch.tensor([t_e2e, t_res, wall], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(args.zmws * args.steps), float(sum(int((r["status"] == 16).sum()) for r in results))],
-                       dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    t_e2e, t_res, wall = [float(x) for x in tt.tolist()]
-    n_total, n_hifi = [float(x) for x in cnt.tolist()]
+    for c in ctxs:
+        c.set_lanes(lanes)
+    zmws = args.zmws or DEFAULT_ZMWS.get(args.config, 1000)
+    M = measure(args, args.config, zmws, args.steps, args.warmup, ctxs, model, rank, world, local, threads, lanes,
+                minutes=args.minutes)
+    others = {}
+    if world == 1 and args.minutes <= 0:
+        for oc in [int(x) for x in args.other_configs.split(",") if x.strip()]:
+            if oc == args.config:
+                continue
+            oz = DEFAULT_ZMWS.get(oc, 1000)
+            R = measure(args, oc, oz, max(2, args.steps // 2), max(1, args.warmup // 2), ctxs, model, rank, world, local,
+                        threads, lanes)
+            others["config%d" % oc] = {
+                "workload": WORKLOADS.get(oc, str(oc)), "zmws_per_step": oz, "steps": R["n_steps"],
+                "value": R["n_total"] / R["t_res"], "e2e": R["n_total"] / R["t_e2e"], "unit": "ZMW/s",
+                "hifi_fraction": R["n_hifi"] / R["n_total"],
+                "fill_alpha_largest_launch_GBps": R["st1"]["top_fill_alpha_bytes"] / max(R["st1"]["top_fill_alpha_ms"], 1e-9) / 1e6,
+                "kernel_ms_single_lane": {k: R["st1"][k] for k in ("ms_fill_alpha", "ms_fill_beta", "ms_score", "ms_poa_align",
+                                                                  "ms_poa_map", "ms_poa_graph")}}
 
     if rank == 0:
+        st, st1 = M["st"], M["st1"]
         peak, peak_src = peaks()
-        # the step's full-population launch (every read of every ZMW): later launches of the same step only
-        # refill the few ZMWs still being refined and are latency-, not bandwidth-, limited
-        fa = st1["top_fill_alpha_bytes"]
-        fa_ms = st1["top_fill_alpha_ms"]
-        achieved = fa / (fa_ms * 1e-3) / 1e9 if fa_ms > 0 else 0.0
         traffic = None
-        try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same launch, `ncu --set full` (profiles/r1_summary.json)
-            if args.config == 2 and args.zmws == 1000:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_summary.json")))["arrow_fill_alpha"]["dram_bytes"]
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the full-population launches (`ncu --set full`)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_summary.json")))
+            if tj.get("config") == args.config:
+                traffic = {k: v.get("dram_bytes") for k, v in tj.get("kernels", {}).items()}
         except Exception:
             traffic = None
+        rl = rooflines(st, st1, peak, peak_src, traffic)
+        dom = max(rl, key=lambda e: e["timed_region"]["ms"])
+        n_l = {"arrow_fill_alpha_kernel": "launches_fill_alpha", "arrow_fill_beta_kernel": "launches_fill_beta",
+               "arrow_score_kernel": "launches_score"}.get(dom["kernel"])
         kern_ms = {k: st1[k] for k in ("ms_fill_alpha", "ms_fill_beta", "ms_score", "ms_pick", "ms_qv", "ms_h2d",
-                                       "ms_poa_align", "ms_draft", "ms_resident", "ms_e2e")}
-        kern_ms["note"] = "one step, single lane (serial kernels); the timed region runs %d overlapping lanes" % lanes
-        launches = sum(st[k] for k in st if k.startswith("launches"))
+                                       "ms_poa_align", "ms_poa_map", "ms_poa_graph", "ms_draft", "ms_resident", "ms_e2e")}
+        kern_ms["note"] = "one step, single lane (serial kernels); the timed region runs %d overlapping lanes x %d contexts" % (lanes, len(ctxs))
         line = {
             "metric": METRIC[args.stage],
-            "value": n_total / t_res, "unit": "ZMW/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "value": M["n_total"] / M["t_res"], "unit": "ZMW/s", "n_gpus": world, "steps": M["n_steps"], "warmup": args.warmup,
+            "ms_per_step": 1e3 * M["t_res"] / M["n_steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS.get(args.config, str(args.config)), "zmws_per_step_per_gpu": args.zmws,
-                       "stage": STAGE_DESC[args.stage],
-                       "l2": "inputs larger than L2 (tens of GB of DP bands per step, new ZMWs every step)",
-                       "parallelism": f"zmw-range-shard x{world}, no collective", "lanes_per_gpu": lanes, "contexts_per_gpu": len(ctxs),
-                       "value_def": "e2e wall time of the calls minus the batch-upload span (inputs resident)"},
-            "hifi_zmws_per_s": n_hifi / t_res, "hifi_fraction": n_hifi / n_total,
-            "e2e": {"value": n_total / t_e2e, "unit": "ZMW/s", "h2d_bytes_per_step": st["h2d_bytes"] / args.steps,
-                    "d2h_bytes_per_step": st["d2h_bytes"] / args.steps, "wall_s": wall,
-                    "step_s": [round(x, 4) for x in step_s]},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": "arrow_fill_alpha_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "bytes_per_launch": fa, "ms_per_launch": fa_ms,
-                         "launch": "largest arrow_fill_alpha launch of one step (all reads of the batch), single lane",
-                         "all_launches_GBps": st1["bytes_fill_alpha"] / max(st1["ms_fill_alpha"], 1e-9) / 1e6},
-            "kernel_ms": kern_ms, "rounds": st["rounds"] / args.steps, "score_items_per_step": st["score_items"] / args.steps,
-            "roofline_poa_align": {"kernel": "poa_align_kernel", "bound": "latency", "achieved":
-                                   st1["bytes_poa_align"] / max(st1["ms_poa_align"], 1e-9) / 1e6, "unit": "GB/s",
-                                   "ms_per_step": st1["ms_poa_align"], "tasks": st1["poa_tasks"]},
-            "clocks": clocks,
+            "config": config_dict(args, args.config, zmws, world, lanes, len(ctxs)),
+            "hifi_zmws_per_s": M["n_hifi"] / M["t_res"], "hifi_fraction": M["n_hifi"] / M["n_total"],
+            "e2e": {"value": M["n_total"] / M["t_e2e"], "unit": "ZMW/s", "h2d_bytes_per_step": st["h2d_bytes"] / M["n_steps"],
+                    "d2h_bytes_per_step": st["d2h_bytes"] / M["n_steps"], "wall_s": M["wall"],
+                    "step_s": [round(x, 4) for x in M["step_s"]]},
+            "gpu_launches": launches_of(st),
+            # the dominant kernel of the timed region: algorithmic bytes per launch / average launch duration, both over
+            # ALL its launches inside the timed region (CUDA events on the launching streams)
+            "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["timed_region"]["achieved"], "peak": peak,
+                         "unit": "GB/s", "frac": dom["timed_region"]["frac"], "traffic": dom["traffic"],
+                         "peak_source": peak_src, "launches": int(st[n_l]) if n_l else None,
+                         "bytes_all_launches": dom["timed_region"]["bytes"], "ms_all_launches": dom["timed_region"]["ms"],
+                         "largest_launch_frac_single_lane": dom["largest_launch"]["frac"],
+                         "note": "timed lane/context configuration: spans of concurrent lanes overlap, so each launch is "
+                                 "slowed by the others; see roofline_kernels for the serial figures"},
+            "roofline_kernels": rl,
+            "kernel_ms": kern_ms, "rounds": st["rounds"] / M["n_steps"], "score_items_per_step": st["score_items"] / M["n_steps"],
+            "other_configs": others,
+            "clocks": M["clocks"],
         }
+        if args.minutes > 0:
+            line["time_boxed"] = {"minutes": args.minutes, "steps_run": M["n_steps"],
+                                  "note": "steady-state rate over the time box; prepared batches are cycled"}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            n = min(args.zmws, args.cpu_sample or max(6 * cores, 24))   # ~10 s of CPU work on the oracle
-            _, arrays = batches[0]
+            n = min(zmws, args.cpu_sample or max(4 * cores, 24))   # ~10-30 s of CPU work on the oracle
+            _, arrays = M["batches"][0]
             dt, ores = oracle_sample(model, arrays, list(range(n)), cores, args.stage)
             # the sample doubles as a parity spot check at full size
-            r = results[0]
+            r = M["results"][0]
             same = sum(int(np.array_equal(r["seq"][r["seq_off"][z]:r["seq_off"][z + 1]], ores[z]["consensus"]))
                        for z in range(n))
+            qv_ok = sum(int(len(ores[z]["qv"]) == r["seq_off"][z + 1] - r["seq_off"][z] and
+                            (len(ores[z]["qv"]) == 0 or
+                             np.max(np.abs(r["qv"][r["seq_off"][z]:r["seq_off"][z + 1]].astype(int) - ores[z]["qv"].astype(int))) <= 1))
+                        for z in range(n))
             line["cpu_baseline"] = {"value": n / dt, "unit": "ZMW/s", "cores": cores, "kind": "port",
                                     "sample": f"first {n} ZMWs of step 0, {cores} threads, {dt:.1f} s",
-                                    "consensus_identical": f"{same}/{n}"}
+                                    "consensus_identical": f"{same}/{n}", "qv_within_1": f"{qv_ok}/{n}"}
         emit(line)
     for c in ctxs:
         c.close()

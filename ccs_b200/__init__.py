@@ -4,4 +4,4 @@ The product is the C ABI in include/ccsgpu.h (libccsgpu.so: hand-written sm_100a
 kernels + C++ host orchestration).  This package is the thin ctypes mirror used by the
 tests and bench.py.
 """
-from ._lib import lib, LIB_PATH, CcsLibraryMissing  # noqa: F401
+from ._lib import lib, simlib, LIB_PATH, SIM_LIB_PATH, CcsLibraryMissing  # noqa: F401

@@ -23,3 +23,18 @@ def lib():
                 "(or `make -C ccs_b200/csrc`). ccs_b200 has no CPU fallback.")
         _lib = ctypes.CDLL(LIB_PATH)
     return _lib
+
+
+SIM_LIB_PATH = os.path.join(_HERE, "libccssim.so")
+_simlib = None
+
+
+def simlib():
+    """The synthetic-data generator (include/ccssim.h): its own library, so that loading test inputs never maps the
+    product (the reference arm of bench.py uses this and the CPU oracle only)."""
+    global _simlib
+    if _simlib is None:
+        if not os.path.exists(SIM_LIB_PATH):
+            raise CcsLibraryMissing(f"{SIM_LIB_PATH} not built: run `make -C ccs_b200/csrc`.")
+        _simlib = ctypes.CDLL(SIM_LIB_PATH)
+    return _simlib

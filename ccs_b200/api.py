@@ -66,7 +66,11 @@ class CStats(C.Structure):
                [("ms_resident", C.c_double), ("ms_e2e", C.c_double), ("n_zmws", C.c_int64),
                 ("top_fill_alpha_bytes", C.c_int64), ("top_fill_alpha_ms", C.c_double),
                 ("ms_poa_map", C.c_double), ("ms_poa_graph", C.c_double), ("launches_poa_graph", C.c_int64),
-                ("bytes_poa_map", C.c_int64)]
+                ("bytes_poa_map", C.c_int64), ("bytes_score", C.c_int64), ("launches_pack", C.c_int64),
+                ("top_fill_beta_bytes", C.c_int64), ("top_fill_beta_ms", C.c_double),
+                ("top_score_bytes", C.c_int64), ("top_score_ms", C.c_double),
+                ("top_poa_align_bytes", C.c_int64), ("top_poa_align_ms", C.c_double),
+                ("top_poa_map_bytes", C.c_int64), ("top_poa_map_ms", C.c_double)]
 
 
 class Batch:

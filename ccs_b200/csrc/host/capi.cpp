@@ -34,8 +34,8 @@ struct ccsgpu_ctx {
     size_t budget = 0;           // device bytes this ctx may use (0 at create -> 85 % of the free memory then)
     size_t lane_budget() const { return n_lanes > 0 ? budget / (size_t)n_lanes : budget; }
     bool generic_score = false;
-    bool reuse_scores = false;
-    int qv_halo = 48;
+    bool reuse_scores = true;
+    int qv_halo = 32;
     double ms_e2e = 0;
     int64_t n_zmws = 0;
     int device = 0;
@@ -498,6 +498,11 @@ int ccsgpu_get_stats(ccsgpu_ctx* ctx, ccs_stats* out, int reset) {
             out->launches_draft += ds.n_align_launches + ds.n_graph_launches;
             out->ms_poa_map += ds.ms_map; out->ms_poa_graph += ds.ms_graph; out->launches_poa_graph += ds.n_graph_launches;
             out->bytes_poa_map += ds.bytes_map;
+            out->bytes_score += s.bytes_score; out->launches_pack += s.n_pack;
+            if (s.top_fill_beta_bytes > out->top_fill_beta_bytes) { out->top_fill_beta_bytes = s.top_fill_beta_bytes; out->top_fill_beta_ms = s.top_fill_beta_ms; }
+            if (s.top_score_bytes > out->top_score_bytes) { out->top_score_bytes = s.top_score_bytes; out->top_score_ms = s.top_score_ms; }
+            if (ds.top_align_bytes > out->top_poa_align_bytes) { out->top_poa_align_bytes = ds.top_align_bytes; out->top_poa_align_ms = ds.top_align_ms; }
+            if (ds.top_map_bytes > out->top_poa_map_bytes) { out->top_poa_map_bytes = ds.top_map_bytes; out->top_poa_map_ms = ds.top_map_ms; }
             out->ms_draft += (k == 0 ? ctx->ms_draft : ctx->extra[k - 1].ms_draft);
         }
         out->ms_e2e = ctx->ms_e2e; out->n_zmws = ctx->n_zmws;

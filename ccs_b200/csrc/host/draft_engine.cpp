@@ -40,13 +40,13 @@ DraftEngine::~DraftEngine() {
     if (stream_) cudaStreamDestroy(stream_);
 }
 
-void DraftEngine::span(double* acc) {
+void DraftEngine::span(double* acc, int64_t bytes, int64_t* top_bytes, double* top_ms) {
     while (ev_used_ + 2 > ev_pool_.size()) {
         cudaEvent_t e;
         CCS_CUDA(cudaEventCreate(&e));
         ev_pool_.push_back(e);
     }
-    Span sp{ev_pool_[ev_used_], ev_pool_[ev_used_ + 1], acc};
+    Span sp{ev_pool_[ev_used_], ev_pool_[ev_used_ + 1], acc, bytes, top_bytes, top_ms};
     ev_used_ += 2;
     CCS_CUDA(cudaEventRecord(sp.a, stream_));
     spans_.push_back(sp);
@@ -57,7 +57,10 @@ void DraftEngine::span_end() { CCS_CUDA(cudaEventRecord(spans_.back().b, stream_
 void DraftEngine::resolve_spans() {   // call after a stream synchronisation
     for (const Span& sp : spans_) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) *sp.acc += ms;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            *sp.acc += ms;
+            if (sp.top_bytes && sp.bytes > *sp.top_bytes) { *sp.top_bytes = sp.bytes; *sp.top_ms = ms; }
+        }
     }
     spans_.clear();
     ev_used_ = 0;
@@ -235,7 +238,15 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         const int nt = (int)round_graphs[k].size();
         if (nt == 0) continue;
         const PoaTask* tk = at<PoaTask>(db, o_tasks[k]);
-        span(&stats.ms_align);
+        int64_t rbytes = 0;
+        for (int g : round_graphs[k]) {
+            // rows of round k: the graph has grown by an unknown (device-side) number of vertices; count the seed length
+            const int64_t rows = lens[work[zlist[g]].poa_reads[0]];
+            stats.rows += rows;
+            rbytes += rows * (kPoaBand + 8 + 4 * kPoaBand) + lens[work[zlist[g]].poa_reads[k + 1]] + rows;
+        }
+        stats.bytes_align += rbytes;
+        span(&stats.ms_align, rbytes, &stats.top_align_bytes, &stats.top_align_ms);
         launch_poa_align(tk, nt, G, d_draft_.p, d_codes_.p, d_rev_.p, d_lo_.p, d_besti_.p, d_moves_.p, d_hrows_.p,
                          d_steps_.p, d_results_.p, stream_);
         span_end();
@@ -243,12 +254,6 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         launch_poa_commit(G, tk, nt, d_codes_.p, d_rev_.p, d_steps_.p, d_results_.p, d_scratch_.p, stream_);
         span_end();
         stats.n_align_launches += 2; stats.n_graph_launches += 1; stats.n_tasks += nt;
-        for (int g : round_graphs[k]) {
-            // rows of round k: the graph has at most seed + bound(earlier reads) vertices; count the seed length
-            const int64_t rows = lens[work[zlist[g]].poa_reads[0]];
-            stats.rows += rows;
-            stats.bytes_align += rows * (kPoaBand + 8 + 4 * kPoaBand) + lens[work[zlist[g]].poa_reads[k + 1]] + rows;
-        }
     }
     // ---- a4: consensus -------------------------------------------------------------------------------------------
     span(&stats.ms_graph);
@@ -297,6 +302,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
             max_J = std::max(max_J, J);
         }
         const int nt = (int)task_read.size(), nj = (int)(lj - li);
+        int64_t mbytes = 0;
         Carver c2;
         const size_t o_j2 = c2.take<PoaVoteJob>(nj), o_v2 = c2.take<PoaVoteRead>((size_t)nt + 1), o_t2 = c2.take<PoaTask>((size_t)nt + 1);
         const size_t bytes2 = c2.off + 64;
@@ -306,6 +312,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         {
             int64_t ro = 0;
             int k = 0;
+            mbytes = 0;
             for (size_t x = li; x < lj; ++x) {
                 const int g = live[x];
                 const int J = h_draft_len_.p[g];
@@ -319,7 +326,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
                     T.codes_off = coff(r); T.row_off = ro; T.tpl_off = voff[g]; T.n = lens[r]; T.graph = -1; T.V = J;
                     T.rev_idx = r;
                     ro += J;
-                    stats.bytes_map += (int64_t)J * (kPoaBand + 8) + lens[r] + J;
+                    mbytes += (int64_t)J * (kPoaBand + 8) + lens[r] + J;
                 }
                 Jb.read_end = k;
             }
@@ -333,7 +340,8 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         CCS_CUDA(launch_poa_kmer_vote(at<PoaVoteJob>(db, o_j2), nj, max_J, at<PoaVoteRead>(db, o_v2), d_codes_.p, d_draft_.p,
                                       d_rev_.p, stream_));
         span_end();
-        span(&stats.ms_map);
+        stats.bytes_map += mbytes;
+        span(&stats.ms_map, mbytes, &stats.top_map_bytes, &stats.top_map_ms);
         launch_poa_align(at<PoaTask>(db, o_t2), nt, G0, d_draft_.p, d_codes_.p, d_rev_.p, d_lo_.p, d_besti_.p, d_moves_.p,
                          nullptr, nullptr, d_results_.p, stream_);
         span_end();

@@ -46,6 +46,8 @@ struct DraftStats {
     int64_t bytes_align = 0;    // algorithmic bytes of the align launches
     int64_t bytes_map = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int64_t top_align_bytes = 0, top_map_bytes = 0;   // largest single launch: algorithmic bytes, CUDA-event ms
+    double top_align_ms = 0, top_map_ms = 0;
 };
 
 class DraftEngine {
@@ -66,13 +68,13 @@ private:
     };
     void poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOutput& out, const std::vector<int32_t>& lens,
                    std::vector<Zw>& work, const std::vector<int>& zlist);
-    void span(double* acc);
+    void span(double* acc, int64_t bytes = 0, int64_t* top_bytes = nullptr, double* top_ms = nullptr);
     void span_end();
     void resolve_spans();
     int device_;
     size_t budget_;
     cudaStream_t stream_ = nullptr;
-    struct Span { cudaEvent_t a, b; double* acc; };
+    struct Span { cudaEvent_t a, b; double* acc; int64_t bytes; int64_t* top_bytes; double* top_ms; };
     std::vector<Span> spans_;
     std::vector<cudaEvent_t> ev_pool_;
     size_t ev_used_ = 0;

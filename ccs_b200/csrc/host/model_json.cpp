@@ -56,6 +56,10 @@ bool numbers_after(const std::string& s, size_t p, size_t want, std::vector<doub
 
 extern "C" {
 
+int ccs_model_sizeof(void) { return (int)sizeof(ccs::ArrowModelParams); }
+
+void ccs_model_synthetic(void* model_out) { ccs::synthetic_model(*(ccs::ArrowModelParams*)model_out); }
+
 int ccs_model_save_json(const void* model, const char* path) {
     const ArrowModelParams& m = *(const ArrowModelParams*)model;
     FILE* f = std::fopen(path, "w");

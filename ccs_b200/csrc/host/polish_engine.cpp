@@ -184,6 +184,7 @@ void ArrowEngine::load(const PolishInput& in) {
     CCS_CUDA(cudaMemcpyAsync(d_pack_.p, h_pack_.p, sizeof(PackJob) * nr, cudaMemcpyHostToDevice, stream_));
     CCS_CUDA(cudaMemcpyAsync(d_trans_.p, h_trans_.p, (size_t)nz * 36 * 4 * sizeof(float), cudaMemcpyHostToDevice, stream_));
     launch_pack_rowcodes(d_pack_.p, nr, d_raw, d_rowcode_.p, stream_);
+    ++stats.n_pack;
     stats.h2d_bytes += (int64_t)sizeof(PackJob) * nr + (int64_t)nz * 36 * 4 * 4;
     // template capacities: room for the template to grow during polishing
     for (int z = 0; z < nz; ++z) {
@@ -319,7 +320,7 @@ void ArrowEngine::fill() {
     span_begin(&stats.ms_fill_alpha, 4 * cells + 8 * (cells / 32) + in_bytes, &stats.top_fill_alpha_bytes, &stats.top_fill_alpha_ms);
     launch_fill_alpha(V, d_order_.p, n, stream_);
     span_end();
-    span_begin(&stats.ms_fill_beta);
+    span_begin(&stats.ms_fill_beta, 4 * cells + 8 * (cells / 32) + in_bytes, &stats.top_fill_beta_bytes, &stats.top_fill_beta_ms);
     launch_fill_beta(V, d_order_.p, n, stream_);
     span_end();
     CCS_CUDA(cudaGetLastError());
@@ -440,7 +441,18 @@ void ArrowEngine::score_ranges(const std::vector<ScoreRange>& ranges, int64_t n_
     CCS_CUDA(cudaMemcpyAsync(d_ranges_.p, h_ranges_.p, sizeof(ScoreRange) * ranges.size(), cudaMemcpyHostToDevice, stream_));
     stats.h2d_bytes += (int64_t)sizeof(ScoreRange) * ranges.size();
     const ArrowBatchView V = view();
-    span_begin(&stats.ms_score);
+    // algorithmic bytes (SURVEY.md 8d B_score): five 128-byte band columns in + 64 bytes of partial sums out per
+    // (covering read, position)
+    int64_t sbytes = 0;
+    if (timing_enabled)
+        for (const ScoreRange& rg : ranges) {
+            const ZmwState& zs = zstate_[rg.zmw];
+            for (int r = zs.read_begin; r < zs.read_end; ++r)
+                if (reads_[r].active)
+                    sbytes += 704ll * std::max(0, std::min(rg.p_end, reads_[r].te) - std::max(rg.p_begin, reads_[r].ts));
+        }
+    stats.bytes_score += sbytes;
+    span_begin(&stats.ms_score, sbytes, &stats.top_score_bytes, &stats.top_score_ms);
     launch_score(V, d_ranges_.p, (int)ranges.size(), n_items, d_delta_.p, stream_, generic_score);
     span_end();
     CCS_CUDA(cudaGetLastError());

@@ -74,6 +74,9 @@ struct EngineStats {
     int64_t rounds = 0;
     int64_t top_fill_alpha_bytes = 0;   // largest single arrow_fill_alpha launch: algorithmic bytes ...
     double top_fill_alpha_ms = 0;       // ... and its CUDA-event duration
+    int64_t top_fill_beta_bytes = 0, top_score_bytes = 0;
+    double top_fill_beta_ms = 0, top_score_ms = 0;
+    int64_t n_pack = 0;
     double ms_resident = 0;   // CUDA-event time of polish() with inputs already in HBM (after load)
     double ms_e2e = 0;        // host wall time of whole stage calls (pack + H2D + kernels + D2H)
     int64_t n_zmws = 0;
@@ -109,11 +112,13 @@ public:
     int device() const { return device_; }
     bool timing_enabled = true;
     int host_threads = 8;         // threads for the per-ZMW host pieces of a round
-    // ConsensusQualities reuses the delta-LLs of positions farther than `neighborhood` from every edit instead of
-    // re-scoring the whole template (-35 % scoring work).  NOT exact: in repeats an edit reaches further, measured
-    // 28 of 1.66 M positions off by more than 1 QV, so it is off by default (CCS_B200_REUSE_SCORES=1 enables it).
-    bool reuse_scores = false;
-    int qv_halo = 48;             // positions within this distance of an edit are re-scored before their QV is taken
+    // ConsensusQualities re-scores only the positions within qv_halo of an edit made after they were last scored (or
+    // never scored) and reuses the stored delta-LLs elsewhere: an edit further away than the halo moves a position's
+    // delta-LLs by less than QV rounding (measured: 0 of 2.76 M positions off by more than 1 QV at halo 20, 32, 48, 64;
+    // scripts/qv_reuse_check.py, profiles/r2_qv_reuse.txt).  -29 % scoring work at halo 32.  CCS_B200_REUSE_SCORES=0
+    // restores the full pass.
+    bool reuse_scores = true;
+    int qv_halo = 32;             // > neighborhood (20): positions within this distance of an edit are re-scored
     bool generic_score = false;   // use the unfactored reference scoring kernel (tests)
 
 private:

@@ -1,7 +1,8 @@
-// C ABI over the synthetic ZMW generator and the chemistry model container
-// (declared in include/ccsgpu.h, "Synthetic data" section).
+// C ABI of libccssim.so: the synthetic ZMW generator (include/ccssim.h).  Test / bench infrastructure, built
+// separately from the product library.
 #include "../common/sim.h"
-#include "../../../include/ccsgpu.h"
+#include "../../../include/ccssim.h"
+#include "../../../include/ccsgpu.h"   // error codes only
 #include <cstring>
 
 using namespace ccs;
@@ -153,7 +154,7 @@ void ccs_sim_batch_copy(const void* h, int32_t* zmw_read_off, int64_t* read_off,
 }  // extern "C"
 
 // ---- synthetic subreads.bam (tests / demos of the `ccs` command line) --------------------------
-#include "bam_io.h"
+#include "../host/bam_io.h"
 
 extern "C" {
 

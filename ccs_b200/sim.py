@@ -1,7 +1,7 @@
-"""Synthetic Sequel-II-shape ZMWs (ctypes over ccs_sim_* in include/ccsgpu.h)."""
+"""Synthetic Sequel-II-shape ZMWs (ctypes over libccssim.so, include/ccssim.h -- not the product library)."""
 import ctypes as C
 import numpy as np
-from ._lib import lib
+from ._lib import simlib as lib
 
 
 class SimConfig(C.Structure):

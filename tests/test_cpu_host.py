@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def declared_functions():
-    hdr = open(os.path.join(ROOT, "include", "ccsgpu.h")).read()
+def declared_functions(header="ccsgpu.h"):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = re.findall(r"\b(ccs(?:gpu)?_[a-z0-9_]+)\s*\(", hdr)
     return sorted(set(names))
@@ -26,9 +26,18 @@ def declared_functions():
 def test_library_exports_every_declared_symbol():
     L = lib()
     names = declared_functions()
-    assert len(names) >= 18
+    assert len(names) >= 14
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/ccsgpu.h but not exported by {LIB_PATH}"
+    # the synthetic-data generator is a library of its own (include/ccssim.h): the product exports none of it
+    from ccs_b200 import simlib, SIM_LIB_PATH
+    S = simlib()
+    sim_names = declared_functions("ccssim.h")
+    assert len(sim_names) >= 9
+    for n in sim_names:
+        assert hasattr(S, n), f"{n} declared in include/ccssim.h but not exported by {SIM_LIB_PATH}"
+        if n.startswith("ccs_sim_"):
+            assert not hasattr(L, n), f"{n} (test infrastructure) leaked into the product library"
 
 
 def test_no_cpu_fallback_without_device():
