@@ -231,7 +231,7 @@ KERNELS = [  # (name, bytes key, ms key, top bytes key, top ms key)
 def rooflines(st, st1, peak, peak_src, traffic):
     """One entry per heavy kernel: algorithmic bytes / CUDA-event time over (a) all launches of the timed region in the
     timed lane/context configuration (concurrent lanes: spans include the other lanes' interference), (b) all launches
-    of one single-lane step (kernels strictly serial), (c) the largest single launch of that step."""
+    of one lane-sized chunk on a single lane (the timed launch shapes, strictly serial), (c) its largest launch."""
     tot = sum(st[k[2]] for k in KERNELS) + st["ms_pick"] + st["ms_qv"] + st["ms_poa_graph"]
     out = []
     for name, bk, mk, tbk, tmk in KERNELS:
@@ -333,10 +333,14 @@ def measure(args, cfg_id, zmws, steps, warmup, ctxs, model, rank, world, local, 
     # `value`: same run with the batch upload taken out (inputs resident): the H2D of the read codes is the only
     # input traffic; its CUDA-event span (per lane, lanes overlap) is subtracted from the wall time of the calls
     t_res = t_e2e - st["ms_h2d"] / 1e3 / max(lanes * len(ctxs), 1)
-    # per-kernel timing pass: one more step on a single lane (kernels strictly serial, no overlap)
+    # per-kernel timing pass: one lane-sized chunk (the launch shapes of the timed region) on a single lane, i.e. the
+    # same kernels strictly serial, without the other lanes' interference
+    sub, _ = make_batch(model, cfg, (steps + warmup + 7) * world * zmws + rank * zmws, max(1, zmws // max(lanes, 1)),
+                        args.draft_error, threads)
     ctx.set_lanes(1)
+    run_step(sub)                       # buffers of the single lane are sized here, not inside the measured pass
     ctx.stats(reset=True)
-    run_step(batches[0][0])
+    run_step(sub)
     torch.cuda.synchronize()
     st1 = ctx.stats()
     ctx.set_lanes(lanes)
@@ -426,7 +430,8 @@ def main():
                "arrow_score_kernel": "launches_score"}.get(dom["kernel"])
         kern_ms = {k: st1[k] for k in ("ms_fill_alpha", "ms_fill_beta", "ms_score", "ms_pick", "ms_qv", "ms_h2d",
                                        "ms_poa_align", "ms_poa_map", "ms_poa_graph", "ms_draft", "ms_resident", "ms_e2e")}
-        kern_ms["note"] = "one step, single lane (serial kernels); the timed region runs %d overlapping lanes x %d contexts" % (lanes, len(ctxs))
+        kern_ms["note"] = ("one lane-sized chunk (%d ZMWs) on a single lane (serial kernels); the timed region runs %d such "
+                           "chunks per step on %d overlapping lanes x %d contexts" % (max(1, zmws // lanes), lanes, lanes, len(ctxs)))
         line = {
             "metric": METRIC[args.stage],
             "value": M["n_total"] / M["t_res"], "unit": "ZMW/s", "n_gpus": world, "steps": M["n_steps"], "warmup": args.warmup,

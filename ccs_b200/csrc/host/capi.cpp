@@ -131,7 +131,15 @@ int ccsgpu_set_lanes(ccsgpu_ctx* ctx, int n_lanes) {
         ctx->last_error = e.what();
         return CCS_ERR_CUDA;
     }
+    if (n_lanes != ctx->n_lanes) {     // the per-lane share of the budget changes: drop the grow-only buffers sized for the old share
+        ctx->engine->release_buffers(); ctx->draft->release_buffers();
+        for (auto& l : ctx->extra) { l.engine->release_buffers(); l.draft->release_buffers(); }
+    }
     ctx->n_lanes = n_lanes;
+    // a lane's device share: ~80 % Polish Stage (bands, row codes, delta rows), ~20 % Draft Stage scratch
+    const size_t draft_budget = std::max<size_t>(ctx->lane_budget() / 5, 256ull << 20);
+    ctx->draft->set_budget(draft_budget);
+    for (auto& l : ctx->extra) l.draft->set_budget(draft_budget);
     const int th = std::max(1, ctx->host_threads / n_lanes);
     ctx->engine->host_threads = th; ctx->draft->host_threads = th;
     for (auto& l : ctx->extra) { l.engine->host_threads = th; l.draft->host_threads = th; }
@@ -272,14 +280,15 @@ static void make_sub(const ccs_batch* in, const ccs_drafts* dr, int z0, int z1, 
 // Contiguous ZMW chunks with ~equal numbers of read bases: at least one per lane, and more (processed in
 // waves, lane k takes chunks k, k+n_lanes, ...) when a chunk's device footprint would exceed the lane's share of
 // the budget.  Footprint estimate per read base: two 128-B band columns + column info (alpha, beta), two row-code
-// copies, ~15 % growth room; plus the per-position delta rows -- ~330 B per read base, rounded up to 400.
+// copies, ~15 % growth room; plus the per-position delta rows -- ~330 B per read base, rounded up to 400; plus the
+// Draft Stage scratch of the same lane (graph pools, DP rows, traceback moves: ~100 B per read base).
 static std::vector<int> split_zmws(const ccs_batch* in, int n_lanes, size_t lane_budget_bytes) {
     std::vector<int> cut(1, 0);
     const int nz = in->n_zmws;
     const int64_t total = in->read_off[in->n_reads];
     int n_chunks = std::max(1, std::min(n_lanes, std::max(1, nz / 8)));
     if (lane_budget_bytes > 0) {
-        const int64_t per_chunk = (int64_t)(lane_budget_bytes / 400);
+        const int64_t per_chunk = (int64_t)(lane_budget_bytes / 500);   // + the Draft Stage's share
         const int need = (int)std::min<int64_t>(nz, (total + per_chunk - 1) / std::max<int64_t>(per_chunk, 1));
         if (need > n_chunks) n_chunks = ((need + n_lanes - 1) / n_lanes) * n_lanes;
     }

@@ -40,6 +40,14 @@ DraftEngine::~DraftEngine() {
     if (stream_) cudaStreamDestroy(stream_);
 }
 
+void DraftEngine::release_buffers() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    d_codes_.release(); d_desc_.release(); d_rev_.release(); d_moves_.release(); d_draft_.release(); d_meta_.release();
+    d_pred0_.release(); d_predx_.release(); d_rank_.release(); d_order_.release(); d_lo_.release(); d_besti_.release();
+    d_hrows_.release(); d_scratch_.release(); d_draft_len_.release(); d_steps_.release(); d_results_.release();
+}
+
 void DraftEngine::span(double* acc, int64_t bytes, int64_t* top_bytes, double* top_ms) {
     while (ev_used_ + 2 > ev_pool_.size()) {
         cudaEvent_t e;

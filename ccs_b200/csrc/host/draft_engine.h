@@ -57,6 +57,8 @@ public:
     void run(const DraftInput& in, const DraftParams& dp, DraftOutput& out);
     DraftStats stats;
     int host_threads = 8;
+    void release_buffers();      // free the (grow-only) device scratch
+    void set_budget(size_t bytes) { if (bytes) budget_ = bytes; }
     // The uploaded read codes of the last run() stay resident for the Polish Stage of the same lane.
     const uint8_t* device_codes() const { return d_codes_.p; }
     cudaStream_t stream() const { return stream_; }

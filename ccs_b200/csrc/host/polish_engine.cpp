@@ -50,6 +50,14 @@ ArrowEngine::~ArrowEngine() {
     if (stream_) cudaStreamDestroy(stream_);
 }
 
+void ArrowEngine::release_buffers() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    d_rowcode_.release(); d_tpl_.release(); d_rawcodes_.release(); d_alpha_.release(); d_beta_.release();
+    d_colinfo_.release(); d_bexp_.release(); d_delta_.release(); d_delta_scratch_.release(); d_qv_.release();
+    d_cand_.release(); d_trans_.release();
+}
+
 cudaEvent_t ArrowEngine::next_event() {
     if (ev_used_ == ev_pool_.size()) {
         cudaEvent_t e;

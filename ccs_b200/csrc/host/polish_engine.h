@@ -108,6 +108,7 @@ public:
 
     EngineStats stats;
     void reset_stats() { stats = EngineStats(); }
+    void release_buffers();       // free the (grow-only) per-batch device buffers, e.g. when the lane count changes
     cudaStream_t stream() const { return stream_; }
     int device() const { return device_; }
     bool timing_enabled = true;

@@ -442,6 +442,10 @@ PolishResult polish(Integrator<Real>& ai) {
     std::set<uint64_t> seen;
     seen.insert(tpl_hash(ai.fwd));
     std::vector<int> sites;   // positions (current coordinates) of last-applied mutations
+    // growth cap (DESIGN.md "Known deviations"): a template that would outgrow its initial length by more than
+    // max(512, J/8) bases (rounded up to a multiple of 16) stops being refined and counts as not converged
+    const int J0 = (int)ai.fwd.size();
+    const int cap = ((J0 + std::max(512, J0 / 8)) + 15) & ~15;
     for (int it = 0; it < ai.cfg.max_iterations; ++it) {
         res.iterations = it + 1;
         const int J = (int)ai.fwd.size();
@@ -469,6 +473,7 @@ PolishResult polish(Integrator<Real>& ai) {
             next = apply_mutations(ai.fwd, best);
         }
         seen.insert(tpl_hash(next));
+        if ((int)next.size() > cap) break;
         // sites in new coordinates
         sites.clear();
         int off = 0;

@@ -135,6 +135,7 @@ void PoaGraph::commit(const PoaAlignment& a, const uint8_t* seq) {
     auto add_edge = [&](int u, int w) {
         if (u < 0) return;
         for (int x : v[u].out) if (x == w) return;
+        if (v[w].in.size() >= 8) return;    // a vertex keeps at most 8 predecessors; later edges are ignored (spec)
         v[u].out.push_back(w);
         v[w].in.push_back(u);
     };
