@@ -18,7 +18,7 @@ void launch_pack_rowcodes(const PackJob* jobs, int n_jobs, const uint8_t* codes,
 // Ranges of one ZMW must be disjoint and non-touching.  generic = reference kernel (every mutation
 // evaluated independently), used by the tests to cross-check the factored kernel.
 void launch_score(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, double* delta,
-                  cudaStream_t stream, bool generic = false);
+                  cudaStream_t stream, bool generic = false, int variant = 0);
 // re-index delta rows after template edits: sites[] = edit positions in NEW coordinates (ascending per job),
 // shifts[] = cumulative length change up to and including that edit
 void launch_remap_delta(const RemapJob* jobs, int n_jobs, const int32_t* sites, const int32_t* shifts, double* delta,

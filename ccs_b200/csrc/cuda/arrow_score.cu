@@ -337,6 +337,7 @@ __device__ __forceinline__ float link_partial(const float y[4], const float bx[4
 }
 
 // tc = shared-memory byte address of the code-major folded table [16 codes][16 contexts] of {mm, gg}
+template <int kUnrollB>
 __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g4, const int src_up, const int src_up2,
                                           const int src_up4, const int src_dn, const unsigned tc, const int q_in,
                                           const bool live, FastOut& out) {
@@ -399,7 +400,8 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g4, const 
     const bool keep2 = rb2 == rb1;
     const bool upok2 = !(start2 && s2 == s1);
     float Xdel[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+    float osub[4], oins[4];
+#pragma unroll kUnrollB
     for (int b = 0; b < 4; ++b) {
         float A[4], G[4], X[4];
 #pragma unroll
@@ -426,7 +428,7 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g4, const 
             for (int x = 0; x < 4; ++x) { Aa[x] = A2[x]; Ga[x] = lds_f1(s2a[x] + 32 * b + 4); }
             if (start2) Ga[0] = 0.f;
             ring_scan(Aa, Ga, src_up, src_up2, src_up4, Y);
-            out.sub[b] = link_partial(Y, bxS, dnS, sla[0], sla[1], sla[2], sla[3], 32 * b, lds_f1(d_p1 + 32 * b));
+            osub[b] = link_partial(Y, bxS, dnS, sla[0], sla[1], sla[2], sla[3], 32 * b, lds_f1(d_p1 + 32 * b));
         }
         {   // INS(before q, b): insertion context (b, t[q]); link into beta column q+1
             float Aa[4], Ga[4], Z[4];
@@ -434,9 +436,11 @@ __device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g4, const 
             for (int x = 0; x < 4; ++x) { Aa[x] = A2[x]; Ga[x] = lds_f1(i2a[x] + 32 * b + 4); }
             if (start2) Ga[0] = 0.f;
             ring_scan(Aa, Ga, src_up, src_up2, src_up4, Z);
-            out.ins[b] = link_partial(Z, bxI, dnI, ila[0], ila[1], ila[2], ila[3], 32 * b, lds_f1(d_t0 + 32 * b));
+            oins[b] = link_partial(Z, bxI, dnI, ila[0], ila[1], ila[2], ila[3], 32 * b, lds_f1(d_t0 + 32 * b));
         }
     }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { out.sub[b] = osub[b]; out.ins[b] = oins[b]; }
     {   // DEL(q): X_{t[q+1]} links straight into beta column q+2 with context (t[q-1], t[q+1])
         const int od = o_m1 + o_p1;
         out.del = link_partial(Xdel, bxD, dnD, n1[0] + od, n1[1] + od, n1[2] + od, n1[3] + od, 0, lds_f1(dbase + od));
@@ -468,7 +472,8 @@ __device__ __forceinline__ double prod_dll(const float prod, const int pexp, con
 // template base, whose substitution is the identity -- and lane 4 + k owns INS(forward base k); per read the lanes'
 // partial link sums are transpose-reduced so that every lane ends up with the total of its own slot and keeps that
 // slot's running product.  The order of the reduction is fixed: results are deterministic.
-__global__ void __launch_bounds__(128, 4) arrow_score_kernel(const ArrowBatchView V, const ScoreRange* __restrict__ ranges,
+template <int kMinBlocks, int kUnrollB>
+__global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const ArrowBatchView V, const ScoreRange* __restrict__ ranges,
                                                           const int n_ranges, const long long n_items,
                                                           double* __restrict__ delta) {
     __shared__ float s_emm[36 * kEmStride];
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(128, 4) arrow_score_kernel(const ArrowBatchVie
 
         if (__any_sync(kFullMask, interior)) {
             FastOut fo;
-            fast_eval(R, g4, src_up, src_up2, src_up4, src_dn, tc, q_sd, interior, fo);
+            fast_eval<kUnrollB>(R, g4, src_up, src_up2, src_up4, src_dn, tc, q_sd, interior, fo);
             // Q[k] = this lane's partial of the slot lane k owns (forward-strand base k & 3; reverse reads see 3 - base)
             const bool rv = rd.strand != 0;
             float Q[8];
@@ -776,11 +781,16 @@ __global__ void __launch_bounds__(256) arrow_remap_delta_kernel(const RemapJob* 
 }  // namespace
 
 void launch_score(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, double* delta,
-                  cudaStream_t stream, bool generic) {
+                  cudaStream_t stream, bool generic, int variant) {
     if (n_items <= 0) return;
     const long long blocks = (n_items + 15) / 16;
     if (generic) arrow_score_generic_kernel<<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
-    else arrow_score_kernel<<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    else if (variant == 1) arrow_score_kernel<4, 4><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    else if (variant == 2) arrow_score_kernel<6, 4><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    else if (variant == 3) arrow_score_kernel<8, 4><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    // default: 5 CTAs per SM (96 registers, 20 warps): measured 9 % faster than 4 CTAs at 128 registers despite the
+    // extra spills -- the kernel is latency / issue bound and wants the warps (profiles/r2_score_variants.txt)
+    else arrow_score_kernel<5, 4><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
 }
 
 void launch_pick(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, const double* delta,

@@ -23,6 +23,7 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kWarpsPerCta = 4;
+constexpr int kRing = 8;            // recent DP rows kept in shared memory (power of two)
 
 __device__ __forceinline__ int row_get(const int* __restrict__ row, const int idx) {
     return ((unsigned)idx < (unsigned)kPoaBand) ? row[idx] : 0;
@@ -33,7 +34,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     const uint8_t* __restrict__ codes, const uint8_t* __restrict__ rev_flags, int32_t* __restrict__ lo_arr,
     int32_t* __restrict__ besti_arr, uint8_t* __restrict__ moves, int32_t* __restrict__ hrows,
     PoaResult* __restrict__ results) {
-    __shared__ int s_row[kWarpsPerCta][kPoaBand];
+    // The last kRing rows stay in shared memory with their vertex ids, band starts and best cells: the predecessors of a
+    // branch vertex are almost always among them (a bubble opened by one read is a few vertices long), so the dependent
+    // chain of a branch vertex does not wait on global memory either.
+    __shared__ int s_ring[kWarpsPerCta][kRing][kPoaBand];
+    __shared__ int s_rid[kWarpsPerCta][kRing], s_rlo[kWarpsPerCta][kRing], s_rbi[kWarpsPerCta][kRing];
     __shared__ int s_meta[kWarpsPerCta][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task_id = blockIdx.x * kWarpsPerCta + warp;
@@ -61,7 +66,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     int32_t* __restrict__ h_r = hrows ? hrows + T.row_off * kPoaBand : nullptr;
     const bool store_h = !linear && h_r != nullptr;
     const int lo_max = max(0, n + 1 - kPoaBand);
-    int* srow = s_row[warp];
+    int* srow = s_ring[warp][kRing - 1];      // "previous row" before the first vertex: zeros
     auto read_base = [&](const int i) -> int {     // oriented base of read position i (0-based)
         return rev ? 3 - (rc[n - 1 - i] & 3) : (rc[i] & 3);
     };
@@ -69,6 +74,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     int gbest = 0, gt = -1, gi = -1;
     int prev_lo = 0, prev_besti = 0, prev_id = -1;
     srow[2 * lane] = 0; srow[2 * lane + 1] = 0;
+    if (lane < kRing) s_rid[warp][lane] = -2;
     int* smeta = s_meta[warp];          // per block of 32 vertices: id, base, in-degree, first predecessor
     __syncwarp();
 
@@ -119,7 +125,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
             int m = 0;
             for (int k = 0; k < npred; ++k) {
                 const int pr = (k == 0) ? first_pred : predx[7 * (int64_t)id + k - 1];
-                m = max(m, (pr == prev_id) ? prev_besti : bi_r[pr]);
+                const unsigned hit = __ballot_sync(kFull, s_rid[warp][lane & (kRing - 1)] == pr) & ((1u << kRing) - 1u);
+                m = max(m, hit ? s_rbi[warp][__ffs(hit) - 1] : bi_r[pr]);
             }
             lo = min(max(m + 1 - kPoaBand / 2, 0), lo_max);
         }
@@ -136,9 +143,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
         }
         for (int k = 0; k < npred; ++k) {
             const int pr = (k == 0) ? first_pred : predx[7 * (int64_t)id + k - 1];
-            const bool adj = (pr == prev_id);
-            const int* __restrict__ row = adj ? srow : (h_r + (size_t)pr * kPoaBand);
-            const int dl = lo - (adj ? prev_lo : lo_r[pr]);
+            const unsigned hit = __ballot_sync(kFull, s_rid[warp][lane & (kRing - 1)] == pr) & ((1u << kRing) - 1u);
+            const int slot = __ffs(hit) - 1;
+            const int* __restrict__ row = hit ? s_ring[warp][slot] : (h_r + (size_t)pr * kPoaBand);
+            const int dl = lo - (hit ? s_rlo[warp][slot] : lo_r[pr]);
             const int a = 2 * lane + dl;
             const int hm1 = row_get(row, a - 1), h0 = row_get(row, a), h1 = row_get(row, a + 1);
             if (rb0 != 255) { const int c = hm1 + sc0; if (c > bm0) { bm0 = c; km0 = k; } }
@@ -172,6 +180,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
         if (H1 > c1) m1 = 3u;
         // row outputs (by vertex id)
         *reinterpret_cast<uchar2*>(mv_r + (size_t)id * kPoaBand + 2 * lane) = make_uchar2((unsigned char)m0, (unsigned char)m1);
+        srow = s_ring[warp][t & (kRing - 1)];
         srow[2 * lane] = H0; srow[2 * lane + 1] = H1;
         if (store_h) *reinterpret_cast<int2*>(h_r + (size_t)id * kPoaBand + 2 * lane) = make_int2(H0, H1);
         // best cell of the row: largest value, smallest read prefix on ties
@@ -184,7 +193,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
         const int rmax = rkey >> 6;
         const int wc = kPoaBand - 1 - (rkey & (kPoaBand - 1));
         const int besti = (rmax > 0) ? lo + wc : lo;
-        if (lane == 0) { lo_r[id] = lo; bi_r[id] = besti; }
+        if (lane == 0) {
+            lo_r[id] = lo; bi_r[id] = besti;
+            s_rid[warp][t & (kRing - 1)] = id; s_rlo[warp][t & (kRing - 1)] = lo; s_rbi[warp][t & (kRing - 1)] = besti;
+        }
         if (rmax > gbest) { gbest = rmax; gt = id; gi = besti; }
         prev_lo = lo; prev_besti = besti; prev_id = id;
         __syncwarp();   // row visible in shared memory before the next vertex reads it

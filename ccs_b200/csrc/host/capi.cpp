@@ -36,6 +36,7 @@ struct ccsgpu_ctx {
     bool generic_score = false;
     bool reuse_scores = true;
     int qv_halo = 32;
+    int score_variant = 0;
     double ms_e2e = 0;
     int64_t n_zmws = 0;
     int device = 0;
@@ -96,6 +97,8 @@ ccsgpu_ctx* ccsgpu_create(int device, const void* model, size_t device_bytes_bud
         ctx->engine->reuse_scores = ctx->reuse_scores;
         if (const char* e = std::getenv("CCS_B200_QV_HALO")) ctx->qv_halo = std::max(0, std::atoi(e));
         ctx->engine->qv_halo = ctx->qv_halo;
+        if (const char* e = std::getenv("CCS_B200_SCORE_VARIANT")) ctx->score_variant = std::atoi(e);
+        ctx->engine->score_variant = ctx->score_variant;
         ctx->budget = device_bytes_budget;
         if (ctx->budget == 0) {
             size_t fr = 0, tot = 0;
@@ -125,6 +128,7 @@ int ccsgpu_set_lanes(ccsgpu_ctx* ctx, int n_lanes) {
             l.engine->generic_score = ctx->generic_score;
             l.engine->reuse_scores = ctx->reuse_scores;
             l.engine->qv_halo = ctx->qv_halo;
+            l.engine->score_variant = ctx->score_variant;
             ctx->extra.push_back(std::move(l));
         }
     } catch (const std::exception& e) {

@@ -5,6 +5,7 @@
 #include "../cuda/poa_launch.h"
 #include "../../../include/ccsgpu.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace ccs {
@@ -29,7 +30,15 @@ template <class T> T* at(uint8_t* base, size_t off) { return reinterpret_cast<T*
 
 DraftEngine::DraftEngine(int device, size_t scratch_budget_bytes) : device_(device), budget_(scratch_budget_bytes) {
     CCS_CUDA(cudaSetDevice(device_));
-    CCS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    {   // the Draft Stage kernels are serial chains over the graph (latency bound, few warps): high priority, so that
+        // their CTAs get SM slots ahead of the other lanes' short-lived scoring CTAs
+        int lo = 0, hi = 0;
+        const char* e = std::getenv("CCS_B200_PRIO");
+        if (!(e && e[0] == '0') && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && hi < lo)
+            CCS_CUDA(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, hi));
+        else
+            CCS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    }
     if (budget_ == 0) budget_ = 12ull << 30;
 }
 

@@ -5,6 +5,7 @@
 #include "parallel.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -26,6 +27,14 @@ ArrowEngine::ArrowEngine(int device, const ArrowModelParams& model, size_t budge
         budget_ = fr - fr / 10;
     }
     CCS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        const char* e = std::getenv("CCS_B200_PRIO");
+        if (!(e && e[0] == '0') && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && hi < lo) {
+            CCS_CUDA(cudaStreamCreateWithPriority(&stream_hi_, cudaStreamNonBlocking, hi));
+            CCS_CUDA(cudaEventCreateWithFlags(&ev_order_, cudaEventDisableTiming));
+        }
+    }
     CCS_CUDA(cudaEventCreate(&evA_));
     CCS_CUDA(cudaEventCreate(&evB_));
     build_emission_tables(model_, em_);
@@ -67,16 +76,16 @@ cudaEvent_t ArrowEngine::next_event() {
     return ev_pool_[ev_used_++];
 }
 
-void ArrowEngine::span_begin(double* acc, int64_t bytes, int64_t* top_bytes, double* top_ms) {
+void ArrowEngine::span_begin(double* acc, int64_t bytes, int64_t* top_bytes, double* top_ms, cudaStream_t s) {
     if (!timing_enabled) return;
     Span sp{next_event(), next_event(), acc, bytes, top_bytes, top_ms};
-    CCS_CUDA(cudaEventRecord(sp.a, stream_));
+    CCS_CUDA(cudaEventRecord(sp.a, s ? s : stream_));
     spans_.push_back(sp);
 }
 
-void ArrowEngine::span_end() {
+void ArrowEngine::span_end(cudaStream_t s) {
     if (!timing_enabled) return;
-    CCS_CUDA(cudaEventRecord(spans_.back().b, stream_));
+    CCS_CUDA(cudaEventRecord(spans_.back().b, s ? s : stream_));
 }
 
 // call only when the stream is known to be idle (after a synchronize)
@@ -325,12 +334,22 @@ void ArrowEngine::fill() {
     const int n = (int)order_.size();
     int64_t cells = 0, in_bytes = 0;
     for (int r : order_) if (r >= 0) { cells += 32ll * (reads_[r].J - 1); in_bytes += reads_[r].I + reads_[r].J; }
-    span_begin(&stats.ms_fill_alpha, 4 * cells + 8 * (cells / 32) + in_bytes, &stats.top_fill_alpha_bytes, &stats.top_fill_alpha_ms);
-    launch_fill_alpha(V, d_order_.p, n, stream_);
-    span_end();
-    span_begin(&stats.ms_fill_beta, 4 * cells + 8 * (cells / 32) + in_bytes, &stats.top_fill_beta_bytes, &stats.top_fill_beta_ms);
-    launch_fill_beta(V, d_order_.p, n, stream_);
-    span_end();
+    cudaStream_t fs = stream_;
+    if (stream_hi_) {      // hand over to the high-priority stream for the two fill kernels, then back
+        CCS_CUDA(cudaEventRecord(ev_order_, stream_));
+        CCS_CUDA(cudaStreamWaitEvent(stream_hi_, ev_order_, 0));
+        fs = stream_hi_;
+    }
+    span_begin(&stats.ms_fill_alpha, 4 * cells + 8 * (cells / 32) + in_bytes, &stats.top_fill_alpha_bytes, &stats.top_fill_alpha_ms, fs);
+    launch_fill_alpha(V, d_order_.p, n, fs);
+    span_end(fs);
+    span_begin(&stats.ms_fill_beta, 4 * cells + 8 * (cells / 32) + in_bytes, &stats.top_fill_beta_bytes, &stats.top_fill_beta_ms, fs);
+    launch_fill_beta(V, d_order_.p, n, fs);
+    span_end(fs);
+    if (stream_hi_) {
+        CCS_CUDA(cudaEventRecord(ev_order_, stream_hi_));
+        CCS_CUDA(cudaStreamWaitEvent(stream_, ev_order_, 0));
+    }
     CCS_CUDA(cudaGetLastError());
     for (auto& zs : zstate_) zs.dirty = false;
     ++stats.n_fill_alpha; ++stats.n_fill_beta;
@@ -461,7 +480,7 @@ void ArrowEngine::score_ranges(const std::vector<ScoreRange>& ranges, int64_t n_
         }
     stats.bytes_score += sbytes;
     span_begin(&stats.ms_score, sbytes, &stats.top_score_bytes, &stats.top_score_ms);
-    launch_score(V, d_ranges_.p, (int)ranges.size(), n_items, d_delta_.p, stream_, generic_score);
+    launch_score(V, d_ranges_.p, (int)ranges.size(), n_items, d_delta_.p, stream_, generic_score, score_variant);
     span_end();
     CCS_CUDA(cudaGetLastError());
     ++stats.n_score;

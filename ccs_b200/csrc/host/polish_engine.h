@@ -121,12 +121,13 @@ public:
     bool reuse_scores = true;
     int qv_halo = 32;             // > neighborhood (20): positions within this distance of an edit are re-scored
     bool generic_score = false;   // use the unfactored reference scoring kernel (tests)
+    int score_variant = 0;        // compile-time variant of the scoring kernel (occupancy target / unroll), for A/B runs
 
 private:
     // in-stream timing: spans are recorded without host syncs and resolved at the next natural sync
     struct Span { cudaEvent_t a, b; double* acc; int64_t bytes; int64_t* top_bytes; double* top_ms; };
-    void span_begin(double* acc, int64_t bytes = 0, int64_t* top_bytes = nullptr, double* top_ms = nullptr);
-    void span_end();
+    void span_begin(double* acc, int64_t bytes = 0, int64_t* top_bytes = nullptr, double* top_ms = nullptr, cudaStream_t s = nullptr);
+    void span_end(cudaStream_t s = nullptr);
     void resolve_spans();
     std::vector<Span> spans_;
     std::vector<cudaEvent_t> ev_pool_;
@@ -145,6 +146,10 @@ private:
     ArrowModelParams model_;
     EmissionTables em_;
     cudaStream_t stream_ = nullptr;
+    // The fill kernels are long serial chains (latency bound, few warps); they run on a HIGH-priority stream so that
+    // their CTAs get SM slots ahead of the short-lived CTAs of the other lanes' scoring kernels and co-reside with them.
+    cudaStream_t stream_hi_ = nullptr;
+    cudaEvent_t ev_order_ = nullptr;              // orders stream_ <-> stream_hi_
     cudaEvent_t evA_ = nullptr, evB_ = nullptr;   // bracket polish() (resident-input time)
 
     // host state of the current batch

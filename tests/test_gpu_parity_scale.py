@@ -159,9 +159,10 @@ def test_zscore_filter_matches_oracle(ctx):
     assert np.array_equal(res["seq"][:n], o["consensus"])
 
 
-def test_iteration_cap_and_growth_cap_match_oracle(ctx):
-    """NON_CONVERGENT two ways: the iteration cap, and a template that outgrows max(512, J/8) extra bases (a short
-    junk draft under long reads keeps gaining insertions)."""
+def test_iteration_cap_and_junk_draft_match_oracle(ctx):
+    """NON_CONVERGENT by the iteration cap; a junk draft loses every read (TOO_MANY_UNUSABLE).  (The template growth
+    cap max(512, J/8) is unreachable with the z-score filter on: reads that would drive such growth are dropped when
+    they are added.)"""
     z, full = _good_zmw(900)
     draft, mp = sim.corrupt(z.tpl, 0.05, seed=2)
     reads = [z.read(k).copy() for k in full]
@@ -170,15 +171,12 @@ def test_iteration_cap_and_growth_cap_match_oracle(ctx):
     assert not o["converged"] and res["status"][0] == 13 and res["iterations"][0] == o["iterations"] == 2
     n = res["seq_off"][1]
     assert np.array_equal(res["seq"][:n], o["consensus"])
-    # growth: a 120-base draft (a prefix of the truth) under reads of the whole 900-base molecule
+    # junk: a 120-base draft (a prefix of the truth) under reads of the whole 900-base molecule -- every read dies or
+    # is dropped on both sides, the ZMW fails with TOO_MANY_UNUSABLE and nothing is emitted
     short = z.tpl[:120].copy()
     res, o = _polish_case(ctx, short, z.snr, reads, strand, [0] * len(reads), [len(short)] * len(reads))
-    assert res["iterations"][0] == o["iterations"] and res["n_applied"][0] == o["n_applied"]
-    n = res["seq_off"][1]
-    if o["n_active"] >= 0.5 * len(reads):
-        assert np.array_equal(res["seq"][:n], o["consensus"])
-        assert (res["status"][0] == 13) == (not o["converged"])
     assert np.array_equal(res["read_status"], o["read_status"])
+    assert o["n_active"] == 0 and res["status"][0] == 11 and res["seq_off"][1] == 0
 
 
 def test_poa_vertex_with_more_than_8_predecessors(ctx):
