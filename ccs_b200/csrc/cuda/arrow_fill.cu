@@ -63,9 +63,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
     const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
     const int J = pinned(valid ? rd.J : 0);
     const int I = rd.I;
-    int Jmax = J;
-#pragma unroll
-    for (int off = 8; off < 32; off <<= 1) Jmax = max(Jmax, __shfl_xor_sync(kFullMask, Jmax, off));
+    const int Jmax = __reduce_max_sync(kFullMask, J);     // warp-uniform trip count (a reduction: provably convergent loop)
 
     const unsigned* __restrict__ rc32 = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off);
     const int wmax = (rd.code_stride >> 2) - 1;
@@ -202,9 +200,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
     const int J = pinned(valid ? rd.J : 0);
     const int I = rd.I;
-    int Jmax = J;
-#pragma unroll
-    for (int off = 8; off < 32; off <<= 1) Jmax = max(Jmax, __shfl_xor_sync(kFullMask, Jmax, off));
+    const int Jmax = __reduce_max_sync(kFullMask, J);     // warp-uniform trip count (a reduction: provably convergent loop)
 
     // second copy of the row codes, shifted by one row: word k holds the codes of rows 4k+1 .. 4k+4
     const unsigned* __restrict__ rc32 = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off + rd.code_stride);

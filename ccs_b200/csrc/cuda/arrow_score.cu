@@ -59,10 +59,8 @@ __device__ __forceinline__ float eval_mutation(const ReadCtx& R, const int g, co
     const int borig = bp - delta;
     const bool terminal = bp > Jp - 1;
     const int last = terminal ? Jp - 1 : bp - 1;
-    int n_ext = live ? max(0, last - a + 1) : 0;
-    int n_max = n_ext;
-    n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 8));
-    n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 16));
+    const int n_ext = live ? max(0, last - a + 1) : 0;
+    const int n_max = __reduce_max_sync(kFullMask, n_ext);      // warp-uniform trip count (provably convergent loop)
 
     // start column a-1
     const int ca = live ? min(a - 1, J - 1) : 0;
@@ -177,9 +175,7 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
     zm.read_begin = zm.read_end = 0; zm.fwd_off = 0; zm.J = 0; zm.delta_off = 0;
     if (have) zm = V.zmws[z];
     const int n_reads = zm.read_end - zm.read_begin;
-    int n_max = n_reads;
-    n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 8));
-    n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 16));
+    const int n_max = __reduce_max_sync(kFullMask, n_reads);
     const int tbase = have ? (V.tpl[zm.fwd_off + p] & 3) : 0;
 
     double acc[9];
@@ -284,6 +280,11 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
 // Reverse-strand reads compute the insertion BEFORE their local q, which is forward INS(p+1):
 // those sums go to slots 9..12 of row p+1 (combined by the consumers).
 // -------------------------------------------------------------------------------------------
+// warp-wide OR through a reduction: the result lives in a uniform register, so the compiler knows that branches on it
+// are convergent (a vote's result is not treated that way, and every shuffle behind such a branch gets wrapped in a
+// WARPSYNC / ENDCOLLECTIVE pair)
+__device__ __forceinline__ bool warp_any(const bool x) { return __reduce_or_sync(kFullMask, (unsigned)x) != 0u; }
+
 struct FastOut { float sub[4]; float del; float ins[4]; int e_sd; int e_in; };   // per-lane partial link sums
 
 constexpr int kReadCache = 48;     // read descriptors of the CTA's ZMW kept in shared memory (more reads: global loads)
@@ -531,9 +532,9 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
     zm.read_begin = zm.read_end = 0; zm.fwd_off = 0; zm.J = 0; zm.delta_off = 0;
     if (have) zm = V.zmws[z];
     const int n_reads = zm.read_end - zm.read_begin;
-    int n_max = n_reads;
-    n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 8));
-    n_max = max(n_max, __shfl_xor_sync(kFullMask, n_max, 16));
+    // warp-uniform trip count through a reduction: the compiler then knows the read loop is convergent and does not
+    // wrap every shuffle inside it in WARPSYNC / ENDCOLLECTIVE pairs
+    const int n_max = __reduce_max_sync(kFullMask, n_reads);
     const int tbase = have ? (V.tpl[zm.fwd_off + p] & 3) : 0;
 
     // this lane's slot: running product(s) and the sums of the contributing reads' base log-likelihoods
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
         }
         const bool cov_sd = usable && p >= rd.ts && p < rd.te;       // SUB / DEL
         const bool cov_in = usable && p > rd.ts && p < rd.te;        // INS (before p)
-        if (!__any_sync(kFullMask, cov_sd)) continue;
+        if (!warp_any(cov_sd)) continue;
 
         ReadCtx R;
         R.rc = V.rowcode + rd.code_off;
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
         const bool prev_interior = rd.strand && p > p_begin && (q_sd + 1 >= 2) && (q_sd + 1 <= rd.J - 4);
         const bool gen_in = cov_in && (rd.strand ? !prev_interior : !interior);
 
-        if (__any_sync(kFullMask, interior)) {
+        if (warp_any(interior)) {
             FastOut fo;
             fast_eval<kUnrollB>(R, g4, src_up, src_up2, src_up4, src_dn, tc, q_sd, interior, fo);
             // Q[k] = this lane's partial of the slot lane k owns (forward-strand base k & 3; reverse reads see 3 - base)
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
                 if (g >= 4 && rv) prod_mul(prB, pxB, tot, e); else prod_mul(prA, pxA, tot, e);
             }
         }
-        if (__any_sync(kFullMask, gen_sd) || __any_sync(kFullMask, gen_in)) {
+        if (warp_any(gen_sd) || warp_any(gen_in)) {
             const int q_in = cov_in ? (rd.strand ? rd.te - p : p - rd.ts) : 1;
             unsigned word_sd = 0, word_in = 0;
 #pragma unroll
@@ -648,7 +649,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
                 const int bf = (m < 3) ? ((tbase + 1 + m) & 3) : (is_ins ? m - 4 : 0);
                 const int bl = rd.strand ? 3 - bf : bf;
                 const bool lv = is_ins ? gen_in : (gen_sd && (m != 3 || rd.J >= 3));
-                if (!__any_sync(kFullMask, is_ins ? gen_in : gen_sd)) continue;
+                if (!warp_any(is_ins ? gen_in : gen_sd)) continue;
                 int e;
                 float val = eval_mutation(R, g, s_emm, s_emi, is_ins ? word_in : word_sd, type,
                                           is_ins ? q_in : q_sd, bl, lv, e);

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
         V = H.V; voff = H.voff;
         ord = poa_order(G, H.order_sel) + voff;
     }
+    V = __reduce_max_sync(kFull, V);      // same value in every lane; as a reduction result it is provably warp-uniform
     const uint32_t* __restrict__ meta = G.meta + voff;
     const int32_t* __restrict__ pred0 = G.pred0 + voff;
     const int32_t* __restrict__ predx = G.predx + 7 * voff;
