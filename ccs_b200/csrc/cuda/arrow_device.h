@@ -19,7 +19,7 @@ constexpr int kRowCodePad = 96;
 constexpr int kDeltaStride = 16;       // doubles per template position in the delta store:
                                       // {SUB A,C,G,T, DEL, INS A,C,G,T, INS' A,C,G,T (reverse-strand share), pad x3}       // sentinel codes after the last real row code
 
-struct ColInfo { int32_t start; int32_t cumexp; };   // per alpha column: band start, cumulative scale exponent
+struct alignas(8) ColInfo { int32_t start; int32_t cumexp; };   // per alpha column: band start, cumulative scale exponent
 
 struct DevRead {
     int64_t code_off;    // rowcode[code_off + i] = 4 * emission code of DP row i (sentinel 48 at i = 0 and i >= I);

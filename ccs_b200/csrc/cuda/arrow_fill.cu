@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
     int x_cur = valid ? 64 + (tp[1] & 15) : 0;
     int x_nxt = (2 < J) ? tp[2] : 0;
 
-    for (int j = 1; j < Jmax; ++j) {
+    auto column = [&](const int j, const bool rescale) {
         const bool alive = j < J;
         int x_pre = 0;
         if (j + 2 < J) x_pre = tp[j + 2];          // prefetch, two columns ahead
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
         // tells the whole octet
         const float m3 = fmaxf(fmaxf(v1, v2), v3);
         const unsigned bal = __ballot_sync(kFullMask, topl && m3 >= thr);
-        if ((j & (kScaleEvery - 1)) == 0) {        // warp-uniform: every 4th column is rescaled (spec)
+        if (rescale) {                             // every 4th column is rescaled (spec); known at compile time here
             // the sign bit of a maximum is 0, so key >> 23 is its biased exponent e: scale by 2^(127-e) (an all-zero
             // or denormal column gives e = 0 -- the read is dead or about to be, and its LL ends up -inf either way)
             const unsigned key = vmax_oct(__float_as_uint(fmaxf(m3, v0)) & 0xffff0000u);
@@ -152,7 +152,14 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
             w2 = rc32[min(8 * (lap + 2) + g, wmax)];
         }
         x_cur = x_nxt; x_nxt = x_pre;
-    }
+    };
+    // columns 1..3, then groups of four starting at a multiple of kScaleEvery (the first of each group is rescaled:
+    // no per-column test, no rotation of the software-pipelined registers), then the tail
+    static_assert(kScaleEvery == 4, "the column loop is unrolled in step with the rescale schedule");
+    int j = 1;
+    for (; j < 4 && j < Jmax; ++j) column(j, false);
+    for (; j + 3 < Jmax; j += 4) { column(j, true); column(j + 1, false); column(j + 2, false); column(j + 3, false); }
+    for (; j < Jmax; ++j) column(j, (j & 3) == 0);
     // alpha(I-1, J-1) lives in slot (I-1) mod 32 of the last column if it is inside the band; lane 0 of the octet reads
     // it back from the column line the octet just wrote (ordered by __syncwarp), then applies the pinned last match
     __syncwarp();
@@ -222,8 +229,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     unsigned w0 = 0x30303030u, w1 = 0x30303030u, wm = 0x30303030u;   // laps L, L+1, L-1 (sentinels)
     bool started = false;
 
-#pragma unroll 2
-    for (int j = Jmax - 1; j >= 1; --j) {
+    auto column = [&](const int j, const bool rescale) {
         const bool alive = j <= J - 1;
         const bool init_col = alive && !started;
         if (init_col) {
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
         v0 = fmaf(G0, xin, A0); v1 = fmaf(G1, xin, A1); v2 = fmaf(G2, xin, A2); v3 = fmaf(G3, xin, A3);
 
         int kcol = 0;
-        if ((j & (kScaleEvery - 1)) == 0) {        // warp-uniform: every 4th column is rescaled (spec)
+        if (rescale) {                             // every 4th column is rescaled (spec); known at compile time here
             const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
             const unsigned key = vmax_oct(__float_as_uint(mx) & 0xffff0000u);
             const float sc = __uint_as_float(0x7f000000u - ((key >> 23) << 23));
@@ -309,7 +315,13 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
             s_nxt = s_cur; s_cur = s_p1; s_p1 = s_p2;
             x_cur = x_p1; x_p1 = x_p2;
         }
-    }
+    };
+    // down to a column = 3 (mod 4), then groups of four whose last column is the rescaled one, then the tail
+    static_assert(kScaleEvery == 4, "the column loop is unrolled in step with the rescale schedule");
+    int j = Jmax - 1;
+    for (; j >= 1 && (j & 3) != 3; --j) column(j, (j & 3) == 0);
+    for (; j >= 4; j -= 4) { column(j, false); column(j - 1, false); column(j - 2, false); column(j - 3, true); }
+    for (; j >= 1; --j) column(j, (j & 3) == 0);
     // the warp's last iteration is column 1 of every live octet: beta(1,1) is cell 1 of lane 0 if row 1 is in the band
     if (valid) {
         if (g == 0) {

@@ -238,7 +238,7 @@ static void collect_results(ArrowEngine& E, int nz, int nr, const uint8_t* cx, c
             rq = J ? 1.0 - e / J : 0.0;
             if (!s.converged) status = CCS_ZMW_NON_CONVERGENT;
             else if (J < pp.min_length) status = CCS_ZMW_TOO_SHORT;
-            else if (J > pp.max_length) status = CCS_ZMW_TOO_LONG;
+            else if (pp.max_length > 0 && J > pp.max_length) status = CCS_ZMW_TOO_LONG;
             else if (rq < pp.min_rq) status = CCS_ZMW_POOR_QUALITY;
             co.seq_len[z] = J;
         }

@@ -137,27 +137,56 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
     }
 
     // ---- a2-a5 on the device, in chunks of ZMWs that fit the scratch budget -------------------------------------
-    std::vector<int> zlist;
-    int64_t bytes = 0;
-    auto flush = [&]() {
-        if (!zlist.empty()) poa_chunk(in, dp, out, lens, work, zlist);
-        zlist.clear();
-        bytes = 0;
-    };
-    for (int z = 0; z < nz; ++z) {
-        const Zw& w = work[z];
-        if (!w.alive) continue;
-        int64_t cap = lens[w.poa_reads[0]] + 8, nmax = 0;
-        for (size_t k = 1; k < w.poa_reads.size(); ++k) {
-            cap += poa_new_vertex_bound(lens[w.poa_reads[k]]);
-            nmax = std::max<int64_t>(nmax, lens[w.poa_reads[k]]);
+    auto run_alive = [&]() {
+        std::vector<int> zlist;
+        int64_t bytes = 0;
+        auto flush = [&]() {
+            if (!zlist.empty()) poa_chunk(in, dp, out, lens, work, zlist);
+            zlist.clear();
+            bytes = 0;
+        };
+        for (int z = 0; z < nz; ++z) {
+            const Zw& w = work[z];
+            if (!w.alive) continue;
+            int64_t cap = lens[w.poa_reads[0]] + 8, nmax = 0;
+            for (size_t k = 1; k < w.poa_reads.size(); ++k) {
+                cap += poa_new_vertex_bound(lens[w.poa_reads[k]]);
+                nmax = std::max<int64_t>(nmax, lens[w.poa_reads[k]]);
+            }
+            const int64_t need = cap * 400 + nmax * 32;
+            if (!zlist.empty() && bytes + need > (int64_t)budget_ * 7 / 10) flush();   // the buffers grow with 25 % slack
+            zlist.push_back(z);
+            bytes += need;
         }
-        const int64_t need = cap * 400 + nmax * 32;
-        if (!zlist.empty() && bytes + need > (int64_t)budget_) flush();
-        zlist.push_back(z);
-        bytes += need;
+        flush();
+    };
+    run_alive();      // draft generator 0: SparsePoa over the first full-length reads, seeded by the first one
+
+    // ---- draft cascade (docs/faq/accuracy-vs-passes.md:41-46): ZMWs whose draft could not be generated or that too few
+    //      subreads map back to get one more try with the robust generator -- seeded by the full-length read closest to
+    //      the median length, over up to 2 * max_poa_reads - 1 reads in order of closeness
+    bool any = false;
+    for (int z = 0; z < nz; ++z) {
+        Zw& w = work[z];
+        w.alive = false;
+        if (w.poa_reads.empty()) continue;
+        if (out.status[z] != CCS_ZMW_DRAFT_FAILURE && out.status[z] != CCS_ZMW_TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT) continue;
+        const int r0 = in.zmw_read_off[z], r1 = in.zmw_read_off[z + 1];
+        std::vector<int32_t> full, sl;
+        for (int r = r0; r < r1; ++r) if (out.keep[r] && (in.cx[r] & 3) == 3) { full.push_back(r); sl.push_back(lens[r]); }
+        std::sort(sl.begin(), sl.end());
+        const int med = sl.empty() ? 0 : sl[sl.size() / 2];
+        std::stable_sort(full.begin(), full.end(), [&](int a, int b) { return std::abs(lens[a] - med) < std::abs(lens[b] - med); });
+        const size_t cap = (size_t)std::max(1, std::min(2 * dp.max_poa_reads - 1, kPoaMaxReads));
+        if (full.size() > cap) full.resize(cap);
+        if (full == w.poa_reads || full.empty() || lens[full[0]] > kPoaMaxRefLen) continue;   // nothing new to try
+        w.poa_reads = full;
+        w.alive = true;
+        out.draft[z].clear();
+        for (int r = r0; r < r1; ++r) out.maps[r] = ReadMap();
+        any = true;
     }
-    flush();
+    if (any) run_alive();
 }
 
 // One chunk of ZMWs through SparsePoa (rounds of align -> traceback -> CommitAdd), FindConsensus and the mapping.
@@ -386,10 +415,16 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         }
         for (size_t x = li; x < lj; ++x) {
             const int z = zlist[live[x]];
-            int mapped_full = 0;
-            for (int r = in.zmw_read_off[z]; r < in.zmw_read_off[z + 1]; ++r)
-                if (out.keep[r] && out.maps[r].mapped && (in.cx[r] & 3) == 3) ++mapped_full;
-            out.status[z] = mapped_full < dp.min_passes ? CCS_ZMW_TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT : CCS_ZMW_SUCCESS;
+            int mapped_full = 0, mapped = 0, kept = 0;
+            for (int r = in.zmw_read_off[z]; r < in.zmw_read_off[z + 1]; ++r) {
+                if (!out.keep[r]) continue;
+                ++kept;
+                if (out.maps[r].mapped) { ++mapped; if ((in.cx[r] & 3) == 3) ++mapped_full; }
+            }
+            // fewer than --min-passes full-length reads, or not more than half of the subreads, map back to the draft
+            // (docs/faq/accuracy-vs-passes.md:31-39)
+            out.status[z] = (mapped_full < dp.min_passes || 2 * mapped <= kept) ? CCS_ZMW_TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT
+                                                                                : CCS_ZMW_SUCCESS;
         }
         li = lj;
     }

@@ -43,52 +43,83 @@ void draft_zmw(const CcsConfig& cfg, int nreads, const uint8_t* codes, const int
     for (int r = 0; r < nreads; ++r) lens[r] = (int)(read_off[r + 1] - read_off[r]);
     const int nfull = filter_reads(lens, cx, cfg.top_passes, keep);
     if (nfull < cfg.min_passes) { out.status = Z_TOO_FEW_PASSES; return; }
-    // SparsePoa over the first max_poa_reads full-length reads
-    PoaGraph g;
-    std::vector<uint8_t> seed;
-    int used = 0;
-    for (int r = 0; r < nreads && used < cfg.max_poa_reads; ++r) {
-        if (!keep[r] || (cx[r] & 3) != 3) continue;
-        const uint8_t* c = codes + read_off[r];
-        if (used == 0) {
-            seed = bases_of(c, lens[r], false);
-            g.add_first(seed.data(), lens[r]);
+    // Draft cascade (docs/faq/accuracy-vs-passes.md:41-46): generator 0 = SparsePoa over the first max_poa_reads
+    // full-length reads, seeded by the first one; if its draft cannot be generated or too few subreads map back to it,
+    // generator 1 = SparsePoa seeded by the full-length read closest to the median length, over up to
+    // 2 * max_poa_reads - 1 reads in order of closeness.  Length gates are final.
+    std::vector<int> full;
+    for (int r = 0; r < nreads; ++r) if (keep[r] && (cx[r] & 3) == 3) full.push_back(r);
+    int kept = 0;
+    for (int r = 0; r < nreads; ++r) kept += keep[r] ? 1 : 0;
+    std::vector<int> first_sel;
+    for (int gen = 0; gen < 2; ++gen) {
+        std::vector<int> sel;
+        if (gen == 0) {
+            for (int r : full) if ((int)sel.size() < std::max(1, std::min(cfg.max_poa_reads, 16))) sel.push_back(r);
+            first_sel = sel;
         } else {
-            std::vector<uint8_t> fwd = bases_of(c, lens[r], false);
-            const bool rev = kmer_vote_reverse(seed.data(), (int)seed.size(), fwd.data(), lens[r]);
-            std::vector<uint8_t> b = rev ? bases_of(c, lens[r], true) : fwd;
-            PoaAlignment a = g.align(b.data(), lens[r]);
-            if (a.score >= lens[r]) g.commit(a, b.data());
+            std::vector<int> sl;
+            for (int r : full) sl.push_back(lens[r]);
+            std::sort(sl.begin(), sl.end());
+            const int med = sl.empty() ? 0 : sl[sl.size() / 2];
+            sel = full;
+            std::stable_sort(sel.begin(), sel.end(), [&](int a, int b) { return std::abs(lens[a] - med) < std::abs(lens[b] - med); });
+            const size_t cap = (size_t)std::max(1, std::min(2 * cfg.max_poa_reads - 1, 16));
+            if (sel.size() > cap) sel.resize(cap);
+            if (sel == first_sel) break;          // nothing new to try
         }
-        ++used;
+        out.draft.clear();
+        out.maps.assign(nreads, ReadMapping());
+        if (sel.empty()) { out.status = Z_DRAFT_FAILURE; return; }
+        PoaGraph g;
+        std::vector<uint8_t> seed;
+        for (size_t k = 0; k < sel.size(); ++k) {
+            const int r = sel[k];
+            const uint8_t* c = codes + read_off[r];
+            if (k == 0) {
+                seed = bases_of(c, lens[r], false);
+                g.add_first(seed.data(), lens[r]);
+            } else {
+                std::vector<uint8_t> fwd = bases_of(c, lens[r], false);
+                const bool rev = kmer_vote_reverse(seed.data(), (int)seed.size(), fwd.data(), lens[r]);
+                std::vector<uint8_t> b = rev ? bases_of(c, lens[r], true) : fwd;
+                PoaAlignment a = g.align(b.data(), lens[r]);
+                if (a.score >= lens[r]) g.commit(a, b.data());
+            }
+        }
+        const int n = g.n_reads;
+        const int min_cov = n < 5 ? 1 : (n + 1) / 2 - 1;
+        std::vector<int> path = g.consensus(min_cov);
+        out.draft.resize(path.size());
+        for (size_t k = 0; k < path.size(); ++k) out.draft[k] = g.v[path[k]].base;
+        const int J = (int)out.draft.size();
+        if (J == 0) { out.status = Z_DRAFT_FAILURE; continue; }
+        if (J < cfg.min_length) { out.status = Z_TOO_SHORT; return; }
+        if (cfg.max_length > 0 && J > cfg.max_length) { out.status = Z_TOO_LONG; return; }
+        // subread -> draft mapping of every kept read
+        int mapped_full = 0, mapped = 0;
+        for (int r = 0; r < nreads; ++r) {
+            if (!keep[r]) continue;
+            const uint8_t* c = codes + read_off[r];
+            std::vector<uint8_t> fwd = bases_of(c, lens[r], false);
+            const bool rev = kmer_vote_reverse(out.draft.data(), J, fwd.data(), lens[r]);
+            std::vector<uint8_t> b = rev ? bases_of(c, lens[r], true) : fwd;
+            ReadMapping m = map_to_template(out.draft.data(), J, b.data(), lens[r]);
+            m.strand = rev ? 1 : 0;
+            if (rev) { const int rs = lens[r] - m.rend, re = lens[r] - m.rstart; m.rstart = rs; m.rend = re; }
+            if (m.mapped && (m.tend - m.tstart < 2 || m.rend - m.rstart < 2)) m.mapped = false;
+            out.maps[r] = m;
+            if (m.mapped) ++mapped;
+            if (m.mapped && (cx[r] & 3) == 3) ++mapped_full;
+        }
+        // fewer than --min-passes full-length reads, or not more than half of the subreads, map back to the draft
+        // (docs/faq/accuracy-vs-passes.md:31-39)
+        if (mapped_full < cfg.min_passes || 2 * mapped <= kept) { out.status = Z_TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT; continue; }
+        out.status = Z_SUCCESS;   // draft stage passed
+        return;
     }
-    const int n = g.n_reads;
-    const int min_cov = n < 5 ? 1 : (n + 1) / 2 - 1;
-    std::vector<int> path = g.consensus(min_cov);
-    out.draft.resize(path.size());
-    for (size_t k = 0; k < path.size(); ++k) out.draft[k] = g.v[path[k]].base;
-    const int J = (int)out.draft.size();
-    if (J == 0) { out.status = Z_DRAFT_FAILURE; return; }
-    if (J < cfg.min_length) { out.status = Z_TOO_SHORT; return; }
-    if (J > cfg.max_length) { out.status = Z_TOO_LONG; return; }
-    // subread -> draft mapping of every kept read
-    int mapped_full = 0;
-    for (int r = 0; r < nreads; ++r) {
-        if (!keep[r]) continue;
-        const uint8_t* c = codes + read_off[r];
-        std::vector<uint8_t> fwd = bases_of(c, lens[r], false);
-        const bool rev = kmer_vote_reverse(out.draft.data(), J, fwd.data(), lens[r]);
-        std::vector<uint8_t> b = rev ? bases_of(c, lens[r], true) : fwd;
-        ReadMapping m = map_to_template(out.draft.data(), J, b.data(), lens[r]);
-        m.strand = rev ? 1 : 0;
-        if (rev) { const int rs = lens[r] - m.rend, re = lens[r] - m.rstart; m.rstart = rs; m.rend = re; }
-        if (m.mapped && (m.tend - m.tstart < 2 || m.rend - m.rstart < 2)) m.mapped = false;
-        out.maps[r] = m;
-        if (m.mapped && (cx[r] & 3) == 3) ++mapped_full;
-    }
-    if (mapped_full < cfg.min_passes) { out.status = Z_TOO_FEW_PASSES_AFTER_DRAFT_ALIGNMENT; return; }
-    out.status = Z_SUCCESS;   // draft stage passed
 }
+
 
 void ccs_zmw(const ccs::ArrowModelParams& model, const CcsConfig& cfg, int nreads, const uint8_t* codes,
              const int64_t* read_off, const uint8_t* cx, const float snr[4], CcsZmwResult& out) {
@@ -130,7 +161,7 @@ void ccs_zmw(const ccs::ArrowModelParams& model, const CcsConfig& cfg, int nread
     const int J = (int)out.seq.size();
     if (!out.pr.converged) out.status = Z_NON_CONVERGENT;
     else if (J < cfg.min_length) out.status = Z_TOO_SHORT;
-    else if (J > cfg.max_length) out.status = Z_TOO_LONG;
+    else if (cfg.max_length > 0 && J > cfg.max_length) out.status = Z_TOO_LONG;
     else if (out.rq < cfg.min_rq) out.status = Z_POOR_QUALITY;
     else out.status = Z_SUCCESS;
 }
