@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     const bool valid = r >= 0 && rd.active && rd.J >= 2 && rd.I >= 2;
     const int J = pinned(valid ? rd.J : 0);
     const int I = rd.I;
-    const int Jmax = __reduce_max_sync(kFullMask, J);     // warp-uniform trip count (a reduction: provably convergent loop)
+    int Jmax = J;
+#pragma unroll
+    for (int off = 8; off < 32; off <<= 1) Jmax = max(Jmax, __shfl_xor_sync(kFullMask, Jmax, off));
 
     // second copy of the row codes, shifted by one row: word k holds the codes of rows 4k+1 .. 4k+4
     const unsigned* __restrict__ rc32 = reinterpret_cast<const unsigned*>(V.rowcode + rd.code_off + rd.code_stride);
@@ -229,7 +231,8 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
     unsigned w0 = 0x30303030u, w1 = 0x30303030u, wm = 0x30303030u;   // laps L, L+1, L-1 (sentinels)
     bool started = false;
 
-    auto column = [&](const int j, const bool rescale) {
+#pragma unroll 2
+    for (int j = Jmax - 1; j >= 1; --j) {
         const bool alive = j <= J - 1;
         const bool init_col = alive && !started;
         if (init_col) {
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
         v0 = fmaf(G0, xin, A0); v1 = fmaf(G1, xin, A1); v2 = fmaf(G2, xin, A2); v3 = fmaf(G3, xin, A3);
 
         int kcol = 0;
-        if (rescale) {                             // every 4th column is rescaled (spec); known at compile time here
+        if ((j & (kScaleEvery - 1)) == 0) {        // warp-uniform: every 4th column is rescaled (spec)
             const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
             const unsigned key = vmax_oct(__float_as_uint(mx) & 0xffff0000u);
             const float sc = __uint_as_float(0x7f000000u - ((key >> 23) << 23));
@@ -315,13 +318,7 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
             s_nxt = s_cur; s_cur = s_p1; s_p1 = s_p2;
             x_cur = x_p1; x_p1 = x_p2;
         }
-    };
-    // down to a column = 3 (mod 4), then groups of four whose last column is the rescaled one, then the tail
-    static_assert(kScaleEvery == 4, "the column loop is unrolled in step with the rescale schedule");
-    int j = Jmax - 1;
-    for (; j >= 1 && (j & 3) != 3; --j) column(j, (j & 3) == 0);
-    for (; j >= 4; j -= 4) { column(j, false); column(j - 1, false); column(j - 2, false); column(j - 3, true); }
-    for (; j >= 1; --j) column(j, (j & 3) == 0);
+    }
     // the warp's last iteration is column 1 of every live octet: beta(1,1) is cell 1 of lane 0 if row 1 is in the band
     if (valid) {
         if (g == 0) {
