@@ -245,7 +245,7 @@ void ArrowEngine::upload_templates_and_reads() {
     }
     if (toff > 0x7fffffffll) throw OomError("template buffer exceeds 2 GiB; use smaller batches");
     h_tpl_.ensure((size_t)toff + 16);
-    std::memset(h_tpl_.p, 0, 64);   // idle lanes of the kernels read the first bytes of the buffer
+    if (toff < 64) std::memset(h_tpl_.p + toff, 0, (size_t)(64 - toff));   // idle lanes of the kernels read the first bytes of the buffer
     // column offsets (serial prefix), then the per-ZMW copies in parallel
     for (int z = 0; z < nz; ++z) {
         const ZmwState& zs = zstate_[z];
@@ -264,6 +264,7 @@ void ArrowEngine::upload_templates_and_reads() {
         const ZmwState& zs = zstate_[z];
         const DevZmw& dz = zmws_[z];
         const int J = dz.J;
+        if (!zs.dirty) return;       // template and spans unchanged since the last upload: its bytes in h_tpl_ still hold
         uint8_t* f = h_tpl_.p + dz.fwd_off;
         uint8_t* rv = h_tpl_.p + dz.rev_off;
         // template bytes carry the trinucleotide index 16*t[j-2] + 4*t[j-1] + t[j] (the base is byte & 3): the fill

@@ -25,5 +25,5 @@ rc = simlib().ccs_sim_write_subreads_bam(b"/tmp/bench.subreads.bam", b"m64000_00
 print("wrote BAM rc", rc, "in", round(time.time() - t, 1), "s")
 PY
 ls -la /tmp/bench.subreads.bam*
-for g in 1 $N; do /usr/bin/time -v ccs_b200/bin/ccs /tmp/bench.subreads.bam /tmp/out_g$g.bam --gpus $g --log-level INFO 2> gpurun_out/cli_gpus$g.log; tail -8 gpurun_out/cli_gpus$g.log | head -7; grep -E "Elapsed \(wall|Maximum resident|Percent of CPU" gpurun_out/cli_gpus$g.log; done
+for g in 1 $N; do ( time ccs_b200/bin/ccs /tmp/bench.subreads.bam /tmp/out_g$g.bam --gpus $g --log-level INFO ) 2> gpurun_out/cli_gpus$g.log; tail -12 gpurun_out/cli_gpus$g.log; done
 cmp /tmp/out_g1.bam /tmp/out_g$N.bam && echo "CLI output identical for 1 and $N GPUs"
