@@ -282,26 +282,107 @@ bool SubreadBamReader::open(const std::string& path, std::string& err, int threa
     return true;
 }
 
-bool SubreadBamReader::next_record(Subread& s) {
+// Every length field of a record is checked against the record before anything is decoded.  Returns the offset of the
+// first tag, or 0 with err set.
+static size_t validate_record(const uint8_t* r, size_t size, std::string& err) {
+    auto bad = [&](const char* why) { err = std::string("malformed BAM record: ") + why; return (size_t)0; };
+    if (size < 32) return bad("implausible record size");
+    const int l_name = r[8];
+    const int n_cigar = rd16(r + 12);
+    const int32_t l_seq = (int32_t)rd32(r + 16);
+    if (l_seq < 0) return bad("negative l_seq");
+    const uint64_t fixed = 32ull + (uint64_t)l_name + 4ull * (uint64_t)n_cigar + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
+    if (fixed > size) return bad("name / cigar / sequence lengths exceed the record");
+    // walk the tags once: types and sizes must stay inside the record
+    const uint8_t* p = r + fixed;
+    const uint8_t* end = r + size;
+    while (p + 3 <= end) {
+        const char ty = (char)p[2];
+        p += 3;
+        size_t sz = 0;
+        switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'Z': case 'H': {
+                const void* z = std::memchr(p, 0, (size_t)(end - p));
+                if (!z) return bad("unterminated string tag");
+                sz = (size_t)((const uint8_t*)z - p) + 1;
+                break;
+            }
+            case 'B': {
+                if (p + 5 > end) return bad("truncated array tag");
+                const char sub = (char)p[0];
+                const uint32_t n = rd32(p + 1);
+                const size_t es = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
+                if ((uint64_t)es * n + 5 > (uint64_t)(end - p)) return bad("array tag exceeds the record");
+                sz = 5 + es * n;
+                break;
+            }
+            default: return bad("unknown tag type");
+        }
+        if (sz > (size_t)(end - p)) return bad("tag exceeds the record");
+        p += sz;
+    }
+    return (size_t)fixed;
+}
+
+// hole number of a validated record: the zm tag, else the read name movie/zmw/qs_qe
+static int32_t record_hole(const uint8_t* r, size_t size, size_t tags_off) {
+    const uint8_t* p = r + tags_off;
+    const uint8_t* end = r + size;
+    while (p + 3 <= end) {
+        const char t0 = (char)p[0], t1 = (char)p[1], ty = (char)p[2];
+        p += 3;
+        size_t sz = 0;
+        switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'Z': case 'H': sz = std::strlen((const char*)p) + 1; break;
+            case 'B': { const char sub = (char)p[0]; const uint32_t n = rd32(p + 1);
+                        sz = 5 + (size_t)((sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4)) * n; break; }
+            default: return 0;
+        }
+        if (t0 == 'z' && t1 == 'm') {
+            if (ty == 'i' || ty == 'I') return (int32_t)rd32(p);
+            if (ty == 's') return (int16_t)rd16(p);
+            if (ty == 'S') return rd16(p);
+            if (ty == 'c') return (int8_t)p[0];
+            if (ty == 'C') return p[0];
+        }
+        p += sz;
+    }
+    const int l_name = r[8];
+    const std::string name((const char*)r + 32, l_name > 0 ? l_name - 1 : 0);
+    const size_t a = name.find('/'), b = name.find('/', a + 1);
+    if (a != std::string::npos && b != std::string::npos) return std::atoi(name.substr(a + 1, b - a - 1).c_str());
+    return 0;
+}
+
+bool SubreadBamReader::next_raw_record(std::vector<uint8_t>& rec, int32_t& hole) {
     uint8_t b4[4];
     if (!error_.empty()) return false;
     if (in_.eof()) return false;                 // clean end of the data (or a damaged container: in_.error())
     auto bad = [&](const char* why) { error_ = std::string("malformed BAM record: ") + why; return false; };
     if (!in_.read(b4, 4)) return bad("truncated record length");
-    std::vector<uint8_t>& rec = rec_;            // reused across records: no 26 KB allocation per subread
     const uint32_t rec_size = rd32(b4);
     constexpr uint32_t kMaxRecord = 64u << 20;   // a subread of 20 M bases: far beyond any real polymerase read
     if (rec_size < 32 || rec_size > kMaxRecord) return bad("implausible record size");
     rec.resize(rec_size);
     if (!in_.read(rec.data(), rec.size())) return bad("truncated record");
-    const uint8_t* r = rec.data();
+    const size_t tags = validate_record(rec.data(), rec.size(), error_);
+    if (!tags) return false;
+    hole = record_hole(rec.data(), rec.size(), tags);
+    return true;
+}
+
+bool decode_subread_record(const uint8_t* r, size_t size, Subread& s, std::vector<uint8_t>& pw, std::string& err) {
+    if (!validate_record(r, size, err)) return false;
+    auto bad = [&](const char* why) { err = std::string("malformed BAM record: ") + why; return false; };
     const int l_name = r[8];
     const int n_cigar = rd16(r + 12);
     const int32_t l_seq = (int32_t)rd32(r + 16);
-    if (l_seq < 0) return bad("negative l_seq");
-    // every length field is checked against the record before anything is decoded
-    const uint64_t fixed = 32ull + (uint64_t)l_name + 4ull * (uint64_t)n_cigar + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
-    if (fixed > rec.size()) return bad("name / cigar / sequence lengths exceed the record");
     const uint8_t* p = r + 32;
     const std::string name((const char*)p, l_name > 0 ? l_name - 1 : 0);
     p += l_name + 4 * n_cigar;
@@ -309,10 +390,9 @@ bool SubreadBamReader::next_record(Subread& s) {
     p += (l_seq + 1) / 2 + l_seq;               // packed bases + qualities
     s.hole = 0; s.qs = 0; s.qe = 0; s.cx = 0;
     s.snr[0] = s.snr[1] = s.snr[2] = s.snr[3] = 0.f;
-    std::vector<uint8_t>& pw = pw_;               // only filled for 16-bit pulse widths
     const uint8_t* pw8 = nullptr;                 // 8-bit pulse widths are used in place
     uint32_t n_pw = 0;
-    const uint8_t* end = r + rec.size();
+    const uint8_t* end = r + size;
     while (p + 3 <= end) {
         const char t0 = (char)p[0], t1 = (char)p[1], ty = (char)p[2];
         p += 3;
@@ -396,8 +476,43 @@ bool SubreadBamReader::next_record(Subread& s) {
     return true;
 }
 
+bool SubreadBamReader::next_record(Subread& s) {
+    int32_t hole = 0;
+    if (!next_raw_record(rec_, hole)) return false;
+    return decode_subread_record(rec_.data(), rec_.size(), s, pw_, error_);
+}
+
+bool decode_zmw(const RawZmw& raw, ZmwSubreads& z, std::string& err) {
+    z.reads.clear();
+    z.hole = raw.hole;
+    std::vector<uint8_t> pw;
+    z.reads.resize(raw.n_records());
+    for (size_t k = 0; k < raw.n_records(); ++k)
+        if (!decode_subread_record(raw.data.data() + raw.rec_off[k], raw.rec_off[k + 1] - raw.rec_off[k], z.reads[k], pw, err)) return false;
+    if (!z.reads.empty()) std::memcpy(z.snr, z.reads[0].snr, sizeof(z.snr));
+    return true;
+}
+
+bool SubreadBamReader::next_zmw_raw(RawZmw& z) {
+    z.data.clear(); z.rec_off.assign(1, 0);
+    if (!have_pending_raw_) {
+        if (!next_raw_record(pending_raw_, pending_raw_hole_)) return false;
+        have_pending_raw_ = true;
+    }
+    z.hole = pending_raw_hole_;
+    while (have_pending_raw_ && pending_raw_hole_ == z.hole) {
+        z.data.insert(z.data.end(), pending_raw_.begin(), pending_raw_.end());
+        z.rec_off.push_back((uint32_t)z.data.size());
+        have_pending_raw_ = next_raw_record(pending_raw_, pending_raw_hole_);
+    }
+    // a damaged file ends the stream with an error; the ZMW being assembled may be missing subreads and is dropped
+    if (!error().empty()) { z.data.clear(); z.rec_off.assign(1, 0); have_pending_raw_ = false; return false; }
+    return true;
+}
+
 bool SubreadBamReader::seek_record(uint64_t voffset) {
     have_pending_ = false;
+    have_pending_raw_ = false;
     return in_.seek(voffset);
 }
 

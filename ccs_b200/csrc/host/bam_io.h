@@ -87,11 +87,25 @@ struct ZmwSubreads {
     std::vector<Subread> reads;
 };
 
+// The records of one ZMW as they sit in the file (validated, not decoded): the reader thread only groups records by
+// hole number; sequence / pulse-width decoding runs in the stage workers (decode_zmw), in parallel.
+struct RawZmw {
+    int32_t hole = 0;
+    std::vector<uint8_t> data;                // records back to back (without their block_size words)
+    std::vector<uint32_t> rec_off;            // n_records + 1 offsets into data
+    size_t n_records() const { return rec_off.empty() ? 0 : rec_off.size() - 1; }
+};
+
+// Decodes one validated record (SEQ + pw -> emission codes, zm qs qe cx sn tags).  false + err on a malformed record.
+bool decode_subread_record(const uint8_t* rec, size_t size, Subread& s, std::vector<uint8_t>& pw_scratch, std::string& err);
+bool decode_zmw(const RawZmw& raw, ZmwSubreads& z, std::string& err);
+
 class SubreadBamReader {
 public:
     // Opens and parses the header.  Fails (chemistry_ok() == false) if the read group lacks the
     // chemistry triple -- fatal in the reference too (docs/changelog.md:66, docs/faq/chemistry.md:7-10).
     bool open(const std::string& path, std::string& err, int threads = 0);   // threads: BGZF inflate workers
+    bool next_zmw_raw(RawZmw& z);             // the same grouping without decoding the records (see RawZmw)
     bool next_zmw(ZmwSubreads& z);            // records of one hole number (consecutive in the file); false at the end
                                               // of the data AND on a damaged file: check error() afterwards
     const std::string& error() const { return error_.empty() ? in_.error() : error_; }
@@ -102,10 +116,14 @@ public:
     bool chemistry_ok() const { return chem_ok_; }
 private:
     bool next_record(Subread& s);
+    bool next_raw_record(std::vector<uint8_t>& rec, int32_t& hole);   // reads + validates one record, finds its hole number
     BgzfReader in_;
     std::string header_, movie_, rg_id_;
     bool chem_ok_ = false, have_pending_ = false;
     Subread pending_;
+    std::vector<uint8_t> pending_raw_;
+    int32_t pending_raw_hole_ = 0;
+    bool have_pending_raw_ = false;
     std::string error_;
     std::vector<uint8_t> rec_, pw_;           // record / 16-bit pulse-width scratch, reused across records
 };

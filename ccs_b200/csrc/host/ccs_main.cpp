@@ -16,6 +16,7 @@
 #include "../../../include/ccsgpu.h"
 #include "bam_io.h"
 #include "draft_host.h"
+#include "parallel.h"
 #include <cuda_runtime.h>
 #include <zlib.h>
 #include <algorithm>
@@ -252,7 +253,8 @@ bool write_hifi_summary(const std::string& path, const Report& r, double seconds
 // One batch travelling through the pipeline.
 struct BatchIO {
     int64_t seq_no = 0;
-    std::vector<ZmwSubreads> zmws;             // with --by-strand: one entry per strand bucket
+    std::vector<RawZmw> raw;                   // as grouped by the reader thread (validated, not decoded)
+    std::vector<ZmwSubreads> zmws;             // decoded by the stage worker; with --by-strand: one entry per strand bucket
     std::vector<uint8_t> strand_tag;           // 0: whole ZMW, 1: fwd bucket, 2: rev bucket
     std::vector<int32_t> zmw_read_off, hole, status, npass, iters, napp, rstatus;
     std::vector<int64_t> read_off, seq_off, ntest;
@@ -392,7 +394,29 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "ccs: cannot write %s\n", o.out.c_str());
         return 1;
     }
+    const int decode_threads = std::max(1, host_threads / std::max(1, n_workers));
     auto process = [&](ccsgpu_ctx* ctx, BatchIO& B) -> int {
+        // decode the records of the batch (SEQ + pw -> emission codes) here, in the stage worker: the reader thread only
+        // inflates and groups, so decoding scales with the number of workers
+        {
+            std::vector<ZmwSubreads> dec(B.raw.size());
+            std::string derr;
+            std::mutex emu;
+            parallel_for((int)B.raw.size(), decode_threads, [&](int k) {
+                std::string e;
+                if (!decode_zmw(B.raw[k], dec[k], e)) { std::lock_guard<std::mutex> g(emu); if (derr.empty()) derr = e; }
+            }, /*min_items_per_thread=*/4);
+            if (!derr.empty()) { B.err = derr; return CCS_ERR_ARG; }
+            B.raw.clear(); B.raw.shrink_to_fit();
+            for (auto& z : dec) {
+                if (o.by_strand) {
+                    ZmwSubreads f, r;
+                    split_by_strand(z, f, r);
+                    B.zmws.push_back(std::move(f)); B.strand_tag.push_back(1);
+                    B.zmws.push_back(std::move(r)); B.strand_tag.push_back(2);
+                } else { B.zmws.push_back(std::move(z)); B.strand_tag.push_back(0); }
+            }
+        }
         const int nz = (int)B.zmws.size();
         B.zmw_read_off.assign(1, 0); B.read_off.assign(1, 0);
         size_t maxlen = 1, total = 0;
@@ -439,21 +463,17 @@ int main(int argc, char** argv) {
         int64_t z_index = 0, seq = 0;
         BatchIO B;
         auto flush = [&]() {
-            if (B.zmws.empty()) return;
+            if (B.raw.empty()) return;
             B.seq_no = seq++;
             todo.push(std::move(B));
             B = BatchIO();
         };
-        ZmwSubreads z;
-        while (!abort_flag.load() && z_index < z_end && reader.next_zmw(z)) {
+        RawZmw z;
+        while (!abort_flag.load() && z_index < z_end && reader.next_zmw_raw(z)) {
             if (z_index >= z_begin) {
-                if (o.by_strand) {
-                    ZmwSubreads f, r;
-                    split_by_strand(z, f, r);
-                    B.zmws.push_back(std::move(f)); B.strand_tag.push_back(1);
-                    B.zmws.push_back(std::move(r)); B.strand_tag.push_back(2);
-                } else { B.zmws.push_back(std::move(z)); B.strand_tag.push_back(0); }
-                if ((int)B.zmws.size() >= o.batch) flush();
+                B.raw.push_back(std::move(z));
+                z = RawZmw();
+                if ((int)B.raw.size() >= o.batch) flush();
             }
             ++z_index;
         }
