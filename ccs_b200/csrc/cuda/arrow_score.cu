@@ -285,6 +285,66 @@ __global__ void __launch_bounds__(128) arrow_score_generic_kernel(const ArrowBat
 // WARPSYNC / ENDCOLLECTIVE pair)
 __device__ __forceinline__ bool warp_any(const bool x) { return __reduce_or_sync(kFullMask, (unsigned)x) != 0u; }
 
+
+// ---- band staging through shared memory (sm_90+ bulk copies, mbarrier completion) ------------------------------
+// A scoring CTA works on 16 consecutive template positions of one ZMW.  Per read it needs alpha columns q-1 and beta
+// columns q+1, q+2 of those positions: ONE contiguous window of <= 19 band columns (plus their column info and beta
+// exponents).  Instead of 15 dependent global loads per (read, position), one elected thread issues four
+// cp.async.bulk copies per (CTA, read) into a double-buffered stage while the previous read is being scored; the
+// octets then read their operands with LDS.  (north_star: "TMA or shared-memory staging of the DP band".)
+constexpr int kStageCols = 20;                 // band columns per stage (19 needed + alignment slack)
+struct __align__(128) ScoreStage {
+    float4 a[kStageCols * 8];                  // alpha columns [jw, jw + nw)
+    float4 b[kStageCols * 8];                  // beta columns  [jw, jw + nw)
+    ColInfo ci[kStageCols + 4];                // column info from an even (16-byte aligned) index
+    int be[kStageCols + 8];                    // beta exponents from a multiple-of-4 index
+};
+struct StageView { const float4* a; const float4* b; const ColInfo* ci; const int* be; int jw; int on; };
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, const unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, const unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, const unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, const unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spin > (1u << 26)) __trap();       // a lost copy must kill the kernel, never hang the device
+    }
+}
+
+// The window of read `rd` a CTA with first position P0 needs: columns [jw, jw + nw); nw = 0: nothing to stage.
+__device__ __forceinline__ void stage_window(const DevRead& rd, const int st, const int P0, int& jw, int& nw) {
+    jw = 0; nw = 0;
+    if (!rd.active || st != 0 || !(P0 < rd.te && P0 + 16 > rd.ts) || rd.J < 6) return;
+    int lo, hi;                                 // local positions q of the CTA's first / last covered position
+    if (!rd.strand) { lo = P0 - rd.ts; hi = lo + 15; } else { hi = rd.te - 1 - P0; lo = hi - 15; }
+    jw = min(max(lo - 1, 0), rd.J - 1);
+    nw = max(0, min(rd.J, hi + 3) - jw);
+    nw = min(nw, kStageCols);
+}
+
+__device__ __forceinline__ void stage_issue(const ArrowBatchView& V, const DevRead& rd, const int jw, const int nw,
+                                            ScoreStage* S, uint64_t* bar) {
+    const long long c0 = rd.col_off + jw;
+    const long long ci0 = c0 & ~1ll, ci1 = (c0 + nw + 1) & ~1ll;
+    const long long be0 = c0 & ~3ll, be1 = (c0 + nw + 3) & ~3ll;
+    const unsigned bytes_col = (unsigned)nw * 128u, bytes_ci = (unsigned)(ci1 - ci0) * 8u, bytes_be = (unsigned)(be1 - be0) * 4u;
+    mbar_expect_tx(bar, 2u * bytes_col + bytes_ci + bytes_be);
+    bulk_g2s(S->a, V.alpha + c0 * 32, bytes_col, bar);
+    bulk_g2s(S->b, V.beta + c0 * 32, bytes_col, bar);
+    bulk_g2s(S->ci, V.colinfo + ci0, bytes_ci, bar);
+    bulk_g2s(S->be, V.beta_exp + be0, bytes_be, bar);
+}
+
 struct FastOut { float sub[4]; float del; float ins[4]; int e_sd; int e_in; };   // per-lane partial link sums
 
 constexpr int kReadCache = 48;     // read descriptors of the CTA's ZMW kept in shared memory (more reads: global loads)
@@ -339,19 +399,34 @@ __device__ __forceinline__ float link_partial(const float y[4], const float bx[4
 
 // tc = shared-memory byte address of the code-major folded table [16 codes][16 contexts] of {mm, gg}
 template <int kUnrollB>
-__device__ __forceinline__ void fast_eval(const ReadCtx& R, const int g4, const int src_up, const int src_up2,
+__device__ __forceinline__ void fast_eval(const ReadCtx& R, const StageView& SV, const int g4, const int src_up, const int src_up2,
                                           const int src_up4, const int src_dn, const unsigned tc, const int q_in,
                                           const bool live, FastOut& out) {
     const int J = R.J;
     const int q = live ? q_in : 2;
     const int jm1 = min(max(q - 1, 0), J - 1), j0 = min(q, J - 1), j1 = min(q + 1, J - 1), j2 = min(q + 2, J - 1);
-    const ColInfo cim1 = R.cinfo[jm1];
-    const int s0 = cim1.start, s1 = R.cinfo[j0].start, s2 = R.cinfo[j1].start, s3 = R.cinfo[j2].start;
-    const float4 a0 = R.acol[(size_t)jm1 * 8];
-    const float4 b1 = R.bcol[(size_t)j1 * 8];
-    const float4 b2 = R.bcol[(size_t)j2 * 8];
-    out.e_sd = cim1.cumexp + R.bexp[j2];
-    out.e_in = cim1.cumexp + R.bexp[j1];
+    ColInfo cim1;
+    int s1, s2, s3, be1, be2;
+    float4 a0, b1, b2;
+    if (SV.on) {                                // operands from the staged window (LDS); idle octets read its first columns
+        const int w = live ? jm1 - SV.jw : 0;   // interior positions lie inside the window by construction
+        cim1 = SV.ci[w];
+        s1 = SV.ci[w + (j0 - jm1)].start; s2 = SV.ci[w + (j1 - jm1)].start; s3 = SV.ci[w + (j2 - jm1)].start;
+        a0 = SV.a[w * 8];
+        b1 = SV.b[(w + (j1 - jm1)) * 8];
+        b2 = SV.b[(w + (j2 - jm1)) * 8];
+        be1 = SV.be[w + (j1 - jm1)]; be2 = SV.be[w + (j2 - jm1)];
+    } else {
+        cim1 = R.cinfo[jm1];
+        s1 = R.cinfo[j0].start; s2 = R.cinfo[j1].start; s3 = R.cinfo[j2].start;
+        a0 = R.acol[(size_t)jm1 * 8];
+        b1 = R.bcol[(size_t)j1 * 8];
+        b2 = R.bcol[(size_t)j2 * 8];
+        be1 = R.bexp[j1]; be2 = R.bexp[j2];
+    }
+    const int s0 = cim1.start;
+    out.e_sd = cim1.cumexp + be2;
+    out.e_in = cim1.cumexp + be1;
     // template bytes carry 16*t[j-2] + 4*t[j-1] + t[j]
     const int x0 = R.tp[j0], x1 = R.tp[j1];
     const int t0 = x0 & 3, tm1 = (x0 >> 2) & 3, cmq = (x0 >> 2) & 15, tp1 = x1 & 3;
@@ -473,7 +548,7 @@ __device__ __forceinline__ double prod_dll(const float prod, const int pexp, con
 // template base, whose substitution is the identity -- and lane 4 + k owns INS(forward base k); per read the lanes'
 // partial link sums are transpose-reduced so that every lane ends up with the total of its own slot and keeps that
 // slot's running product.  The order of the reduction is fixed: results are deterministic.
-template <int kMinBlocks, int kUnrollB>
+template <int kMinBlocks, int kUnrollB, bool kStage>
 __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const ArrowBatchView V, const ScoreRange* __restrict__ ranges,
                                                           const int n_ranges, const long long n_items,
                                                           double* __restrict__ delta) {
@@ -483,6 +558,12 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
     __shared__ DevRead s_rd[kReadCache];                     // the ZMW's read descriptors, statuses, base LLs
     __shared__ int s_st[kReadCache];
     __shared__ double s_bl[kReadCache];
+    __shared__ ScoreStage s_stage[kStage ? 2 : 1];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    if (kStage && threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     for (int k = threadIdx.x; k < 36 * kEmStride; k += blockDim.x) s_emm[k] = V.em_match[k];
     for (int k = threadIdx.x; k < 17 * kEmStride; k += blockDim.x) s_emi[k] = V.em_ins[k];
 
@@ -534,8 +615,26 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
     const int n_reads = zm.read_end - zm.read_begin;
     // warp-uniform trip count through a reduction: the compiler then knows the read loop is convergent and does not
     // wrap every shuffle inside it in WARPSYNC / ENDCOLLECTIVE pairs
-    const int n_max = __reduce_max_sync(kFullMask, n_reads);
+    int n_max = __reduce_max_sync(kFullMask, n_reads);
     const int tbase = have ? (V.tpl[zm.fwd_off + p] & 3) : 0;
+    // staged variant: the read loop carries a CTA barrier, so every warp of the CTA runs the same number of iterations
+    // (the CTA's ZMW has nrc cached reads; reads beyond the cache are scored from global memory)
+    const int P0 = rg.p_begin + (int)(item0 - rg.first);          // first position of this CTA
+    unsigned ph0 = 0, ph1 = 0;                                     // mbarrier phase parity of the two stages
+    if (kStage) {
+        int n_cta = 0;
+        if (item0 < n_items) { const DevZmw zc = V.zmws[z]; n_cta = zc.read_end - zc.read_begin; }
+        n_max = __reduce_max_sync(kFullMask, n_cta);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k0 = 0; k0 < 2; ++k0)
+                if (k0 < nrc) {
+                    int jw, nw;
+                    stage_window(s_rd[k0], s_st[k0], P0, jw, nw);
+                    if (nw > 0) stage_issue(V, s_rd[k0], jw, nw, &s_stage[k0], &s_bar[k0]);
+                }
+        }
+    }
 
     // this lane's slot: running product(s) and the sums of the contributing reads' base log-likelihoods
     float prA = 1.f, prB = 1.f;          // A: SUB / DEL / INS from forward reads;  B: INS' (reverse-strand share of row p+1)
@@ -554,7 +653,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
         }
         // start the next read's three column lines (and its column info) on their way from HBM to L2 while this one
         // is being scored: lanes 0..3 of the octet take one line each
-        if (have && k + 1 < nrc) {
+        if (!kStage && have && k + 1 < nrc) {
             const DevRead& nx = s_rd[k + 1];
             if (nx.active && p >= nx.ts && p < nx.te) {
                 const int qn = nx.strand ? nx.te - 1 - p : p - nx.ts;
@@ -572,7 +671,22 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
         }
         const bool cov_sd = usable && p >= rd.ts && p < rd.te;       // SUB / DEL
         const bool cov_in = usable && p > rd.ts && p < rd.te;        // INS (before p)
-        if (!warp_any(cov_sd)) continue;
+        StageView SV;
+        SV.a = nullptr; SV.b = nullptr; SV.ci = nullptr; SV.be = nullptr; SV.jw = 0; SV.on = 0;
+        if (kStage && k < nrc) {       // wait for this read's window (CTA-uniform decision from the cached descriptor)
+            int jw, nw;
+            stage_window(s_rd[k], s_st[k], P0, jw, nw);
+            if (nw > 0) {
+                const int bsel = k & 1;
+                mbar_wait(&s_bar[bsel], bsel ? ph1 : ph0);
+                if (bsel) ph1 ^= 1u; else ph0 ^= 1u;
+                const long long c0 = s_rd[k].col_off + jw;
+                SV.a = s_stage[bsel].a + g; SV.b = s_stage[bsel].b + g;
+                SV.ci = s_stage[bsel].ci + (int)(c0 & 1ll); SV.be = s_stage[bsel].be + (int)(c0 & 3ll);
+                SV.jw = jw; SV.on = 1;
+            }
+        }
+        if (warp_any(cov_sd)) {
 
         ReadCtx R;
         R.rc = V.rowcode + rd.code_off;
@@ -595,7 +709,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
 
         if (warp_any(interior)) {
             FastOut fo;
-            fast_eval<kUnrollB>(R, g4, src_up, src_up2, src_up4, src_dn, tc, q_sd, interior, fo);
+            fast_eval<kUnrollB>(R, SV, g4, src_up, src_up2, src_up4, src_dn, tc, q_sd, interior, fo);
             // Q[k] = this lane's partial of the slot lane k owns (forward-strand base k & 3; reverse reads see 3 - base)
             const bool rv = rd.strand != 0;
             float Q[8];
@@ -657,6 +771,18 @@ __global__ void __launch_bounds__(128, kMinBlocks) arrow_score_kernel(const Arro
                 const bool take = is_ins ? gen_in : gen_sd;
                 const int owner = (m < 3) ? bf : ((m == 3) ? tbase : 4 + bf);
                 if (take && g == owner) prod_mul(prA, pxA, val, e);
+            }
+        }
+        }   // warp_any(cov_sd)
+        if (kStage) {
+            __syncthreads();               // every warp is done with stage k & 1
+            if (threadIdx.x == 0 && k + 2 < nrc) {
+                int jw, nw;
+                stage_window(s_rd[k + 2], s_st[k + 2], P0, jw, nw);
+                if (nw > 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async writes
+                    stage_issue(V, s_rd[k + 2], jw, nw, &s_stage[k & 1], &s_bar[k & 1]);
+                }
             }
         }
     }
@@ -786,12 +912,12 @@ void launch_score(const ArrowBatchView& V, const ScoreRange* ranges, int n_range
     if (n_items <= 0) return;
     const long long blocks = (n_items + 15) / 16;
     if (generic) arrow_score_generic_kernel<<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
-    else if (variant == 1) arrow_score_kernel<4, 4><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
-    else if (variant == 2) arrow_score_kernel<6, 4><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
-    else if (variant == 3) arrow_score_kernel<8, 4><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    else if (variant == 1) arrow_score_kernel<4, 4, false><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    else if (variant == 2) arrow_score_kernel<5, 4, true><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    else if (variant == 3) arrow_score_kernel<4, 4, true><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
     // default: 5 CTAs per SM (96 registers, 20 warps): measured 9 % faster than 4 CTAs at 128 registers despite the
     // extra spills -- the kernel is latency / issue bound and wants the warps (profiles/r2_score_variants.txt)
-    else arrow_score_kernel<5, 4><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
+    else arrow_score_kernel<5, 4, false><<<(unsigned)blocks, 128, 0, stream>>>(V, ranges, n_ranges, n_items, delta);
 }
 
 void launch_pick(const ArrowBatchView& V, const ScoreRange* ranges, int n_ranges, long long n_items, const double* delta,

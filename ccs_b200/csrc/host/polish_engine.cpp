@@ -313,8 +313,8 @@ void ArrowEngine::upload_templates_and_reads() {
     d_ll_alpha_.ensure((size_t)nr + 1); d_ll_beta_.ensure((size_t)nr + 1); d_base_ll_.ensure((size_t)nr + 1);
     d_alpha_.ensure((size_t)(cols + 2) * 32, budget_);
     d_beta_.ensure((size_t)(cols + 2) * 32, budget_);
-    d_colinfo_.ensure((size_t)cols + 2, budget_);
-    d_bexp_.ensure((size_t)cols + 2, budget_);
+    d_colinfo_.ensure((size_t)cols + 8, budget_);      // the staged scoring kernel copies 16-byte aligned pieces: slack at the end
+    d_bexp_.ensure((size_t)cols + 8, budget_);
     h_reads_.ensure((size_t)nr + 1); h_zmws_.ensure((size_t)nz + 1); h_order_.ensure(order_.size() + 16);
     h_status_.ensure((size_t)nr + 1);
     std::memcpy(h_reads_.p, reads_.data(), sizeof(DevRead) * nr);
