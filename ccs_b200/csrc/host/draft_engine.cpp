@@ -176,10 +176,11 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
         for (int r = r0; r < r1; ++r) if (out.keep[r] && (in.cx[r] & 3) == 3) { full.push_back(r); sl.push_back(lens[r]); }
         std::sort(sl.begin(), sl.end());
         const int med = sl.empty() ? 0 : sl[sl.size() / 2];
+        full.erase(std::remove(full.begin(), full.end(), w.poa_reads[0]), full.end());   // not the seed that just failed
         std::stable_sort(full.begin(), full.end(), [&](int a, int b) { return std::abs(lens[a] - med) < std::abs(lens[b] - med); });
         const size_t cap = (size_t)std::max(1, std::min(2 * dp.max_poa_reads - 1, kPoaMaxReads));
         if (full.size() > cap) full.resize(cap);
-        if (full == w.poa_reads || full.empty() || lens[full[0]] > kPoaMaxRefLen) continue;   // nothing new to try
+        if (full.empty() || lens[full[0]] > kPoaMaxRefLen) continue;   // nothing new to try
         w.poa_reads = full;
         w.alive = true;
         out.draft[z].clear();

@@ -46,7 +46,7 @@ void draft_zmw(const CcsConfig& cfg, int nreads, const uint8_t* codes, const int
     // Draft cascade (docs/faq/accuracy-vs-passes.md:41-46): generator 0 = SparsePoa over the first max_poa_reads
     // full-length reads, seeded by the first one; if its draft cannot be generated or too few subreads map back to it,
     // generator 1 = SparsePoa seeded by the full-length read closest to the median length, over up to
-    // 2 * max_poa_reads - 1 reads in order of closeness.  Length gates are final.
+    // 2 * max_poa_reads - 1 reads in order of closeness (the seed that just failed is left out).  Length gates are final.
     std::vector<int> full;
     for (int r = 0; r < nreads; ++r) if (keep[r] && (cx[r] & 3) == 3) full.push_back(r);
     int kept = 0;
@@ -62,11 +62,11 @@ void draft_zmw(const CcsConfig& cfg, int nreads, const uint8_t* codes, const int
             for (int r : full) sl.push_back(lens[r]);
             std::sort(sl.begin(), sl.end());
             const int med = sl.empty() ? 0 : sl[sl.size() / 2];
-            sel = full;
+            for (int r : full) if (first_sel.empty() || r != first_sel[0]) sel.push_back(r);   // not the seed that just failed
             std::stable_sort(sel.begin(), sel.end(), [&](int a, int b) { return std::abs(lens[a] - med) < std::abs(lens[b] - med); });
             const size_t cap = (size_t)std::max(1, std::min(2 * cfg.max_poa_reads - 1, 16));
             if (sel.size() > cap) sel.resize(cap);
-            if (sel == first_sel) break;          // nothing new to try
+            if (sel.empty()) break;               // nothing new to try
         }
         out.draft.clear();
         out.maps.assign(nreads, ReadMapping());

@@ -204,3 +204,53 @@ def test_poa_vertex_with_more_than_8_predecessors(ctx):
         mapped, strand, ts, te, rs, re = o["maps"][k]
         if mapped:
             assert (d["tstart"][k], d["tend"][k], d["rstart"][k], d["rend"][k]) == (ts, te, rs, re)
+
+
+def test_draft_cascade_matches_oracle(ctx):
+    """Draft cascade (docs/faq/accuracy-vs-passes.md:41-46): when the first full-length read is junk, generator 0 seeds the
+    POA with it, nothing threads, too few subreads map back to that "draft"; generator 1 (seed = the full-length read closest
+    to the median length, more reads) recovers the ZMW.  A ZMW made of unrelated reads only stays failed after both.
+    Statuses, drafts and mappings agree with the oracle bit for bit."""
+    cfg = sim.get_config(1, insert_mean=1200)
+    zs = []
+    for i in range(4):
+        z = sim.simulate_zmw(MODEL, cfg, 40 + i)
+        other = sim.simulate_zmw(MODEL, cfg, 900 + i)
+        reads = [z.read(k).copy() for k in range(z.n_reads)]
+        first_full = int(np.flatnonzero(z.cx == 3)[0])
+        junk = other.read(int(np.flatnonzero(other.cx == 3)[0])).copy()
+        reads[first_full] = junk                      # a full-length pass of a different molecule in the seed's place
+        if i == 3:                                    # hopeless: every full-length pass comes from a different molecule
+            for k in np.flatnonzero(z.cx == 3):
+                o2 = sim.simulate_zmw(MODEL, cfg, 2000 + 17 * int(k))
+                reads[int(k)] = o2.read(int(np.flatnonzero(o2.cx == 3)[0])).copy()
+        zz = sim.Zmw()
+        zz.hole = z.hole; zz.snr = z.snr; zz.cx = z.cx
+        zz.read_off = np.zeros(len(reads) + 1, np.int64); zz.read_off[1:] = np.cumsum([len(r) for r in reads])
+        zz.codes = np.concatenate(reads); zz.strand = z.strand; zz.tstart = z.tstart; zz.tend = z.tend
+        zs.append(zz)
+    batch = api.Batch(zs)
+    d = ctx.draft(batch)
+    res = ctx.ccs(batch)
+    n_ok = 0
+    for zi, z in enumerate(zs):
+        reads = [z.read(k) for k in range(z.n_reads)]
+        o = O.draft_zmw(z.snr, reads, z.cx)
+        assert d["status"][zi] == o["status"], (zi, d["status"][zi], o["status"])
+        assert np.array_equal(d["tpl"][d["tpl_off"][zi]:d["tpl_off"][zi + 1]], o["draft"]), zi
+        r0 = batch.zmw_read_off[zi]
+        if o["status"] == 16:
+            n_ok += 1
+            for k in range(z.n_reads):
+                mapped, strand, ts, te, rs, re = o["maps"][k]
+                if mapped:
+                    assert (d["strand"][r0 + k], d["tstart"][r0 + k], d["tend"][r0 + k], d["rstart"][r0 + k],
+                            d["rend"][r0 + k]) == (strand, ts, te, rs, re), (zi, k)
+                else:
+                    assert d["tend"][r0 + k] == 0
+        oc = O.ccs_zmw(MODEL, z.snr, reads, z.cx)
+        assert res["status"][zi] == oc["status"], (zi, res["status"][zi], oc["status"])
+        if oc["status"] in (16, 14, 13):
+            s0, s1 = res["seq_off"][zi], res["seq_off"][zi + 1]
+            assert np.array_equal(res["seq"][s0:s1], oc["seq"])
+    assert n_ok == 3 and d["status"][3] in (7, 8)     # the cascade rescued the three; the hopeless one stays failed
