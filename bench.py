@@ -417,14 +417,17 @@ def main():
     if rank == 0:
         st, st1 = M["st"], M["st1"]
         peak, peak_src = peaks()
-        traffic = None
+        traffic, traffic_any = None, {}
         try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the full-population launches (`ncu --set full`)
             tj = json.load(open(os.path.join(ROOT, "profiles", "r2_summary.json")))
-            if tj.get("config") == args.config:
-                traffic = {k: v.get("dram_bytes") for k, v in tj.get("kernels", {}).items()}
+            traffic_any = {k: v.get("dram_bytes") for k, v in tj.get("kernels", {}).items()}
+            if tj.get("config") == args.config and zmws == 1000:
+                traffic = traffic_any
         except Exception:
             traffic = None
         rl = rooflines(st, st1, peak, peak_src, traffic)
+        for e in rl:   # the ncu capture is of a config-2, 1000-ZMW, single-lane launch: quoted with its own context
+            e["traffic_ncu_config2_1000zmw_launch"] = traffic_any.get(e["kernel"].split(" ")[0])
         dom = max(rl, key=lambda e: e["timed_region"]["ms"])
         n_l = {"arrow_fill_alpha_kernel": "launches_fill_alpha", "arrow_fill_beta_kernel": "launches_fill_beta",
                "arrow_score_kernel": "launches_score"}.get(dom["kernel"])

@@ -1,4 +1,5 @@
-"""Turns gpurun_out/r1_full_*.ncu-rep + the launch list into profiles/r1_summary.md / .json (run here, no GPU)."""
+"""Turns gpurun_out/r2_full_*.ncu-rep + the launch list into profiles/r2_summary.md / .json (run here, no GPU).
+Usage: python scripts/summarize_profiles.py [round-tag, default r2]"""
 import collections
 import csv
 import io
@@ -6,7 +7,9 @@ import json
 import subprocess
 import sys
 
-KERNELS = ["arrow_fill_alpha", "arrow_fill_beta", "arrow_score", "poa_align"]
+KERNELS = ["arrow_fill_alpha", "arrow_fill_beta", "arrow_score", "poa_align", "poa_map", "poa_commit", "poa_consensus",
+           "arrow_pack_rowcodes"]
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
@@ -50,14 +53,19 @@ def stalls(rep):
 
 def main():
     res = {}
-    for k in KERNELS:
-        rep = "gpurun_out/r1_full_%s.ncu-rep" % k
+    import os
+    kernels = [k for k in KERNELS if os.path.exists("gpurun_out/%s_full_%s.ncu-rep" % (TAG, k))]
+    for k in kernels:
+        rep = "gpurun_out/%s_full_%s.ncu-rep" % (TAG, k)
         d = raw(rep)
-        d["stall_pct"] = stalls(rep)
+        try:
+            d["stall_pct"] = stalls(rep)
+        except Exception:
+            d["stall_pct"] = {}
         d["dram_bytes"] = d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
         res[k] = d
     # launch list
-    rows = list(csv.reader(open("gpurun_out/r1_launches_bench.csv")))
+    rows = list(csv.reader(open("gpurun_out/%s_launches_bench.csv" % TAG)))
     hdr = None
     agg = collections.OrderedDict()
     for r in rows:
@@ -71,15 +79,19 @@ def main():
     tot = sum(sum(v) for v in agg.values())
     res["launch_list"] = {n: {"launches": len(v), "total_ms": round(sum(v), 2), "share": round(sum(v) / tot, 3),
                               "max_ms": round(max(v), 2)} for n, v in agg.items()}
-    json.dump(res, open("profiles/r1_summary.json", "w"), indent=1)
-    with open("profiles/r1_summary.md", "w") as f:
-        f.write("# Round-1 ncu summary (B200, config 2: 1000 ZMWs, 10 kb x 10 passes, full captures with `bench.py --lanes 1 --contexts 1`)\n\n")
-        f.write("Source: `gpurun_out/r1_full_*.ncu-rep` (`ncu --set full --clock-control none --import-source on`, first launch of "
-                "each kernel = the full-population launch) and `profiles/r1_launches_bench.csv` (`ncu --metrics "
-                "gpu__time_duration.sum --clock-control none` over `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`; per-launch times "
-                "are cold-cache and serialised, compare shares). Regenerate with `python scripts/summarize_profiles.py`.\n\n")
+    out = {"config": 2, "kernels": {k + "_kernel" if not k.startswith("poa_map") else "poa_align_kernel(map)": res[k] for k in kernels},
+           "launch_list": res["launch_list"]}
+    json.dump(out, open("profiles/%s_summary.json" % TAG, "w"), indent=1)
+    with open("profiles/%s_summary.md" % TAG, "w") as f:
+        f.write("# Round-2 ncu summary (B200, config 2: 1000 ZMWs, 10 kb x 10 passes, full captures with `bench.py --config 2 --lanes 1 --contexts 1`)\n\n")
+        f.write("Source: `gpurun_out/%s_full_*.ncu-rep` (`ncu --set full --clock-control none --import-source on`, first launch of "
+                "each kernel = the full-population launch; `poa_map` = the 5th `poa_align_kernel` launch, the subread -> draft mapping) and "
+                "`profiles/%s_launches_bench.csv` (`ncu --metrics gpu__time_duration.sum --clock-control none` over the default "
+                "`python bench.py --steps 2 --warmup 1 --no-cpu-baseline` = config 3, 2 contexts x 4 lanes; per-launch times "
+                "are cold-cache and serialised, compare shares). Commands: `scripts/gpu_profile_r2.sh`; regenerate with "
+                "`python scripts/summarize_profiles.py`.\n\n" % (TAG, TAG))
         f.write("| kernel | duration ms | DRAM read GB | DRAM write GB | DRAM %peak | issue-active % | warp-instr | regs | warps active % | top stalls (% of samples) |\n|---|---|---|---|---|---|---|---|---|---|\n")
-        for k in KERNELS:
+        for k in kernels:
             d = res[k]
             f.write("| %s | %.2f | %.3f | %.3f | %.1f | %.1f | %.3g | %d | %.1f | %s |\n" % (
                 k, d["gpu__time_duration.sum"] * 1e3, d.get("dram__bytes_read.sum", 0) / 1e9,
@@ -88,11 +100,11 @@ def main():
                 int(d.get("launch__registers_per_thread", 0)), d.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0),
                 ", ".join("%s %.0f" % kv for kv in d["stall_pct"].items())))
         f.write("\nTensor pipe instructions: %s (none by design: no dense contraction on this path).\n\n" %
-                {k: res[k].get("sm__inst_executed_pipe_tensor.sum", 0) for k in KERNELS})
+                {k: res[k].get("sm__inst_executed_pipe_tensor.sum", 0) for k in kernels})
         f.write("## Launch list of the bench command (share of summed kernel time)\n\n| kernel | launches | total ms | share | max ms |\n|---|---|---|---|---|\n")
         for n, v in res["launch_list"].items():
             f.write("| %s | %d | %.2f | %.3f | %.2f |\n" % (n, v["launches"], v["total_ms"], v["share"], v["max_ms"]))
-    print(open("profiles/r1_summary.md").read())
+    print(open("profiles/%s_summary.md" % TAG).read())
 
 
 if __name__ == "__main__":
