@@ -73,6 +73,12 @@ def config_dict(args, cfg_id, zmws, world, lanes, contexts):
             "value_def": "e2e wall time of the calls minus the batch-upload span (inputs resident)"}
 
 
+def shard_first_index(step, rank, world, zmws):
+    """first ZMW index of `rank` in `step`: every step deals `zmws` consecutive ZMWs to each rank, ranks in order (ZMW-range
+    sharding) -- the ranges of all (step, rank) pairs tile the index space without overlap"""
+    return (step * world + rank) * zmws
+
+
 def make_batch(model, cfg, first, n, draft_error, threads):
     from ccs_b200 import sim, api
     a = sim.simulate_batch(model, cfg, first, n, draft_error, threads)
@@ -268,7 +274,7 @@ def measure(args, cfg_id, zmws, steps, warmup, ctxs, model, rank, world, local, 
 
     # distinct synthetic ZMW index range per rank and per step (working set >> L2: tens of GB of DP bands)
     def step_batch(step):
-        first = (step * world + rank) * zmws
+        first = shard_first_index(step, rank, world, zmws)
         return make_batch(model, cfg, first, zmws, args.draft_error, threads)
 
     def run_step(b, c=None):

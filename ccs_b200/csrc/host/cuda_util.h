@@ -30,20 +30,13 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 // thread per lane waiting on its stream most of the time -- ten spinning threads per GPU starve the host logic of the
 // other ranks on a shared box (measured: 4 GPUs on one box dropped to 63 % per-GPU throughput).  A blocking-sync event
 // puts the thread to sleep until the GPU interrupt arrives.
-inline cudaError_t stream_sync_blocking(cudaStream_t s) {
-    static thread_local cudaEvent_t ev = nullptr;
-    static thread_local int ev_dev = -1;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (!ev || ev_dev != dev) {
-        if (ev) cudaEventDestroy(ev);
-        ev = nullptr;
-        e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-        ev_dev = dev;
-    }
-    e = cudaEventRecord(ev, s);
+// The event is owned by the caller (an engine creates one with make_blocking_event() and destroys it with the engine):
+// a thread_local event would leak one event per short-lived lane thread.
+inline cudaError_t make_blocking_event(cudaEvent_t* ev) {
+    return cudaEventCreateWithFlags(ev, cudaEventBlockingSync | cudaEventDisableTiming);
+}
+inline cudaError_t stream_sync_blocking(cudaStream_t s, cudaEvent_t ev) {
+    cudaError_t e = cudaEventRecord(ev, s);
     if (e != cudaSuccess) return e;
     return cudaEventSynchronize(ev);
 }

@@ -39,6 +39,7 @@ DraftEngine::DraftEngine(int device, size_t scratch_budget_bytes) : device_(devi
         else
             CCS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     }
+    CCS_CUDA(make_blocking_event(&ev_sync_));
     if (budget_ == 0) budget_ = 12ull << 30;
 }
 
@@ -46,6 +47,7 @@ DraftEngine::~DraftEngine() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
     for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
+    if (ev_sync_) cudaEventDestroy(ev_sync_);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -312,7 +314,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
     CCS_CUDA(cudaMemcpyAsync(h_draft_.p, d_draft_.p, (size_t)pool, cudaMemcpyDeviceToHost, stream_));
     stats.d2h_bytes += pool + 4ll * ng;
     { HostPhase hp("draft.a2-a4 gpu (wait)");
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     CCS_CUDA(cudaGetLastError());
     resolve_spans();
     }
@@ -397,7 +399,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         CCS_CUDA(cudaMemcpyAsync(h_rev_.p, d_rev_.p, (size_t)in.n_reads, cudaMemcpyDeviceToHost, stream_));
         stats.d2h_bytes += (int64_t)sizeof(PoaResult) * nt + in.n_reads;
         { HostPhase hp("draft.a5 gpu map (wait)");
-        CCS_CUDA(stream_sync_blocking(stream_));
+        CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
         CCS_CUDA(cudaGetLastError());
         resolve_spans();
         }

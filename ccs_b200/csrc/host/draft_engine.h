@@ -76,6 +76,7 @@ private:
     int device_;
     size_t budget_;
     cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_sync_ = nullptr;      // blocking-sync event (owned by the engine)
     struct Span { cudaEvent_t a, b; double* acc; int64_t bytes; int64_t* top_bytes; double* top_ms; };
     std::vector<Span> spans_;
     std::vector<cudaEvent_t> ev_pool_;

@@ -37,6 +37,7 @@ ArrowEngine::ArrowEngine(int device, const ArrowModelParams& model, size_t budge
     }
     CCS_CUDA(cudaEventCreate(&evA_));
     CCS_CUDA(cudaEventCreate(&evB_));
+    CCS_CUDA(make_blocking_event(&ev_sync_));
     build_emission_tables(model_, em_);
     for (auto* b : {&d_emm_, &d_emi_, &d_trans_, &d_alpha_, &d_beta_}) b->budget_used = &used_;
     d_rowcode_.budget_used = &used_; d_tpl_.budget_used = &used_; d_colinfo_.budget_used = &used_;
@@ -47,7 +48,7 @@ ArrowEngine::ArrowEngine(int device, const ArrowModelParams& model, size_t budge
     CCS_CUDA(cudaMemcpyAsync(d_emi_.p, em_.em_ins, sizeof(em_.em_ins), cudaMemcpyHostToDevice, stream_));
     d_counter_.ensure(4);
     h_counter_.ensure(4);
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
 }
 
 ArrowEngine::~ArrowEngine() {
@@ -364,7 +365,7 @@ void ArrowEngine::sync_statuses() {
     HostPhase hp("polish.fill (wait)");
     const int nr = (int)reads_.size();
     CCS_CUDA(cudaMemcpyAsync(h_status_.p, d_status_.p, sizeof(int32_t) * nr, cudaMemcpyDeviceToHost, stream_));
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     resolve_spans();
     stats.d2h_bytes += 4ll * nr;
     for (int r = 0; r < nr; ++r) {
@@ -386,7 +387,7 @@ void ArrowEngine::zscore_filter(double min_zscore) {
     const int nr = (int)reads_.size(), nz = (int)zstate_.size();
     h_ll_.ensure((size_t)2 * nr + 2);
     CCS_CUDA(cudaMemcpyAsync(h_ll_.p, d_ll_alpha_.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream_));
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     stats.d2h_bytes += 8ll * nr;
     std::atomic<int> dropped(0);
     parallel_for(nz, host_threads, [&](int z) {
@@ -430,7 +431,7 @@ void ArrowEngine::read_lls(double* ll_alpha, double* ll_beta, int32_t* status) {
     h_ll_.ensure((size_t)2 * nr + 2);
     CCS_CUDA(cudaMemcpyAsync(h_ll_.p, d_ll_alpha_.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream_));
     CCS_CUDA(cudaMemcpyAsync(h_ll_.p + nr, d_ll_beta_.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream_));
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     stats.d2h_bytes += 16ll * nr;
     for (int r = 0; r < nr; ++r) {
         const bool filled = status_[r] == 0 || status_[r] == 1 || status_[r] == 3;
@@ -445,7 +446,7 @@ void ArrowEngine::dump_pair(int r, float* alpha, float* beta, int32_t* start, in
     const int J = rd.J;
     if (J <= 0) return;
     std::vector<ColInfo> ci(J);
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     if (alpha) CCS_CUDA(cudaMemcpy(alpha, d_alpha_.p + rd.col_off * 32, sizeof(float) * 32 * J, cudaMemcpyDeviceToHost));
     if (beta) CCS_CUDA(cudaMemcpy(beta, d_beta_.p + rd.col_off * 32, sizeof(float) * 32 * J, cudaMemcpyDeviceToHost));
     CCS_CUDA(cudaMemcpy(ci.data(), d_colinfo_.p + rd.col_off, sizeof(ColInfo) * J, cudaMemcpyDeviceToHost));
@@ -514,7 +515,7 @@ int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
         launch_pick(V, d_ranges_.p, n_ranges_, n_range_items_, d_delta_.p, d_cand_.p, (int)d_cand_.cap, d_counter_.p, stream_);
         span_end();
         CCS_CUDA(cudaMemcpyAsync(h_counter_.p, d_counter_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-        CCS_CUDA(stream_sync_blocking(stream_));
+        CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
         resolve_spans();
         ++stats.n_pick;
         const int64_t n = h_counter_.p[0];
@@ -522,7 +523,7 @@ int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
             h_cand_.ensure((size_t)n + 1);
             if (n > 0) {
                 CCS_CUDA(cudaMemcpyAsync(h_cand_.p, d_cand_.p, sizeof(Candidate) * n, cudaMemcpyDeviceToHost, stream_));
-                CCS_CUDA(stream_sync_blocking(stream_));
+                CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
                 stats.d2h_bytes += (int64_t)sizeof(Candidate) * n;
                 out.assign(h_cand_.p, h_cand_.p + n);
             }
@@ -535,7 +536,7 @@ int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
 
 void ArrowEngine::download_delta(int z, double* out) {
     const DevZmw& dz = zmws_[z];
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     std::vector<double> tmp((size_t)dz.J * kDeltaStride);
     CCS_CUDA(cudaMemcpy(tmp.data(), d_delta_.p + dz.delta_off * kDeltaStride, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
     for (int p = 0; p < dz.J; ++p)
@@ -689,7 +690,7 @@ void ArrowEngine::polish(const PolishParams& pp) {
     }
     { HostPhase hp("polish.qv (wait)"); consensus_qvs(); }
     CCS_CUDA(cudaEventRecord(evB_, stream_));
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     CCS_CUDA(cudaEventSynchronize(evB_));
     float ms = 0;
     cudaEventElapsedTime(&ms, evA_, evB_);
@@ -721,7 +722,7 @@ void ArrowEngine::remap_deltas() {
     CCS_CUDA(cudaMemcpyAsync(d_remap_jobs_.p, jobs.data(), sizeof(RemapJob) * jobs.size(), cudaMemcpyHostToDevice, stream_));
     CCS_CUDA(cudaMemcpyAsync(d_remap_sites_.p, sites.data(), 4 * sites.size(), cudaMemcpyHostToDevice, stream_));
     CCS_CUDA(cudaMemcpyAsync(d_remap_shifts_.p, shifts.data(), 4 * shifts.size(), cudaMemcpyHostToDevice, stream_));
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     launch_remap_delta(d_remap_jobs_.p, (int)jobs.size(), d_remap_sites_.p, d_remap_shifts_.p, d_delta_.p,
                        d_delta_scratch_.p, stream_);
 }
@@ -773,7 +774,7 @@ void ArrowEngine::consensus_qvs() {
     launch_qv(V, d_delta_.p, d_qv_.p, first, d_ranges_.p, (int)ranges.size(), stream_);
     span_end();
     CCS_CUDA(cudaMemcpyAsync(h_qv_.p, d_qv_.p, (size_t)total_delta_rows_, cudaMemcpyDeviceToHost, stream_));
-    CCS_CUDA(stream_sync_blocking(stream_));
+    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     resolve_spans();
     CCS_CUDA(cudaGetLastError());
     ++stats.n_qv;

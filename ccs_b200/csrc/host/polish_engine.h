@@ -150,6 +150,7 @@ private:
     // their CTAs get SM slots ahead of the short-lived CTAs of the other lanes' scoring kernels and co-reside with them.
     cudaStream_t stream_hi_ = nullptr;
     cudaEvent_t ev_order_ = nullptr;              // orders stream_ <-> stream_hi_
+    cudaEvent_t ev_sync_ = nullptr;               // blocking-sync event of stream_sync_blocking (owned: no per-thread leak)
     cudaEvent_t evA_ = nullptr, evB_ = nullptr;   // bracket polish() (resident-input time)
 
     // host state of the current batch

@@ -73,3 +73,18 @@ def test_two_rank_sharding_equals_single_process():
     single = _consensus_of(range(n_total))
     assert merged == single                       # byte-identical, in ZMW order (ordered merge)
     assert shard_range(10, 0, 3) == (0, 3) and shard_range(10, 2, 3) == (6, 10)
+
+
+def test_bench_step_sharding_tiles_the_index_space():
+    """bench.py's own range arithmetic (product-side sharding of the synthetic ZMW index space under torchrun): the
+    (step, rank) ranges are disjoint and tile [0, steps * world * zmws)."""
+    import bench
+    for world, zmws, steps in ((1, 600, 5), (2, 1000, 4), (8, 600, 3)):
+        seen = []
+        for step in range(steps):
+            for rank in range(world):
+                f = bench.shard_first_index(step, rank, world, zmws)
+                seen.append((f, f + zmws))
+        seen.sort()
+        assert seen[0][0] == 0 and seen[-1][1] == steps * world * zmws
+        assert all(seen[k][1] == seen[k + 1][0] for k in range(len(seen) - 1))
