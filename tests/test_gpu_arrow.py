@@ -155,3 +155,31 @@ def test_polish_many_passes_matches_oracle(ctx):
         assert np.array_equal(res["read_status"][r0:r1], o["read_status"])
         assert np.nanmax(np.abs(res["read_ll"][r0:r1] - o["read_ll"])) < LL_TOL
         assert res["n_applied"][zi] == o["n_applied"]
+
+
+@pytest.mark.timeout(600)
+def test_score_kernel_variants_agree(ctx):
+    """Compile-time variants of arrow_score_kernel (occupancy targets; the staged variant that brings each read's band
+    window into shared memory with cp.async.bulk + mbarrier) and the unfactored generic kernel give the same delta-LLs:
+    the variants bit for bit (same arithmetic, different operand paths), the generic one within 2e-4."""
+    import os
+    cfg = sim.get_config(2, insert_mean=1500, frac_low_snr=0.0, frac_few_passes=0.0)
+    zs = [sim.simulate_zmw(MODEL, cfg, 60 + i) for i in range(4)]
+    drafts = []
+    for z in zs:
+        d, mp = sim.corrupt(z.tpl, 0.02, seed=z.hole + 3)
+        drafts.append((d, z.strand, mp[z.tstart], mp[z.tend]))
+    batch = api.Batch(zs, drafts)
+    base, rll0, _ = ctx.score_all(batch)
+    for var in ("1", "2", "3"):
+        os.environ["CCS_B200_SCORE_VARIANT"] = var
+        try:
+            c = api.Context(MODEL)
+            d, rll, _ = c.score_all(batch)
+            c.close()
+        finally:
+            os.environ.pop("CCS_B200_SCORE_VARIANT", None)
+        fin = np.isfinite(base)
+        assert np.array_equal(fin, np.isfinite(d)), var
+        assert np.array_equal(base[fin], d[fin]), (var, float(np.max(np.abs(base[fin] - d[fin]))))
+        assert np.array_equal(rll0, rll)
