@@ -44,7 +44,8 @@ class CDraftsOut(C.Structure):
 class CPolishCfg(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("separation", C.c_int32), ("neighborhood", C.c_int32),
                 ("min_length", C.c_int32), ("max_length", C.c_int32), ("min_rq", C.c_double),
-                ("ab_mismatch_tol", C.c_double), ("min_active_fraction", C.c_double), ("min_zscore", C.c_double)]
+                ("ab_mismatch_tol", C.c_double), ("min_active_fraction", C.c_double), ("min_zscore", C.c_double),
+                ("window_size", C.c_int32), ("window_overlap", C.c_int32)]
 
 
 class CResults(C.Structure):

@@ -217,7 +217,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
 // input of the CommitAdd kernel; rows are stored by vertex id, so each step is a dependent global load.
 __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
     const PoaTask* __restrict__ tasks, const int n_tasks, const PoaGraphView G, const int32_t* __restrict__ lo_arr,
-    const uint8_t* __restrict__ moves, PoaStep* __restrict__ steps, PoaResult* __restrict__ results) {
+    const uint8_t* __restrict__ moves, PoaStep* __restrict__ steps, PoaResult* __restrict__ results,
+    int32_t* __restrict__ grid) {
     __shared__ __align__(16) uint8_t s_mv[kWarpsPerCta][32 * kPoaBand];
     __shared__ int s_lo[kWarpsPerCta][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -275,6 +276,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
         if (lane == 0) { r.path_len = len; results[task_id] = r; }
         return;
     }
+    // windowing: grid[t / 64] = number of oriented read bases placed before template position t on the path (the base
+    // matched there, or the next one when t is deleted), for every t that is a multiple of kWindowGrid
+    int32_t* __restrict__ gr = (grid != nullptr && T.grid_off >= 0 && lane == 0) ? grid + T.grid_off : nullptr;
     bool done = t < 0;
     while (!done) {
         const int wbase = max(t - 31, 0);
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
             const unsigned kind = m & 3u, k = m >> 2;
             if (kind == 0u) { done = true; break; }
             ++len;
+            if (gr != nullptr && kind != 3u && (t & (kWindowGrid - 1)) == 0) gr[t / kWindowGrid] = (kind == 1u) ? i - 1 : i;
             if (kind == 1u) {           // match / mismatch: read base i-1 on template position t
                 if (r.last_t < 0) { r.last_t = t; r.last_i = i - 1; }
                 r.first_t = t; r.first_i = i - 1;
@@ -316,12 +321,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
 
 void launch_poa_align(const PoaTask* tasks, int n_tasks, const PoaGraphView& G, const uint8_t* drafts, const uint8_t* codes,
                       const uint8_t* rev_flags, int32_t* lo, int32_t* besti, uint8_t* moves, int32_t* hrows,
-                      PoaStep* steps, PoaResult* results, cudaStream_t stream) {
+                      PoaStep* steps, PoaResult* results, cudaStream_t stream, int32_t* grid) {
     if (n_tasks <= 0) return;
     const int blocks = (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta;
     poa_align_kernel<<<blocks, kWarpsPerCta * 32, 0, stream>>>(tasks, n_tasks, G, drafts, codes, rev_flags, lo, besti,
                                                                moves, hrows, results);
-    poa_traceback_kernel<<<blocks, kWarpsPerCta * 32, 0, stream>>>(tasks, n_tasks, G, lo, moves, steps, results);
+    poa_traceback_kernel<<<blocks, kWarpsPerCta * 32, 0, stream>>>(tasks, n_tasks, G, lo, moves, steps, results, grid);
 }
 
 }  // namespace ccs

@@ -19,6 +19,7 @@ constexpr int kPoaMaxReads = 16;      // reads threaded into one graph (spans ke
 constexpr int kPoaKmer = 11;
 constexpr int kPoaVoteBases = 2048;   // orientation vote: k-mers of the read's first 2048 bases (spec)
 constexpr int kPoaMaxRefLen = 131072; // longest k-mer vote reference (hash set in shared memory)
+constexpr int kWindowGrid = 64;       // window borders of the Polish Stage lie on multiples of 64 draft bases (spec)
 
 // A threaded read creates at most floor(2n/7) vertices: it is threaded only if score >= n, every new vertex costs
 // at least 4 and a reused one earns 3, so 3(n - x) - 4x >= n.
@@ -60,7 +61,8 @@ struct PoaTask {
     int32_t V;             // linear tasks: template length (DAG tasks read the graph header)
     int32_t rev_idx;       // index of the read's orientation flag (0 forward, 1 reverse complement)
     int64_t scratch_off;   // DAG tasks: the graph's bookkeeping scratch (ints), >= 5 n + 4 cap + 16
-    int64_t pad_;
+    int64_t grid_off;      // linear tasks: where the traceback records the read position at every kWindowGrid-th template
+                           // base (windowing, DESIGN.md "Windowing"); < 0: not recorded
 };
 static_assert(sizeof(PoaTask) == 64, "PoaTask layout");
 

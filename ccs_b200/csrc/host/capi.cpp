@@ -3,7 +3,9 @@
 #include "polish_engine.h"
 #include "parallel.h"
 #include "draft_engine.h"
+#include "window_host.h"
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <memory>
@@ -157,6 +159,7 @@ void ccs_polish_cfg_default(ccs_polish_cfg* c) {
     c->max_iterations = p.max_iterations; c->separation = p.separation; c->neighborhood = p.neighborhood;
     c->min_length = p.min_length; c->max_length = p.max_length; c->min_rq = p.min_rq;
     c->ab_mismatch_tol = p.ab_mismatch_tol; c->min_active_fraction = p.min_active_fraction; c->min_zscore = p.min_zscore;
+    c->window_size = p.window_size; c->window_overlap = p.window_overlap;
 }
 
 int ccsgpu_fill_alpha_beta(ccsgpu_ctx* ctx, int32_t n_pairs, const int64_t* tpl_off, const uint8_t* tpl,
@@ -193,13 +196,25 @@ int ccsgpu_score_all(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_drafts* dra
     });
 }
 
+// CCS_B200_WINDOW=size[,overlap] overrides the caller's windowing (A/B runs; 0 = one window per draft)
+static void window_env_override(PolishParams& pp) {
+    const char* e = std::getenv("CCS_B200_WINDOW");
+    if (!e || !*e) return;
+    int a = 0, b = -1;
+    const int n = std::sscanf(e, "%d,%d", &a, &b);
+    if (n >= 1) pp.window_size = round_to_window_grid(a);
+    if (n >= 2 && b >= 0) pp.window_overlap = round_to_window_grid(b);
+}
+
 static PolishParams to_params(const ccs_polish_cfg* cfg) {
     PolishParams pp;
     if (cfg) {
         pp.max_iterations = cfg->max_iterations; pp.separation = cfg->separation; pp.neighborhood = cfg->neighborhood;
         pp.min_length = cfg->min_length; pp.max_length = cfg->max_length; pp.min_rq = cfg->min_rq;
         pp.ab_mismatch_tol = cfg->ab_mismatch_tol; pp.min_active_fraction = cfg->min_active_fraction; pp.min_zscore = cfg->min_zscore;
+        pp.window_size = round_to_window_grid(cfg->window_size); pp.window_overlap = round_to_window_grid(cfg->window_overlap);
     }
+    window_env_override(pp);
     return pp;
 }
 
@@ -247,6 +262,78 @@ static void collect_results(ArrowEngine& E, int nz, int nr, const uint8_t* cx, c
         int np = 0;
         for (int r = s.read_begin; r < s.read_end; ++r)
             if (E.reads()[r].active && cx && (cx[r] & 3) == 3) ++np;
+        co.n_passes[z] = np;
+    }
+}
+
+// Results of a windowed chunk: the polished window cores of every ZMW are concatenated (docs/how-does-ccs-work.md:108-110);
+// a subread reports the first failure among its windows, else the sum of its window log-likelihoods.
+static void collect_windowed(ArrowEngine& E, const WindowPlan& P, int nz, int nr, const int32_t* zmw_read_off,
+                             const uint8_t* cx, const PolishParams& pp, const int32_t* draft_status, ChunkOut& co) {
+    const auto& zs = E.zmw_states();
+    const auto& qv = E.qvs();
+    const int nwr = P.n_reads();
+    co.seq.clear(); co.qv.clear();
+    co.seq_len.assign(nz, 0); co.n_tested.assign(nz, 0); co.rq.assign(nz, 0.f);
+    co.status.assign(nz, 0); co.n_passes.assign(nz, 0); co.iterations.assign(nz, 0); co.n_applied.assign(nz, 0);
+    co.read_ll.assign(nr, NAN); co.read_status.assign(nr, 4);
+    std::vector<double> wll((size_t)nwr + 1, NAN);
+    std::vector<int32_t> wst((size_t)nwr + 1, 4);
+    E.read_lls(wll.data(), nullptr, wst.data());
+    {
+        std::vector<uint8_t> seen((size_t)nr, 0);
+        for (int k = 0; k < nwr; ++k) {
+            const int r = P.parent[k];
+            if (!seen[r]) { seen[r] = 1; co.read_status[r] = 0; co.read_ll[r] = 0.0; }
+            if (co.read_status[r] != 0) continue;
+            if (wst[k] != 0) { co.read_status[r] = wst[k]; co.read_ll[r] = NAN; }
+            else co.read_ll[r] += wll[k];
+        }
+    }
+    static const std::vector<double> err_of_qv = [] { std::vector<double> t(256); for (int q = 0; q < 256; ++q) t[q] = std::pow(10.0, -0.1 * q); return t; }();
+    for (int z = 0; z < nz; ++z) {
+        const int w0 = P.zmw_win_off[z], w1 = P.zmw_win_off[z + 1];
+        int status = CCS_ZMW_SUCCESS;
+        double rq = 0.0;
+        bool failed = false, converged = true;
+        for (int w = w0; w < w1; ++w) {
+            const ZmwState& s = zs[w];
+            failed |= s.failed || qv[w].size() != s.tpl.size();
+            converged &= s.converged;
+            co.iterations[z] = std::max(co.iterations[z], s.iterations);
+            co.n_applied[z] += s.n_applied;
+            co.n_tested[z] += s.n_tested;
+        }
+        if (draft_status && draft_status[z] != CCS_ZMW_SUCCESS) status = draft_status[z];
+        else if (P.zmw_empty[z] || w1 == w0) status = CCS_ZMW_EMPTY_WINDOW_DURING_POLISHING;
+        else if (failed) status = CCS_ZMW_TOO_MANY_UNUSABLE;
+        else {
+            const size_t s_mark = co.seq.size();
+            for (int w = w0; w < w1; ++w) {
+                const ZmwState& s = zs[w];
+                const int b = std::max(0, s.core_b), e = std::min((int)s.tpl.size(), s.core_e);
+                if (e > b) {
+                    co.seq.insert(co.seq.end(), s.tpl.begin() + b, s.tpl.begin() + e);
+                    co.qv.insert(co.qv.end(), qv[w].begin() + b, qv[w].begin() + e);
+                }
+            }
+            const int J = (int)(co.seq.size() - s_mark);
+            double e = 0;
+            for (int j = 0; j < J; ++j) e += err_of_qv[co.qv[s_mark + j]];
+            rq = J ? 1.0 - e / J : 0.0;
+            if (!converged) status = CCS_ZMW_NON_CONVERGENT;
+            else if (J < pp.min_length) status = CCS_ZMW_TOO_SHORT;
+            else if (pp.max_length > 0 && J > pp.max_length) status = CCS_ZMW_TOO_LONG;
+            else if (rq < pp.min_rq) status = CCS_ZMW_POOR_QUALITY;
+            co.seq_len[z] = J;
+        }
+        co.rq[z] = (float)rq; co.status[z] = status;
+    }
+    // np: full-length subreads that took part in every window they cover
+    for (int z = 0; z < nz; ++z) {
+        int np = 0;
+        for (int r = zmw_read_off[z]; r < zmw_read_off[z + 1]; ++r)
+            if (co.read_status[r] == 0 && cx && (cx[r] & 3) == 3) ++np;
         co.n_passes[z] = np;
     }
 }
@@ -435,34 +522,32 @@ static void ccs_chunk(ccsgpu_ctx* ctx, int lane, const ccs_batch* in, const Draf
     { HostPhase hp("ccs.draft total"); lane_draft(ctx, lane).run(to_draft_input(in), dpar, d); }
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (lane == 0) ctx->ms_draft += ms; else ctx->extra[lane - 1].ms_draft += ms;
-    // ZMWs that failed the draft get an empty template and no reads
+    // Windowing (window_host.h): every window of every draft that passed is a ZMW of the Arrow engine, its reads are slices
+    // of the resident subread codes; a short draft is one window, i.e. the plain per-ZMW problem
     const int nz = in->n_zmws, nr = in->n_reads;
-    std::vector<int64_t> tpl_off(nz + 1, 0);
-    for (int z = 0; z < nz; ++z)
-        tpl_off[z + 1] = tpl_off[z] + (d.status[z] == CCS_ZMW_SUCCESS ? (int64_t)d.draft[z].size() : 0);
-    std::vector<uint8_t> tpl((size_t)tpl_off[nz] + 1), strand(nr);
-    std::vector<int32_t> ts(nr), te(nr), rs(nr), re(nr);
-    for (int z = 0; z < nz; ++z) {
-        const bool ok = d.status[z] == CCS_ZMW_SUCCESS;
-        if (ok) std::memcpy(tpl.data() + tpl_off[z], d.draft[z].data(), d.draft[z].size());
-        for (int r = in->zmw_read_off[z]; r < in->zmw_read_off[z + 1]; ++r) {
-            const ReadMap& m = d.maps[r];
-            const bool use = ok && m.mapped;
-            strand[r] = (uint8_t)m.strand;
-            ts[r] = use ? m.tstart : 0; te[r] = use ? m.tend : 0;
-            rs[r] = use ? m.rstart : 0; re[r] = use ? m.rend : 0;
-        }
+    WindowPlan P;
+    {
+        HostPhase hp("ccs.window plan");
+        std::vector<uint8_t> ok((size_t)nz);
+        for (int z = 0; z < nz; ++z) ok[z] = d.status[z] == CCS_ZMW_SUCCESS;
+        WindowParams wp;
+        wp.size = pp.window_size; wp.overlap = pp.window_overlap;
+        build_window_plan(nz, in->zmw_read_off, in->read_off, in->snr, d.draft, ok.data(), d.maps.data(), d.grid.data(),
+                          d.grid_off.data(), wp, P);
     }
     PolishInput p;
-    p.n_zmws = nz; p.n_reads = nr; p.zmw_read_off = in->zmw_read_off; p.read_off = in->read_off; p.codes = in->codes;
-    p.snr = in->snr; p.tpl_off = tpl_off.data(); p.tpl = tpl.data(); p.strand = strand.data();
-    p.tstart = ts.data(); p.tend = te.data(); p.rstart = rs.data(); p.rend = re.data();
+    p.n_zmws = P.n_windows(); p.n_reads = P.n_reads(); p.zmw_read_off = P.win_read_off.data(); p.codes = in->codes;
+    p.snr = P.snr.data(); p.tpl_off = P.tpl_off.data(); p.tpl = P.tpl.data(); p.strand = P.strand.data();
+    p.tstart = P.ts.data(); p.tend = P.te.data();
+    p.code_start = P.code_start.data(); p.code_len = P.code_len.data(); p.code_base = nr ? in->read_off[0] : 0;
+    p.read_group = P.parent.data(); p.n_groups = nr; p.zmw_group = P.win_zmw.data();
+    p.core_b = P.core_b.data(); p.core_e = P.core_e.data(); p.growth_min = P.growth_min.data();
     p.d_codes = lane_draft(ctx, lane).device_codes();   // uploaded once by the Draft Stage of this lane, still resident
     ArrowEngine& E = lane_engine(ctx, lane);
     E.load(p);
     E.polish(pp);
     HostPhase hp("ccs.collect_results");
-    collect_results(E, nz, nr, in->cx, pp, d.status.data(), co);
+    collect_windowed(E, P, nz, nr, in->zmw_read_off, in->cx, pp, d.status.data(), co);
 }
 
 int ccsgpu_ccs(ccsgpu_ctx* ctx, const ccs_batch* in, const ccs_draft_cfg* dcfg, const ccs_polish_cfg* pcfg,

@@ -57,6 +57,7 @@ void DraftEngine::release_buffers() {
     d_codes_.release(); d_desc_.release(); d_rev_.release(); d_moves_.release(); d_draft_.release(); d_meta_.release();
     d_pred0_.release(); d_predx_.release(); d_rank_.release(); d_order_.release(); d_lo_.release(); d_besti_.release();
     d_hrows_.release(); d_scratch_.release(); d_draft_len_.release(); d_steps_.release(); d_results_.release();
+    d_grid_.release();
 }
 
 void DraftEngine::span(double* acc, int64_t bytes, int64_t* top_bytes, double* top_ms) {
@@ -92,6 +93,8 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
     out.draft.assign(nz, {});
     out.maps.assign(nr, ReadMap());
     out.keep.assign(nr, 0);
+    out.grid.clear();
+    out.grid_off.assign(nr, -1);
     if (nz == 0) return;
     std::vector<int32_t> lens(nr);
     for (int r = 0; r < nr; ++r) lens[r] = (int32_t)(in.read_off[r + 1] - in.read_off[r]);
@@ -186,7 +189,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
         w.poa_reads = full;
         w.alive = true;
         out.draft[z].clear();
-        for (int r = r0; r < r1; ++r) out.maps[r] = ReadMap();
+        for (int r = r0; r < r1; ++r) { out.maps[r] = ReadMap(); out.grid_off[r] = -1; }
         any = true;
     }
     if (any) run_alive();
@@ -358,6 +361,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         h_desc_.ensure(bytes2);
         d_desc_.ensure(bytes2);
         hb = h_desc_.p; db = d_desc_.p;
+        int64_t grid_total = 0;
         {
             int64_t ro = 0;
             int k = 0;
@@ -374,6 +378,8 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
                     std::memset(&T, 0, sizeof(T));
                     T.codes_off = coff(r); T.row_off = ro; T.tpl_off = voff[g]; T.n = lens[r]; T.graph = -1; T.V = J;
                     T.rev_idx = r;
+                    T.grid_off = grid_total;
+                    grid_total += J / kWindowGrid + 1;
                     ro += J;
                     mbytes += (int64_t)J * (kPoaBand + 8) + lens[r] + J;
                 }
@@ -382,6 +388,8 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         }
         d_lo_.ensure((size_t)rows + 16); d_besti_.ensure((size_t)rows + 16); d_moves_.ensure((size_t)rows * kPoaBand + 16);
         d_results_.ensure((size_t)nt + 1); h_results_.ensure((size_t)nt + 1);
+        d_grid_.ensure((size_t)grid_total + 16); h_grid_.ensure((size_t)grid_total + 16);
+        CCS_CUDA(cudaMemsetAsync(d_grid_.p, 0xff, sizeof(int32_t) * (size_t)grid_total, stream_));
         CCS_CUDA(cudaMemcpyAsync(d_desc_.p, h_desc_.p, bytes2, cudaMemcpyHostToDevice, stream_));
         stats.h2d_bytes += (int64_t)bytes2;
         PoaGraphView G0 = G;     // linear tasks never touch the graph arrays
@@ -392,10 +400,12 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         stats.bytes_map += mbytes;
         span(&stats.ms_map, mbytes, &stats.top_map_bytes, &stats.top_map_ms);
         launch_poa_align(at<PoaTask>(db, o_t2), nt, G0, d_draft_.p, d_codes_.p, d_rev_.p, d_lo_.p, d_besti_.p, d_moves_.p,
-                         nullptr, nullptr, d_results_.p, stream_);
+                         nullptr, nullptr, d_results_.p, stream_, d_grid_.p);
         span_end();
         stats.n_graph_launches += 1; stats.n_align_launches += 2; stats.n_tasks += nt; stats.rows += rows;
         CCS_CUDA(cudaMemcpyAsync(h_results_.p, d_results_.p, sizeof(PoaResult) * nt, cudaMemcpyDeviceToHost, stream_));
+        CCS_CUDA(cudaMemcpyAsync(h_grid_.p, d_grid_.p, sizeof(int32_t) * (size_t)grid_total, cudaMemcpyDeviceToHost, stream_));
+        stats.d2h_bytes += 4 * grid_total;
         CCS_CUDA(cudaMemcpyAsync(h_rev_.p, d_rev_.p, (size_t)in.n_reads, cudaMemcpyDeviceToHost, stream_));
         stats.d2h_bytes += (int64_t)sizeof(PoaResult) * nt + in.n_reads;
         { HostPhase hp("draft.a5 gpu map (wait)");
@@ -403,10 +413,13 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         CCS_CUDA(cudaGetLastError());
         resolve_spans();
         }
+        const int64_t grid_base = (int64_t)out.grid.size();
+        out.grid.insert(out.grid.end(), h_grid_.p, h_grid_.p + grid_total);
         for (int k = 0; k < nt; ++k) {
             const PoaResult& pr = h_results_.p[k];
             const int r = task_read[k];
             ReadMap& m = out.maps[r];
+            out.grid_off[r] = grid_base + at<PoaTask>(hb, o_t2)[k].grid_off;
             m.score = pr.score;
             m.strand = h_rev_.p[r];
             if (pr.first_t < 0) continue;

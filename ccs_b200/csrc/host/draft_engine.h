@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <vector>
 #include "../cuda/poa_device.h"
+#include "draft_host.h"
 #include "cuda_util.h"
 
 namespace ccs {
@@ -29,13 +30,15 @@ struct DraftInput {
     const uint8_t* cx = nullptr;
 };
 
-struct ReadMap { int32_t mapped = 0, strand = 0, tstart = 0, tend = 0, rstart = 0, rend = 0, score = 0; };
-
 struct DraftOutput {
     std::vector<int32_t> status;               // per ZMW: ccs_zmw_status (SUCCESS = draft stage passed)
     std::vector<std::vector<uint8_t>> draft;   // per ZMW
     std::vector<ReadMap> maps;                 // per read
     std::vector<uint8_t> keep;                 // per read: survived FilterReads
+    // windowing: grid[grid_off[r] + k] = bases of the ORIENTED read r placed before draft position k * kWindowGrid on its
+    // mapping path (-1 where the path does not pass); grid_off[r] < 0: read not mapped
+    std::vector<int32_t> grid;
+    std::vector<int64_t> grid_off;
 };
 
 struct DraftStats {
@@ -83,11 +86,11 @@ private:
     size_t ev_used_ = 0;
     DevBuf<uint8_t> d_codes_, d_desc_, d_rev_, d_moves_, d_draft_;
     DevBuf<uint32_t> d_meta_;
-    DevBuf<int32_t> d_pred0_, d_predx_, d_rank_, d_order_, d_lo_, d_besti_, d_hrows_, d_scratch_, d_draft_len_;
+    DevBuf<int32_t> d_pred0_, d_predx_, d_rank_, d_order_, d_lo_, d_besti_, d_hrows_, d_scratch_, d_draft_len_, d_grid_;
     DevBuf<PoaStep> d_steps_;
     DevBuf<PoaResult> d_results_;
     PinBuf<uint8_t> h_codes_, h_desc_, h_draft_, h_rev_;
-    PinBuf<int32_t> h_draft_len_;
+    PinBuf<int32_t> h_draft_len_, h_grid_;
     PinBuf<PoaResult> h_results_;
 };
 

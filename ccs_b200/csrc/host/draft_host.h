@@ -9,6 +9,10 @@
 
 namespace ccs {
 
+// Placement of one subread on the draft (ExtractMappedRead): strand, draft span [tstart, tend), aligned part of the
+// read [rstart, rend) in its native orientation.
+struct ReadMap { int32_t mapped = 0, strand = 0, tstart = 0, tend = 0, rstart = 0, rend = 0, score = 0; };
+
 // FilterReads (docs/how-does-ccs-work.md:19-32): drop reads <50 % or >200 % of the median length,
 // cap the full-length passes at top_passes; returns the number of full-length reads kept.
 inline int filter_reads(const int32_t* lens, const uint8_t* cx, int n, int top_passes, uint8_t* keep) {

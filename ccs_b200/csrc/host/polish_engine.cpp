@@ -131,7 +131,15 @@ void ArrowEngine::load(const PolishInput& in) {
     // row codes: two 16-byte aligned copies per read (row i, and row i+1 for the backward pass), pre-multiplied by 4 =
     // byte offset into an emission-table row -- encoded ON THE DEVICE from the resident codes (arrow_pack.cu)
     int64_t code_total = 0;
-    auto rlen = [&](int r) -> int64_t { return in.rstart ? std::max(0, in.rend[r] - in.rstart[r]) : (in.read_off[r + 1] - in.read_off[r]); };
+    const bool sliced = in.code_start != nullptr;
+    if (sliced && (!in.code_len || !in.d_codes)) throw std::invalid_argument("sliced reads need code_len and resident codes");
+    auto rlen = [&](int r) -> int64_t {
+        if (sliced) return in.code_len[r];
+        return in.rstart ? std::max(0, in.rend[r] - in.rstart[r]) : (in.read_off[r + 1] - in.read_off[r]);
+    };
+    read_group_.clear(); zmw_group_.clear(); n_groups_ = 0;
+    if (in.read_group) { read_group_.assign(in.read_group, in.read_group + nr); n_groups_ = in.n_groups; }
+    if (in.zmw_group) zmw_group_.assign(in.zmw_group, in.zmw_group + nz);
     std::vector<int64_t> coffs(nr + 1, 0);
     for (int r = 0; r < nr; ++r) {
         const bool mapped = in.tend[r] > in.tstart[r];        // unmapped reads are never touched: no row codes
@@ -144,14 +152,16 @@ void ArrowEngine::load(const PolishInput& in) {
         zs.read_end = in.zmw_read_off[z + 1];
         zs.tpl.assign(in.tpl + in.tpl_off[z], in.tpl + in.tpl_off[z + 1]);
         zs.seen.assign(1, tpl_hash(zs.tpl));
+        zs.core_b = in.core_b ? in.core_b[z] : 0;
+        zs.core_e = in.core_e ? in.core_e[z] : (int32_t)zs.tpl.size();
     }
-    const int64_t raw_base = nr ? in.read_off[0] : 0;
+    const int64_t raw_base = sliced ? in.code_base : (nr ? in.read_off[0] : 0);
     h_pack_.ensure((size_t)nr + 1);
     parallel_for(nr, host_threads, [&](int r) {
         DevRead& rd = reads_[r];
         std::memset(&rd, 0, sizeof(rd));
         const int64_t I = rlen(r);
-        const int64_t soff = in.read_off[r] + (in.rstart ? in.rstart[r] : 0);
+        const int64_t soff = sliced ? in.code_start[r] : in.read_off[r] + (in.rstart ? in.rstart[r] : 0);
         const uint8_t* src = in.codes + soff;
         const int64_t stride = (coffs[r + 1] - coffs[r]) / 2;
         rd.code_off = coffs[r];
@@ -174,16 +184,29 @@ void ArrowEngine::load(const PolishInput& in) {
     }
     d_rowcode_.ensure((size_t)code_total + 64, budget_);
     d_pack_.ensure((size_t)nr + 1);
-    // transitions
+    // transitions and z-score moments per ZMW; the windows of one draft share their SNR: computed once per run of equal SNRs
     h_trans_.ensure((size_t)nz * 36 * 4);
-    for (int z = 0; z < nz; ++z) {
-        ZmwTransitions zt;
-        build_zmw_transitions(model_, in.snr + 4 * z, zt);
-        std::memcpy(h_trans_.p + (size_t)z * 36 * 4, zt.tr, sizeof(zt.tr));
-    }
     d_trans_.ensure((size_t)nz * 36 * 4, budget_);
     zs_mom_.resize((size_t)nz);
-    parallel_for(nz, host_threads, [&](int z) { zscore_moments(model_, in.snr + 4 * z, zs_mom_[z]); });
+    {
+        std::vector<int> leader((size_t)nz), leaders;
+        for (int z = 0; z < nz; ++z) {
+            leader[z] = (z > 0 && std::memcmp(in.snr + 4 * z, in.snr + 4 * (z - 1), 4 * sizeof(float)) == 0) ? leader[z - 1] : z;
+            if (leader[z] == z) leaders.push_back(z);
+        }
+        parallel_for((int)leaders.size(), host_threads, [&](int k) {
+            const int z = leaders[k];
+            ZmwTransitions zt;
+            build_zmw_transitions(model_, in.snr + 4 * z, zt);
+            std::memcpy(h_trans_.p + (size_t)z * 36 * 4, zt.tr, sizeof(zt.tr));
+            zscore_moments(model_, in.snr + 4 * z, zs_mom_[z]);
+        });
+        for (int z = 0; z < nz; ++z)
+            if (leader[z] != z) {
+                std::memcpy(h_trans_.p + (size_t)z * 36 * 4, h_trans_.p + (size_t)leader[z] * 36 * 4, 36 * 4 * sizeof(float));
+                zs_mom_[z] = zs_mom_[leader[z]];
+            }
+    }
     span_begin(&stats.ms_h2d);
     const uint8_t* d_raw = in.d_codes;
     if (!d_raw) {     // stand-alone Polish Stage: the engine uploads the read codes itself
@@ -207,7 +230,7 @@ void ArrowEngine::load(const PolishInput& in) {
     // template capacities: room for the template to grow during polishing
     for (int z = 0; z < nz; ++z) {
         const int J = (int)zstate_[z].tpl.size();
-        tpl_cap_[z] = ((J + std::max(512, J / 8)) + 15) & ~15;
+        tpl_cap_[z] = ((J + std::max(in.growth_min ? in.growth_min[z] : 512, J / 8)) + 15) & ~15;
     }
     // fixed column slots per read (span + the template's growth room), so unchanged ZMWs keep their bands
     col_base_.assign(nr, 0); col_cap_.assign(nr, 0);
@@ -389,7 +412,9 @@ void ArrowEngine::zscore_filter(double min_zscore) {
     CCS_CUDA(cudaMemcpyAsync(h_ll_.p, d_ll_alpha_.p, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream_));
     CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
     stats.d2h_bytes += 8ll * nr;
-    std::atomic<int> dropped(0);
+    // expectation and variance of every live read's log-likelihood on its template slice
+    std::vector<double> r_mean((size_t)nr, 0.0), r_var((size_t)nr, 0.0);
+    std::vector<uint8_t> live((size_t)nr, 0);
     parallel_for(nz, host_threads, [&](int z) {
         const ZmwState& zs = zstate_[z];
         const ZscoreMoments& M = zs_mom_[z];
@@ -408,18 +433,32 @@ void ArrowEngine::zscore_filter(double min_zscore) {
             }
         }
         for (int r = zs.read_begin; r < zs.read_end; ++r) {
-            DevRead& rd = reads_[r];
+            const DevRead& rd = reads_[r];
             if (!rd.active || status_[r] != 0) continue;
             const int s = rd.strand ? 1 : 0;
             const int b0 = s ? J - rd.te : rd.ts, b1 = s ? J - rd.ts : rd.te;      // slice [b0, b1) on strand s
             const int t0 = s ? 3 - zs.tpl[J - 1 - b0] : zs.tpl[b0];
-            const double mean = M.first_mean[t0] + (pm[s][b1 - 1] - pm[s][b0]);
-            const double var = M.first_var[t0] + (pv[s][b1 - 1] - pv[s][b0]);
-            const double zsc = (h_ll_.p[r] - mean) / std::sqrt(var);
-            if (zsc < min_zscore) { rd.active = 0; status_[r] = 5; dropped.fetch_add(1, std::memory_order_relaxed); }
+            r_mean[r] = M.first_mean[t0] + (pm[s][b1 - 1] - pm[s][b0]);
+            r_var[r] = M.first_var[t0] + (pv[s][b1 - 1] - pv[s][b0]);
+            live[r] = 1;
         }
     });
-    if (dropped.load() > 0) {      // the scoring kernel reads the statuses on the device
+    // a read is judged on the sum over its group (the windows of one subread), in read order
+    int dropped = 0;
+    if (read_group_.empty()) {
+        for (int r = 0; r < nr; ++r)
+            if (live[r] && (h_ll_.p[r] - r_mean[r]) / std::sqrt(r_var[r]) < min_zscore) { reads_[r].active = 0; status_[r] = 5; ++dropped; }
+    } else {
+        std::vector<double> g_ll((size_t)n_groups_, 0.0), g_mean((size_t)n_groups_, 0.0), g_var((size_t)n_groups_, 0.0);
+        for (int r = 0; r < nr; ++r)
+            if (live[r]) { const int g = read_group_[r]; g_ll[g] += h_ll_.p[r]; g_mean[g] += r_mean[r]; g_var[g] += r_var[r]; }
+        for (int r = 0; r < nr; ++r) {
+            if (!live[r]) continue;
+            const int g = read_group_[r];
+            if ((g_ll[g] - g_mean[g]) / std::sqrt(g_var[g]) < min_zscore) { reads_[r].active = 0; status_[r] = 5; ++dropped; }
+        }
+    }
+    if (dropped > 0) {      // the scoring kernel reads the statuses on the device
         std::memcpy(h_status_.p, status_.data(), sizeof(int32_t) * nr);
         CCS_CUDA(cudaMemcpyAsync(d_status_.p, h_status_.p, sizeof(int32_t) * nr, cudaMemcpyHostToDevice, stream_));
         stats.h2d_bytes += 4ll * nr;
@@ -563,6 +602,14 @@ void ArrowEngine::polish(const PolishParams& pp) {
         if (act == 0 || act < pp.min_active_fraction * zs.n_mapped) { zs.failed = true; zs.done = true; }
     };
     for (int z = 0; z < nz; ++z) check_usable(z);
+    if (!zmw_group_.empty())      // a draft with an unusable window is not polished at all
+        for (int z = 0; z < nz;) {
+            int e = z;
+            bool bad = false;
+            while (e < nz && zmw_group_[e] == zmw_group_[z]) { bad |= zstate_[e].failed; ++e; }
+            if (bad) for (int k = z; k < e; ++k) zstate_[k].done = true;
+            z = e;
+        }
 
     std::vector<Candidate> cands;
     for (int it = 0; it < pp.max_iterations; ++it) {
@@ -658,6 +705,14 @@ void ArrowEngine::polish(const PolishParams& pp) {
                     else if (m.type == 2) { if (m.pos < rd.ts) --ds; if (m.pos < rd.te) --de; }
                 }
                 rd.ts += ds; rd.te += de;
+            }
+            {   // the window core's borders move like a read's tstart: an insertion at a border goes to its left
+                int db = 0, de = 0;
+                for (const auto& m : best) {
+                    if (m.type == 1) { if (m.pos <= zs.core_b) ++db; if (m.pos <= zs.core_e) ++de; }
+                    else if (m.type == 2) { if (m.pos < zs.core_b) --db; if (m.pos < zs.core_e) --de; }
+                }
+                zs.core_b += db; zs.core_e += de;
             }
             if (reuse_scores) {
                 // carry the per-position "stale" marks over to the new coordinates (same shifts as remap_deltas) and

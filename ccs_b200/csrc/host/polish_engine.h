@@ -30,6 +30,19 @@ struct PolishInput {
     // optional: the same codes already resident on this device (the lane's Draft Stage uploaded them);
     // d_codes[k] is codes[read_off[0] + k].  NULL: the engine uploads them itself.
     const uint8_t* d_codes = nullptr;
+    // ---- windowed input (window_host.h): every "ZMW" is a window of a draft, every "read" a slice of a subread --------
+    // code_start / code_len (both or neither): the slice of `codes` each read occupies (absolute offsets), replacing
+    // read_off / rstart / rend; needs d_codes with d_codes[k] = codes[code_base + k].
+    const int64_t* code_start = nullptr;
+    const int32_t* code_len = nullptr;
+    int64_t code_base = 0;
+    const int32_t* read_group = nullptr;     // [n_reads] reads of one group (a subread's windows) share one z-score verdict
+    int32_t n_groups = 0;
+    const int32_t* zmw_group = nullptr;      // [n_zmws] windows of one group (a draft) are consecutive; a group whose window is
+                                             // unusable when polishing starts is not polished at all
+    const int32_t* core_b = nullptr;         // [n_zmws] borders of the window core, tracked through the edits;
+    const int32_t* core_e = nullptr;         //          NULL: the whole template
+    const int32_t* growth_min = nullptr;     // [n_zmws] template growth room max(growth_min, J/8); NULL: 512
 };
 
 struct PolishParams {
@@ -42,6 +55,8 @@ struct PolishParams {
     int32_t max_length = 50000;    // --max-length
     double min_active_fraction = 0.5;   // TOO_MANY_UNUSABLE below this share of mapped reads
     double min_zscore = -3.4;           // POOR_ZSCORE: reads whose LL z-score against the draft is lower are dropped
+    int32_t window_size = 1024;         // windowing (window_host.h), applied by ccsgpu_ccs
+    int32_t window_overlap = 64;
 };
 
 struct HostMutation { int32_t type, pos, base; double score; };
@@ -61,6 +76,7 @@ struct ZmwState {
     std::vector<uint64_t> seen;        // template hashes (cycle guard)
     std::vector<int32_t> sites;        // positions of the last-applied mutations (new coordinates)
     int32_t n_mapped = 0;
+    int32_t core_b = 0, core_e = 0;    // borders of the window core in current template coordinates (ApplyMutations keeps them)
 };
 
 struct EngineStats {
@@ -164,6 +180,9 @@ private:
     std::vector<int32_t> col_cap_;           // columns reserved for it
     std::vector<int32_t> tpl_cap_;           // per-ZMW template capacity in the device buffer
     std::vector<ZscoreMoments> zs_mom_;      // per ZMW: expected-LL moments per context (POOR_ZSCORE filter)
+    std::vector<int32_t> read_group_;        // per read: z-score group (empty: every read on its own)
+    int32_t n_groups_ = 0;
+    std::vector<int32_t> zmw_group_;         // per ZMW: group of windows (empty: every ZMW on its own)
     int64_t total_cols_ = 0, total_delta_rows_ = 0;
     double ab_tol_ = 1e-3;
     int64_t score_mark_ = 0;                 // stats.n_score when the current polish() began

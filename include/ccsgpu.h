@@ -134,6 +134,12 @@ typedef struct ccs_polish_cfg {
     double  ab_mismatch_tol;      /* 1e-3: |1 - LL_alpha/LL_beta| above this drops the read */
     double  min_active_fraction;  /* 0.5: fewer usable reads -> TOO_MANY_UNUSABLE */
     double  min_zscore;           /* -3.4: a read whose LL z-score against the draft is lower is dropped (POOR_ZSCORE) */
+    /* Windowing (docs/how-does-ccs-work.md:57-61,108-110), ccsgpu_ccs only: a draft of at least 2 * window_size bases is
+     * polished as floor(J / window_size) independent windows (cores of window_size bases, the last one running to the
+     * end, each padded by window_overlap bases on both sides) whose polished cores are concatenated.  Both are rounded up
+     * to multiples of 64; window_size 0 = one window per draft. */
+    int32_t window_size;          /* 1024 */
+    int32_t window_overlap;       /* 64 */
 } ccs_polish_cfg;
 void ccs_polish_cfg_default(ccs_polish_cfg* cfg);
 

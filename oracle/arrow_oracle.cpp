@@ -292,6 +292,7 @@ void Integrator<Real>::init(const ccs::ArrowModelParams& m, const float snr[4], 
     fwd.assign(tpl, tpl + J);
     revcomp(fwd, rev);
     reads.clear(); recs.clear(); active.clear();
+    mark_b = 0; mark_e = J;
 }
 
 template <class Real>
@@ -306,13 +307,19 @@ void Integrator<Real>::add_read(const MappedRead& r) {
 }
 
 template <class Real>
-double Integrator<Real>::zscore(size_t r) const {
+void Integrator<Real>::zmoments(size_t r, double& mean, double& var) const {
     const MappedRead& rd = reads[r];
     const int J = (int)fwd.size();
     const int len = rd.tend - rd.tstart;
     const uint8_t* t = rd.strand ? rev.data() + (J - rd.tend) : fwd.data() + rd.tstart;
-    double mean = tab.zs_first_mean[t[0]], var = tab.zs_first_var[t[0]];
+    mean = tab.zs_first_mean[t[0]]; var = tab.zs_first_var[t[0]];
     for (int j = 1; j < len; ++j) { const int ctx = 4 * t[j - 1] + t[j]; mean += tab.zs_mean[ctx]; var += tab.zs_var[ctx]; }
+}
+
+template <class Real>
+double Integrator<Real>::zscore(size_t r) const {
+    double mean, var;
+    zmoments(r, mean, var);
     return (recs[r].ll() - mean) / std::sqrt(var);
 }
 
@@ -398,6 +405,14 @@ void Integrator<Real>::apply(const std::vector<Mutation>& muts) {
         rd.tstart += ds;
         rd.tend += de;
     }
+    {
+        int db = 0, de = 0;
+        for (const auto& m : muts) {
+            if (m.type == MUT_INS) { if (m.pos <= mark_b) ++db; if (m.pos <= mark_e) ++de; }
+            else if (m.type == MUT_DEL) { if (m.pos < mark_b) --db; if (m.pos < mark_e) --de; }
+        }
+        mark_b += db; mark_e += de;
+    }
     refill_all();
 }
 
@@ -443,9 +458,9 @@ PolishResult polish(Integrator<Real>& ai) {
     seen.insert(tpl_hash(ai.fwd));
     std::vector<int> sites;   // positions (current coordinates) of last-applied mutations
     // growth cap (DESIGN.md "Known deviations"): a template that would outgrow its initial length by more than
-    // max(512, J/8) bases (rounded up to a multiple of 16) stops being refined and counts as not converged
+    // max(growth_min = 512, J/8) bases (rounded up to a multiple of 16) stops being refined and counts as not converged
     const int J0 = (int)ai.fwd.size();
-    const int cap = ((J0 + std::max(512, J0 / 8)) + 15) & ~15;
+    const int cap = ((J0 + std::max(ai.cfg.growth_min, J0 / 8)) + 15) & ~15;
     for (int it = 0; it < ai.cfg.max_iterations; ++it) {
         res.iterations = it + 1;
         const int J = (int)ai.fwd.size();

@@ -111,6 +111,7 @@ struct PolishConfig {
     int band_width = 32;
     double ab_mismatch_tol = 1e-3;
     double min_zscore = -3.4;     // AddRead drops a read whose LL lies further below its expectation (POOR_ZSCORE)
+    int growth_min = 512;         // growth cap: the template may outgrow its first length by max(growth_min, J/8) bases
 };
 
 struct PolishResult {
@@ -132,6 +133,10 @@ struct Integrator {
     void init(const ccs::ArrowModelParams& m, const float snr[4], const uint8_t* tpl, int J, const PolishConfig& c);
     void add_read(const MappedRead& r);
     double zscore(size_t r) const;           // (LL - E[LL]) / sd[LL] of read r on its template slice
+    void zmoments(size_t r, double& mean, double& var) const;   // E[LL], Var[LL] of read r on its template slice
+    // Two template borders tracked through ApplyMutations like a read's tstart (an insertion at the border goes to
+    // its left, a deletion of the base at the border to its right): the window core of DESIGN.md "Windowing".
+    int mark_b = 0, mark_e = 0;
     void refill_all();
     void refill(size_t r);
     double ll() const;                       // sum over active reads

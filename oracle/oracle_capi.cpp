@@ -180,13 +180,16 @@ int oracle_score_all(const void* model, const float* snr, const uint8_t* draft, 
 
 
 // ---- draft stage / whole pipeline ------------------------------------------------------
-// cfg_i[8] = {min_passes, top_passes, max_poa_reads, min_length, max_length, max_iterations(-1 default), 0, 0}
+// cfg_i[8] = {min_passes, top_passes, max_poa_reads, min_length, max_length, max_iterations(-1 default),
+//            window_size (<0: default; rounded up to a multiple of 64), window_overlap (likewise)}
 // cfg_d[4] = {min_snr, min_rq, min_active_fraction, min_zscore}
 static CcsConfig make_cfg(const int32_t* ci, const double* cd) {
     CcsConfig c;
     if (ci) {
         c.min_passes = ci[0]; c.top_passes = ci[1]; c.max_poa_reads = ci[2]; c.min_length = ci[3]; c.max_length = ci[4];
         if (ci[5] >= 0) c.polish.max_iterations = ci[5];
+        if (ci[6] >= 0) c.window_size = (ci[6] + WINDOW_GRID - 1) / WINDOW_GRID * WINDOW_GRID;
+        if (ci[7] >= 0) c.window_overlap = (ci[7] + WINDOW_GRID - 1) / WINDOW_GRID * WINDOW_GRID;
     }
     if (cd) { c.min_snr = cd[0]; c.min_rq = cd[1]; c.min_active_fraction = cd[2]; c.polish.min_zscore = cd[3]; }
     return c;

@@ -121,6 +121,45 @@ void draft_zmw(const CcsConfig& cfg, int nreads, const uint8_t* codes, const int
 }
 
 
+std::vector<Window> make_windows(int J, int W, int OV) {
+    std::vector<Window> ws;
+    if (W <= 0 || J < 2 * W) { ws.push_back(Window{0, J, 0, J}); return ws; }
+    const int n = J / W;
+    for (int k = 0; k < n; ++k) {
+        Window w;
+        w.c0 = k * W;
+        w.c1 = (k == n - 1) ? J : (k + 1) * W;
+        w.a = std::max(0, w.c0 - OV);
+        w.b = std::min(J, w.c1 + OV);
+        ws.push_back(w);
+    }
+    return ws;
+}
+
+std::vector<WindowRead> window_reads(const Window& w, const std::vector<ReadMapping>& maps, const std::vector<int>& lens) {
+    std::vector<WindowRead> out;
+    for (int r = 0; r < (int)maps.size(); ++r) {
+        const ReadMapping& m = maps[r];
+        if (!m.mapped) continue;
+        if (std::min(m.tend, w.c1) - std::max(m.tstart, w.c0) < 1) continue;      // does not reach the core
+        const int lo = std::max(w.a, m.tstart), hi = std::min(w.b, m.tend);
+        if (hi - lo < 2) continue;
+        const int n = lens[r];
+        const int rs_o = m.strand ? n - m.rend : m.rstart, re_o = m.strand ? n - m.rstart : m.rend;   // oriented read
+        const int s_o = (lo == m.tstart) ? rs_o : m.grid[lo / WINDOW_GRID];
+        const int e_o = (hi == m.tend) ? re_o : m.grid[hi / WINDOW_GRID];
+        if (e_o - s_o < 2) continue;
+        WindowRead x;
+        x.parent = r; x.strand = m.strand; x.ts = lo - w.a; x.te = hi - w.a;
+        x.ns = m.strand ? n - e_o : s_o; x.ne = m.strand ? n - s_o : e_o;                              // native slice
+        out.push_back(x);
+    }
+    return out;
+}
+
+// Polish Stage of one ZMW: every window is an Arrow problem of its own (template = the padded draft slice, reads = the
+// slices of the mapped subreads that the subread -> draft alignment places on it); the polished cores are concatenated
+// (docs/how-does-ccs-work.md:57-61,108-110).  A read is judged (POOR_ZSCORE) on the sum over its windows.
 void ccs_zmw(const ccs::ArrowModelParams& model, const CcsConfig& cfg, int nreads, const uint8_t* codes,
              const int64_t* read_off, const uint8_t* cx, const float snr[4], CcsZmwResult& out) {
     std::vector<char> keep;
@@ -128,40 +167,103 @@ void ccs_zmw(const ccs::ArrowModelParams& model, const CcsConfig& cfg, int nread
     out.read_ll.assign(nreads, NAN);
     out.read_status.assign(nreads, 4);
     if (out.status != Z_SUCCESS) return;
-    Integrator<double> ai;
-    ai.init(model, snr, out.draft.data(), (int)out.draft.size(), cfg.polish);
-    std::vector<int> idx;
-    int n_mapped = 0;
-    for (int r = 0; r < nreads; ++r) {
-        const ReadMapping& m = out.maps[r];
-        if (!m.mapped) continue;
-        MappedRead mr;
-        mr.codes.assign(codes + read_off[r] + m.rstart, codes + read_off[r] + m.rend);
-        mr.strand = m.strand; mr.tstart = m.tstart; mr.tend = m.tend;
-        ai.add_read(mr);
-        idx.push_back(r);
-        ++n_mapped;
+    const int J = (int)out.draft.size();
+    const std::vector<Window> wins = make_windows(J, cfg.window_size, cfg.window_overlap);
+    const int nw = (int)wins.size();
+    PolishConfig pc = cfg.polish;
+    pc.min_zscore = -1e300;                       // the z-score is taken over all windows of a read, below
+    pc.growth_min = nw > 1 ? 128 : 512;
+    std::vector<int> lens(nreads);
+    for (int r = 0; r < nreads; ++r) lens[r] = (int)(read_off[r + 1] - read_off[r]);
+    std::vector<Integrator<double>> ais((size_t)nw);
+    std::vector<std::vector<int>> parent((size_t)nw);
+    for (int k = 0; k < nw; ++k) {
+        const Window& w = wins[k];
+        Integrator<double>& ai = ais[k];
+        ai.init(model, snr, out.draft.data() + w.a, w.b - w.a, pc);
+        ai.mark_b = w.c0 - w.a;
+        ai.mark_e = w.c1 - w.a;
+        for (const WindowRead& x : window_reads(w, out.maps, lens)) {
+            MappedRead mr;
+            mr.codes.assign(codes + read_off[x.parent] + x.ns, codes + read_off[x.parent] + x.ne);
+            mr.strand = x.strand; mr.tstart = x.ts; mr.tend = x.te;
+            ai.add_read(mr);
+            parent[k].push_back(x.parent);
+        }
+        if (parent[k].empty()) { out.status = Z_EMPTY_WINDOW_DURING_POLISHING; return; }
     }
-    auto usable = [&]() { const int a = ai.n_active(); return a > 0 && a >= cfg.min_active_fraction * n_mapped; };
+    // POOR_ZSCORE (Integrator::AddRead): z of the read's summed log-likelihood against its summed expectation
+    {
+        std::vector<double> ll(nreads, 0.0), mean(nreads, 0.0), var(nreads, 0.0);
+        std::vector<int> cnt(nreads, 0);
+        for (int k = 0; k < nw; ++k)
+            for (size_t x = 0; x < parent[k].size(); ++x) {
+                if (!ais[k].active[x]) continue;
+                double mu, va;
+                ais[k].zmoments(x, mu, va);
+                const int r = parent[k][x];
+                ll[r] += ais[k].recs[x].ll(); mean[r] += mu; var[r] += va; ++cnt[r];
+            }
+        for (int k = 0; k < nw; ++k)
+            for (size_t x = 0; x < parent[k].size(); ++x) {
+                const int r = parent[k][x];
+                if (ais[k].active[x] && cnt[r] > 0 && (ll[r] - mean[r]) / std::sqrt(var[r]) < cfg.polish.min_zscore) {
+                    ais[k].active[x] = 0;
+                    ais[k].recs[x].status = READ_POOR_ZSCORE;
+                }
+            }
+    }
+    auto usable = [&]() {
+        for (int k = 0; k < nw; ++k) {
+            const int a = ais[k].n_active();
+            if (!(a > 0 && a >= cfg.min_active_fraction * (double)parent[k].size())) return false;
+        }
+        return true;
+    };
     bool failed = !usable();
+    out.pr = PolishResult();
     if (!failed) {
-        out.pr = polish(ai);
+        out.pr.converged = true;
+        for (int k = 0; k < nw; ++k) {
+            const PolishResult p = polish(ais[k]);
+            out.pr.converged = out.pr.converged && p.converged;
+            out.pr.iterations = std::max(out.pr.iterations, p.iterations);
+            out.pr.n_tested += p.n_tested;
+            out.pr.n_applied += p.n_applied;
+        }
         failed = !usable();
     }
-    for (size_t k = 0; k < idx.size(); ++k) {
-        out.read_status[idx[k]] = ai.recs[k].status;
-        out.read_ll[idx[k]] = ai.active[k] ? ai.recs[k].ll() : NAN;
+    // per read: the first failure among its windows, else the sum of its window log-likelihoods
+    {
+        std::vector<int> seen(nreads, 0);
+        for (int k = 0; k < nw; ++k)
+            for (size_t x = 0; x < parent[k].size(); ++x) {
+                const int r = parent[k][x];
+                const int st = ais[k].recs[x].status;
+                if (!seen[r]) { seen[r] = 1; out.read_status[r] = READ_VALID; out.read_ll[r] = 0.0; }
+                if (out.read_status[r] != READ_VALID) continue;
+                if (st != READ_VALID || !ais[k].active[x]) { out.read_status[r] = st; out.read_ll[r] = NAN; }
+                else out.read_ll[r] += ais[k].recs[x].ll();
+            }
     }
     if (failed) { out.status = Z_TOO_MANY_UNUSABLE; return; }
-    consensus_qvs(ai, out.qv);
-    out.seq = ai.fwd;
+    out.seq.clear(); out.qv.clear();
+    for (int k = 0; k < nw; ++k) {
+        std::vector<uint8_t> q;
+        consensus_qvs(ais[k], q);
+        const int b = std::max(0, ais[k].mark_b), e = std::min((int)ais[k].fwd.size(), ais[k].mark_e);
+        if (e > b) {
+            out.seq.insert(out.seq.end(), ais[k].fwd.begin() + b, ais[k].fwd.begin() + e);
+            out.qv.insert(out.qv.end(), q.begin() + b, q.begin() + e);
+        }
+    }
     out.rq = predicted_accuracy(out.qv);
     out.np = 0;
-    for (size_t k = 0; k < idx.size(); ++k) if (ai.active[k] && (cx[idx[k]] & 3) == 3) ++out.np;
-    const int J = (int)out.seq.size();
+    for (int r = 0; r < nreads; ++r) if (out.read_status[r] == READ_VALID && (cx[r] & 3) == 3) ++out.np;
+    const int Jc = (int)out.seq.size();
     if (!out.pr.converged) out.status = Z_NON_CONVERGENT;
-    else if (J < cfg.min_length) out.status = Z_TOO_SHORT;
-    else if (cfg.max_length > 0 && J > cfg.max_length) out.status = Z_TOO_LONG;
+    else if (Jc < cfg.min_length) out.status = Z_TOO_SHORT;
+    else if (cfg.max_length > 0 && Jc > cfg.max_length) out.status = Z_TOO_LONG;
     else if (out.rq < cfg.min_rq) out.status = Z_POOR_QUALITY;
     else out.status = Z_SUCCESS;
 }

@@ -22,8 +22,18 @@ struct CcsConfig {
     int min_length = 10, max_length = 50000;
     double min_rq = 0.99;
     double min_active_fraction = 0.5;
+    // Windowing (docs/how-does-ccs-work.md:57-61; DESIGN.md "Windowing"): a draft of at least 2 * window_size bases is
+    // polished as floor(J / window_size) windows -- cores [k W, (k+1) W), the last one running to the end -- each
+    // padded by window_overlap bases on both sides; 0 = one window.  Both are multiples of WINDOW_GRID.
+    int window_size = 1024, window_overlap = 64;
     PolishConfig polish;
 };
+
+struct Window { int a, b, c0, c1; };   // padded template range [a, b), core [c0, c1)
+std::vector<Window> make_windows(int J, int window_size, int window_overlap);
+// the slice of read `parent` (native coordinates [ns, ne)) that the mapping places on window template range [ts, te)
+struct WindowRead { int parent, ns, ne, strand, ts, te; };
+std::vector<WindowRead> window_reads(const Window& w, const std::vector<ReadMapping>& maps, const std::vector<int>& lens);
 
 struct CcsZmwResult {
     int status = Z_EXCEPTION_THROWN;

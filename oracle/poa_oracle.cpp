@@ -254,6 +254,16 @@ ReadMapping map_to_template(const uint8_t* tpl, int J, const uint8_t* read_bases
         }
     }
     if (fv < 0) return m;
+    m.grid.assign((size_t)J / WINDOW_GRID + 1, -1);
+    int consumed = fr;
+    for (const PathStep& st : a.path) {
+        if (st.move == PM_MATCH) {
+            if (st.vertex % WINDOW_GRID == 0) m.grid[st.vertex / WINDOW_GRID] = st.readpos;
+            consumed = st.readpos + 1;
+        } else if (st.move == PM_DEL) {
+            if (st.vertex % WINDOW_GRID == 0) m.grid[st.vertex / WINDOW_GRID] = consumed;
+        } else if (st.move == PM_INS) consumed = st.readpos + 1;
+    }
     m.tstart = fv; m.tend = lv + 1; m.rstart = fr; m.rend = lr + 1;
     m.mapped = a.score >= n;
     return m;

@@ -43,7 +43,15 @@ struct PoaGraph {
 // true if the reverse complement of `read` shares more K-mers with `ref` than `read` does
 bool kmer_vote_reverse(const uint8_t* ref, int nref, const uint8_t* read, int n);
 
-struct ReadMapping { int strand = 0, tstart = 0, tend = 0, rstart = 0, rend = 0, score = 0; bool mapped = false; };
+constexpr int WINDOW_GRID = 64;        // windowing (DESIGN.md "Windowing"): window borders lie on multiples of 64 template bases
+
+struct ReadMapping {
+    int strand = 0, tstart = 0, tend = 0, rstart = 0, rend = 0, score = 0;
+    bool mapped = false;
+    // grid[k] = number of bases of the ORIENTED read placed before template position k * WINDOW_GRID on the alignment
+    // path (the base matched there, or the next one when the position is deleted); -1 where the path does not pass
+    std::vector<int> grid;
+};
 // align read (already oriented by the vote) to a linear template; extents of the aligned part
 ReadMapping map_to_template(const uint8_t* tpl, int J, const uint8_t* read_bases, int n);
 

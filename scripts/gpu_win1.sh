@@ -1,0 +1,14 @@
+# windowing, first GPU pass: parity tests that exercise long inserts, smoke, A/B bench
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_draft.py tests/test_gpu_arrow.py -x -q -m gpu 2>&1 | tail -3
+timeout 900 python -m pytest "tests/test_gpu_parity_scale.py" -x -q -m gpu 2>&1 | tail -5
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+for w in 0 1024 512; do
+CCS_B200_WINDOW=$w python bench.py --steps 4 --warmup 2 --no-cpu-baseline --other-configs 2,5 > gpurun_out/w_$w.json 2> gpurun_out/w_$w.err
+python - <<PY
+import json; d=json.load(open('gpurun_out/w_$w.json')); print('window $w e2e',round(d['e2e']['value'],1), [ (k, round(v['e2e'],1), {a:round(b,1) for a,b in v['kernel_ms_single_lane'].items()}) for k,v in d.get('other_configs',{}).items()])
+for r in d.get('roofline_kernels',[]): print('  ', r['kernel'], 'timed', round(r['timed_region']['frac'],3), 'single', round(r['single_lane_all_launches']['frac'],3), 'ms', round(r['single_lane_all_launches']['ms'],1), 'largest', round(r['largest_launch']['frac'],3))
+PY
+tail -2 gpurun_out/w_$w.err
+done

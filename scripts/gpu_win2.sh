@@ -1,0 +1,19 @@
+# windowing: lanes x contexts x batch matrix on config 3 (+ host phase profile of one run)
+mkdir -p gpurun_out
+run() { # lanes contexts zmws
+python bench.py --steps 4 --warmup 2 --no-cpu-baseline --other-configs '' --lanes $1 --contexts $2 --zmws $3 > gpurun_out/m_$1_$2_$3.json 2> gpurun_out/m_$1_$2_$3.err
+python - <<PY
+import json; d=json.load(open('gpurun_out/m_$1_$2_$3.json')); print('L$1 C$2 Z$3 e2e',round(d['e2e']['value'],1), [round(x,3) for x in d['e2e']['step_s']])
+PY
+}
+run 4 2 600
+run 2 2 600
+run 1 2 600
+run 1 3 600
+run 2 3 600
+run 4 2 1200
+run 2 2 1200
+run 1 2 1200
+run 1 4 1200
+CCS_B200_HOST_PROFILE=1 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --other-configs '' --lanes 1 --contexts 1 --zmws 600 > gpurun_out/hp.json 2> gpurun_out/hp.err
+grep -A40 "host phases" gpurun_out/hp.err | tail -45

@@ -129,8 +129,9 @@ def score_all(model, snr, draft, reads, strand, tstart, tend, W=32):
 
 
 def _cfg_arrays(min_passes=3, top_passes=60, max_poa_reads=5, min_length=10, max_length=50000, max_iterations=-1,
-                min_snr=2.5, min_rq=0.99, min_active_fraction=0.5, min_zscore=-3.4):
-    ci = np.array([min_passes, top_passes, max_poa_reads, min_length, max_length, max_iterations, 0, 0], np.int32)
+                min_snr=2.5, min_rq=0.99, min_active_fraction=0.5, min_zscore=-3.4, window_size=-1, window_overlap=-1):
+    ci = np.array([min_passes, top_passes, max_poa_reads, min_length, max_length, max_iterations, window_size,
+                   window_overlap], np.int32)
     cd = np.array([min_snr, min_rq, min_active_fraction, min_zscore])
     return ci, cd
 

@@ -203,6 +203,42 @@ def test_draft_host_helpers_match_oracle(tmp_path):
     assert out.stdout.startswith("ok:")
 
 
+def test_window_host_matches_oracle(tmp_path):
+    """Windowing of the Polish Stage (ccs_b200/csrc/host/window_host.h: window layout, read slices from the mapping grid,
+    core borders, empty windows) against the oracle's make_windows / window_reads."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "window_host_parity")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", exe,
+                           os.path.join(ROOT, "tests", "host", "window_host_parity.cpp"),
+                           os.path.join(ROOT, "oracle", "pipeline_oracle.cpp"),
+                           os.path.join(ROOT, "oracle", "poa_oracle.cpp"),
+                           os.path.join(ROOT, "oracle", "arrow_oracle.cpp")])
+    out = subprocess.run([exe, "60"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert out.stdout.startswith("ok:")
+
+
+def test_oracle_windowed_polish_equals_whole_template_polish():
+    """Windowing is a pure decomposition (docs/how-does-ccs-work.md:57-61,108-110): on a 4 kb molecule the concatenated
+    cores of four independently polished windows are the consensus -- and, within 1, the QVs -- of polishing the whole
+    template at once."""
+    model = O.synthetic_model()
+    cfg = sim.get_config(2, insert_mean=4200)
+    for seed in (0, 1):
+        z = sim.simulate_zmw(model, cfg, seed)
+        reads = [z.read(k) for k in range(z.n_reads)]
+        whole = O.ccs_zmw(model, z.snr, reads, z.cx, window_size=0)
+        win = O.ccs_zmw(model, z.snr, reads, z.cx, window_size=1024, window_overlap=64)
+        assert whole["status"] == win["status"] == 16
+        assert np.array_equal(whole["seq"], win["seq"])
+        assert np.max(np.abs(whole["qv"].astype(int) - win["qv"].astype(int))) <= 1
+        assert np.array_equal(whole["read_status"], win["read_status"])
+
+
 def test_polish_host_helpers_match_oracle(tmp_path):
     """Candidate order + BestMutations (separation), Template::ApplyMutations and the de-duplicated candidate count of
     ccs_b200/csrc/host/polish_host.h against the oracle's best_mutations / apply_mutations / mutation_is_canonical."""
