@@ -23,32 +23,38 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kWarpsPerCta = 4;
-constexpr int kRing = 8;            // recent DP rows kept in shared memory (power of two)
+
+constexpr int kRing = 8;            // recent DP rows of a graph task kept in shared memory (power of two)
+constexpr int kNeg = -(1 << 29);
 
 __device__ __forceinline__ int row_get(const int* __restrict__ row, const int idx) {
     return ((unsigned)idx < (unsigned)kPoaBand) ? row[idx] : 0;
 }
 
+// One warp per (graph | draft, read) task, one 64-cell row per vertex in topological order, two adjacent cells per lane.
+// The band of every row of a 32-row block is known when the block starts (block-anchored band rule, DESIGN.md "Draft
+// stage"): the lanes fetch the block's vertices and place their bands in one go, and nothing per row depends on a
+// reduction over the previous row any more -- the per-row dependent chain is {neighbour cells, candidates, the in-row
+// insertion scan}.  The previous row stays in REGISTERS: when the only predecessor is the previous vertex (every vertex
+// of a draft, most vertices of a graph) and the band moved by 0 or 1 cells, its three operands are the lane's own two
+// cells and one shuffle, and the read bases move along with the band (one new base per lane and row).  Other rows take
+// the general path (predecessor rows from a shared-memory ring of the last 8 rows, else from global memory).  The best
+// cell of the task is tracked per lane and reduced once at the end; only the anchor row of a block is reduced.
+template <bool kDag>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     const PoaTask* __restrict__ tasks, const int n_tasks, const PoaGraphView G, const uint8_t* __restrict__ drafts,
     const uint8_t* __restrict__ codes, const uint8_t* __restrict__ rev_flags, int32_t* __restrict__ lo_arr,
-    int32_t* __restrict__ besti_arr, uint8_t* __restrict__ moves, int32_t* __restrict__ hrows,
-    PoaResult* __restrict__ results) {
-    // The last kRing rows stay in shared memory with their vertex ids, band starts and best cells: the predecessors of a
-    // branch vertex are almost always among them (a bubble opened by one read is a few vertices long), so the dependent
-    // chain of a branch vertex does not wait on global memory either.
-    __shared__ int s_ring[kWarpsPerCta][kRing][kPoaBand];
-    __shared__ int s_rid[kWarpsPerCta][kRing], s_rlo[kWarpsPerCta][kRing], s_rbi[kWarpsPerCta][kRing];
-    __shared__ int s_meta[kWarpsPerCta][128];
+    uint8_t* __restrict__ moves, int32_t* __restrict__ hrows, PoaResult* __restrict__ results) {
+    __shared__ int s_ring[kDag ? kWarpsPerCta : 1][kRing][kPoaBand];
+    __shared__ int s_rid[kDag ? kWarpsPerCta : 1][kRing], s_rlo[kDag ? kWarpsPerCta : 1][kRing];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task_id = blockIdx.x * kWarpsPerCta + warp;
     if (task_id >= n_tasks) return;
     const PoaTask T = tasks[task_id];
-    const bool linear = T.graph < 0;
     int V = T.V;
     int64_t voff = 0;
     const int32_t* __restrict__ ord = nullptr;
-    if (!linear) {
+    if (kDag) {
         const PoaGraphHdr& H = G.hdr[T.graph];
         V = H.V; voff = H.voff;
         ord = poa_order(G, H.order_sel) + voff;
@@ -57,156 +63,172 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     const uint32_t* __restrict__ meta = G.meta + voff;
     const int32_t* __restrict__ pred0 = G.pred0 + voff;
     const int32_t* __restrict__ predx = G.predx + 7 * voff;
+    const int32_t* __restrict__ colv = G.col + voff;
     const uint8_t* __restrict__ tplb = drafts + T.tpl_off;
-    const uint8_t* __restrict__ rc = codes + T.codes_off;
     const int n = T.n;
     const bool rev = rev_flags[T.rev_idx] != 0;
-    int32_t* __restrict__ lo_r = lo_arr + T.row_off;
-    int32_t* __restrict__ bi_r = besti_arr + T.row_off;
-    uint8_t* __restrict__ mv_r = moves + T.row_off * kPoaBand;
-    int32_t* __restrict__ h_r = hrows ? hrows + T.row_off * kPoaBand : nullptr;
-    const bool store_h = !linear && h_r != nullptr;
-    const int lo_max = max(0, n + 1 - kPoaBand);
-    int* srow = s_ring[warp][kRing - 1];      // "previous row" before the first vertex: zeros
-    auto read_base = [&](const int i) -> int {     // oriented base of read position i (0-based)
-        return rev ? 3 - (rc[n - 1 - i] & 3) : (rc[i] & 3);
+    // oriented base of read position q: (rbp[q * rdir] & 3) ^ rxor
+    const uint8_t* __restrict__ rbp = codes + T.codes_off + (rev ? n - 1 : 0);
+    const int rdir = rev ? -1 : 1, rxor = rev ? 3 : 0;
+    auto read_base = [&](const int i) -> int {     // oriented base in front of read prefix i, 255 outside the read
+        return (i >= 1 && i <= n) ? ((rbp[(i - 1) * rdir] & 3) ^ rxor) : 255;
     };
+    int32_t* __restrict__ lo_r = lo_arr + T.row_off;
+    uint8_t* __restrict__ mv_r = moves + T.row_off * kPoaBand;
+    int32_t* __restrict__ h_r = (kDag && hrows) ? hrows + T.row_off * kPoaBand : nullptr;
+    const int lo_max = max(0, n + 1 - kPoaBand);
+    const int wslot = kDag ? warp : 0;
+    if (kDag && lane < kRing) s_rid[wslot][lane] = -2;
 
-    int gbest = 0, gt = -1, gi = -1;
-    int prev_lo = 0, prev_besti = 0, prev_id = -1;
-    srow[2 * lane] = 0; srow[2 * lane + 1] = 0;
-    if (lane < kRing) s_rid[warp][lane] = -2;
-    int* smeta = s_meta[warp];          // per block of 32 vertices: id, base, in-degree, first predecessor
-    __syncwarp();
+    int lbest = 0, lt = 0x7fffffff, li = 0, lid = -1;    // this lane's best cell: value, row (topological index), prefix, vertex
+    // anchor of the current block: band start, best cell, best score and seed coordinate of the row in front of it
+    // (block 0: the cell in front of the first row)
+    int a_lo = 0, a_bi = 0, a_max = kPoaAnchorMin, a_col = -1;
+    int pH0 = 0, pH1 = 0, prev_lo = 0, prev_id = -1;     // previous row (registers)
+    int rb0 = 255, rb1 = 255;                            // read bases in front of the lane's two prefixes
+    if (kDag) __syncwarp();
 
-    for (int t = 0; t < V; ++t) {
-        // Vertex metadata does not depend on the DP state: every 32 vertices the lanes fetch one
-        // vertex each so that the per-vertex dependent chain below never waits on global memory for them.
-        if ((t & 31) == 0) {
-            const int tt = min(t + lane, V - 1);
-            int mid = tt, mb, mn, mf = tt - 1;
-            if (linear) { mb = tplb[tt]; mn = (tt > 0) ? 1 : 0; }
-            else {
-                mid = ord[tt];
-                const uint32_t m = meta[mid];
-                mb = (int)(m & 3u); mn = (int)((m >> 2) & 15u); mf = pred0[mid];
+    for (int t0 = 0; t0 < V; t0 += kPoaBlock) {
+        // ---- the block's vertices (one per lane) and their bands
+        const int tt = min(t0 + lane, V - 1);
+        int mid = tt, mb, mn, mf = tt - 1, mcol = tt;
+        if (!kDag) { mb = tplb[tt]; mn = (tt > 0) ? 1 : 0; }
+        else {
+            mid = ord[tt];
+            const uint32_t m = meta[mid];
+            mb = (int)(m & 3u); mn = (int)((m >> 2) & 15u); mf = pred0[mid]; mcol = colv[mid];
+        }
+        int mlo = (a_max >= kPoaAnchorMin) ? a_bi + (mcol - a_col) - kPoaBand / 2 : a_lo - kPoaBandDecay;
+        mlo = min(max(mlo, 0), lo_max);
+        if (t0 + lane < V) lo_r[mid] = mlo;
+        if (kDag) __syncwarp();      // a later row of the block may look the band start of an earlier one up
+        const int nrows = min(kPoaBlock, V - t0);
+
+        for (int r = 0; r < nrows; ++r) {
+            const int t = t0 + r;
+            const int id = __shfl_sync(kFull, mid, r), vb = __shfl_sync(kFull, mb, r), npred = __shfl_sync(kFull, mn, r);
+            const int first_pred = __shfl_sync(kFull, mf, r), lo = __shfl_sync(kFull, mlo, r);
+            const int dl = lo - prev_lo;
+            const int i0 = lo + 2 * lane, i1 = i0 + 1;
+            int c0, c1;
+            unsigned m0, m1;
+            if (npred == 1 && first_pred == prev_id) {
+                // the only predecessor is the previous row, held in registers as band cells 2*lane, 2*lane + 1
+                int hm1, h0, h1;
+                if (dl == 1) {            // band moved with the diagonal: own two cells + the next lane's first
+                    hm1 = pH0; h0 = pH1;
+                    h1 = __shfl_down_sync(kFull, pH0, 1);
+                    if (lane == 31) h1 = 0;
+                    rb0 = rb1; rb1 = read_base(i1);
+                } else if (dl == 0) {     // band stayed: the previous lane's second cell + own two
+                    hm1 = __shfl_up_sync(kFull, pH1, 1);
+                    if (lane == 0) hm1 = 0;
+                    h0 = pH0; h1 = pH1;
+                } else {                  // any other move (a new anchor, an irregular seed coordinate): cells by index
+                    const int a = 2 * lane + dl;
+                    const int q0 = __shfl_sync(kFull, pH0, ((a - 1) >> 1) & 31), q1 = __shfl_sync(kFull, pH1, ((a - 1) >> 1) & 31);
+                    const int r0 = __shfl_sync(kFull, pH0, (a >> 1) & 31), r1 = __shfl_sync(kFull, pH1, (a >> 1) & 31);
+                    const int u0 = __shfl_sync(kFull, pH0, ((a + 1) >> 1) & 31), u1 = __shfl_sync(kFull, pH1, ((a + 1) >> 1) & 31);
+                    hm1 = ((unsigned)(a - 1) < (unsigned)kPoaBand) ? (((a - 1) & 1) ? q1 : q0) : 0;
+                    h0 = ((unsigned)a < (unsigned)kPoaBand) ? ((a & 1) ? r1 : r0) : 0;
+                    h1 = ((unsigned)(a + 1) < (unsigned)kPoaBand) ? (((a + 1) & 1) ? u1 : u0) : 0;
+                    rb0 = read_base(i0); rb1 = read_base(i1);
+                }
+                const int bm0 = (rb0 != 255) ? hm1 + ((rb0 == vb) ? kPoaMatch : kPoaMismatch) : 0;
+                const int bm1 = (rb1 != 255) ? h0 + ((rb1 == vb) ? kPoaMatch : kPoaMismatch) : 0;
+                const int bd0 = (i0 <= n) ? h0 + kPoaDel : 0;
+                const int bd1 = (i1 <= n) ? h1 + kPoaDel : 0;
+                // match wins ties against deletion; candidates must be > 0.  Predecessor index 0 = the only one.
+                c0 = max(max(bm0, bd0), 0); c1 = max(max(bm1, bd1), 0);
+                m0 = (c0 == 0) ? 0u : ((bm0 >= bd0) ? 1u : 2u);
+                m1 = (c1 == 0) ? 0u : ((bm1 >= bd1) ? 1u : 2u);
+            } else {
+                rb0 = read_base(i0); rb1 = read_base(i1);
+                const int sc0 = (rb0 == vb) ? kPoaMatch : kPoaMismatch;
+                const int sc1 = (rb1 == vb) ? kPoaMatch : kPoaMismatch;
+                int bm0 = 0, bm1 = 0, bd0 = 0, bd1 = 0;        // best match / deletion candidates (must be > 0 to count)
+                int km0 = 0, km1 = 0, kd0 = 0, kd1 = 0;
+                if (npred == 0) {
+                    if (rb0 != 255 && sc0 > 0) { bm0 = sc0; km0 = 63; }
+                    if (rb1 != 255 && sc1 > 0) { bm1 = sc1; km1 = 63; }
+                }
+                if (kDag) {
+                    for (int k = 0; k < npred; ++k) {
+                        const int pr = (k == 0) ? first_pred : predx[7 * (int64_t)id + k - 1];
+                        const unsigned hit = __ballot_sync(kFull, s_rid[wslot][lane & (kRing - 1)] == pr) & ((1u << kRing) - 1u);
+                        const int slot = __ffs(hit) - 1;
+                        const int* __restrict__ row = hit ? s_ring[wslot][slot] : (h_r + (size_t)pr * kPoaBand);
+                        const int a = 2 * lane + lo - (hit ? s_rlo[wslot][slot] : lo_r[pr]);
+                        const int hm1 = row_get(row, a - 1), h0 = row_get(row, a), h1 = row_get(row, a + 1);
+                        if (rb0 != 255) { const int c = hm1 + sc0; if (c > bm0) { bm0 = c; km0 = k; } }
+                        if (rb1 != 255) { const int c = h0 + sc1; if (c > bm1) { bm1 = c; km1 = k; } }
+                        if (i0 <= n) { const int c = h0 + kPoaDel; if (c > bd0) { bd0 = c; kd0 = k; } }
+                        if (i1 <= n) { const int c = h1 + kPoaDel; if (c > bd1) { bd1 = c; kd1 = k; } }
+                    }
+                }
+                // match wins ties against deletion (oracle evaluation order)
+                if (bm0 >= bd0) { c0 = bm0; m0 = bm0 > 0 ? (1u | (km0 << 2)) : 0u; } else { c0 = bd0; m0 = 2u | (kd0 << 2); }
+                if (bm1 >= bd1) { c1 = bm1; m1 = bm1 > 0 ? (1u | (km1 << 2)) : 0u; } else { c1 = bd1; m1 = 2u | (kd1 << 2); }
             }
-            __syncwarp();
-            smeta[lane] = mid; smeta[32 + lane] = mb; smeta[64 + lane] = mn; smeta[96 + lane] = mf;
-            __syncwarp();
-        }
-        const int id = smeta[t & 31];
-        const int vb = smeta[32 + (t & 31)];
-        const int npred = smeta[64 + (t & 31)];
-        const int first_pred = smeta[96 + (t & 31)];
-        int lo, c0, c1;
-        unsigned m0, m1;
-        int i0, i1;
-        if (npred == 1 && first_pred == prev_id) {
-            // fast path (every vertex of a linear template, almost every vertex of a POA graph): the only
-            // predecessor is the previous row, which sits in shared memory
-            lo = min(max(prev_besti + 1 - kPoaBand / 2, 0), lo_max);
-            i0 = lo + 2 * lane; i1 = i0 + 1;
-            const int a = 2 * lane + (lo - prev_lo);
-            const int hm1 = row_get(srow, a - 1), h0 = row_get(srow, a), h1 = row_get(srow, a + 1);
-            const bool v0 = (i0 >= 1 && i0 <= n), v1 = (i1 >= 1 && i1 <= n);
-            const int rb0 = v0 ? read_base(i0 - 1) : 255, rb1 = v1 ? read_base(i1 - 1) : 255;
-            const int bm0 = v0 ? hm1 + ((rb0 == vb) ? kPoaMatch : kPoaMismatch) : 0;
-            const int bm1 = v1 ? h0 + ((rb1 == vb) ? kPoaMatch : kPoaMismatch) : 0;
-            const int bd0 = (i0 <= n) ? h0 + kPoaDel : 0;
-            const int bd1 = (i1 <= n) ? h1 + kPoaDel : 0;
-            // match wins ties against deletion; candidates must be > 0.  Predecessor index 0 = the only one.
-            c0 = max(max(bm0, bd0), 0); c1 = max(max(bm1, bd1), 0);
-            m0 = (c0 == 0) ? 0u : ((bm0 >= bd0) ? 1u : 2u);
-            m1 = (c1 == 0) ? 0u : ((bm1 >= bd1) ? 1u : 2u);
-        } else {
-        // band start from the predecessors' best cells
-        lo = 0;
-        if (npred > 0) {
-            int m = 0;
-            for (int k = 0; k < npred; ++k) {
-                const int pr = (k == 0) ? first_pred : predx[7 * (int64_t)id + k - 1];
-                const unsigned hit = __ballot_sync(kFull, s_rid[warp][lane & (kRing - 1)] == pr) & ((1u << kRing) - 1u);
-                m = max(m, hit ? s_rbi[warp][__ffs(hit) - 1] : bi_r[pr]);
-            }
-            lo = min(max(m + 1 - kPoaBand / 2, 0), lo_max);
-        }
-        i0 = lo + 2 * lane; i1 = i0 + 1;
-        const int rb0 = (i0 >= 1 && i0 <= n) ? read_base(i0 - 1) : 255;
-        const int rb1 = (i1 >= 1 && i1 <= n) ? read_base(i1 - 1) : 255;
-        const int sc0 = (rb0 == vb) ? kPoaMatch : kPoaMismatch;
-        const int sc1 = (rb1 == vb) ? kPoaMatch : kPoaMismatch;
-        int bm0 = 0, bm1 = 0, bd0 = 0, bd1 = 0;        // best match / deletion candidates (must be > 0 to count)
-        int km0 = 0, km1 = 0, kd0 = 0, kd1 = 0;
-        if (npred == 0) {
-            if (rb0 != 255 && sc0 > 0) { bm0 = sc0; km0 = 63; }
-            if (rb1 != 255 && sc1 > 0) { bm1 = sc1; km1 = 63; }
-        }
-        for (int k = 0; k < npred; ++k) {
-            const int pr = (k == 0) ? first_pred : predx[7 * (int64_t)id + k - 1];
-            const unsigned hit = __ballot_sync(kFull, s_rid[warp][lane & (kRing - 1)] == pr) & ((1u << kRing) - 1u);
-            const int slot = __ffs(hit) - 1;
-            const int* __restrict__ row = hit ? s_ring[warp][slot] : (h_r + (size_t)pr * kPoaBand);
-            const int dl = lo - (hit ? s_rlo[warp][slot] : lo_r[pr]);
-            const int a = 2 * lane + dl;
-            const int hm1 = row_get(row, a - 1), h0 = row_get(row, a), h1 = row_get(row, a + 1);
-            if (rb0 != 255) { const int c = hm1 + sc0; if (c > bm0) { bm0 = c; km0 = k; } }
-            if (rb1 != 255) { const int c = h0 + sc1; if (c > bm1) { bm1 = c; km1 = k; } }
-            if (i0 <= n) { const int c = h0 + kPoaDel; if (c > bd0) { bd0 = c; kd0 = k; } }
-            if (i1 <= n) { const int c = h1 + kPoaDel; if (c > bd1) { bd1 = c; kd1 = k; } }
-        }
-        // match wins ties against deletion (oracle evaluation order)
-        if (bm0 >= bd0) { c0 = bm0; m0 = bm0 > 0 ? (1u | (km0 << 2)) : 0u; } else { c0 = bd0; m0 = 2u | (kd0 << 2); }
-        if (bm1 >= bd1) { c1 = bm1; m1 = bm1 > 0 ? (1u | (km1 << 2)) : 0u; } else { c1 = bd1; m1 = 2u | (kd1 << 2); }
-        }
-        __syncwarp();   // everyone has read the previous row
-        // insertion chain: H[c] = max(C[c], H[c-1] + INS) over the row's cells with i <= n
-        const int NEG = -(1 << 29);
-        int x0 = (i0 <= n) ? c0 - kPoaIns * (2 * lane) : NEG;
-        int x1 = (i1 <= n) ? c1 - kPoaIns * (2 * lane + 1) : NEG;
-        x1 = max(x1, x0);
-        int sc = x1;
+            // insertion chain: H[c] = max(C[c], H[c-1] + INS) over the row's cells with i <= n
+            int x0 = (i0 <= n) ? c0 - kPoaIns * (2 * lane) : kNeg;
+            int x1 = (i1 <= n) ? c1 - kPoaIns * (2 * lane + 1) : kNeg;
+            x1 = max(x1, x0);
+            int sc = x1;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int y = __shfl_up_sync(kFull, sc, off);
-            if (lane >= off) sc = max(sc, y);
+            for (int off = 1; off < 32; off <<= 1) {
+                const int y = __shfl_up_sync(kFull, sc, off);
+                if (lane >= off) sc = max(sc, y);
+            }
+            int carry = __shfl_up_sync(kFull, sc, 1);
+            if (lane == 0) carry = kNeg;
+            x0 = max(x0, carry);
+            x1 = max(x1, x0);
+            const int H0 = (i0 <= n) ? x0 + kPoaIns * (2 * lane) : 0;
+            const int H1 = (i1 <= n) ? x1 + kPoaIns * (2 * lane + 1) : 0;
+            if (H0 > c0) m0 = 3u;
+            if (H1 > c1) m1 = 3u;
+            // row outputs (by vertex id)
+            *reinterpret_cast<uchar2*>(mv_r + (size_t)id * kPoaBand + 2 * lane) = make_uchar2((unsigned char)m0, (unsigned char)m1);
+            if (kDag) {
+                __syncwarp();   // everyone has read the ring
+                int* srow = s_ring[wslot][t & (kRing - 1)];
+                srow[2 * lane] = H0; srow[2 * lane + 1] = H1;
+                if (lane == 0) { s_rid[wslot][t & (kRing - 1)] = id; s_rlo[wslot][t & (kRing - 1)] = lo; }
+                if (h_r != nullptr) *reinterpret_cast<int2*>(h_r + (size_t)id * kPoaBand + 2 * lane) = make_int2(H0, H1);
+                __syncwarp();   // row visible in shared memory before the next vertex reads it
+            }
+            // this lane's best cell so far: the first row that reaches its maximum, smaller prefix first within a row
+            if (H0 > lbest) { lbest = H0; lt = t; li = i0; lid = id; }
+            if (H1 > lbest) { lbest = H1; lt = t; li = i1; lid = id; }
+            pH0 = H0; pH1 = H1; prev_lo = lo; prev_id = id;
         }
-        int carry = __shfl_up_sync(kFull, sc, 1);
-        if (lane == 0) carry = NEG;
-        x0 = max(x0, carry);
-        x1 = max(x1, x0);
-        int H0 = (i0 <= n) ? x0 + kPoaIns * (2 * lane) : 0;
-        int H1 = (i1 <= n) ? x1 + kPoaIns * (2 * lane + 1) : 0;
-        if (H0 > c0) m0 = 3u;
-        if (H1 > c1) m1 = 3u;
-        // row outputs (by vertex id)
-        *reinterpret_cast<uchar2*>(mv_r + (size_t)id * kPoaBand + 2 * lane) = make_uchar2((unsigned char)m0, (unsigned char)m1);
-        srow = s_ring[warp][t & (kRing - 1)];
-        srow[2 * lane] = H0; srow[2 * lane + 1] = H1;
-        if (store_h) *reinterpret_cast<int2*>(h_r + (size_t)id * kPoaBand + 2 * lane) = make_int2(H0, H1);
-        // best cell of the row: largest value, smallest read prefix on ties
-        // one reduction: key = value * 64 + (63 - cell) -- the maximum key is the largest value and, among equals,
-        // the smallest cell (scores are >= 0 and < 2^25)
-        const int hv = max(H0, H1);
-        const int cell = (H0 >= H1) ? 2 * lane : 2 * lane + 1;
-        const int rkey = __reduce_max_sync(kFull, hv * kPoaBand + (kPoaBand - 1 - cell));
-        static_assert(kPoaBand == 64, "key packing assumes 64 cells per row");
-        const int rmax = rkey >> 6;
-        const int wc = kPoaBand - 1 - (rkey & (kPoaBand - 1));
-        const int besti = (rmax > 0) ? lo + wc : lo;
-        if (lane == 0) {
-            lo_r[id] = lo; bi_r[id] = besti;
-            s_rid[warp][t & (kRing - 1)] = id; s_rlo[warp][t & (kRing - 1)] = lo; s_rbi[warp][t & (kRing - 1)] = besti;
+        // ---- anchor of the next block = this block's last row: best cell = largest value, smallest prefix on ties
+        // (key = value * 64 + (63 - cell); scores are >= 0 and < 2^25)
+        {
+            const int hv = max(pH0, pH1);
+            const int cell = (pH0 >= pH1) ? 2 * lane : 2 * lane + 1;
+            const int rkey = __reduce_max_sync(kFull, hv * kPoaBand + (kPoaBand - 1 - cell));
+            static_assert(kPoaBand == 64, "key packing assumes 64 cells per row");
+            a_max = rkey >> 6;
+            a_lo = prev_lo;
+            a_bi = (a_max > 0) ? prev_lo + (kPoaBand - 1 - (rkey & (kPoaBand - 1))) : prev_lo;
+            a_col = __shfl_sync(kFull, mcol, nrows - 1);
         }
-        if (rmax > gbest) { gbest = rmax; gt = id; gi = besti; }
-        prev_lo = lo; prev_besti = besti; prev_id = id;
-        __syncwarp();   // row visible in shared memory before the next vertex reads it
     }
-    if (lane == 0) {
-        PoaResult r;
-        r.score = gbest; r.end_t = gt; r.end_i = gi; r.path_len = 0;
-        r.first_t = r.first_i = r.last_t = r.last_i = -1;
-        results[task_id] = r;
+    // ---- best cell of the task: largest value; the first row in topological order; the smallest prefix
+    {
+        const int gbest = __reduce_max_sync(kFull, lbest);
+        const int bt = __reduce_min_sync(kFull, (lbest == gbest && gbest > 0) ? lt : 0x7fffffff);
+        const int bi = __reduce_min_sync(kFull, (lbest == gbest && gbest > 0 && lt == bt) ? li : 0x7fffffff);
+        const unsigned who = __ballot_sync(kFull, lbest == gbest && gbest > 0 && lt == bt && li == bi);
+        const int gid = who ? __shfl_sync(kFull, lid, __ffs(who) - 1) : -1;
+        if (lane == 0) {
+            PoaResult r;
+            r.score = gbest; r.end_t = gid; r.end_i = who ? bi : -1; r.path_len = 0;
+            r.first_t = r.first_i = r.last_t = r.last_i = -1;
+            results[task_id] = r;
+        }
     }
 }
 
@@ -323,9 +345,14 @@ void launch_poa_align(const PoaTask* tasks, int n_tasks, const PoaGraphView& G, 
                       const uint8_t* rev_flags, int32_t* lo, int32_t* besti, uint8_t* moves, int32_t* hrows,
                       PoaStep* steps, PoaResult* results, cudaStream_t stream, int32_t* grid) {
     if (n_tasks <= 0) return;
+    (void)besti;
     const int blocks = (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta;
-    poa_align_kernel<<<blocks, kWarpsPerCta * 32, 0, stream>>>(tasks, n_tasks, G, drafts, codes, rev_flags, lo, besti,
-                                                               moves, hrows, results);
+    if (hrows == nullptr)        // linear templates (subread -> draft mapping)
+        poa_align_kernel<false><<<blocks, kWarpsPerCta * 32, 0, stream>>>(tasks, n_tasks, G, drafts, codes, rev_flags, lo, moves,
+                                                                         nullptr, results);
+    else                         // sequence-to-graph rounds
+        poa_align_kernel<true><<<blocks, kWarpsPerCta * 32, 0, stream>>>(tasks, n_tasks, G, drafts, codes, rev_flags, lo, moves,
+                                                                        hrows, results);
     poa_traceback_kernel<<<blocks, kWarpsPerCta * 32, 0, stream>>>(tasks, n_tasks, G, lo, moves, steps, results, grid);
 }
 

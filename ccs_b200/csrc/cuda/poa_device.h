@@ -19,6 +19,10 @@ constexpr int kPoaMaxReads = 16;      // reads threaded into one graph (spans ke
 constexpr int kPoaKmer = 11;
 constexpr int kPoaVoteBases = 2048;   // orientation vote: k-mers of the read's first 2048 bases (spec)
 constexpr int kPoaMaxRefLen = 131072; // longest k-mer vote reference (hash set in shared memory)
+// band rule of the aligner (spec, DESIGN.md "Draft stage"): the rows of a block of 32 share one anchor row
+constexpr int kPoaBlock = 32;
+constexpr int kPoaAnchorMin = 20;     // an anchor row whose best score is lower carries no alignment yet ...
+constexpr int kPoaBandDecay = 16;     // ... the band then moves this many cells back towards the read start
 constexpr int kWindowGrid = 64;       // window borders of the Polish Stage lie on multiples of 64 draft bases (spec)
 
 // A threaded read creates at most floor(2n/7) vertices: it is threaded only if score >= n, every new vertex costs
@@ -44,6 +48,8 @@ struct PoaGraphView {
     int32_t* predx;        // [slot][7]
     int32_t* rank;
     int32_t* order[2];
+    int32_t* col;          // seed coordinate: the index of a seed vertex; a vertex added later takes the value of the old
+                           // vertex it was placed behind (0 at the head) -- what the aligner's band moves by
 };
 // constant indices only: a dynamically indexed member array would be copied to local memory
 #if defined(__CUDACC__)

@@ -66,6 +66,7 @@ CCS_HD void poa_graph_init(X& x, const PoaGraphView& G, int g, const PoaReadAcc&
         G.pred0[H.voff + i] = i - 1;
         G.rank[H.voff + i] = i;
         G.order[0][H.voff + i] = i;
+        G.col[H.voff + i] = i;
     }
     if (x.tid() == 0) {
         H.V = n; H.n_reads = 1; H.n_spans = n ? 1 : 0; H.order_sel = 0; H.error = 0;
@@ -124,6 +125,7 @@ CCS_HD void poa_graph_commit(X& x, const PoaGraphView& G, int g, const PoaStep* 
         if (isnew[f]) {
             G.meta[o + c] = poa_meta(R.base(s.readpos), prev >= 0 ? 1 : 0, 1);
             G.pred0[o + c] = prev;
+            G.col[o + c] = (anchor[f] >= 0) ? G.col[o + steps[L - 1 - anchor[f]].vertex] : 0;
             if (f == L - 1 || !isnew[f + 1]) add[arank[f] + 1] = f - anchor[f];   // run length (anchor -1: f + 1)
         } else {
             uint32_t m = G.meta[o + c] + (1u << 8);       // nReads + 1

@@ -57,7 +57,7 @@ void DraftEngine::release_buffers() {
     d_codes_.release(); d_desc_.release(); d_rev_.release(); d_moves_.release(); d_draft_.release(); d_meta_.release();
     d_pred0_.release(); d_predx_.release(); d_rank_.release(); d_order_.release(); d_lo_.release(); d_besti_.release();
     d_hrows_.release(); d_scratch_.release(); d_draft_len_.release(); d_steps_.release(); d_results_.release();
-    d_grid_.release();
+    d_grid_.release(); d_col_.release();
 }
 
 void DraftEngine::span(double* acc, int64_t bytes, int64_t* top_bytes, double* top_ms) {
@@ -266,7 +266,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         }
     }
     d_meta_.ensure((size_t)pool + 16); d_pred0_.ensure((size_t)pool + 16); d_predx_.ensure((size_t)pool * 7 + 16);
-    d_rank_.ensure((size_t)pool + 16); d_order_.ensure((size_t)pool * 2 + 16);
+    d_rank_.ensure((size_t)pool + 16); d_order_.ensure((size_t)pool * 2 + 16); d_col_.ensure((size_t)pool + 16);
     d_lo_.ensure((size_t)pool + 16); d_besti_.ensure((size_t)pool + 16);
     d_moves_.ensure((size_t)pool * kPoaBand + 16); d_hrows_.ensure((size_t)pool * kPoaBand + 16);
     d_scratch_.ensure((size_t)soff[ng] + 16); d_steps_.ensure((size_t)stoff[ng] + 16);
@@ -278,6 +278,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
     PoaGraphView G;
     G.hdr = at<PoaGraphHdr>(db, o_hdr); G.meta = d_meta_.p; G.pred0 = d_pred0_.p; G.predx = d_predx_.p; G.rank = d_rank_.p;
     G.order[0] = d_order_.p; G.order[1] = d_order_.p + pool;
+    G.col = d_col_.p;
 
     // ---- a3 (seeding): orientation of the POA reads against the seed; a2: seed chains + SparsePoa rounds ----------
     span(&stats.ms_graph);

@@ -14,6 +14,7 @@ void PoaGraph::add_first(const uint8_t* seq, int n) {
     for (int i = 0; i < n; ++i) {
         v[i].base = seq[i]; v[i].nreads = 1;
         v[i].prev = i - 1; v[i].next = (i + 1 < n) ? i + 1 : -1;
+        v[i].col = i;
         if (i > 0) { v[i].in.push_back(i - 1); v[i - 1].out.push_back(i); }
     }
     head = n ? 0 : -1; tail = n - 1;
@@ -35,7 +36,7 @@ PoaAlignment PoaGraph::align(const uint8_t* seq, int n) const {
     order(ord, rank);
     const int V = (int)ord.size(), W = POA_BAND;
     if (V == 0 || n == 0) return res;
-    std::vector<int> H((size_t)V * W, 0), lo(V, 0), besti(V, 0);
+    std::vector<int> H((size_t)V * W, 0), lo(V, 0), besti(V, 0), rowmax(V, 0);
     std::vector<uint8_t> mv((size_t)V * W, 0);
     auto hget = [&](int t, int i) -> int {
         const int c = i - lo[t];
@@ -49,12 +50,15 @@ PoaAlignment PoaGraph::align(const uint8_t* seq, int n) const {
         for (int u : vx.in) preds.push_back(rank[u]);
         std::sort(preds.begin(), preds.end());
         assert(preds.size() <= 8);
-        int l = 0;
-        if (!preds.empty()) {
-            int m = 0;
-            for (int p : preds) m = std::max(m, besti[p]);
-            l = m + 1 - W / 2;
-        }
+        // Band rule: the rows of a block of POA_BLOCK share one anchor, the last row of the previous block.  If the anchor
+        // carries an alignment (best score >= POA_ANCHOR_MIN) the band is centred on the anchor's best cell, moved by the
+        // difference of the seed coordinates; otherwise it moves POA_BAND_DECAY cells back towards the read start.  The
+        // first block is anchored on the cell in front of the first row.
+        const int a = (t / POA_BLOCK) * POA_BLOCK - 1;
+        int l;
+        if (a < 0) l = (vx.col + 1) - W / 2;
+        else if (rowmax[a] >= POA_ANCHOR_MIN) l = besti[a] + (vx.col - v[ord[a]].col) - W / 2;
+        else l = lo[a] - POA_BAND_DECAY;
         l = std::max(0, std::min(l, std::max(0, n + 1 - W)));
         lo[t] = l;
         int* h = &H[(size_t)t * W];
@@ -91,6 +95,7 @@ PoaAlignment PoaGraph::align(const uint8_t* seq, int n) const {
         int bi = l, bv = -1;
         for (int c = 0; c < W; ++c) if (l + c <= n && h[c] > bv) { bv = h[c]; bi = l + c; }
         besti[t] = bi;
+        rowmax[t] = std::max(bv, 0);
         if (bv > gbest) { gbest = bv; gt = t; gi = bi; }
     }
     res.score = gbest;
@@ -151,6 +156,7 @@ void PoaGraph::commit(const PoaAlignment& a, const uint8_t* seq) {
             if (tail < 0) tail = id;
         } else {
             nv.prev = after; nv.next = v[after].next;
+            nv.col = v[after].col;
             v.push_back(nv);
             if (v[after].next >= 0) v[v[after].next].prev = id; else tail = id;
             v[after].next = id;

@@ -13,6 +13,11 @@ namespace oracle {
 
 constexpr int POA_MATCH = 3, POA_MISMATCH = -5, POA_INS = -4, POA_DEL = -4;
 constexpr int POA_BAND = 64;
+// band rule (DESIGN.md "Draft stage"): rows are taken in blocks of POA_BLOCK; the band of every row of a block is placed
+// from the block's anchor row (the last row of the previous block)
+constexpr int POA_BLOCK = 32;
+constexpr int POA_ANCHOR_MIN = 20;     // an anchor row whose best score is lower carries no alignment yet
+constexpr int POA_BAND_DECAY = 16;     // ... the band then moves this many cells back towards the read start
 constexpr int POA_KMER = 11;
 constexpr int POA_VOTE_BASES = 2048;   // orientation vote: k-mers of the read's first 2048 bases (DESIGN.md "Draft stage")
 
@@ -26,7 +31,9 @@ struct PoaAlignment {
 };
 
 struct PoaGraph {
-    struct Vertex { uint8_t base; int nreads; int next, prev; std::vector<int> in, out; };
+    // col: seed coordinate of the vertex -- its index for a seed vertex; a vertex added later takes the value of the
+    // vertex it was placed behind (0 at the head)
+    struct Vertex { uint8_t base; int nreads; int next, prev; std::vector<int> in, out; int col = 0; };
     std::vector<Vertex> v;
     int head = -1, tail = -1;
     std::vector<std::pair<int, int>> spans;   // (first, last) vertex of every threaded read

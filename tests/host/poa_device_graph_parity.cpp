@@ -88,8 +88,8 @@ int main(int argc, char** argv) {
         PoaGraphHdr hdr{};
         hdr.voff = 16; hdr.cap = cap;            // a non-zero pool offset exercises the addressing
         std::vector<uint32_t> meta(hdr.voff + cap);
-        std::vector<int32_t> pred0(hdr.voff + cap), predx(7 * (hdr.voff + cap)), rank(hdr.voff + cap), ordA(hdr.voff + cap), ordB(hdr.voff + cap);
-        PoaGraphView G{&hdr, meta.data(), pred0.data(), predx.data(), rank.data(), {ordA.data(), ordB.data()}};
+        std::vector<int32_t> pred0(hdr.voff + cap), predx(7 * (hdr.voff + cap)), rank(hdr.voff + cap), ordA(hdr.voff + cap), ordB(hdr.voff + cap), col(hdr.voff + cap);
+        PoaGraphView G{&hdr, meta.data(), pred0.data(), predx.data(), rank.data(), {ordA.data(), ordB.data()}, col.data()};
         std::vector<int32_t> scratch(5 * 2000 + 4 * cap + 16), sm(64);
         std::vector<uint8_t> cons(cap);
         int32_t cons_len = 0;
@@ -110,6 +110,7 @@ int main(int argc, char** argv) {
                 const int id = ord[t];
                 if (dord[t] != id) return fail("order (vertex ids are handed out in path order)", trial, round);
                 if (rank[hdr.voff + id] != t) return fail("rank", trial, round);
+                if (col[hdr.voff + id] != og.v[id].col) return fail("seed coordinate", trial, round);
                 const auto& vx = og.v[id];
                 const uint32_t m = meta[hdr.voff + id];
                 if (poa_meta_base(m) != vx.base) return fail("base", trial, round);
