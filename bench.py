@@ -70,6 +70,8 @@ def config_dict(args, cfg_id, zmws, world, lanes, contexts):
             "stage": STAGE_DESC[args.stage],
             "l2": "inputs larger than L2 (tens of GB of DP bands per step, new ZMWs every step)",
             "parallelism": f"zmw-range-shard x{world}, no collective", "lanes_per_gpu": lanes, "contexts_per_gpu": contexts,
+            "windowing": "drafts >= 2048 bases polished as 1024-base windows with 64 bases of overlap (library default), "
+                         "on both arms",
             "value_def": "e2e wall time of the calls minus the batch-upload span (inputs resident)"}
 
 
@@ -425,7 +427,8 @@ def main():
         peak, peak_src = peaks()
         traffic, traffic_any = None, {}
         try:   # dram__bytes_read.sum + dram__bytes_write.sum per launch of the full-population launches (`ncu --set full`)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_summary.json")))
+            pj = os.path.join(ROOT, "profiles", "r2b_summary.json")
+            tj = json.load(open(pj if os.path.exists(pj) else os.path.join(ROOT, "profiles", "r2_summary.json")))
             traffic_any = {k: v.get("dram_bytes") for k, v in tj.get("kernels", {}).items()}
             if tj.get("config") == args.config and zmws == 1000:
                 traffic = traffic_any

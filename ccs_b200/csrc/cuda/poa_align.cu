@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     const uint8_t* __restrict__ codes, const uint8_t* __restrict__ rev_flags, int32_t* __restrict__ lo_arr,
     uint8_t* __restrict__ moves, int32_t* __restrict__ hrows, PoaResult* __restrict__ results) {
     __shared__ int s_ring[kDag ? kWarpsPerCta : 1][kRing][kPoaBand];
-    __shared__ int s_rid[kDag ? kWarpsPerCta : 1][kRing], s_rlo[kDag ? kWarpsPerCta : 1][kRing];
+    __shared__ int s_rlo[kDag ? kWarpsPerCta : 1][kRing];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task_id = blockIdx.x * kWarpsPerCta + warp;
     if (task_id >= n_tasks) return;
@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     const int32_t* __restrict__ pred0 = G.pred0 + voff;
     const int32_t* __restrict__ predx = G.predx + 7 * voff;
     const int32_t* __restrict__ colv = G.col + voff;
+    const int32_t* __restrict__ rankv = G.rank + voff;
     const uint8_t* __restrict__ tplb = drafts + T.tpl_off;
     const int n = T.n;
     const bool rev = rev_flags[T.rev_idx] != 0;
@@ -78,25 +79,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
     int32_t* __restrict__ h_r = (kDag && hrows) ? hrows + T.row_off * kPoaBand : nullptr;
     const int lo_max = max(0, n + 1 - kPoaBand);
     const int wslot = kDag ? warp : 0;
-    if (kDag && lane < kRing) s_rid[wslot][lane] = -2;
 
     int lbest = 0, lt = 0x7fffffff, li = 0, lid = -1;    // this lane's best cell: value, row (topological index), prefix, vertex
     // anchor of the current block: band start, best cell, best score and seed coordinate of the row in front of it
     // (block 0: the cell in front of the first row)
     int a_lo = 0, a_bi = 0, a_max = kPoaAnchorMin, a_col = -1;
-    int pH0 = 0, pH1 = 0, prev_lo = 0, prev_id = -1;     // previous row (registers)
+    int pH0 = 0, pH1 = 0, prev_lo = 0;                   // previous row (registers)
     int rb0 = 255, rb1 = 255;                            // read bases in front of the lane's two prefixes
-    if (kDag) __syncwarp();
 
     for (int t0 = 0; t0 < V; t0 += kPoaBlock) {
         // ---- the block's vertices (one per lane) and their bands
         const int tt = min(t0 + lane, V - 1);
-        int mid = tt, mb, mn, mf = tt - 1, mcol = tt;
-        if (!kDag) { mb = tplb[tt]; mn = (tt > 0) ? 1 : 0; }
+        // mw = base | in-degree << 2; md = how many rows back each predecessor lies (one byte each, 255 = further than
+        // the ring): predecessor ids and ranks are looked up here, 32 vertices at a time, off the per-row dependent chain
+        int mid = tt, mcol = tt;
+        uint32_t mw, md0 = 0xffffff01u, md1 = 0xffffffffu;
+        if (!kDag) mw = (uint32_t)tplb[tt] | ((tt > 0) ? 4u : 0u);
         else {
             mid = ord[tt];
-            const uint32_t m = meta[mid];
-            mb = (int)(m & 3u); mn = (int)((m >> 2) & 15u); mf = pred0[mid]; mcol = colv[mid];
+            mw = meta[mid] & 63u;
+            mcol = colv[mid];
+            const int nin = (int)(mw >> 2);
+            md0 = 0xffffffffu;
+            for (int k = 0; k < nin; ++k) {
+                const int p = (k == 0) ? pred0[mid] : predx[7 * (int64_t)mid + k - 1];
+                const uint32_t d = (uint32_t)min(tt - rankv[p], 255);
+                if (k < 4) md0 = (md0 & ~(0xffu << (8 * k))) | (d << (8 * k));
+                else md1 = (md1 & ~(0xffu << (8 * (k - 4)))) | (d << (8 * (k - 4)));
+            }
         }
         int mlo = (a_max >= kPoaAnchorMin) ? a_bi + (mcol - a_col) - kPoaBand / 2 : a_lo - kPoaBandDecay;
         mlo = min(max(mlo, 0), lo_max);
@@ -106,13 +116,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
 
         for (int r = 0; r < nrows; ++r) {
             const int t = t0 + r;
-            const int id = __shfl_sync(kFull, mid, r), vb = __shfl_sync(kFull, mb, r), npred = __shfl_sync(kFull, mn, r);
-            const int first_pred = __shfl_sync(kFull, mf, r), lo = __shfl_sync(kFull, mlo, r);
+            const int id = kDag ? __shfl_sync(kFull, mid, r) : t;
+            const uint32_t vw = __shfl_sync(kFull, mw, r);
+            const int vb = (int)(vw & 3u), npred = (int)(vw >> 2);
+            const int lo = __shfl_sync(kFull, mlo, r);
+            const uint32_t d0 = kDag ? __shfl_sync(kFull, md0, r) : 1u;
             const int dl = lo - prev_lo;
             const int i0 = lo + 2 * lane, i1 = i0 + 1;
             int c0, c1;
             unsigned m0, m1;
-            if (npred == 1 && first_pred == prev_id) {
+            if (npred == 1 && (d0 & 255u) == 1u) {
                 // the only predecessor is the previous row, held in registers as band cells 2*lane, 2*lane + 1
                 int hm1, h0, h1;
                 if (dl == 1) {            // band moved with the diagonal: own two cells + the next lane's first
@@ -153,12 +166,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
                     if (rb1 != 255 && sc1 > 0) { bm1 = sc1; km1 = 63; }
                 }
                 if (kDag) {
+                    const uint32_t d1 = (npred > 4) ? __shfl_sync(kFull, md1, r) : 0xffffffffu;
                     for (int k = 0; k < npred; ++k) {
-                        const int pr = (k == 0) ? first_pred : predx[7 * (int64_t)id + k - 1];
-                        const unsigned hit = __ballot_sync(kFull, s_rid[wslot][lane & (kRing - 1)] == pr) & ((1u << kRing) - 1u);
-                        const int slot = __ffs(hit) - 1;
-                        const int* __restrict__ row = hit ? s_ring[wslot][slot] : (h_r + (size_t)pr * kPoaBand);
-                        const int a = 2 * lane + lo - (hit ? s_rlo[wslot][slot] : lo_r[pr]);
+                        // a predecessor at most kRing rows back sits in the ring slot of its rank; others come from global memory
+                        const int d = (int)(((k < 4 ? d0 : d1) >> (8 * (k & 3))) & 255u);
+                        const bool near = d <= kRing;
+                        const int slot = (t - d) & (kRing - 1);
+                        int pr = 0;
+                        if (!near) pr = (k == 0) ? pred0[id] : predx[7 * (int64_t)id + k - 1];
+                        const int* __restrict__ row = near ? s_ring[wslot][slot] : (h_r + (size_t)pr * kPoaBand);
+                        const int a = 2 * lane + lo - (near ? s_rlo[wslot][slot] : lo_r[pr]);
                         const int hm1 = row_get(row, a - 1), h0 = row_get(row, a), h1 = row_get(row, a + 1);
                         if (rb0 != 255) { const int c = hm1 + sc0; if (c > bm0) { bm0 = c; km0 = k; } }
                         if (rb1 != 255) { const int c = h0 + sc1; if (c > bm1) { bm1 = c; km1 = k; } }
@@ -194,14 +211,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
                 __syncwarp();   // everyone has read the ring
                 int* srow = s_ring[wslot][t & (kRing - 1)];
                 srow[2 * lane] = H0; srow[2 * lane + 1] = H1;
-                if (lane == 0) { s_rid[wslot][t & (kRing - 1)] = id; s_rlo[wslot][t & (kRing - 1)] = lo; }
+                if (lane == 0) s_rlo[wslot][t & (kRing - 1)] = lo;
                 if (h_r != nullptr) *reinterpret_cast<int2*>(h_r + (size_t)id * kPoaBand + 2 * lane) = make_int2(H0, H1);
                 __syncwarp();   // row visible in shared memory before the next vertex reads it
             }
             // this lane's best cell so far: the first row that reaches its maximum, smaller prefix first within a row
             if (H0 > lbest) { lbest = H0; lt = t; li = i0; lid = id; }
             if (H1 > lbest) { lbest = H1; lt = t; li = i1; lid = id; }
-            pH0 = H0; pH1 = H1; prev_lo = lo; prev_id = id;
+            pH0 = H0; pH1 = H1; prev_lo = lo;
         }
         // ---- anchor of the next block = this block's last row: best cell = largest value, smallest prefix on ties
         // (key = value * 64 + (63 - cell); scores are >= 0 and < 2^25)
@@ -252,8 +269,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
     const uint8_t* __restrict__ mv_r = moves + T.row_off * kPoaBand;
     int t = r.end_t, i = r.end_i, len = 0;
     if (T.graph >= 0) {
-        // rows are stored by vertex id; a path mostly walks down consecutive ids (the seed chain, or the vertices one
-        // earlier read added), so a window of 32 ids is re-staged only when the path jumps
+        // Rows are stored by vertex id and a path mostly runs down consecutive ids along a diagonal (a match whose only
+        // candidate predecessor is the vertex before it).  A window of 32 consecutive ids -- band starts, first
+        // predecessors, 64-byte move rows: one coalesced read -- is staged in shared memory and re-staged only when the
+        // path leaves it.  Every iteration the lanes look at the next cells of the diagonal at once, (t - j, i - j), and
+        // the walk advances over the whole run of plain matches in front of it; the cell that ends the run (a mismatch
+        // placed on another predecessor, a deletion, an insertion, the local start) is decoded from lane 0's cell.
         __shared__ int s_p0[kWarpsPerCta][32];
         const int64_t voff = G.hdr[T.graph].voff;
         const int32_t* __restrict__ pred0 = G.pred0 + voff;
@@ -274,9 +295,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
                 }
                 __syncwarp();
             }
-            const int c = i - s_lo[warp][t - wbase];
-            if ((unsigned)c >= (unsigned)kPoaBand) break;
-            const unsigned m = s_mv[warp][(t - wbase) * kPoaBand + c];
+            const int tj = t - lane, ij = i - lane;
+            int pj = -2;
+            unsigned mj = 0u;
+            bool inb = false;
+            if (tj >= wbase) {
+                const int c = ij - s_lo[warp][tj - wbase];
+                pj = s_p0[warp][tj - wbase];
+                inb = (unsigned)c < (unsigned)kPoaBand;
+                if (inb) mj = s_mv[warp][(tj - wbase) * kPoaBand + c];
+            }
+            const unsigned okm = __ballot_sync(kFull, inb && mj == 1u && pj == tj - 1);
+            const int run = (okm == kFull) ? 32 : __ffs(~okm) - 1;      // plain matches in a row, lane 0 first
+            if (run > 0) {
+                if (lane < run && len + lane < T.n) out[len + lane] = PoaStep{tj, ij - 1};
+                if (r.last_t < 0) { r.last_t = t; r.last_i = i - 1; }
+                r.first_t = t - (run - 1); r.first_i = i - 1 - (run - 1);
+                len += run; t -= run; i -= run;
+                continue;
+            }
+            // one step from lane 0's cell
+            const bool in0 = __shfl_sync(kFull, inb ? 1 : 0, 0) != 0;
+            if (!in0) break;
+            const unsigned m = __shfl_sync(kFull, mj, 0);
+            const int p0 = __shfl_sync(kFull, pj, 0);
             const unsigned kind = m & 3u, k = m >> 2;
             if (kind == 0u) break;
             if (kind == 1u) {           // match / mismatch: read base i-1 on vertex t
@@ -285,10 +327,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
                 if (r.last_t < 0) { r.last_t = t; r.last_i = i - 1; }
                 r.first_t = t; r.first_i = i - 1;
                 if (k == 63u) break;
-                t = (k == 0u) ? s_p0[warp][t - wbase] : predx[7 * (int64_t)t + k - 1];
+                t = (k == 0u) ? p0 : predx[7 * (int64_t)t + k - 1];
                 i -= 1;
             } else if (kind == 2u) {    // deletion: vertex skipped
-                t = (k == 0u) ? s_p0[warp][t - wbase] : predx[7 * (int64_t)t + k - 1];
+                t = (k == 0u) ? p0 : predx[7 * (int64_t)t + k - 1];
             } else {                    // insertion: read base i-1 without a vertex
                 if (lane == 0 && len < T.n) out[len] = PoaStep{-1, i - 1};
                 ++len;

@@ -66,7 +66,7 @@ struct PoaTask {
     int32_t graph;         // graph slot, or -1: linear template (every vertex t has the single predecessor t-1)
     int32_t V;             // linear tasks: template length (DAG tasks read the graph header)
     int32_t rev_idx;       // index of the read's orientation flag (0 forward, 1 reverse complement)
-    int64_t scratch_off;   // DAG tasks: the graph's bookkeeping scratch (ints), >= 5 n + 4 cap + 16
+    int64_t scratch_off;   // DAG tasks: the graph's bookkeeping scratch (ints), >= 5 n + 12 cap + 16
     int64_t grid_off;      // linear tasks: where the traceback records the read position at every kWindowGrid-th template
                            // base (windowing, DESIGN.md "Windowing"); < 0: not recorded
 };

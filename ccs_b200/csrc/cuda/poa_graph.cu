@@ -55,11 +55,12 @@ __global__ void __launch_bounds__(kGraphThreads) poa_consensus_kernel(const PoaG
                                                                       const int64_t* __restrict__ scratch_off,
                                                                       int32_t* __restrict__ scratch, uint8_t* __restrict__ draft,
                                                                       int32_t* __restrict__ draft_len) {
+    __shared__ int32_t sh[kPoaConsShared];
     const int k = blockIdx.x;
     if (k >= n_graphs) return;
     CtaExec x;
     const int g = graphs[k];
-    poa_graph_consensus(x, G, g, scratch + scratch_off[g], draft + G.hdr[g].voff, draft_len + g);
+    poa_graph_consensus(x, G, g, scratch + scratch_off[g], draft + G.hdr[g].voff, draft_len + g, sh);
 }
 
 // One CTA per vote job: hash set of the reference's sampled 11-mers in shared memory, then one warp per read.

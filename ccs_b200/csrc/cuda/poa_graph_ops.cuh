@@ -182,9 +182,19 @@ CCS_HD void poa_graph_commit(X& x, const PoaGraphView& G, int g, const PoaStep* 
 }
 
 // FindConsensus: score(v) = 2 * nReads - max(spanning reads, minCov), best-scoring path, ties to the lowest rank.
-// scratch: 4 * V ints.  Writes the consensus bases to out[0..*out_len); *out_len <= V.
+// scratch: 12 * V ints.  sh: kPoaConsShared ints of fast scratch (shared memory on the device).  Writes the consensus
+// bases to out[0..*out_len); *out_len <= V.
+//
+// The best-path recurrence is a serial walk over the ranks; everything it needs is prepared in parallel first -- per rank
+// the score, the kind of vertex and, for a general vertex, the RANKS of its predecessors -- and handed to the walking
+// thread in chunks staged through `sh`, together with a window of the reach values it produced itself: the walk touches
+// global memory only for a predecessor more than a chunk behind.
+constexpr int kPoaConsChunk = 512;
+constexpr int kPoaConsShared = kPoaConsChunk * (2 + kPoaMaxPred) + 2 * kPoaConsChunk;
+
 template <class X>
-CCS_HD void poa_graph_consensus(X& x, const PoaGraphView& G, int g, int32_t* scratch, uint8_t* out, int32_t* out_len) {
+CCS_HD void poa_graph_consensus(X& x, const PoaGraphView& G, int g, int32_t* scratch, uint8_t* out, int32_t* out_len,
+                                int32_t* sh) {
     const PoaGraphHdr& H = G.hdr[g];
     const int64_t o = H.voff;
     const int V = H.V;
@@ -192,9 +202,10 @@ CCS_HD void poa_graph_consensus(X& x, const PoaGraphView& G, int g, int32_t* scr
     const int min_cov = n < 5 ? 1 : (n + 1) / 2 - 1;
     const int32_t* ord = poa_order(G, H.order_sel) + o;
     int32_t* sc = scratch;                    // [V] vertex score by rank
-    int32_t* kind = scratch + V;              // [V] 1: single predecessor at rank t-1; 2: no predecessor; 0: general
+    int32_t* kind = scratch + V;              // [V] -1: single predecessor at rank t-1; 0: none; k > 0: k predecessors (general)
     int32_t* reach = scratch + 2 * (int64_t)V;
     int32_t* bp = scratch + 3 * (int64_t)V;
+    int32_t* prk = scratch + 4 * (int64_t)V;  // [V][8] predecessor ranks of general vertices, in predecessor order
     const int T = x.nthreads(), tid = x.tid();
     for (int t = tid; t < V; t += T) {
         const int id = ord[t];
@@ -204,30 +215,52 @@ CCS_HD void poa_graph_consensus(X& x, const PoaGraphView& G, int g, int32_t* scr
             cov += (G.rank[o + H.span_first[s]] <= t && t <= G.rank[o + H.span_last[s]]) ? 1 : 0;
         sc[t] = 2 * poa_meta_nreads(m) - (cov > min_cov ? cov : min_cov);
         const int nin = poa_meta_nin(m);
-        kind[t] = (nin == 0) ? 2 : ((nin == 1 && G.rank[o + G.pred0[o + id]] == t - 1) ? 1 : 0);
+        int kd = nin;
+        if (nin == 1 && G.rank[o + G.pred0[o + id]] == t - 1) kd = -1;
+        else
+            for (int e = 0; e < nin; ++e) {
+                const int p = (e == 0) ? G.pred0[o + id] : G.predx[7 * (o + id) + e - 1];
+                prk[(int64_t)t * kPoaMaxPred + e] = G.rank[o + p];
+            }
+        kind[t] = kd;
     }
     x.sync();
-    if (tid == 0) {
-        int best = 0, bt = -1, prev = 0;
-        for (int t = 0; t < V; ++t) {
-            int m = 0, mp = -1;
-            const int k = kind[t];
-            if (k == 1) { if (prev > 0) { m = prev; mp = t - 1; } }
-            else if (k == 0) {
-                const int id = ord[t];
-                const int nin = poa_meta_nin(G.meta[o + id]);
-                for (int e = 0; e < nin; ++e) {            // predecessors are sorted by rank: first maximum = lowest rank
-                    const int p = (e == 0) ? G.pred0[o + id] : G.predx[7 * (o + id) + e - 1];
-                    const int q = G.rank[o + p];
-                    const int rq = reach[q];
-                    if (rq > m) { m = rq; mp = q; }
-                }
-            }
-            prev = sc[t] + m;
-            reach[t] = prev;
-            bp[t] = mp;
-            if (bt < 0 || prev > best) { best = prev; bt = t; }
+    int32_t* s_sc = sh;                                        // [chunk]
+    int32_t* s_kind = sh + kPoaConsChunk;                      // [chunk]
+    int32_t* s_prk = sh + 2 * kPoaConsChunk;                   // [chunk][8]
+    int32_t* s_reach = sh + (2 + kPoaMaxPred) * kPoaConsChunk; // [2 * chunk] reach of ranks >= c0 - chunk, slot = rank mod (2 chunk)
+    int best = 0, bt = -1, prev = 0;                           // state of the walking thread
+    for (int c0 = 0; c0 < V; c0 += kPoaConsChunk) {
+        const int nc = (V - c0 < kPoaConsChunk) ? V - c0 : kPoaConsChunk;
+        for (int j = tid; j < nc; j += T) {
+            s_sc[j] = sc[c0 + j];
+            const int kd = kind[c0 + j];
+            s_kind[j] = kd;
+            for (int e = 0; e < kd; ++e) s_prk[j * kPoaMaxPred + e] = prk[(int64_t)(c0 + j) * kPoaMaxPred + e];
         }
+        x.sync();
+        if (tid == 0) {
+            for (int j = 0; j < nc; ++j) {
+                const int t = c0 + j;
+                int m = 0, mp = -1;
+                const int k = s_kind[j];
+                if (k < 0) { if (prev > 0) { m = prev; mp = t - 1; } }
+                else
+                    for (int e = 0; e < k; ++e) {              // predecessors are sorted by rank: first maximum = lowest rank
+                        const int q = s_prk[j * kPoaMaxPred + e];
+                        const int rq = (q >= c0 - kPoaConsChunk) ? s_reach[q & (2 * kPoaConsChunk - 1)] : reach[q];
+                        if (rq > m) { m = rq; mp = q; }
+                    }
+                prev = s_sc[j] + m;
+                s_reach[t & (2 * kPoaConsChunk - 1)] = prev;
+                reach[t] = prev;
+                bp[t] = mp;
+                if (bt < 0 || prev > best) { best = prev; bt = t; }
+            }
+        }
+        x.sync();
+    }
+    if (tid == 0) {
         // backtrack into sc[] (no longer needed), reversed
         int len = 0;
         for (int k = bt; k >= 0; k = bp[k]) sc[len++] = ord[k];

@@ -158,7 +158,7 @@ void DraftEngine::run(const DraftInput& in, const DraftParams& dp, DraftOutput& 
                 cap += poa_new_vertex_bound(lens[w.poa_reads[k]]);
                 nmax = std::max<int64_t>(nmax, lens[w.poa_reads[k]]);
             }
-            const int64_t need = cap * 400 + nmax * 32;
+            const int64_t need = cap * 440 + nmax * 32;
             if (!zlist.empty() && bytes + need > (int64_t)budget_ * 7 / 10) flush();   // the buffers grow with 25 % slack
             zlist.push_back(z);
             bytes += need;
@@ -214,7 +214,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         }
         cap = (cap + 15) & ~15ll;                          // rows stay 16-byte aligned in every pool
         voff[g + 1] = voff[g] + cap;
-        soff[g + 1] = soff[g] + 5 * nmax + 4 * cap + 16;
+        soff[g + 1] = soff[g] + 5 * nmax + 12 * cap + 16;     // CommitAdd: 5 n + V + 1; FindConsensus: 12 V
         stoff[g + 1] = stoff[g] + nmax;
         max_rounds = std::max(max_rounds, (int)w.poa_reads.size() - 1);
         max_ref = std::max(max_ref, lens[w.poa_reads[0]]);

@@ -621,14 +621,21 @@ void ArrowEngine::polish(const PolishParams& pp) {
             if (zs.done) continue;
             const int J = (int)zs.tpl.size();
             zs.iterations = it + 1;
+            // mutations are tested within test_margin bases of the window core only (the whole template when it is one window)
+            const int tb = std::max(0, zs.core_b - pp.test_margin), te = std::min(J, zs.core_e + pp.test_margin);
             if (it == 0) {
-                ranges.push_back(ScoreRange{z, 0, J, 0, first});
-                first += pad16(J);
-                zs.n_tested += count_canonical(zs.tpl, 0, J);
+                if (te > tb) {
+                    ranges.push_back(ScoreRange{z, tb, te, 0, first});
+                    first += pad16(te - tb);
+                    zs.n_tested += count_canonical(zs.tpl, tb, te);
+                }
             } else {
                 // union of +-neighborhood around the last-applied sites
                 std::vector<std::pair<int, int>> iv;
-                for (int s : zs.sites) iv.push_back({std::max(0, s - pp.neighborhood), std::min(J, s + pp.neighborhood + 1)});
+                for (int s : zs.sites) {
+                    const int b = std::max(tb, s - pp.neighborhood), e = std::min(te, s + pp.neighborhood + 1);
+                    if (e > b) iv.push_back({b, e});
+                }
                 std::sort(iv.begin(), iv.end());
                 int cb = -1, ce = -1;
                 auto flush = [&]() {
@@ -798,15 +805,19 @@ void ArrowEngine::consensus_qvs() {
         // With reuse_scores only the positions whose stored delta-LLs predate an edit within qv_halo of them (or that
         // were never scored) are scored again; a ZMW that lost a read after scoring began is scored again in full
         const int J = (int)zs.tpl.size();
+        // only the window core goes into the result: QVs outside it are never looked at
+        const int qb = std::max(0, zs.core_b), qe = std::min(J, zs.core_e);
         if (!reuse_scores || zs.stale_scores || zs.stale.size() != (size_t)J) {
-            rescoring.push_back(ScoreRange{z, 0, J, 0, first_rs});
-            first_rs += pad16((int64_t)J);
+            if (qe > qb) {
+                rescoring.push_back(ScoreRange{z, qb, qe, 0, first_rs});
+                first_rs += pad16((int64_t)(qe - qb));
+            }
         } else {
-            int p = 0;
-            while (p < J) {
+            int p = qb;
+            while (p < qe) {
                 if (!zs.stale[p]) { ++p; continue; }
                 int e = p + 1, last = p;                       // merge runs separated by short clean gaps
-                while (e < J && e - last <= 8) { if (zs.stale[e]) last = e; ++e; }
+                while (e < qe && e - last <= 8) { if (zs.stale[e]) last = e; ++e; }
                 rescoring.push_back(ScoreRange{z, p, last + 1, 0, first_rs});
                 first_rs += pad16((int64_t)(last + 1 - p));
                 p = last + 2;                                  // ranges of one ZMW must not touch

@@ -57,6 +57,7 @@ struct PolishParams {
     double min_zscore = -3.4;           // POOR_ZSCORE: reads whose LL z-score against the draft is lower are dropped
     int32_t window_size = 1024;         // windowing (window_host.h), applied by ccsgpu_ccs
     int32_t window_overlap = 64;
+    int32_t test_margin = 48;           // mutations are tested within this many bases of a window's core only
 };
 
 struct HostMutation { int32_t type, pos, base; double score; };

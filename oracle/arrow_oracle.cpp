@@ -464,10 +464,14 @@ PolishResult polish(Integrator<Real>& ai) {
     for (int it = 0; it < ai.cfg.max_iterations; ++it) {
         res.iterations = it + 1;
         const int J = (int)ai.fwd.size();
-        std::vector<char> want(J + 1, it == 0 ? 1 : 0);
-        if (it > 0)
+        // positions tested this round: round 0 everything, later +-neighborhood around the sites just edited -- always
+        // within test_margin bases of the window core
+        const int tb = std::max(0, ai.mark_b - ai.cfg.test_margin), te = std::min(J, ai.mark_e + ai.cfg.test_margin);
+        std::vector<char> want(J + 1, 0);
+        if (it == 0) for (int p = tb; p < te; ++p) want[p] = 1;
+        else
             for (int s : sites)
-                for (int p = std::max(0, s - ai.cfg.neighborhood); p <= std::min(J, s + ai.cfg.neighborhood); ++p) want[p] = 1;
+                for (int p = std::max(tb, s - ai.cfg.neighborhood); p <= std::min(te - 1, s + ai.cfg.neighborhood); ++p) want[p] = 1;
         std::vector<std::pair<double, Mutation>> scored;
         for (int p = 0; p <= J; ++p) {
             if (!want[p]) continue;

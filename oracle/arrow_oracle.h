@@ -112,6 +112,8 @@ struct PolishConfig {
     double ab_mismatch_tol = 1e-3;
     double min_zscore = -3.4;     // AddRead drops a read whose LL lies further below its expectation (POOR_ZSCORE)
     int growth_min = 512;         // growth cap: the template may outgrow its first length by max(growth_min, J/8) bases
+    int test_margin = 48;         // mutations are tested within this many bases of the window core [mark_b, mark_e) only; the
+                                  // rest of a window's padding is context (DESIGN.md "Windowing"); whole templates: everything
 };
 
 struct PolishResult {

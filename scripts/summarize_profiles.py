@@ -7,7 +7,7 @@ import json
 import subprocess
 import sys
 
-KERNELS = ["arrow_fill_alpha", "arrow_fill_beta", "arrow_score", "poa_align", "poa_map", "poa_commit", "poa_consensus",
+KERNELS = ["arrow_fill_alpha", "arrow_fill_beta", "arrow_score", "poa_align", "poa_map", "poa_traceback", "poa_commit", "poa_consensus",
            "arrow_pack_rowcodes"]
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",

@@ -90,7 +90,7 @@ int main(int argc, char** argv) {
         std::vector<uint32_t> meta(hdr.voff + cap);
         std::vector<int32_t> pred0(hdr.voff + cap), predx(7 * (hdr.voff + cap)), rank(hdr.voff + cap), ordA(hdr.voff + cap), ordB(hdr.voff + cap), col(hdr.voff + cap);
         PoaGraphView G{&hdr, meta.data(), pred0.data(), predx.data(), rank.data(), {ordA.data(), ordB.data()}, col.data()};
-        std::vector<int32_t> scratch(5 * 2000 + 4 * cap + 16), sm(64);
+        std::vector<int32_t> scratch(5 * 2000 + 12 * cap + 16), sm(64), sh(kPoaConsShared);
         std::vector<uint8_t> cons(cap);
         int32_t cons_len = 0;
 
@@ -130,7 +130,7 @@ int main(int argc, char** argv) {
                 const int n = og.n_reads;
                 if (n != hdr.n_reads) return fail("n_reads", trial, round);
                 const std::vector<int> oc = og.consensus(n < 5 ? 1 : (n + 1) / 2 - 1);
-                run_team(team, [&](TeamExec& x) { poa_graph_consensus(x, G, 0, scratch.data(), cons.data(), &cons_len); });
+                run_team(team, [&](TeamExec& x) { poa_graph_consensus(x, G, 0, scratch.data(), cons.data(), &cons_len, sh.data()); });
                 if ((int)oc.size() != cons_len) return fail("consensus length", trial, round);
                 for (size_t k = 0; k < oc.size(); ++k) if (cons[k] != og.v[oc[k]].base) return fail("consensus base", trial, round);
             }

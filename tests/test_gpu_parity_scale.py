@@ -254,3 +254,39 @@ def test_draft_cascade_matches_oracle(ctx):
             s0, s1 = res["seq_off"][zi], res["seq_off"][zi + 1]
             assert np.array_equal(res["seq"][s0:s1], oc["seq"])
     assert n_ok == 3 and d["status"][3] in (7, 8)     # the cascade rescued the three; the hopeless one stays failed
+
+
+@pytest.mark.parametrize("wsize,wover", [(512, 64), (256, 128), (0, 64)])
+def test_windowing_parameters_match_oracle(ctx, wsize, wover):
+    """Windowing (docs/how-does-ccs-work.md:57-61,108-110) with non-default window sizes, and switched off: the same cuts,
+    read slices, per-window polish and stitching as the oracle -- identical status, consensus, iteration and mutation
+    counts and read statuses, QV within 1, summed per-read LL within 1e-4 -- including a ZMW with a partial pass that ends
+    inside a window and one that is too short to be split."""
+    cfg = sim.get_config(3, insert_mean=2600)
+    zs = [sim.simulate_zmw(MODEL, cfg, 500 + i) for i in range(5)]
+    zs.append(sim.simulate_zmw(MODEL, sim.get_config(2, insert_mean=700), 77))
+    batch = api.Batch(zs)
+    pc = ctx.default_polish_cfg()
+    pc.window_size = wsize; pc.window_overlap = wover
+    res = ctx.ccs(batch, None, pc)
+    n_multi = 0
+    for zi, z in enumerate(zs):
+        reads = [z.read(k) for k in range(z.n_reads)]
+        o = O.ccs_zmw(MODEL, z.snr, reads, z.cx, window_size=wsize, window_overlap=wover)
+        assert res["status"][zi] == o["status"], (zi, res["status"][zi], o["status"])
+        s0, s1 = res["seq_off"][zi], res["seq_off"][zi + 1]
+        if o["status"] not in (16, 14, 13):
+            assert s1 == s0
+            continue
+        assert np.array_equal(res["seq"][s0:s1], o["seq"]), zi
+        assert np.max(np.abs(res["qv"][s0:s1].astype(int) - o["qv"].astype(int))) <= 1, zi
+        assert res["iterations"][zi] == o["iterations"] and res["n_applied"][zi] == o["n_applied"], zi
+        assert res["n_tested"][zi] == o["n_tested"], zi
+        r0, r1 = batch.zmw_read_off[zi], batch.zmw_read_off[zi + 1]
+        assert np.array_equal(res["read_status"][r0:r1], o["read_status"]), zi
+        both = ~np.isnan(o["read_ll"])
+        assert np.array_equal(~np.isnan(res["read_ll"][r0:r1]), both), zi
+        assert np.max(np.abs(res["read_ll"][r0:r1][both] - o["read_ll"][both])) < 1e-4, zi
+        if wsize and len(o["seq"]) >= 2 * wsize:
+            n_multi += 1
+    assert (n_multi >= 4) == (wsize > 0)
