@@ -7,11 +7,12 @@
 //   H[v][i] = max(C[v][i], H[v][i-1] + INS)            -- in-row chain = warp prefix-max scan
 //
 // int32 max-plus arithmetic, bit-exact against the oracle.  The graph is device resident (poa_device.h): the
-// kernel walks order[t], rows are stored by vertex id.  Each lane owns two adjacent cells; the previous row
-// lives in shared memory (the common predecessor), older rows are re-read from global memory only when a
-// vertex has a non-adjacent predecessor.  Reads are the uploaded emission codes, oriented on the fly.  Per
-// vertex the kernel writes 64 B of traceback moves (+ 256 B of scores for DAGs): algorithmic bytes per task
-// = V * (64 [+256] + 8) + n.
+// kernel walks order[t], rows are stored by vertex id.  Each lane owns two adjacent cells; the previous row lives in
+// registers (the common predecessor), the last 8 rows of a graph task in a shared-memory ring, older rows are re-read
+// from global memory only when a vertex has a predecessor further back.  The band of every row of a 32-row block is
+// placed from the block's anchor row (block-anchored band rule, DESIGN.md "Draft stage").  Reads are the uploaded
+// emission codes, oriented on the fly.  Per vertex the kernel writes 64 B of traceback moves and its band start
+// (+ 256 B of scores for DAGs): algorithmic bytes per task = V * (64 [+256] + 4) + n.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "poa_device.h"
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
     }
     // windowing: grid[t / 64] = number of oriented read bases placed before template position t on the path (the base
     // matched there, or the next one when t is deleted), for every t that is a multiple of kWindowGrid
-    int32_t* __restrict__ gr = (grid != nullptr && T.grid_off >= 0 && lane == 0) ? grid + T.grid_off : nullptr;
+    int32_t* __restrict__ gr = (grid != nullptr && T.grid_off >= 0) ? grid + T.grid_off : nullptr;
     bool done = t < 0;
     while (!done) {
         const int wbase = max(t - 31, 0);
@@ -357,13 +358,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
         }
         __syncwarp();
         while (t >= wbase) {
-            const int c = i - s_lo[warp][t - wbase];
-            if ((unsigned)c >= (unsigned)kPoaBand) { done = true; break; }
-            const unsigned m = s_mv[warp][(t - wbase) * kPoaBand + c];
+            // the lanes look at the next cells of the diagonal at once, (t - j, i - j): the walk advances over the whole
+            // run of matches placed on the position before them (move byte 1; the first row of the draft carries 253)
+            const int tj = t - lane, ij = i - lane;
+            unsigned mj = 0u;
+            bool inb = false;
+            if (tj >= wbase) {
+                const int c = ij - s_lo[warp][tj - wbase];
+                inb = (unsigned)c < (unsigned)kPoaBand;
+                if (inb) mj = s_mv[warp][(tj - wbase) * kPoaBand + c];
+            }
+            const unsigned okm = __ballot_sync(kFull, inb && mj == 1u);
+            const int run = (okm == kFull) ? 32 : __ffs(~okm) - 1;
+            if (run > 0) {
+                if (gr != nullptr && lane < run && (tj & (kWindowGrid - 1)) == 0) gr[tj / kWindowGrid] = ij - 1;
+                if (r.last_t < 0) { r.last_t = t; r.last_i = i - 1; }
+                r.first_t = t - (run - 1); r.first_i = i - 1 - (run - 1);
+                len += run; t -= run; i -= run;
+                continue;
+            }
+            // one step from lane 0's cell
+            if (__shfl_sync(kFull, inb ? 1 : 0, 0) == 0) { done = true; break; }
+            const unsigned m = __shfl_sync(kFull, mj, 0);
             const unsigned kind = m & 3u, k = m >> 2;
             if (kind == 0u) { done = true; break; }
             ++len;
-            if (gr != nullptr && kind != 3u && (t & (kWindowGrid - 1)) == 0) gr[t / kWindowGrid] = (kind == 1u) ? i - 1 : i;
+            if (gr != nullptr && lane == 0 && kind != 3u && (t & (kWindowGrid - 1)) == 0) gr[t / kWindowGrid] = (kind == 1u) ? i - 1 : i;
             if (kind == 1u) {           // match / mismatch: read base i-1 on template position t
                 if (r.last_t < 0) { r.last_t = t; r.last_i = i - 1; }
                 r.first_t = t; r.first_i = i - 1;
@@ -384,10 +404,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_traceback_kernel(
 }  // namespace
 
 void launch_poa_align(const PoaTask* tasks, int n_tasks, const PoaGraphView& G, const uint8_t* drafts, const uint8_t* codes,
-                      const uint8_t* rev_flags, int32_t* lo, int32_t* besti, uint8_t* moves, int32_t* hrows,
+                      const uint8_t* rev_flags, int32_t* lo, uint8_t* moves, int32_t* hrows,
                       PoaStep* steps, PoaResult* results, cudaStream_t stream, int32_t* grid) {
     if (n_tasks <= 0) return;
-    (void)besti;
     const int blocks = (n_tasks + kWarpsPerCta - 1) / kWarpsPerCta;
     if (hrows == nullptr)        // linear templates (subread -> draft mapping)
         poa_align_kernel<false><<<blocks, kWarpsPerCta * 32, 0, stream>>>(tasks, n_tasks, G, drafts, codes, rev_flags, lo, moves,

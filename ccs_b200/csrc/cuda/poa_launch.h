@@ -5,11 +5,11 @@
 
 namespace ccs {
 
-// Runs the DP (one warp per task) and the traceback on `stream`.  hrows may be NULL when every task is linear;
+// Runs the DP (one warp per task) and the traceback on `stream`.  hrows == NULL: every task is linear (mapping);
 // steps are written for DAG tasks only; grid (optional): linear tasks with grid_off >= 0 record the read position at
 // every kWindowGrid-th template base of their path.
 void launch_poa_align(const PoaTask* tasks, int n_tasks, const PoaGraphView& G, const uint8_t* drafts, const uint8_t* codes,
-                      const uint8_t* rev_flags, int32_t* lo, int32_t* besti, uint8_t* moves, int32_t* hrows,
+                      const uint8_t* rev_flags, int32_t* lo, uint8_t* moves, int32_t* hrows,
                       PoaStep* steps, PoaResult* results, cudaStream_t stream, int32_t* grid = nullptr);
 
 // seeds[k]: {graph, codes_off, n} of the seed read of graph k

@@ -55,7 +55,7 @@ void DraftEngine::release_buffers() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
     d_codes_.release(); d_desc_.release(); d_rev_.release(); d_moves_.release(); d_draft_.release(); d_meta_.release();
-    d_pred0_.release(); d_predx_.release(); d_rank_.release(); d_order_.release(); d_lo_.release(); d_besti_.release();
+    d_pred0_.release(); d_predx_.release(); d_rank_.release(); d_order_.release(); d_lo_.release();
     d_hrows_.release(); d_scratch_.release(); d_draft_len_.release(); d_steps_.release(); d_results_.release();
     d_grid_.release(); d_col_.release();
 }
@@ -267,7 +267,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
     }
     d_meta_.ensure((size_t)pool + 16); d_pred0_.ensure((size_t)pool + 16); d_predx_.ensure((size_t)pool * 7 + 16);
     d_rank_.ensure((size_t)pool + 16); d_order_.ensure((size_t)pool * 2 + 16); d_col_.ensure((size_t)pool + 16);
-    d_lo_.ensure((size_t)pool + 16); d_besti_.ensure((size_t)pool + 16);
+    d_lo_.ensure((size_t)pool + 16);
     d_moves_.ensure((size_t)pool * kPoaBand + 16); d_hrows_.ensure((size_t)pool * kPoaBand + 16);
     d_scratch_.ensure((size_t)soff[ng] + 16); d_steps_.ensure((size_t)stoff[ng] + 16);
     d_results_.ensure((size_t)ng + 1); d_draft_.ensure((size_t)pool + 16); d_draft_len_.ensure((size_t)ng + 1);
@@ -296,11 +296,11 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
             // rows of round k: the graph has grown by an unknown (device-side) number of vertices; count the seed length
             const int64_t rows = lens[work[zlist[g]].poa_reads[0]];
             stats.rows += rows;
-            rbytes += rows * (kPoaBand + 8 + 4 * kPoaBand) + lens[work[zlist[g]].poa_reads[k + 1]] + rows;
+            rbytes += rows * (kPoaBand + 4 + 4 * kPoaBand) + lens[work[zlist[g]].poa_reads[k + 1]] + rows;
         }
         stats.bytes_align += rbytes;
         span(&stats.ms_align, rbytes, &stats.top_align_bytes, &stats.top_align_ms);
-        launch_poa_align(tk, nt, G, d_draft_.p, d_codes_.p, d_rev_.p, d_lo_.p, d_besti_.p, d_moves_.p, d_hrows_.p,
+        launch_poa_align(tk, nt, G, d_draft_.p, d_codes_.p, d_rev_.p, d_lo_.p, d_moves_.p, d_hrows_.p,
                          d_steps_.p, d_results_.p, stream_);
         span_end();
         span(&stats.ms_graph);
@@ -348,7 +348,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
             const int J = h_draft_len_.p[g];
             int nk = 0;
             for (int r = in.zmw_read_off[z]; r < in.zmw_read_off[z + 1]; ++r) nk += out.keep[r];
-            if (lj > li && (rows + (int64_t)nk * J) * (kPoaBand + 8) > (int64_t)budget_) break;
+            if (lj > li && (rows + (int64_t)nk * J) * (kPoaBand + 4) > (int64_t)budget_) break;
             for (int r = in.zmw_read_off[z]; r < in.zmw_read_off[z + 1]; ++r)
                 if (out.keep[r]) { task_read.push_back(r); task_g.push_back(g); }
             rows += (int64_t)nk * J;
@@ -382,12 +382,12 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
                     T.grid_off = grid_total;
                     grid_total += J / kWindowGrid + 1;
                     ro += J;
-                    mbytes += (int64_t)J * (kPoaBand + 8) + lens[r] + J;
+                    mbytes += (int64_t)J * (kPoaBand + 4) + lens[r] + J;
                 }
                 Jb.read_end = k;
             }
         }
-        d_lo_.ensure((size_t)rows + 16); d_besti_.ensure((size_t)rows + 16); d_moves_.ensure((size_t)rows * kPoaBand + 16);
+        d_lo_.ensure((size_t)rows + 16); d_moves_.ensure((size_t)rows * kPoaBand + 16);
         d_results_.ensure((size_t)nt + 1); h_results_.ensure((size_t)nt + 1);
         d_grid_.ensure((size_t)grid_total + 16); h_grid_.ensure((size_t)grid_total + 16);
         CCS_CUDA(cudaMemsetAsync(d_grid_.p, 0xff, sizeof(int32_t) * (size_t)grid_total, stream_));
@@ -400,7 +400,7 @@ void DraftEngine::poa_chunk(const DraftInput& in, const DraftParams& dp, DraftOu
         span_end();
         stats.bytes_map += mbytes;
         span(&stats.ms_map, mbytes, &stats.top_map_bytes, &stats.top_map_ms);
-        launch_poa_align(at<PoaTask>(db, o_t2), nt, G0, d_draft_.p, d_codes_.p, d_rev_.p, d_lo_.p, d_besti_.p, d_moves_.p,
+        launch_poa_align(at<PoaTask>(db, o_t2), nt, G0, d_draft_.p, d_codes_.p, d_rev_.p, d_lo_.p, d_moves_.p,
                          nullptr, nullptr, d_results_.p, stream_, d_grid_.p);
         span_end();
         stats.n_graph_launches += 1; stats.n_align_launches += 2; stats.n_tasks += nt; stats.rows += rows;

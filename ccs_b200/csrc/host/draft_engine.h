@@ -86,7 +86,7 @@ private:
     size_t ev_used_ = 0;
     DevBuf<uint8_t> d_codes_, d_desc_, d_rev_, d_moves_, d_draft_;
     DevBuf<uint32_t> d_meta_;
-    DevBuf<int32_t> d_pred0_, d_predx_, d_rank_, d_order_, d_lo_, d_besti_, d_hrows_, d_scratch_, d_draft_len_, d_grid_, d_col_;
+    DevBuf<int32_t> d_pred0_, d_predx_, d_rank_, d_order_, d_lo_, d_hrows_, d_scratch_, d_draft_len_, d_grid_, d_col_;
     DevBuf<PoaStep> d_steps_;
     DevBuf<PoaResult> d_results_;
     PinBuf<uint8_t> h_codes_, h_desc_, h_draft_, h_rev_;

@@ -88,8 +88,9 @@ def main():
                 "each kernel = the full-population launch; `poa_map` = the 5th `poa_align_kernel` launch, the subread -> draft mapping) and "
                 "`profiles/%s_launches_bench.csv` (`ncu --metrics gpu__time_duration.sum --clock-control none` over the default "
                 "`python bench.py --steps 2 --warmup 1 --no-cpu-baseline` = config 3, 2 contexts x 4 lanes; per-launch times "
-                "are cold-cache and serialised, compare shares). Commands: `scripts/gpu_profile_r2.sh`; regenerate with "
-                "`python scripts/summarize_profiles.py`.\n\n" % (TAG, TAG))
+                "are cold-cache and serialised, compare shares). Commands: `scripts/gpu_profile_%s.sh` (r2b: fill / score captures "
+                "by `gpu_profile_r2b.sh`; Draft Stage kernels and the launch list re-captured on the final kernels by "
+                "`gpu_profile_r2c.sh`); regenerate with `python scripts/summarize_profiles.py %s`.\n\n" % (TAG, TAG, TAG, TAG))
         f.write("| kernel | duration ms | DRAM read GB | DRAM write GB | DRAM %peak | issue-active % | warp-instr | regs | warps active % | top stalls (% of samples) |\n|---|---|---|---|---|---|---|---|---|---|\n")
         for k in kernels:
             d = res[k]
