@@ -15,6 +15,7 @@
 // (+ 256 B of scores for DAGs): algorithmic bytes per task = V * (64 [+256] + 4) + n.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 #include "poa_device.h"
 #include "poa_launch.h"
 
@@ -124,9 +125,63 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
             const uint32_t d0 = kDag ? __shfl_sync(kFull, md0, r) : 1u;
             const int dl = lo - prev_lo;
             const int i0 = lo + 2 * lane, i1 = i0 + 1;
-            int c0, c1;
-            unsigned m0, m1;
-            if (npred == 1 && (d0 & 255u) == 1u) {
+            // interior row (warp-uniform): every cell is a real read prefix with a base in front of it -- no validity tests
+            const bool interior = lo >= 1 && lo + kPoaBand <= n;
+            // insertion chain H[c] = max(C[c], H[c-1] + INS) over the row's cells with i <= n, row outputs, best cell
+            auto finish = [&](auto tag, const int c0, const int c1, unsigned m0, unsigned m1) {
+                constexpr bool kIn = decltype(tag)::value;       // interior row: every cell valid
+                const int ofs = -kPoaIns * (2 * lane);
+                int x0 = c0 + ofs, x1 = c1 + ofs - kPoaIns;
+                if (!kIn) {
+                    if (i0 > n) x0 = kNeg;
+                    if (i1 > n) x1 = kNeg;
+                }
+                x1 = max(x1, x0);
+                int sc = x1;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int y = __shfl_up_sync(kFull, sc, off);
+                    if (lane >= off) sc = max(sc, y);
+                }
+                int carry = __shfl_up_sync(kFull, sc, 1);
+                if (lane == 0) carry = kNeg;
+                x0 = max(x0, carry);
+                x1 = max(x1, x0);
+                int H0 = x0 - ofs, H1 = x1 - ofs + kPoaIns;
+                if (!kIn) {
+                    if (i0 > n) H0 = 0;
+                    if (i1 > n) H1 = 0;
+                }
+                if (H0 > c0) m0 = 3u;
+                if (H1 > c1) m1 = 3u;
+                // row outputs (by vertex id)
+                *reinterpret_cast<uchar2*>(mv_r + (size_t)id * kPoaBand + 2 * lane) = make_uchar2((unsigned char)m0, (unsigned char)m1);
+                if (kDag) {
+                    __syncwarp();   // everyone has read the ring
+                    int* srow = s_ring[wslot][t & (kRing - 1)];
+                    srow[2 * lane] = H0; srow[2 * lane + 1] = H1;
+                    if (lane == 0) s_rlo[wslot][t & (kRing - 1)] = lo;
+                    if (h_r != nullptr) *reinterpret_cast<int2*>(h_r + (size_t)id * kPoaBand + 2 * lane) = make_int2(H0, H1);
+                    __syncwarp();   // row visible in shared memory before the next vertex reads it
+                }
+                // this lane's best cell so far: the first row that reaches its maximum, smaller prefix first within a row
+                if (H0 > lbest) { lbest = H0; lt = t; li = i0; lid = id; }
+                if (H1 > lbest) { lbest = H1; lt = t; li = i1; lid = id; }
+                pH0 = H0; pH1 = H1; prev_lo = lo;
+            };
+            if (npred == 1 && (d0 & 255u) == 1u && dl == 1 && interior) {
+                // hot path: the only predecessor is the previous row (registers), the band moved with the diagonal, every
+                // cell is valid -- own two cells + the next lane's first, one new read base
+                const int hm1 = pH0, h0 = pH1;
+                int h1 = __shfl_down_sync(kFull, pH0, 1);
+                if (lane == 31) h1 = 0;
+                rb0 = rb1;
+                rb1 = (rbp[(i1 - 1) * rdir] & 3) ^ rxor;
+                const int bm0 = hm1 + ((rb0 == vb) ? kPoaMatch : kPoaMismatch), bm1 = h0 + ((rb1 == vb) ? kPoaMatch : kPoaMismatch);
+                const int bd0 = h0 + kPoaDel, bd1 = h1 + kPoaDel;
+                const int c0 = max(max(bm0, bd0), 0), c1 = max(max(bm1, bd1), 0);
+                finish(std::true_type(), c0, c1, (c0 == 0) ? 0u : ((bm0 >= bd0) ? 1u : 2u), (c1 == 0) ? 0u : ((bm1 >= bd1) ? 1u : 2u));
+            } else if (npred == 1 && (d0 & 255u) == 1u) {
                 // the only predecessor is the previous row, held in registers as band cells 2*lane, 2*lane + 1
                 int hm1, h0, h1;
                 if (dl == 1) {            // band moved with the diagonal: own two cells + the next lane's first
@@ -153,9 +208,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
                 const int bd0 = (i0 <= n) ? h0 + kPoaDel : 0;
                 const int bd1 = (i1 <= n) ? h1 + kPoaDel : 0;
                 // match wins ties against deletion; candidates must be > 0.  Predecessor index 0 = the only one.
-                c0 = max(max(bm0, bd0), 0); c1 = max(max(bm1, bd1), 0);
-                m0 = (c0 == 0) ? 0u : ((bm0 >= bd0) ? 1u : 2u);
-                m1 = (c1 == 0) ? 0u : ((bm1 >= bd1) ? 1u : 2u);
+                const int c0 = max(max(bm0, bd0), 0), c1 = max(max(bm1, bd1), 0);
+                finish(std::false_type(), c0, c1, (c0 == 0) ? 0u : ((bm0 >= bd0) ? 1u : 2u), (c1 == 0) ? 0u : ((bm1 >= bd1) ? 1u : 2u));
             } else {
                 rb0 = read_base(i0); rb1 = read_base(i1);
                 const int sc0 = (rb0 == vb) ? kPoaMatch : kPoaMismatch;
@@ -185,41 +239,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
                     }
                 }
                 // match wins ties against deletion (oracle evaluation order)
+                int c0, c1;
+                unsigned m0, m1;
                 if (bm0 >= bd0) { c0 = bm0; m0 = bm0 > 0 ? (1u | (km0 << 2)) : 0u; } else { c0 = bd0; m0 = 2u | (kd0 << 2); }
                 if (bm1 >= bd1) { c1 = bm1; m1 = bm1 > 0 ? (1u | (km1 << 2)) : 0u; } else { c1 = bd1; m1 = 2u | (kd1 << 2); }
+                finish(std::false_type(), c0, c1, m0, m1);
             }
-            // insertion chain: H[c] = max(C[c], H[c-1] + INS) over the row's cells with i <= n
-            int x0 = (i0 <= n) ? c0 - kPoaIns * (2 * lane) : kNeg;
-            int x1 = (i1 <= n) ? c1 - kPoaIns * (2 * lane + 1) : kNeg;
-            x1 = max(x1, x0);
-            int sc = x1;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int y = __shfl_up_sync(kFull, sc, off);
-                if (lane >= off) sc = max(sc, y);
-            }
-            int carry = __shfl_up_sync(kFull, sc, 1);
-            if (lane == 0) carry = kNeg;
-            x0 = max(x0, carry);
-            x1 = max(x1, x0);
-            const int H0 = (i0 <= n) ? x0 + kPoaIns * (2 * lane) : 0;
-            const int H1 = (i1 <= n) ? x1 + kPoaIns * (2 * lane + 1) : 0;
-            if (H0 > c0) m0 = 3u;
-            if (H1 > c1) m1 = 3u;
-            // row outputs (by vertex id)
-            *reinterpret_cast<uchar2*>(mv_r + (size_t)id * kPoaBand + 2 * lane) = make_uchar2((unsigned char)m0, (unsigned char)m1);
-            if (kDag) {
-                __syncwarp();   // everyone has read the ring
-                int* srow = s_ring[wslot][t & (kRing - 1)];
-                srow[2 * lane] = H0; srow[2 * lane + 1] = H1;
-                if (lane == 0) s_rlo[wslot][t & (kRing - 1)] = lo;
-                if (h_r != nullptr) *reinterpret_cast<int2*>(h_r + (size_t)id * kPoaBand + 2 * lane) = make_int2(H0, H1);
-                __syncwarp();   // row visible in shared memory before the next vertex reads it
-            }
-            // this lane's best cell so far: the first row that reaches its maximum, smaller prefix first within a row
-            if (H0 > lbest) { lbest = H0; lt = t; li = i0; lid = id; }
-            if (H1 > lbest) { lbest = H1; lt = t; li = i1; lid = id; }
-            pH0 = H0; pH1 = H1; prev_lo = lo;
         }
         // ---- anchor of the next block = this block's last row: best cell = largest value, smallest prefix on ties
         // (key = value * 64 + (63 - cell); scores are >= 0 and < 2^25)
