@@ -464,6 +464,11 @@ def main():
                          "largest_launch_frac_single_lane": dom["largest_launch"]["frac"],
                          "note": "timed lane/context configuration: spans of concurrent lanes overlap, so each launch is "
                                  "slowed by the others; see roofline_kernels for the serial figures"},
+            # all kernels of the timed region against its wall clock: algorithmic bytes of the fills, the scoring and the
+            # aligner launches / wall time of the K steps (the per-kernel spans above overlap; this one does not)
+            "roofline_whole_step": (lambda b: {"bytes": b, "wall_s": M["wall"], "achieved": b / M["wall"] / 1e9, "peak": peak,
+                                               "unit": "GB/s", "frac": b / M["wall"] / 1e9 / peak})(
+                float(st["bytes_fill_alpha"] + st["bytes_fill_beta"] + st["bytes_score"] + st["bytes_poa_align"] + st["bytes_poa_map"])),
             "roofline_kernels": rl,
             "kernel_ms": kern_ms, "rounds": st["rounds"] / M["n_steps"], "score_items_per_step": st["score_items"] / M["n_steps"],
             "other_configs": others,

@@ -58,6 +58,9 @@ void usage() {
                  "  --max-length INT     Maximum draft length before polishing (0: no limit). [50000]\n"
                  "  --min-rq FLOAT       Minimum predicted accuracy in [0, 1]. [0.99]\n"
                  "  --by-strand          Generate a consensus for each strand.\n"
+                 "  --window-size INT    Polish drafts of 2x this length and longer as independent windows of this many bases\n"
+                 "                       (rounded up to a multiple of 64; 0: never split). [1024]\n"
+                 "  --window-overlap INT Bases of padding on both sides of a window. [64]\n"
                  "  --chunk i/N          Operate on a single chunk. Format i/N, where i in [1,N].\n"
                  "  -j,--num-threads INT Number of host threads to use, 0 means autodetection. [0]\n"
                  "  --report-file FILE   Where to write the results report. [<out prefix>.ccs_report.txt]\n"
@@ -90,6 +93,8 @@ bool parse(int argc, char** argv, Options& o) {
         else if (a == "--max-length") o.d.max_length = o.p.max_length = std::atoi(val("--max-length"));
         else if (a == "--min-rq") o.p.min_rq = std::atof(val("--min-rq"));
         else if (a == "--by-strand") o.by_strand = true;
+        else if (a == "--window-size") o.p.window_size = std::max(0, std::atoi(val("--window-size")));
+        else if (a == "--window-overlap") o.p.window_overlap = std::max(0, std::atoi(val("--window-overlap")));
         else if (a == "--report-file") o.report = val("--report-file");
         else if (a == "--report-json") o.report_json = val("--report-json");
         else if (a == "--metrics-json") o.metrics = val("--metrics-json");
