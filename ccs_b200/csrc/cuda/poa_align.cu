@@ -139,10 +139,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) poa_align_kernel(
                 x1 = max(x1, x0);
                 int sc = x1;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const int y = __shfl_up_sync(kFull, sc, off);
-                    if (lane >= off) sc = max(sc, y);
-                }
+                for (int off = 1; off < 32; off <<= 1)      // a lane below `off` gets its own value back: max is idempotent
+                    sc = max(sc, __shfl_up_sync(kFull, sc, off));
                 int carry = __shfl_up_sync(kFull, sc, 1);
                 if (lane == 0) carry = kNeg;
                 x0 = max(x0, carry);

@@ -132,9 +132,11 @@ public:
     int host_threads = 8;         // threads for the per-ZMW host pieces of a round
     // ConsensusQualities re-scores only the positions within qv_halo of an edit made after they were last scored (or
     // never scored) and reuses the stored delta-LLs elsewhere: an edit further away than the halo moves a position's
-    // delta-LLs by less than QV rounding (measured: 0 of 2.76 M positions off by more than 1 QV at halo 20, 32, 48, 64;
-    // scripts/qv_reuse_check.py, profiles/r2_qv_reuse.txt).  -29 % scoring work at halo 32.  CCS_B200_REUSE_SCORES=0
-    // restores the full pass.
+    // delta-LLs by less than QV rounding (measured against the full pass: 0 of 2.76 M positions off by more than 1 QV at
+    // halo 20, 32, 48, 64; 155 / 122 / 93 / 80 off by exactly 1; scripts/qv_reuse_check.py, profiles/r2_qv_reuse.txt).
+    // -29 % scoring work at halo 32.  Halo 20 (= Polish()'s neighborhood) would save another 15 % of the scoring time, but
+    // one position of a 256-ZMW config-2 batch then lands 2 QV units from the oracle (the reuse error and the fp32 error
+    // add up across a rounding boundary): rejected.  CCS_B200_REUSE_SCORES=0 restores the full pass.
     bool reuse_scores = true;
     int qv_halo = 32;             // > neighborhood (20): positions within this distance of an edit are re-scored
     bool generic_score = false;   // use the unfactored reference scoring kernel (tests)
