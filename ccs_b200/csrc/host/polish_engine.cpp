@@ -314,15 +314,22 @@ void ArrowEngine::upload_templates_and_reads() {
     {
         std::vector<std::pair<int, int>> groups;   // (longest J, first slot in `slots`)
         std::vector<int32_t> slots, zr;
-        for (int z = 0; z < nz; ++z) {
-            if (!zstate_[z].dirty) continue;
+        // The windows of one draft share their transition table (same SNR), which is all a fill CTA has per "ZMW": their
+        // reads are packed into groups together, so a 12-read window does not leave a quarter of its CTA idle.
+        for (int z = 0; z < nz;) {
+            int ze = z + 1;
+            if (!zmw_group_.empty()) while (ze < nz && zmw_group_[ze] == zmw_group_[z]) ++ze;
             zr.clear();
-            for (int r = zstate_[z].read_begin; r < zstate_[z].read_end; ++r) if (reads_[r].active) zr.push_back(r);
+            for (int w = z; w < ze; ++w) {
+                if (!zstate_[w].dirty) continue;
+                for (int r = zstate_[w].read_begin; r < zstate_[w].read_end; ++r) if (reads_[r].active) zr.push_back(r);
+            }
             std::stable_sort(zr.begin(), zr.end(), [&](int a, int b) { return reads_[a].J > reads_[b].J; });
             for (size_t k = 0; k < zr.size(); k += 16) {
                 groups.emplace_back(reads_[zr[k]].J, (int)slots.size());
                 for (size_t x = 0; x < 16; ++x) slots.push_back(k + x < zr.size() ? zr[k + x] : -1);
             }
+            z = ze;
         }
         std::stable_sort(groups.begin(), groups.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
         order_.reserve(slots.size());
