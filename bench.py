@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--config", type=int, default=3, help="BASELINE.json config id (3 = largest single-GPU config)")
     ap.add_argument("--other-configs", default="2,5", help="configs also measured (fewer steps) at N=1; '' = none")
     ap.add_argument("--draft-error", type=float, default=0.02)
+    ap.add_argument("--max-poa-reads", type=int, default=0, help="override the Draft Stage's max_poa_reads (0 = library default)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="ZMWs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=4, help="concurrent engine lanes per context (0 = library default)")
@@ -267,6 +268,8 @@ def measure(args, cfg_id, zmws, steps, warmup, ctxs, model, rank, world, local, 
     ctx = ctxs[0]
     pcfg = ctx.default_polish_cfg()
     dcfg = ctx.default_draft_cfg()
+    if args.max_poa_reads > 0:
+        dcfg.max_poa_reads = args.max_poa_reads
 
     def barrier():
         torch.cuda.synchronize()
