@@ -36,7 +36,8 @@ __device__ __forceinline__ unsigned vmax_oct(unsigned key) {
     return key;
 }
 
-__global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
+template <int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) arrow_fill_alpha_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
                                                                const int n_items) {
     __shared__ __align__(128) float2 s_t3[kT3Rows * kEmStride];
     {
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(128) arrow_fill_alpha_kernel(const ArrowBatchV
     }
 }
 
-__global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
+template <int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) arrow_fill_beta_kernel(const ArrowBatchView V, const int32_t* __restrict__ order,
                                                               const int n_items) {
     __shared__ __align__(128) float2 s_t2[kT2Rows * kEmStride];
     {
@@ -346,12 +348,21 @@ __global__ void __launch_bounds__(128) arrow_fill_beta_kernel(const ArrowBatchVi
 // (longest template first), padded with -1; a group's first entry is a real read.
 void launch_fill_alpha(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream) {
     if (n_items <= 0) return;
-    arrow_fill_alpha_kernel<<<(n_items + 15) / 16, 128, 0, stream>>>(V, order, n_items);
+    // occupancy target (CTAs of 128 threads per SM): CCS_B200_FILL_VARIANT = 0 (compiler's choice), 10, 12 -- for A/B runs
+    static const int variant = [] { const char* e = std::getenv("CCS_B200_FILL_VARIANT"); return e ? std::atoi(e) : 0; }();
+    const int grid = (n_items + 15) / 16;
+    if (variant == 12) arrow_fill_alpha_kernel<12><<<grid, 128, 0, stream>>>(V, order, n_items);
+    else if (variant == 10) arrow_fill_alpha_kernel<10><<<grid, 128, 0, stream>>>(V, order, n_items);
+    else arrow_fill_alpha_kernel<0><<<grid, 128, 0, stream>>>(V, order, n_items);
 }
 
 void launch_fill_beta(const ArrowBatchView& V, const int32_t* order, int n_items, cudaStream_t stream) {
     if (n_items <= 0) return;
-    arrow_fill_beta_kernel<<<(n_items + 15) / 16, 128, 0, stream>>>(V, order, n_items);
+    static const int variant = [] { const char* e = std::getenv("CCS_B200_FILL_VARIANT"); return e ? std::atoi(e) : 0; }();
+    const int grid = (n_items + 15) / 16;
+    if (variant == 12) arrow_fill_beta_kernel<10><<<grid, 128, 0, stream>>>(V, order, n_items);
+    else if (variant == 10) arrow_fill_beta_kernel<8><<<grid, 128, 0, stream>>>(V, order, n_items);
+    else arrow_fill_beta_kernel<0><<<grid, 128, 0, stream>>>(V, order, n_items);
 }
 
 }  // namespace ccs

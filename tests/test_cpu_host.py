@@ -54,6 +54,7 @@ def test_cfg_defaults():
     p = api.CPolishCfg(); L.ccs_polish_cfg_default(C.byref(p))
     assert (p.max_iterations, p.separation, p.neighborhood) == (40, 10, 20)
     assert p.min_rq == pytest.approx(0.99)          # rq >= 0.99 <=> HiFi, docs/faq/reads-bam.md:38
+    assert (p.window_size, p.window_overlap) == (1024, 64)   # windowing, docs/how-does-ccs-work.md:57-61
     d = api.CDraftCfg(); L.ccs_draft_cfg_default(C.byref(d))
     assert (d.min_passes, d.top_passes) == (3, 60)  # --top-passes 60, docs/faq/accuracy-vs-passes.md:48-52
     assert d.min_snr == pytest.approx(2.5)
