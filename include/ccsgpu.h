@@ -74,7 +74,7 @@ typedef enum ccs_read_status {
 /* The model is an opaque POD blob of ccs_model_sizeof() bytes (ccs::ArrowModelParams). */
 int  ccs_model_sizeof(void);
 void ccs_model_synthetic(void* model_out);
-/* Arrow model <-> JSON, the chemistry-bundle mechanism ($SMRT_CHEMISTRY_BUNDLE_DIR/arrow/*.json,
+/* Arrow model <-> JSON, the chemistry-bundle mechanism ($SMRT_CHEMISTRY_BUNDLE_DIR/arrow/<name>.json,
  * /root/reference/docs/faq/chemistry.md:28-56).  CCS_ERR_CHEMISTRY for an unsupported form / malformed file. */
 int  ccs_model_save_json(const void* model, const char* path);
 int  ccs_model_load_json(const char* path, void* model_out);

@@ -33,8 +33,12 @@ def _oracle_many(zs):
         return list(ex.map(lambda z: O.ccs_zmw(MODEL, z["snr"], z["reads"], z["cx"]), zs))
 
 
+SCALE = max(1, int(os.environ.get("CCS_PARITY_SCALE", "1")))      # CCS_PARITY_SCALE=2 doubles the batches (profiles/)
+
+
 @pytest.mark.parametrize("cfg_id,n", [(2, 256), (3, 64), (5, 64)])
 def test_bench_scale_parity_with_oracle(ctx, cfg_id, n):
+    n *= SCALE
     cfg = sim.get_config(cfg_id)
     a = sim.simulate_batch(MODEL, cfg, 20_000, n, -1.0, CORES)
     b = api.Batch.from_arrays(a["zmw_read_off"], a["read_off"], a["codes"], a["snr"], a["cx"], a["hole"])
