@@ -560,19 +560,24 @@ int64_t ArrowEngine::pick(std::vector<Candidate>& out) {
         span_begin(&stats.ms_pick);
         launch_pick(V, d_ranges_.p, n_ranges_, n_range_items_, d_delta_.p, d_cand_.p, (int)d_cand_.cap, d_counter_.p, stream_);
         span_end();
+        // one synchronisation per round: the counter and a first slab of candidates come back together (late rounds have
+        // a handful of candidates; the first round of a big chunk fetches the rest with a second copy)
+        const size_t slab = std::min<size_t>(d_cand_.cap, 16384);
+        h_cand_.ensure(slab + 1);
         CCS_CUDA(cudaMemcpyAsync(h_counter_.p, d_counter_.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        CCS_CUDA(cudaMemcpyAsync(h_cand_.p, d_cand_.p, sizeof(Candidate) * slab, cudaMemcpyDeviceToHost, stream_));
         CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
         resolve_spans();
         ++stats.n_pick;
         const int64_t n = h_counter_.p[0];
         if ((size_t)n <= d_cand_.cap) {
-            h_cand_.ensure((size_t)n + 1);
-            if (n > 0) {
+            if ((size_t)n > slab) {
+                h_cand_.ensure((size_t)n + 1);      // (grow-only; the slab is copied again with the rest)
                 CCS_CUDA(cudaMemcpyAsync(h_cand_.p, d_cand_.p, sizeof(Candidate) * n, cudaMemcpyDeviceToHost, stream_));
                 CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
-                stats.d2h_bytes += (int64_t)sizeof(Candidate) * n;
-                out.assign(h_cand_.p, h_cand_.p + n);
             }
+            stats.d2h_bytes += (int64_t)sizeof(Candidate) * std::max<int64_t>(n, (int64_t)slab);
+            out.assign(h_cand_.p, h_cand_.p + n);
             return n;
         }
         cap = (size_t)n + 1024;   // overflow: grow and retry once
@@ -787,11 +792,15 @@ void ArrowEngine::remap_deltas() {
     if (jobs.empty() || !d_delta_.p) return;
     d_delta_scratch_.ensure((size_t)(scratch + 2) * kDeltaStride);
     d_remap_jobs_.ensure(jobs.size()); d_remap_sites_.ensure(sites.size() + 1); d_remap_shifts_.ensure(shifts.size() + 1);
-    // small pageable copies: synchronous with respect to the host buffers, ordered on the engine stream
-    CCS_CUDA(cudaMemcpyAsync(d_remap_jobs_.p, jobs.data(), sizeof(RemapJob) * jobs.size(), cudaMemcpyHostToDevice, stream_));
-    CCS_CUDA(cudaMemcpyAsync(d_remap_sites_.p, sites.data(), 4 * sites.size(), cudaMemcpyHostToDevice, stream_));
-    CCS_CUDA(cudaMemcpyAsync(d_remap_shifts_.p, shifts.data(), 4 * shifts.size(), cudaMemcpyHostToDevice, stream_));
-    CCS_CUDA(stream_sync_blocking(stream_, ev_sync_));
+    // staged through pinned buffers of the engine: no synchronisation here (the next round's remap comes after this
+    // round's fill and pick synchronisations, so the buffers are free again by then)
+    h_remap_jobs_.ensure(jobs.size()); h_remap_ints_.ensure(sites.size() + shifts.size() + 2);
+    std::memcpy(h_remap_jobs_.p, jobs.data(), sizeof(RemapJob) * jobs.size());
+    std::memcpy(h_remap_ints_.p, sites.data(), 4 * sites.size());
+    std::memcpy(h_remap_ints_.p + sites.size(), shifts.data(), 4 * shifts.size());
+    CCS_CUDA(cudaMemcpyAsync(d_remap_jobs_.p, h_remap_jobs_.p, sizeof(RemapJob) * jobs.size(), cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_remap_sites_.p, h_remap_ints_.p, 4 * sites.size(), cudaMemcpyHostToDevice, stream_));
+    CCS_CUDA(cudaMemcpyAsync(d_remap_shifts_.p, h_remap_ints_.p + sites.size(), 4 * shifts.size(), cudaMemcpyHostToDevice, stream_));
     launch_remap_delta(d_remap_jobs_.p, (int)jobs.size(), d_remap_sites_.p, d_remap_shifts_.p, d_delta_.p,
                        d_delta_scratch_.p, stream_);
 }

@@ -217,6 +217,8 @@ private:
     PinBuf<double> h_ll_;
     PinBuf<ScoreRange> h_ranges_, h_ranges_qv_;   // two host lists: the QV list is staged while the scoring list's copy may still be in flight
     PinBuf<Candidate> h_cand_;
+    PinBuf<RemapJob> h_remap_jobs_;
+    PinBuf<int32_t> h_remap_ints_;
 };
 
 }  // namespace ccs
