@@ -260,11 +260,28 @@ CCS_HD void poa_graph_consensus(X& x, const PoaGraphView& G, int g, int32_t* scr
         }
         x.sync();
     }
-    if (tid == 0) {
-        // backtrack into sc[] (no longer needed), reversed
-        int len = 0;
-        for (int k = bt; k >= 0; k = bp[k]) sc[len++] = ord[k];
-        *out_len = len;
+    // Backtrack into sc[] (no longer needed), reversed.  Back pointers lead to lower ranks, mostly the next lower one: the
+    // chunks are staged again from the last one down (back pointers and vertex ids), and the walking thread follows the
+    // path through shared memory instead of chasing one global load per vertex.
+    {
+        int k = bt, len = 0;                                   // state of the walking thread
+        int32_t* s_bp = s_kind;
+        int32_t* s_id = s_prk;
+        int32_t* s_stop = s_reach;                             // [0]: the path has ended (or never began)
+        for (int c0 = (V > 0 ? ((V - 1) / kPoaConsChunk) * kPoaConsChunk : 0); c0 >= 0 && V > 0; c0 -= kPoaConsChunk) {
+            const int nc = (V - c0 < kPoaConsChunk) ? V - c0 : kPoaConsChunk;
+            for (int j = tid; j < nc; j += T) { s_bp[j] = bp[c0 + j]; s_id[j] = ord[c0 + j]; }
+            x.sync();
+            if (tid == 0) {
+                while (k >= c0) { sc[len++] = s_id[k - c0]; k = s_bp[k - c0]; }
+                s_stop[0] = (k < 0) ? 1 : 0;
+            }
+            x.sync();
+            const int stop = s_stop[0];
+            x.sync();
+            if (stop) break;
+        }
+        if (tid == 0) *out_len = len;
     }
     x.sync();
     const int len = *out_len;
