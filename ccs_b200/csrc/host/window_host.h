@@ -96,7 +96,7 @@ inline void build_window_plan(int32_t nz, const int32_t* zmw_read_off, const int
                 const int32_t rs_o = m.strand ? n - m.rend : m.rstart, re_o = m.strand ? n - m.rstart : m.rend;
                 const int32_t s_o = (lo == m.tstart) ? rs_o : grid[grid_off[r] + lo / kWindowGrid];
                 const int32_t e_o = (hi == m.tend) ? re_o : grid[grid_off[r] + hi / kWindowGrid];
-                if (e_o - s_o < 2) continue;
+                if (e_o - s_o < 2 || s_o < 0 || e_o > n) continue;       // (the path passes every grid point inside its span)
                 const int32_t ns = m.strand ? n - e_o : s_o;                             // native slice [ns, ns + len)
                 P.parent.push_back(r);
                 P.code_start.push_back(read_off[r] + ns);

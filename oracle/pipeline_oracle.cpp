@@ -148,7 +148,7 @@ std::vector<WindowRead> window_reads(const Window& w, const std::vector<ReadMapp
         const int rs_o = m.strand ? n - m.rend : m.rstart, re_o = m.strand ? n - m.rstart : m.rend;   // oriented read
         const int s_o = (lo == m.tstart) ? rs_o : m.grid[lo / WINDOW_GRID];
         const int e_o = (hi == m.tend) ? re_o : m.grid[hi / WINDOW_GRID];
-        if (e_o - s_o < 2) continue;
+        if (e_o - s_o < 2 || s_o < 0 || e_o > n) continue;
         WindowRead x;
         x.parent = r; x.strand = m.strand; x.ts = lo - w.a; x.te = hi - w.a;
         x.ns = m.strand ? n - e_o : s_o; x.ne = m.strand ? n - s_o : e_o;                              // native slice
