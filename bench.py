@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--config", type=int, default=3, help="BASELINE.json config id (3 = largest single-GPU config)")
     ap.add_argument("--other-configs", default="2,5", help="configs also measured (fewer steps) at N=1; '' = none")
     ap.add_argument("--draft-error", type=float, default=0.02)
+    ap.add_argument("--deep-launch-zmws", type=int, default=2000,
+                    help="N=1 only: after the timed runs, one config-2 batch of this many ZMWs on a single lane with the whole "
+                         "device budget -- arrow_fill_alpha in one deep launch (0 = skip)")
     ap.add_argument("--max-poa-reads", type=int, default=0, help="override the Draft Stage's max_poa_reads (0 = library default)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="ZMWs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -496,6 +499,31 @@ def main():
             line["cpu_baseline"] = {"value": n / dt, "unit": "ZMW/s", "cores": cores, "kind": "port",
                                     "sample": f"first {n} ZMWs of step 0, {cores} threads, {dt:.1f} s",
                                     "consensus_identical": f"{same}/{n}", "qv_within_1": f"{qv_ok}/{n}"}
+        if world == 1 and args.minutes <= 0 and args.deep_launch_zmws > 0:
+            # arrow_fill_alpha (and beta) in ONE deep launch: the stage contexts of the timed runs are closed, a fresh
+            # context gets the whole device budget and a single lane, and a config-2 batch goes through it once
+            for c in ctxs:
+                c.close()
+            ctxs = []
+            try:
+                big = api.Context(model, device=local, budget_bytes=int(torch.cuda.mem_get_info()[0] * 0.85))
+                big.set_lanes(1)
+                bb, _ = make_batch(model, sim.get_config(2), 7_000_000, args.deep_launch_zmws, args.draft_error, threads)
+                big.stats(reset=True)
+                big.ccs(bb, big.default_draft_cfg(), big.default_polish_cfg())
+                torch.cuda.synchronize()
+                sb = big.stats()
+                big.close()
+
+                def _top(bk, mk):
+                    gb = sb[bk] / max(sb[mk], 1e-9) / 1e6
+                    return {"bytes": sb[bk], "ms": sb[mk], "achieved": gb, "unit": "GB/s", "peak": peak, "frac": gb / peak}
+                line["deep_launch"] = {
+                    "workload": "config 2, %d ZMWs in one chunk on one lane (largest launch of each fill kernel, CUDA events)" % args.deep_launch_zmws,
+                    "arrow_fill_alpha_kernel": _top("top_fill_alpha_bytes", "top_fill_alpha_ms"),
+                    "arrow_fill_beta_kernel": _top("top_fill_beta_bytes", "top_fill_beta_ms")}
+            except Exception as e:      # the probe must never cost the bench line
+                line["deep_launch"] = {"error": str(e)[:200]}
         emit(line)
     for c in ctxs:
         c.close()
